@@ -1,0 +1,97 @@
+"""Python mirror of the C ABI in include/crgpu.h (ctypes over libcrgpu.so).
+
+This is plumbing for tests and bench.py, not a second implementation: every call goes straight into the CUDA
+library.  If libcrgpu.so is missing or no CUDA device is present the calls raise -- there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcrgpu.so")
+
+ROLZ, LZP = 0, 1
+
+_lib = None
+
+
+class CrgpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("crgpu error %d: %s" % (code, msg))
+        self.code = code
+
+
+def load(path: str | None = None):
+    """Loads libcrgpu.so (once).  Raises FileNotFoundError if the CUDA extension has not been built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise FileNotFoundError(p + " is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                                "(comprox_b200 has no CPU fallback)")
+    L = ctypes.CDLL(p)
+    L.crgpu_strerror.restype = ctypes.c_char_p
+    L.crgpu_debug_fetch.restype = ctypes.c_int64
+    if path is None:
+        _lib = L
+    return L
+
+
+def _check(L, rc):
+    if rc != 0:
+        raise CrgpuError(rc, L.crgpu_strerror(rc).decode())
+
+
+class Handle:
+    """One crgpu_handle: the state a reference *process* holds in globals (models, dictionary, filter state)."""
+
+    def __init__(self, variant: int = ROLZ, device: int = 0, stream: int | None = None, lib=None):
+        self.L = lib or load()
+        self.h = ctypes.c_void_p()
+        _check(self.L, self.L.crgpu_create(ctypes.byref(self.h), variant, device, ctypes.c_void_p(stream or 0)))
+        self.variant = variant
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.crgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def reset_models(self):
+        _check(self.L, self.L.crgpu_reset_models(self.h))
+
+    def lzencode(self, blocks, chain_ends: bool = True):
+        """lzencode() of consecutive blocks of one model chain; returns the list of payloads."""
+        blocks = [bytes(b) for b in blocks]
+        n = len(blocks)
+        data = b"".join(blocks)
+        sizes = (ctypes.c_uint32 * max(n, 1))(*[len(b) for b in blocks])
+        osz = (ctypes.c_uint32 * max(n, 1))()
+        cap = len(data) + 64 * n + 1024
+        out = ctypes.create_string_buffer(cap)
+        _check(self.L, self.L.crgpu_lzencode(self.h, data, sizes, n, int(chain_ends), out, ctypes.c_uint64(cap), osz))
+        res, p = [], 0
+        for i in range(n):
+            res.append(out.raw[p:p + osz[i]])
+            p += osz[i]
+        return res
+
+    def debug_fetch(self, what: str, dtype="uint8"):
+        import numpy as np
+        n = self.L.crgpu_debug_fetch(self.h, what.encode(), None, ctypes.c_uint64(0))
+        if n < 0:
+            _check(self.L, int(n))
+        buf = np.empty(int(n), dtype=np.uint8)
+        if n:
+            self.L.crgpu_debug_fetch(self.h, what.encode(), buf.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint64(int(n)))
+        return buf.view(dtype)

@@ -1,0 +1,114 @@
+// cr_common.cuh -- shared definitions for the comprox-b200 CUDA library.
+//
+// Two ways to compile the kernels in this directory:
+//   * nvcc, sm_100a (the product: libcrgpu.so).  This is the only thing the C ABI ever runs.
+//   * g++ with -DCRGPU_SIM (tests/sim only).  "Kernel-logic simulation": every kernel that is written as
+//     independent threads (no __syncthreads / shared memory / warp intrinsics) is executed thread by thread
+//     on the host so its integer logic can be checked against the oracle in a container without a GPU.
+//     The simulation is a TEST HARNESS.  It is never linked into libcrgpu.so, and the product library has no
+//     CPU code path: crgpu_create() fails when no CUDA device is present.
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifdef CRGPU_SIM
+// ------------------------------------------------------------------ host simulation shim (tests only)
+#include <algorithm>
+#include <vector>
+struct crsim_dim3 { unsigned x, y, z; crsim_dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
+typedef crsim_dim3 dim3;
+extern thread_local crsim_dim3 threadIdx, blockIdx, blockDim, gridDim;
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(...)
+typedef void* cudaStream_t;
+typedef int cudaError_t;
+#define cudaSuccess 0
+template <class T> static inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
+template <class T> static inline T atomicMin(T* p, T v) { T o = *p; if (v < o) *p = v; return o; }
+template <class T> static inline T atomicMax(T* p, T v) { T o = *p; if (v > o) *p = v; return o; }
+template <class T> static inline T atomicOr(T* p, T v) { T o = *p; *p = o | v; return o; }
+template <class T> static inline T atomicCAS(T* p, T c, T v) { T o = *p; if (o == c) *p = v; return o; }
+static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
+static inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+#define CR_LAUNCH(kernel, grid, block, stream, ...)                                            \
+    do {                                                                                       \
+        crsim_dim3 g_ = (grid), b_ = (block);                                                  \
+        gridDim = g_; blockDim = b_;                                                           \
+        for (unsigned bz = 0; bz < g_.z; bz++) for (unsigned by = 0; by < g_.y; by++) for (unsigned bx = 0; bx < g_.x; bx++) \
+        for (unsigned tz = 0; tz < b_.z; tz++) for (unsigned ty = 0; ty < b_.y; ty++) for (unsigned tx = 0; tx < b_.x; tx++) { \
+            blockIdx = crsim_dim3(bx, by, bz); threadIdx = crsim_dim3(tx, ty, tz);             \
+            kernel(__VA_ARGS__);                                                               \
+        }                                                                                      \
+    } while (0)
+static inline int cudaMalloc(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 2; }
+static inline int cudaFree(void* p) { free(p); return 0; }
+static inline int cudaMallocHost(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 2; }
+static inline int cudaFreeHost(void* p) { free(p); return 0; }
+enum { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+static inline int cudaMemcpyAsync(void* d, const void* s, size_t n, int, cudaStream_t) { if (n) memmove(d, s, n); return 0; }
+static inline int cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { if (n) memset(d, v, n); return 0; }
+static inline int cudaStreamSynchronize(cudaStream_t) { return 0; }
+static inline int cudaGetLastError() { return 0; }
+static inline const char* cudaGetErrorString(int) { return "sim"; }
+#else
+// ------------------------------------------------------------------ real CUDA
+#include <cuda_runtime.h>
+#define CR_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#endif
+
+#define CR_HD __host__ __device__ __forceinline__
+#define CR_D  __device__ __forceinline__
+
+// error codes of the C ABI
+#include "../../include/crgpu.h"
+
+#define CR_CUDA(expr)                                                                          \
+    do {                                                                                       \
+        cudaError_t e_ = (cudaError_t)(expr);                                                  \
+        if (e_ != cudaSuccess) {                                                               \
+            fprintf(stderr, "crgpu: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return CRGPU_ERR_CUDA;                                                             \
+        }                                                                                      \
+    } while (0)
+#define CR_TRY(expr) do { int r_ = (expr); if (r_ != CRGPU_OK) return r_; } while (0)
+
+static inline unsigned cr_div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------ device memory arena-ish helper
+// A growable device buffer: keeps its allocation between calls so steady-state runs do no cudaMalloc.
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t n) {
+        if (n <= cap) return CRGPU_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + 256;
+        if (cudaMalloc(&p, want) != cudaSuccess) { p = nullptr; return CRGPU_ERR_OOM; }
+        cap = want;
+        return CRGPU_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+// ------------------------------------------------------------------ small device helpers
+CR_HD uint32_t cr_ld32(const uint8_t* p) { return p[0] | p[1] << 8 | p[2] << 16 | (uint32_t)p[3] << 24; }
+CR_HD bool cr_is_lower(uint32_t c) { return c - 'a' < 26u; }
+CR_HD bool cr_is_upper(uint32_t c) { return c - 'A' < 26u; }
+CR_HD bool cr_is_alpha(uint32_t c) { return ((c | 32) - 'a') < 26u; }
+
+// common prefix length of a[0..) and b[0..), capped at `cap` (<= 255)
+CR_HD uint32_t cr_cpl(const uint8_t* a, const uint8_t* b, uint32_t cap) {
+    uint32_t j = 0;
+    while (j < cap && a[j] == b[j]) j++;
+    return j;
+}

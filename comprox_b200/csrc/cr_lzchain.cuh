@@ -1,0 +1,352 @@
+// cr_lzchain.cuh -- host orchestration of one window of an lzencode chain (ROLZ or LZP + PPM + range coder).
+//
+// A "chain" is a run of blocks that share adaptive model state: the dictionary payload is a
+// chain of one block; all data blocks of a container form the second chain.  A window is a group of
+// consecutive blocks of a chain that is resident in HBM at once.  Everything model-independent (histograms,
+// match finding, parse resolution) is parallel over all positions of the window; the model passes are
+// parallel over contexts; only the range coders are serial, one per (block, stream).
+#pragma once
+#include <vector>
+#include "cr_common.cuh"
+#include "cr_prims.cuh"
+#include "cr_chain.cuh"
+#include "cr_rolz.cuh"
+#include "cr_lzp.cuh"
+#include "cr_ppm.cuh"
+#include "cr_rc.cuh"
+
+enum { CR_ROLZ = 0, CR_LZP = 1 };
+
+struct BlockIO {
+    uint64_t off;        // in: offset of the dictionary-coded block in the window buffer
+    uint32_t size;       // in
+    uint8_t  filt, prec; // in: bytes 4,5 of the container block header (prefix_mode 1)
+    uint64_t out_off;    // out: offset of prefix+payload in the output buffer
+    uint32_t out_size;   // out: payload size (without prefix)
+    uint32_t raw;        // out: 1 = stored ("cannot compress")
+};
+
+struct LzChain {
+    cudaStream_t stream = 0;
+    Prims prims;
+    int variant = CR_ROLZ;
+    // ---- persistent model state (the reference's file-scope `m`, src/rolzmain/cr-coder.c:52-56)
+    DevBuf s_o3b, s_o3c, s_o2, s_o1, s_m0;
+    PpmState st;
+    uint32_t chain_ctx = 0;
+    bool inited = false;
+    // ---- window work buffers (kept between calls)
+    DevBuf b_blocks, b_segoff, b_seglen, b_hist, b_esc1, b_first, b_ctxout;
+    DevBuf b_k0, b_k1, b_v0, b_v1, b_ks0, b_M, b_S, b_span, b_tidx;
+    DevBuf b_segs, b_xt, b_entry, b_cnt, b_scan;
+    DevBuf b_evctx, b_evsym, b_tokend, b_pred, b_T1, b_T2, b_TS, b_side;
+    DevBuf b_escrec, b_esccount, b_k64a, b_k64b, b_ord, b_flag, b_escord;
+    DevBuf b_dense, b_denseside, b_streams, b_rcres, b_rcout, b_copy, b_hdr;
+    // ---- sizes of the last window (for the debug/trace fetch used by the tests)
+    uint32_t last_nev = 0, last_nside = 0, last_nesc = 0, last_nent = 0;
+    size_t last_dtotal = 0;
+    float ms_match = 0, ms_model = 0, ms_rc = 0;
+
+    int init(int variant_, cudaStream_t s) {
+        variant = variant_; stream = s; prims.stream = s;
+        CR_TRY(s_o3b.reserve(PPM_O3_SLOTS)); CR_TRY(s_o3c.reserve(PPM_O3_SLOTS));
+        CR_TRY(s_o2.reserve((size_t)65536 * PPM_O2_STRIDE)); CR_TRY(s_o1.reserve(65536)); CR_TRY(s_m0.reserve(2 * 256 * 2));
+        st.o3_byte = s_o3b.as<uint8_t>(); st.o3_conf = s_o3c.as<uint8_t>(); st.o2 = s_o2.as<uint8_t>();
+        st.o1 = s_o1.as<uint8_t>(); st.m0 = s_m0.as<uint16_t>();
+        inited = true;
+        return reset_models();
+    }
+    void release() {
+        DevBuf* all[] = { &s_o3b, &s_o3c, &s_o2, &s_o1, &s_m0, &b_blocks, &b_segoff, &b_seglen, &b_hist, &b_esc1, &b_first, &b_ctxout,
+            &b_k0, &b_k1, &b_v0, &b_v1, &b_ks0, &b_M, &b_S, &b_span, &b_tidx, &b_segs, &b_xt, &b_entry, &b_cnt, &b_scan,
+            &b_evctx, &b_evsym, &b_tokend, &b_pred, &b_T1, &b_T2, &b_TS, &b_side, &b_escrec, &b_esccount, &b_k64a, &b_k64b, &b_ord,
+            &b_flag, &b_escord, &b_dense, &b_denseside, &b_streams, &b_rcres, &b_rcout, &b_copy, &b_hdr, &prims.temp };
+        for (DevBuf* b : all) b->release();
+        inited = false;
+    }
+    // reset_models(): src/rolzmain/cr-coder.c:78-96 / src/ropmain/cr-coder.c:73-83
+    int reset_models() {
+        CR_CUDA(cudaMemsetAsync(st.o3_byte, 0, PPM_O3_SLOTS, stream));
+        CR_CUDA(cudaMemsetAsync(st.o3_conf, 0, PPM_O3_SLOTS, stream));
+        CR_LAUNCH(k_ppm_reset, dim3(65536 / 256), dim3(256), stream, st);
+        chain_ctx = 0;
+        return CRGPU_OK;
+    }
+
+    template <class T> int upload(DevBuf& b, const std::vector<T>& v) {
+        CR_TRY(b.reserve(v.size() * sizeof(T) + 16));
+        CR_CUDA(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, stream));
+        return CRGPU_OK;
+    }
+    template <class T> int download(std::vector<T>& v, const void* src, size_t n) {
+        v.resize(n);
+        CR_CUDA(cudaMemcpyAsync(v.data(), src, n * sizeof(T), cudaMemcpyDeviceToHost, stream));
+        CR_CUDA(cudaStreamSynchronize(stream));
+        return CRGPU_OK;
+    }
+
+    // Encode blk[0..nb) (consecutive blocks of this chain, dictionary-coded bytes at dD + off) into `out` at
+    // out_base.  prefix_mode 0: [u32 payload_len] (dictionary payload, src/main.c:169);
+    // 1: [u32 payload_len, u8 filt, u8 prec] (data block header, src/main.c:199-204); 2: none.
+    // chain_ends: no further block of this chain follows (an aborted last block is then harmless).
+    int encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, int prefix_mode, bool chain_ends, DevBuf& out, size_t out_base, size_t& out_total);
+};
+
+__global__ void k_first_bytes(const uint8_t* __restrict__ D, const LzBlock* __restrict__ blocks, uint32_t nb, uint8_t* __restrict__ first) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    for (uint32_t i = 0; i < 16; i++) first[b * 16 + i] = i < blocks[b].size ? D[blocks[b].off + i] : 0;
+}
+
+// escape byte + PPM context carried into each block; serial over the blocks of the window (nb steps)
+__global__ void k_rolz_finish_blocks(const uint8_t* __restrict__ D, LzBlock* __restrict__ blocks, uint32_t nb, const uint8_t* __restrict__ esc1,
+                                     uint32_t ctx_in, uint32_t* __restrict__ ctx_out) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    uint32_t c = ctx_in;
+    for (uint32_t b = 0; b < nb; b++) {
+        blocks[b].esc = esc1[b];
+        blocks[b].cin = c;
+        c = rz_ctx_at(D + blocks[b].off, blocks[b].size, c);
+    }
+    *ctx_out = c;
+}
+
+static inline int cr_bits_for(uint32_t n) { int b = 0; while ((1u << b) < n) b++; return b; }
+
+inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, int prefix_mode, bool chain_ends, DevBuf& out, size_t out_base, size_t& out_total) {
+    const uint32_t nb = (uint32_t)blk.size();
+    if (nb == 0) { out_total = 0; return CRGPU_OK; }
+    const uint32_t hdr_size = variant == CR_ROLZ ? 16 : 20;
+    const uint32_t prefix = prefix_mode == 0 ? 4 : prefix_mode == 1 ? 6 : 0;
+
+    // ---- block table
+    std::vector<LzBlock> hb(nb);
+    std::vector<uint64_t> segoff(nb);
+    std::vector<uint32_t> seglen(nb);
+    uint32_t nent = 0, maxsize = 0;
+    size_t dtotal = 0;
+    for (uint32_t b = 0; b < nb; b++) {
+        memset(&hb[b], 0, sizeof(LzBlock));
+        hb[b].off = blk[b].off; hb[b].size = blk[b].size; hb[b].eoff = nent;
+        hb[b].ctx4 = blk[b].size >= 4194304;
+        uint32_t first_entry = variant == CR_ROLZ ? 16 : LZP_FIRST;
+        if (variant == CR_LZP && blk[b].size < 16) first_entry = blk[b].size;      // stored without coding (src/ropmain/cr-coder.c:140)
+        nent += blk[b].size > first_entry ? blk[b].size - first_entry : 0;
+        segoff[b] = blk[b].off; seglen[b] = blk[b].size;
+        if (blk[b].size > maxsize) maxsize = blk[b].size;
+        if (blk[b].off + blk[b].size > dtotal) dtotal = blk[b].off + blk[b].size;
+    }
+    last_nent = nent; last_dtotal = dtotal;
+    CR_TRY(upload(b_blocks, hb)); CR_TRY(upload(b_segoff, segoff)); CR_TRY(upload(b_seglen, seglen));
+    LzBlock* d_blocks = b_blocks.as<LzBlock>();
+
+    // ---- escape byte per block (rarest byte), first bytes, carried contexts
+    CR_TRY(b_hist.reserve((size_t)nb * 256 * 4)); CR_TRY(b_esc1.reserve(nb)); CR_TRY(b_first.reserve((size_t)nb * 16)); CR_TRY(b_ctxout.reserve(16));
+    CR_CUDA(cudaMemsetAsync(b_hist.p, 0, (size_t)nb * 256 * 4, stream));
+    if (maxsize) CR_LAUNCH(k_hist256, dim3(cr_div_up(maxsize, CR_HIST_TILE), nb), dim3(256), stream, dD, b_segoff.as<uint64_t>(), b_seglen.as<uint32_t>(), b_hist.as<uint32_t>());
+    CR_LAUNCH(k_pick_escapes, dim3(cr_div_up(nb, 64)), dim3(64), stream, b_hist.as<uint32_t>(), nb, (uint8_t*)nullptr, b_esc1.as<uint8_t>());
+    CR_LAUNCH(k_first_bytes, dim3(cr_div_up(nb, 64)), dim3(64), stream, dD, d_blocks, nb, b_first.as<uint8_t>());
+
+    // ---- per-position tokens
+    CR_TRY(b_span.reserve(dtotal + 16)); CR_TRY(b_tidx.reserve(dtotal + 16));
+    const int bbits = cr_bits_for(nb);
+    if (variant == CR_ROLZ) {
+        CR_LAUNCH(k_rolz_finish_blocks, dim3(1), dim3(1), stream, dD, d_blocks, nb, b_esc1.as<uint8_t>(), chain_ctx, b_ctxout.as<uint32_t>());
+        CR_TRY(b_k0.reserve((size_t)nent * 4 + 16)); CR_TRY(b_k1.reserve((size_t)nent * 4 + 16)); CR_TRY(b_ks0.reserve((size_t)nent * 4 + 16));
+        CR_TRY(b_v0.reserve((size_t)nent * 4 + 16)); CR_TRY(b_v1.reserve((size_t)nent * 4 + 16));
+        CR_TRY(b_M.reserve((size_t)nent * 2 * 5 + 16)); CR_TRY(b_S.reserve((size_t)nent * 2 + 16));
+        if (nent) {
+            CR_LAUNCH(k_rolz_keys, dim3(cr_div_up(maxsize, 256), nb), dim3(256), stream, dD, d_blocks, b_k0.as<uint32_t>(), b_ks0.as<uint32_t>(), b_v0.as<uint32_t>());
+            CR_TRY(cr_sort_pairs<uint32_t>(prims, b_k0.as<uint32_t>(), b_k1.as<uint32_t>(), b_v0.as<uint32_t>(), b_v1.as<uint32_t>(), nent, 0, RZ_BUCKET_BITS + bbits));
+            CR_LAUNCH(k_rolz_match_main, dim3(cr_div_up(nent, 128)), dim3(128), stream, dD, d_blocks, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nent, b_M.as<uint16_t>());
+            CR_TRY(cr_sort_pairs<uint32_t>(prims, b_ks0.as<uint32_t>(), b_k1.as<uint32_t>(), b_v0.as<uint32_t>(), b_v1.as<uint32_t>(), nent, 0, 8 + bbits));
+            CR_LAUNCH(k_rolz_match_short, dim3(cr_div_up(nent, 128)), dim3(128), stream, dD, d_blocks, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nent, b_M.as<uint16_t>(), b_S.as<uint16_t>());
+        }
+        if (maxsize) CR_LAUNCH(k_rolz_tokens, dim3(cr_div_up(maxsize, 256), nb), dim3(256), stream, d_blocks, b_M.as<uint16_t>(), b_S.as<uint16_t>(), nent, b_span.as<uint8_t>(), b_tidx.as<uint8_t>());
+    } else {
+        CR_LAUNCH(k_lzp_finish_blocks, dim3(cr_div_up(nb, 64)), dim3(64), stream, d_blocks, nb, b_esc1.as<uint8_t>());
+        CR_TRY(b_k0.reserve((size_t)nent * 4 + 16)); CR_TRY(b_k1.reserve((size_t)nent * 4 + 16));
+        CR_TRY(b_v0.reserve((size_t)nent * 4 + 16)); CR_TRY(b_v1.reserve((size_t)nent * 4 + 16));
+        CR_TRY(b_M.reserve((size_t)nent * 12 + 16));
+        uint32_t* cand = b_M.as<uint32_t>();
+        for (int kind = 0; kind < 3 && nent; kind++) {
+            CR_LAUNCH(k_lzp_keys, dim3(cr_div_up(maxsize, 256), nb), dim3(256), stream, dD, d_blocks, kind, b_k0.as<uint32_t>(), b_v0.as<uint32_t>());
+            CR_TRY(cr_sort_pairs<uint32_t>(prims, b_k0.as<uint32_t>(), b_k1.as<uint32_t>(), b_v0.as<uint32_t>(), b_v1.as<uint32_t>(), nent, 0, lzp_hash_bits(kind) + bbits));
+            CR_LAUNCH(k_lzp_prev, dim3(cr_div_up(nent, 256)), dim3(256), stream, d_blocks, kind, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nent, cand + (size_t)kind * nent);
+        }
+        if (maxsize) CR_LAUNCH(k_lzp_tokens, dim3(cr_div_up(maxsize, 256), nb), dim3(256), stream, dD, d_blocks, cand, cand + nent, cand + 2 * (size_t)nent, b_span.as<uint8_t>());
+    }
+
+    // ---- resolve the parse (cr_chain.cuh)
+    std::vector<ChainSeg> segs(nb);
+    for (uint32_t b = 0; b < nb; b++) {
+        segs[b].off = blk[b].off; segs[b].len = blk[b].size;
+        segs[b].start = variant == CR_ROLZ ? 1 : (blk[b].size < 16 ? blk[b].size : LZP_FIRST);
+    }
+    for (uint32_t b = 0; b < nb; b++) if (segs[b].start > 255) { segs[b].len = 0; segs[b].start = 0; }   // tiny stored LZP block: nothing to walk
+    const uint32_t nchunk = cr_chain_layout(segs.data(), nb);
+    CR_TRY(upload(b_segs, segs));
+    CR_TRY(b_xt.reserve((size_t)nchunk * 256 + 16)); CR_TRY(b_entry.reserve(nchunk + 16));
+    CR_TRY(b_cnt.reserve((size_t)(nchunk + 1) * 4 * 3 + 16)); CR_TRY(b_scan.reserve((size_t)(nchunk + 1) * 4 * 3 + 16));
+    const ChainSeg* d_segs = b_segs.as<ChainSeg>();
+    uint32_t* cnt = b_cnt.as<uint32_t>(); uint32_t* scan = b_scan.as<uint32_t>();
+    CR_CUDA(cudaMemsetAsync(cnt, 0, (size_t)(nchunk + 1) * 4 * 3, stream));
+    if (nchunk) {
+        CR_LAUNCH(k_chain_exits, dim3(cr_div_up(nchunk, 64)), dim3(64), stream, b_span.as<uint8_t>(), d_segs, nb, nchunk, b_xt.as<uint8_t>());
+        CR_LAUNCH(k_chain_entries, dim3(cr_div_up(nb, 32)), dim3(32), stream, d_segs, nb, b_xt.as<uint8_t>(), b_entry.as<uint8_t>());
+        if (variant == CR_ROLZ) {
+            RolzCount f = { dD, d_blocks, b_tidx.as<uint8_t>(), cnt, cnt + (nchunk + 1), cnt + 2 * (nchunk + 1) };
+            CR_LAUNCH(k_chain_walk<RolzCount>, dim3(cr_div_up(nchunk, 64)), dim3(64), stream, b_span.as<uint8_t>(), d_segs, nb, nchunk, b_entry.as<uint8_t>(), f);
+        } else {
+            LzpCount f = { dD, d_blocks, cnt, cnt + (nchunk + 1), cnt + 2 * (nchunk + 1) };
+            CR_LAUNCH(k_chain_walk<LzpCount>, dim3(cr_div_up(nchunk, 64)), dim3(64), stream, b_span.as<uint8_t>(), d_segs, nb, nchunk, b_entry.as<uint8_t>(), f);
+        }
+    }
+    for (int k = 0; k < 3; k++) CR_TRY(cr_exclusive_sum(prims, cnt + k * (nchunk + 1), scan + k * (nchunk + 1), nchunk + 1));
+    std::vector<uint32_t> hscan; std::vector<uint8_t> hfirst, hesc;
+    CR_TRY(download(hscan, scan, (size_t)(nchunk + 1) * 3));
+    CR_TRY(download(hfirst, b_first.p, (size_t)nb * 16));
+    CR_TRY(download(hesc, b_esc1.p, nb));
+    const uint32_t* sc_ev = hscan.data(); const uint32_t* sc_a = sc_ev + (nchunk + 1); const uint32_t* sc_b = sc_a + (nchunk + 1);
+    // ROLZ: a = match tokens, b = escape literals -> side symbols 2a+b.  LZP: a = tokens closing... unused.
+    const uint32_t nev = sc_ev[nchunk];
+    const uint32_t nside = variant == CR_ROLZ ? 2 * sc_a[nchunk] + sc_b[nchunk] : 0;
+    last_nev = nev; last_nside = nside;
+
+    // ---- events
+    CR_TRY(b_evctx.reserve((size_t)nev * 4 + 16)); CR_TRY(b_evsym.reserve(nev + 16)); CR_TRY(b_tokend.reserve(nev + 16)); CR_TRY(b_pred.reserve(nev + 16));
+    CR_TRY(b_T1.reserve((size_t)nev * 8 + 16)); CR_TRY(b_side.reserve((size_t)nside * 2 + 16)); CR_TRY(b_TS.reserve((size_t)nside * 8 + 16));
+    if (nchunk) {
+        if (variant == CR_ROLZ) {
+            RolzEmit f = { dD, d_blocks, b_tidx.as<uint8_t>(), scan, scan + (nchunk + 1), scan + 2 * (nchunk + 1), b_evctx.as<uint32_t>(), b_evsym.as<uint8_t>(), b_side.as<uint16_t>() };
+            CR_LAUNCH(k_chain_walk<RolzEmit>, dim3(cr_div_up(nchunk, 64)), dim3(64), stream, b_span.as<uint8_t>(), d_segs, nb, nchunk, b_entry.as<uint8_t>(), f);
+        } else {
+            CR_TRY(b_ord.reserve((size_t)(nchunk + 1) * 4 + 16));
+            CR_LAUNCH(k_lzp_ctx_in, dim3(cr_div_up(nchunk + 1, 128)), dim3(128), stream, cnt + (nchunk + 1), cnt + 2 * (nchunk + 1), nchunk, chain_ctx, b_ord.as<uint32_t>());
+            CR_CUDA(cudaMemcpyAsync(b_ctxout.p, b_ord.as<uint32_t>() + nchunk, 4, cudaMemcpyDeviceToDevice, stream));
+            LzpEmit f = { dD, d_blocks, scan, b_ord.as<uint32_t>(), b_evctx.as<uint32_t>(), b_evsym.as<uint8_t>(), b_tokend.as<uint8_t>() };
+            CR_LAUNCH(k_chain_walk<LzpEmit>, dim3(cr_div_up(nchunk, 64)), dim3(64), stream, b_span.as<uint8_t>(), d_segs, nb, nchunk, b_entry.as<uint8_t>(), f);
+        }
+    } else if (variant == CR_LZP) {
+        std::vector<uint32_t> keep(1, chain_ctx);
+        CR_TRY(upload(b_ctxout, keep));
+    }
+
+    // ---- model passes
+    uint32_t nesc = 0;
+    CR_TRY(b_esccount.reserve(16));
+    CR_CUDA(cudaMemsetAsync(b_esccount.p, 0, 4, stream));
+    if (nev) {
+        CR_TRY(b_k0.reserve((size_t)nev * 4 + 16)); CR_TRY(b_k1.reserve((size_t)nev * 4 + 16));
+        CR_TRY(b_v0.reserve((size_t)nev * 4 + 16)); CR_TRY(b_v1.reserve((size_t)nev * 4 + 16));
+        CR_TRY(b_escrec.reserve((size_t)nev * sizeof(EscRec) + 16));
+        const dim3 ge(cr_div_up(nev, 256)), te(256);
+        CR_LAUNCH(k_o3_keys, ge, te, stream, b_evctx.as<uint32_t>(), b_evsym.as<uint8_t>(), nev, b_k0.as<uint32_t>(), b_v0.as<uint32_t>());
+        CR_TRY(cr_sort_pairs<uint32_t>(prims, b_k0.as<uint32_t>(), b_k1.as<uint32_t>(), b_v0.as<uint32_t>(), b_v1.as<uint32_t>(), nev, 0, 22));
+        CR_LAUNCH(k_o3_pass, dim3(cr_div_up(nev, 128)), dim3(128), stream, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nev, st, b_pred.as<uint8_t>());
+        CR_LAUNCH(k_o2_keys, ge, te, stream, b_evctx.as<uint32_t>(), b_evsym.as<uint8_t>(), b_pred.as<uint8_t>(), nev, b_k0.as<uint32_t>(), b_v0.as<uint32_t>());
+        CR_TRY(cr_sort_pairs<uint32_t>(prims, b_k0.as<uint32_t>(), b_k1.as<uint32_t>(), b_v0.as<uint32_t>(), b_v1.as<uint32_t>(), nev, 0, 16));
+        CR_LAUNCH(k_o2_pass, dim3(cr_div_up(nev, 128)), dim3(128), stream, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nev, st, b_T1.as<uint64_t>(), b_escrec.as<EscRec>(), b_esccount.as<uint32_t>());
+        std::vector<uint32_t> hc;
+        CR_TRY(download(hc, b_esccount.p, 1));
+        nesc = hc[0];
+        if (nesc) {
+            CR_TRY(b_k64a.reserve((size_t)nesc * 8 + 16)); CR_TRY(b_k64b.reserve((size_t)nesc * 8 + 16)); CR_TRY(b_ord.reserve((size_t)nesc * 4 + 16));
+            CR_TRY(b_T2.reserve((size_t)nesc * 8 + 16));
+            const dim3 gx(cr_div_up(nesc, 256));
+            CR_LAUNCH(k_o1_keys, gx, te, stream, b_escrec.as<EscRec>(), nesc, b_k64a.as<uint64_t>(), b_v0.as<uint32_t>());
+            CR_TRY(cr_sort_pairs<uint64_t>(prims, b_k64a.as<uint64_t>(), b_k64b.as<uint64_t>(), b_v0.as<uint32_t>(), b_v1.as<uint32_t>(), nesc, 0, 32));
+            CR_LAUNCH(k_o1_ordinals, gx, te, stream, b_v1.as<uint32_t>(), nesc, b_ord.as<uint32_t>());
+            CR_TRY(cr_sort_pairs<uint64_t>(prims, b_k64a.as<uint64_t>(), b_k64b.as<uint64_t>(), b_v0.as<uint32_t>(), b_v1.as<uint32_t>(), nesc, 0, 40));
+            CR_LAUNCH(k_o1_pass, dim3(cr_div_up(nesc, 64)), dim3(64), stream, b_k64b.as<uint64_t>(), b_v1.as<uint32_t>(), nesc, b_escrec.as<EscRec>(), b_ord.as<uint32_t>(), st, b_T2.as<uint64_t>());
+        }
+    }
+    last_nesc = nesc;
+    if (nside) CR_LAUNCH(k_side_models, dim3(1), dim3(1), stream, b_side.as<uint16_t>(), nside, st, b_TS.as<uint64_t>());
+
+    // ---- dense triple streams
+    CR_TRY(b_flag.reserve((size_t)(nev + 1) * 4 + 16)); CR_TRY(b_escord.reserve((size_t)(nev + 1) * 4 + 16));
+    CR_TRY(b_dense.reserve(((size_t)nev + nesc) * sizeof(Tri) + 16)); CR_TRY(b_denseside.reserve((size_t)nside * sizeof(Tri) + 16));
+    CR_LAUNCH(k_esc_flags, dim3(cr_div_up(nev + 1, 256)), dim3(256), stream, b_T1.as<uint64_t>(), nev, b_flag.as<uint32_t>());
+    CR_TRY(cr_exclusive_sum(prims, b_flag.as<uint32_t>(), b_escord.as<uint32_t>(), nev + 1));
+    if (nev) CR_LAUNCH(k_expand_main, dim3(cr_div_up(nev, 256)), dim3(256), stream, b_T1.as<uint64_t>(), b_T2.as<uint64_t>(), b_escord.as<uint32_t>(),
+                       variant == CR_LZP ? b_tokend.as<uint8_t>() : (const uint8_t*)nullptr, nev, b_dense.as<Tri>());
+    if (nside) CR_LAUNCH(k_expand_side, dim3(cr_div_up(nside, 256)), dim3(256), stream, b_TS.as<uint64_t>(), nside, b_denseside.as<Tri>());
+
+    // ---- range coding: one serial coder per (block, stream)
+    const uint32_t spb = variant == CR_ROLZ ? 2 : 1;
+    std::vector<RcStream> streams((size_t)nb * spb);
+    std::vector<uint32_t> num_idx(nb, 0);
+    size_t rc_total = 0;
+    for (uint32_t b = 0; b < nb; b++) {
+        const uint32_t c0 = segs[b].chunk0, c1 = c0 + segs[b].nchunk;
+        RcStream& m = streams[(size_t)b * spb];
+        memset(&m, 0, sizeof m);
+        m.ev_begin = sc_ev[c0]; m.ev_end = sc_ev[c1]; m.is_main = 1;
+        m.limit = blk[b].size > hdr_size ? blk[b].size - hdr_size : 0;
+        m.out_off = rc_total; m.out_cap = blk[b].size + 16; rc_total += m.out_cap;
+        if (variant == CR_ROLZ) {
+            RcStream& s = streams[(size_t)b * spb + 1];
+            memset(&s, 0, sizeof s);
+            s.ev_begin = 2 * sc_a[c0] + sc_b[c0]; s.ev_end = 2 * sc_a[c1] + sc_b[c1]; s.is_main = 0; s.limit = 0xFFFFFFFFu;
+            s.out_off = rc_total; s.out_cap = 3 * (s.ev_end - s.ev_begin) + 16; rc_total += s.out_cap;
+            num_idx[b] = (sc_a[c1] - sc_a[c0]) + (sc_b[c1] - sc_b[c0]);
+        }
+    }
+    CR_TRY(upload(b_streams, streams));
+    CR_TRY(b_rcres.reserve(streams.size() * sizeof(RcResult) + 16)); CR_TRY(b_rcout.reserve(rc_total + 16));
+    CR_LAUNCH(k_range_encode, dim3(cr_div_up(streams.size(), 32)), dim3(32), stream, b_dense.as<Tri>(), b_denseside.as<Tri>(), b_escord.as<uint32_t>(),
+              b_streams.as<RcStream>(), (uint32_t)streams.size(), b_rcout.as<uint8_t>(), b_rcres.as<RcResult>());
+    std::vector<RcResult> res; std::vector<uint32_t> hctx;
+    CR_TRY(download(res, b_rcres.p, streams.size()));
+    CR_TRY(download(hctx, b_ctxout.p, 1)); chain_ctx = hctx[0];
+
+    // ---- payload layout + headers (src/rolzmain/cr-coder.c:241-262, src/ropmain/cr-coder.c:212-228)
+    std::vector<CopyDesc> copies; std::vector<HeaderDesc> hdrs(nb);
+    size_t pos = out_base;
+    for (uint32_t b = 0; b < nb; b++) {
+        const RcStream& m = streams[(size_t)b * spb]; const RcResult& rm = res[(size_t)b * spb];
+        const bool stored = rm.aborted || (variant == CR_LZP && blk[b].size < 16);
+        if (rm.aborted && !(chain_ends && b == nb - 1)) {
+            fprintf(stderr, "crgpu: block %u of %u hit 'cannot compress' in the middle of a model chain (SURVEY.md F11)\n", b, nb);
+            return CRGPU_ERR_MIDCHAIN_ABORT;
+        }
+        HeaderDesc& h = hdrs[b];
+        memset(&h, 0, sizeof h);
+        uint8_t* hp = h.bytes + prefix;
+        uint32_t payload;
+        blk[b].raw = stored; blk[b].out_off = pos;
+        if (stored) {
+            payload = hdr_size + blk[b].size;
+            CopyDesc c = { blk[b].off, pos + prefix + hdr_size, blk[b].size, 1 }; copies.push_back(c);
+        } else if (variant == CR_ROLZ) {
+            const RcStream& s = streams[(size_t)b * spb + 1]; const RcResult& rs = res[(size_t)b * spb + 1];
+            payload = 16 + rm.nbytes + rs.nbytes;
+            hp[0] = hfirst[b * 16]; hp[1] = 1; hp[2] = hesc[b];
+            uint32_t v[3] = { blk[b].size, num_idx[b], 16 + rm.nbytes };
+            memcpy(hp + 4, v, 12);
+            CopyDesc c0 = { m.out_off, pos + prefix + 16, rm.nbytes, 0 }; copies.push_back(c0);
+            CopyDesc c1 = { s.out_off, pos + prefix + 16 + rm.nbytes, rs.nbytes, 0 }; copies.push_back(c1);
+        } else {
+            payload = 20 + rm.nbytes;
+            hp[0] = 1; memcpy(hp + 4, &blk[b].size, 4); hp[8] = hesc[b]; memcpy(hp + 9, &hfirst[b * 16], 9);
+            CopyDesc c0 = { m.out_off, pos + prefix + 20, rm.nbytes, 0 }; copies.push_back(c0);
+        }
+        if (prefix) memcpy(h.bytes, &payload, 4);
+        if (prefix == 6) { h.bytes[4] = blk[b].filt; h.bytes[5] = blk[b].prec; }
+        h.dst = pos; h.len = prefix + hdr_size;
+        blk[b].out_size = payload;
+        pos += prefix + payload;
+    }
+    out_total = pos - out_base;
+    if (out.cap < pos) {   // grow, preserving what earlier windows wrote
+        DevBuf nb2; CR_TRY(nb2.reserve(pos + pos / 4));
+        if (out.p && out_base) CR_CUDA(cudaMemcpyAsync(nb2.p, out.p, out_base, cudaMemcpyDeviceToDevice, stream));
+        CR_CUDA(cudaStreamSynchronize(stream));
+        out.release(); out = nb2;
+    }
+    CR_TRY(upload(b_copy, copies)); CR_TRY(upload(b_hdr, hdrs));
+    CR_LAUNCH(k_write_headers, dim3(cr_div_up(nb, 64)), dim3(64), stream, b_hdr.as<HeaderDesc>(), nb, out.as<uint8_t>());
+    if (!copies.empty()) CR_LAUNCH(k_copy_segments, dim3(64, (unsigned)copies.size()), dim3(256), stream, b_copy.as<CopyDesc>(), b_rcout.as<uint8_t>(), dD, out.as<uint8_t>());
+    return CRGPU_OK;
+}

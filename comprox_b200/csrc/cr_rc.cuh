@@ -1,0 +1,125 @@
+// cr_rc.cuh -- the carry-propagating 32-bit range coder (src/cr-rangecoder.c:35-79) and payload assembly.
+//
+// One coder per (block, stream): the reference re-initialises `coder` and `idx_coder` for every block
+// (src/rolzmain/cr-coder.c:181-182), so streams are independent chains; inside a stream every step depends on
+// the previous range, which makes this the serial floor of the whole encoder.  The triples arrive fully
+// resolved from the model passes, and the divisor's reciprocal is precomputed in parallel (k_expand), so the
+// dependent chain per symbol is  umulhi -> mul/sub -> compare/add -> mul -> normalise.
+#pragma once
+#include "cr_common.cuh"
+#include "cr_ppm.cuh"
+
+struct Tri {             // one range_encoder_encode call
+    uint32_t cum;
+    uint32_t frq;        // bit 31: last triple of a token (the reference tests "cannot compress" there)
+    uint32_t sum;
+    uint32_t magic;      // floor(2^32 / sum), saturated: q = umulhi(range, magic) is range/sum or one less
+};
+#define TRI_TOKEND 0x80000000u
+
+CR_HD uint32_t rc_magic(uint32_t sum) { return sum <= 1 ? 0xFFFFFFFFu : (uint32_t)(0x100000000ull / sum); }
+
+__global__ void k_esc_flags(const uint64_t* __restrict__ T1, uint32_t n, uint32_t* __restrict__ flag) {
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e > n) return;
+    flag[e] = e < n ? (uint32_t)(T1[e] >> 63) : 0;       // n+1 entries so that the scan also yields the total
+}
+
+// dense main-stream triples: event e lands at e + (#escapes before e); an escape is followed by its o1 triple.
+// tokend[e] == 0 marks events that do not close a token (LZP codes a match as two events); nullptr = all close.
+__global__ void k_expand_main(const uint64_t* __restrict__ T1, const uint64_t* __restrict__ T2, const uint32_t* __restrict__ escord,
+                              const uint8_t* __restrict__ tokend, uint32_t n, Tri* __restrict__ dense) {
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    uint64_t t = T1[e];
+    uint32_t o = escord[e], esc = (uint32_t)(t >> 63);
+    uint32_t endflag = (!tokend || tokend[e]) ? TRI_TOKEND : 0;
+    Tri a;
+    a.cum = (uint32_t)t & 0xFFFFFF; a.frq = (uint32_t)(t >> 24) & 0xFFFF; a.sum = (uint32_t)(t >> 40) & 0x7FFFFF;
+    a.magic = rc_magic(a.sum);
+    if (!esc) a.frq |= endflag;
+    dense[(size_t)e + o] = a;
+    if (esc) {
+        uint64_t u = T2[o];
+        Tri b;
+        b.cum = (uint32_t)u & 0xFFFFFF; b.frq = ((uint32_t)(u >> 24) & 0xFFFF) | endflag; b.sum = (uint32_t)(u >> 40) & 0x7FFFFF;
+        b.magic = rc_magic(b.sum);
+        dense[(size_t)e + o + 1] = b;
+    }
+}
+__global__ void k_expand_side(const uint64_t* __restrict__ TS, uint32_t n, Tri* __restrict__ dense) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t t = TS[i];
+    Tri a;
+    a.cum = (uint32_t)t & 0xFFFFFF; a.frq = (uint32_t)(t >> 24) & 0xFFFF; a.sum = (uint32_t)(t >> 40) & 0x7FFFFF;
+    a.magic = rc_magic(a.sum);
+    dense[i] = a;
+}
+
+struct RcStream {
+    uint32_t ev_begin, ev_end;   // main: event range (dense range = + escord); side: dense range directly
+    uint32_t is_main;
+    uint32_t limit;              // abort once this many bytes are out at a token end (main only; 0xFFFFFFFF = never)
+    uint64_t out_off;            // into the rc output buffer
+    uint32_t out_cap;
+    uint32_t pad;
+};
+struct RcResult { uint32_t nbytes; uint32_t aborted; };
+
+struct RcCoder {
+    uint32_t low, range, follow, carry, cache, n, cap;
+    uint8_t* out;
+    CR_D void put(uint32_t b) { if (n < cap) out[n] = (uint8_t)b; n++; }
+    CR_D void shift_out() {                                   // renormalize(), cr-rangecoder.c:44-58
+        if (low < 0xFF000000u || carry) {
+            put(cache + carry);
+            for (; follow; follow--) put(carry - 1);
+            cache = low >> 24;
+            carry = 0;
+        } else follow++;
+        low <<= 8;
+    }
+};
+
+__global__ void k_range_encode(const Tri* __restrict__ dense_main, const Tri* __restrict__ dense_side, const uint32_t* __restrict__ escord,
+                               const RcStream* __restrict__ streams, uint32_t nstreams, uint8_t* __restrict__ outbuf, RcResult* __restrict__ res) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nstreams) return;
+    const RcStream S = streams[s];
+    const Tri* tri = S.is_main ? dense_main : dense_side;
+    size_t i0 = S.ev_begin, i1 = S.ev_end;
+    if (S.is_main) { i0 += escord[S.ev_begin]; i1 += escord[S.ev_end]; }
+    RcCoder c;
+    c.low = 0; c.range = 0xFFFFFFFFu; c.follow = 0; c.carry = 0; c.cache = 0; c.n = 0; c.cap = S.out_cap; c.out = outbuf + S.out_off;
+    uint32_t aborted = 0;
+    for (size_t i = i0; i < i1; i++) {
+        const Tri t = tri[i];
+        uint32_t q = __umulhi(c.range, t.magic);
+        uint32_t rem = c.range - q * t.sum;
+        if (rem >= t.sum) q++;
+        uint32_t nl = c.low + t.cum * q;
+        c.carry += nl < c.low;
+        c.low = nl;
+        c.range = q * (t.frq & 0x7FFFFFFFu);
+        while (c.range < (1u << 24)) { c.range <<= 8; c.shift_out(); }
+        if ((t.frq & TRI_TOKEND) && c.n >= S.limit) { aborted = 1; break; }     // cr-coder.c:231-233
+    }
+    if (!aborted) for (int k = 0; k < 5; k++) c.shift_out();                    // range_encoder_flush
+    res[s].nbytes = c.n;
+    res[s].aborted = aborted;
+}
+
+// ------------------------------------------------------------------ payload assembly
+struct CopyDesc { uint64_t src, dst; uint32_t len; uint32_t src_buf; };   // src_buf: 0 = rc output, 1 = dictionary-coded data
+__global__ void k_copy_segments(const CopyDesc* __restrict__ descs, const uint8_t* __restrict__ buf0, const uint8_t* __restrict__ buf1, uint8_t* __restrict__ dst) {
+    const CopyDesc d = descs[blockIdx.y];
+    const uint8_t* src = (d.src_buf ? buf1 : buf0) + d.src;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < d.len; i += gridDim.x * blockDim.x) dst[d.dst + i] = src[i];
+}
+struct HeaderDesc { uint64_t dst; uint32_t len; uint8_t bytes[36]; };
+__global__ void k_write_headers(const HeaderDesc* __restrict__ h, uint32_t n, uint8_t* __restrict__ dst) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (uint32_t k = 0; k < h[i].len; k++) dst[h[i].dst + k] = h[i].bytes[k];
+}

@@ -1,0 +1,112 @@
+// crgpu_api.cu -- the C ABI declared in include/crgpu.h.
+#include "../../include/crgpu.h"
+#include "cr_lzchain.cuh"
+#include <string>
+
+#ifdef CRGPU_SIM
+thread_local crsim_dim3 threadIdx, blockIdx, blockDim, gridDim;
+#endif
+
+struct crgpu_handle {
+    int device = 0;
+    int variant = CRGPU_ROLZ;
+    cudaStream_t stream = 0;
+    LzChain chain;
+    DevBuf d_in, d_out;
+};
+
+extern "C" const char* crgpu_strerror(int code) {
+    switch (code) {
+        case CRGPU_OK: return "ok";
+        case CRGPU_ERR_NO_DEVICE: return "no CUDA device (this library has no CPU path)";
+        case CRGPU_ERR_CUDA: return "CUDA runtime error";
+        case CRGPU_ERR_ARG: return "bad argument";
+        case CRGPU_ERR_VOCAB_OVERFLOW: return "more than 325000 distinct words (reference prune is order dependent)";
+        case CRGPU_ERR_HASH_COLLISION: return "word hash collision";
+        case CRGPU_ERR_MIDCHAIN_ABORT: return "a non-final block could not be compressed (reference desyncs here too)";
+        case CRGPU_ERR_UNSUPPORTED: return "unsupported option";
+        case CRGPU_ERR_OOM: return "out of device memory";
+    }
+    return "unknown error";
+}
+
+extern "C" int crgpu_create(crgpu_handle** out, int variant, int device, void* stream) {
+    if (!out || (variant != CRGPU_ROLZ && variant != CRGPU_LZP)) return CRGPU_ERR_ARG;
+#ifndef CRGPU_SIM
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+        fprintf(stderr, "crgpu: no usable CUDA device %d (found %d); there is no CPU fallback\n", device, ndev);
+        return CRGPU_ERR_NO_DEVICE;
+    }
+    CR_CUDA(cudaSetDevice(device));
+#endif
+    crgpu_handle* h = new crgpu_handle();
+    h->device = device; h->variant = variant; h->stream = (cudaStream_t)stream;
+    int rc = h->chain.init(variant, h->stream);
+    if (rc != CRGPU_OK) { delete h; return rc; }
+    *out = h;
+    return CRGPU_OK;
+}
+
+extern "C" void crgpu_destroy(crgpu_handle* h) {
+    if (!h) return;
+#ifndef CRGPU_SIM
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+#endif
+    h->chain.release(); h->d_in.release(); h->d_out.release();
+    delete h;
+}
+
+extern "C" int crgpu_reset_models(crgpu_handle* h) {
+    if (!h) return CRGPU_ERR_ARG;
+    return h->chain.reset_models();
+}
+
+extern "C" int crgpu_lzencode(crgpu_handle* h, const uint8_t* in, const uint32_t* sizes, uint32_t nblocks, int chain_ends,
+                              uint8_t* out, uint64_t out_cap, uint32_t* out_sizes) {
+    if (!h || !sizes || !out_sizes || (nblocks && !in)) return CRGPU_ERR_ARG;
+#ifndef CRGPU_SIM
+    CR_CUDA(cudaSetDevice(h->device));
+#endif
+    std::vector<BlockIO> blk(nblocks);
+    size_t total = 0;
+    for (uint32_t b = 0; b < nblocks; b++) {
+        memset(&blk[b], 0, sizeof(BlockIO));
+        blk[b].off = total; blk[b].size = sizes[b];
+        total += ((size_t)sizes[b] + 15) & ~(size_t)15;          // keep blocks 16-byte aligned in the window
+    }
+    CR_TRY(h->d_in.reserve(total + 64));
+    for (uint32_t b = 0; b < nblocks; b++) {
+        size_t src = 0; for (uint32_t k = 0; k < b; k++) src += sizes[k];
+        CR_CUDA(cudaMemcpyAsync(h->d_in.as<uint8_t>() + blk[b].off, in + src, sizes[b], cudaMemcpyHostToDevice, h->stream));
+    }
+    size_t out_total = 0;
+    CR_TRY(h->chain.encode_window(h->d_in.as<uint8_t>(), blk, 2, chain_ends != 0, h->d_out, 0, out_total));
+    if (out_total > out_cap) return CRGPU_ERR_ARG;
+    CR_CUDA(cudaMemcpyAsync(out, h->d_out.p, out_total, cudaMemcpyDeviceToHost, h->stream));
+    CR_CUDA(cudaStreamSynchronize(h->stream));
+    for (uint32_t b = 0; b < nblocks; b++) out_sizes[b] = blk[b].out_size;
+    return CRGPU_OK;
+}
+
+extern "C" int64_t crgpu_debug_fetch(crgpu_handle* h, const char* what, void* dst, uint64_t cap) {
+    if (!h || !what) return CRGPU_ERR_ARG;
+    LzChain& c = h->chain;
+    std::string w(what);
+    const void* src = nullptr; uint64_t bytes = 0;
+    if (w == "span") { src = c.b_span.p; bytes = c.last_dtotal; }
+    else if (w == "tidx") { src = c.b_tidx.p; bytes = c.last_dtotal; }
+    else if (w == "ev_ctx") { src = c.b_evctx.p; bytes = (uint64_t)c.last_nev * 4; }
+    else if (w == "ev_sym") { src = c.b_evsym.p; bytes = c.last_nev; }
+    else if (w == "pred") { src = c.b_pred.p; bytes = c.last_nev; }
+    else if (w == "dense") { src = c.b_dense.p; bytes = ((uint64_t)c.last_nev + c.last_nesc) * sizeof(Tri); }
+    else if (w == "dense_side") { src = c.b_denseside.p; bytes = (uint64_t)c.last_nside * sizeof(Tri); }
+    else return CRGPU_ERR_ARG;
+    uint64_t n = bytes < cap ? bytes : cap;
+    if (n && dst) {
+        if (cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) return CRGPU_ERR_CUDA;
+        if (cudaStreamSynchronize(h->stream) != cudaSuccess) return CRGPU_ERR_CUDA;
+    }
+    return (int64_t)bytes;
+}

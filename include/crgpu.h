@@ -1,0 +1,66 @@
+/*
+ * crgpu.h -- C ABI of libcrgpu.so, the B200-native (sm_100a CUDA) replacement for comprox's
+ * block-compression hot path.  Plain C types only; every buffer is caller-owned HOST memory unless a
+ * function says otherwise.  All functions return CRGPU_OK (0) or a negative CRGPU_ERR_* code; there is no
+ * CPU fallback -- without a CUDA device crgpu_create() fails with CRGPU_ERR_NO_DEVICE.
+ *
+ * Each entry point names the reference interface (file:line under /root/reference) it replaces.  A handle
+ * owns the state the reference keeps in file-scope statics (adaptive models, dictionary trie, filter
+ * continuation state), so -- unlike the reference -- several handles can coexist in one process.
+ * Like the reference, a single handle is not thread-safe.
+ */
+#ifndef CRGPU_H
+#define CRGPU_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRGPU_OK                    0
+#define CRGPU_ERR_NO_DEVICE        -1
+#define CRGPU_ERR_CUDA             -2
+#define CRGPU_ERR_ARG              -3
+#define CRGPU_ERR_VOCAB_OVERFLOW   -4   /* > 325000 distinct words: reference prune is order dependent (src/cr-dicpick.c:115-144) */
+#define CRGPU_ERR_HASH_COLLISION   -5
+#define CRGPU_ERR_MIDCHAIN_ABORT   -6   /* a non-final block hit "cannot compress" (src/rolzmain/cr-coder.c:231-233) */
+#define CRGPU_ERR_UNSUPPORTED      -7
+#define CRGPU_ERR_OOM              -8
+
+#define CRGPU_ROLZ 0   /* comprolz: src/rolzmain */
+#define CRGPU_LZP  1   /* comprop : src/ropmain  */
+
+typedef struct crgpu_handle crgpu_handle;
+
+/* Creates a handle on CUDA device `device`.  `stream` is a cudaStream_t passed as void* (NULL = the legacy
+ * default stream); all work of the handle is enqueued on it.  `variant` selects the lzencode implementation
+ * exactly as linking src/rolzmain or src/ropmain does in the reference (Makefile:12-27). */
+int  crgpu_create(crgpu_handle** out, int variant, int device, void* stream);
+void crgpu_destroy(crgpu_handle* h);
+const char* crgpu_strerror(int code);
+
+/* reset_models()  -- src/main.c:57, src/rolzmain/cr-coder.c:78-96, src/ropmain/cr-coder.c:73-83 */
+int crgpu_reset_models(crgpu_handle* h);
+
+/* lzencode(ib, ob, print)  -- src/main.c:58, src/rolzmain/cr-coder.c:139-264, src/ropmain/cr-coder.c:119-229.
+ * Batch form: encodes `nblocks` CONSECUTIVE blocks of the current model chain in one call (the reference
+ * calls lzencode once per block; models carry over from block to block and from call to call).
+ * in        : the blocks' bytes back to back (what dictionary_encode produced)
+ * sizes     : nblocks sizes
+ * out       : receives the payloads back to back; out_sizes[i] = size of payload i
+ * chain_ends: nonzero if reset_models() follows before any further block (as after the dictionary payload,
+ *             src/main.c:164-165, or at end of file). */
+int crgpu_lzencode(crgpu_handle* h, const uint8_t* in, const uint32_t* sizes, uint32_t nblocks, int chain_ends,
+                   uint8_t* out, uint64_t out_cap, uint32_t* out_sizes);
+
+/* Test / profiling aid: copies an intermediate array of the most recent lzencode window to the host.
+ * what: "span" (u8 per position), "tidx" (u8 per position), "ev_ctx" (u32 per event), "ev_sym" (u8 per event),
+ *       "pred" (u8 per event), "dense" (4 x u32 per main-stream triple), "dense_side" (4 x u32 per side triple).
+ * Returns the number of BYTES available (copies min(cap, available)), or a negative error. */
+int64_t crgpu_debug_fetch(crgpu_handle* h, const char* what, void* dst, uint64_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,90 @@
+"""GPU parity: crgpu_lzencode (C ABI, CUDA) against the CPU oracle on the same seeded inputs. Bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+import oracle_ffi as O
+from comprox_b200 import api
+
+pytestmark = pytest.mark.gpu
+
+
+def _diagnose(h, orc_variant, blocks, want, got):
+    """On a mismatch, localise it to a stage using the oracle's traces (tokens -> events -> triples)."""
+    orc = O.Oracle(orc_variant)
+    orc.trace(True)
+    for b in blocks:
+        orc.lzencode(b)
+    msg = []
+    ev = orc.events()
+    g_ctx = h.debug_fetch("ev_ctx", "uint32")
+    g_sym = h.debug_fetch("ev_sym", "uint8")
+    msg.append("events oracle=%d gpu=%d" % (len(ev), len(g_ctx)))
+    n = min(len(ev), len(g_ctx))
+    bad = np.nonzero((ev[:n, 0] != g_ctx[:n]) | ((ev[:n, 1] & 255) != g_sym[:n]))[0]
+    msg.append("first event mismatch: %s" % (bad[:5].tolist(),))
+    tr = orc.triples()
+    main = tr[tr[:, 3] == 0][:, :3]
+    d = h.debug_fetch("dense", "uint32").reshape(-1, 4)
+    n = min(len(main), len(d))
+    gm = d[:n, :3].copy()
+    gm[:, 1] &= 0x7FFFFFFF
+    bad = np.nonzero((gm != main[:n]).any(axis=1))[0]
+    msg.append("main triples oracle=%d gpu=%d first mismatch %s" % (len(main), len(d), bad[:5].tolist()))
+    if len(bad):
+        i = bad[0]
+        msg.append("  oracle %s gpu %s" % (main[i].tolist(), gm[i].tolist()))
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/diagnose.txt", "a") as f:
+        f.write("\n".join(msg) + "\n")
+    return "\n".join(msg)
+
+
+def _run(gpulib, variant, blocks):
+    orc = O.Oracle(variant)
+    want = [orc.lzencode(b) for b in blocks]
+    with api.Handle(variant, lib=gpulib) as h:
+        got = h.lzencode(blocks)
+        if got != want:
+            pytest.fail("payload mismatch sizes want=%s got=%s\n%s" % ([len(w) for w in want], [len(g) for g in got],
+                                                                     _diagnose(h, variant, blocks, want, got)))
+
+
+@pytest.mark.parametrize("variant", [api.ROLZ, api.LZP])
+@pytest.mark.parametrize("name", sorted(cases.lz_cases().keys()))
+def test_gpu_lzencode_matches_oracle(gpulib, variant, name):
+    _run(gpulib, variant, cases.lz_cases()[name])
+
+
+@pytest.mark.parametrize("variant", [api.ROLZ, api.LZP])
+def test_gpu_lzencode_dict_coded_text_8m(gpulib, variant):
+    """8 MiB of Markov text, dictionary-coded by the oracle, 1 MiB blocks -> 8 chained blocks; also 4-byte contexts."""
+    _run(gpulib, variant, cases.dict_coded_text(8 << 20, 1 << 20, seed=21, variant=variant))
+
+
+def test_gpu_lzencode_ctx4_block(gpulib):
+    """One block >= 4 MiB switches the ROLZ hash to 4 context bytes (src/rolzmain/cr-coder.c:162)."""
+    from comprox_b200 import synth
+    _run(gpulib, api.ROLZ, [synth.markov_text(5 << 20, seed=31)])
+
+
+@pytest.mark.parametrize("variant", [api.ROLZ, api.LZP])
+def test_gpu_chain_across_calls(gpulib, variant):
+    blocks = cases.dict_coded_text(1 << 20, 1 << 18, seed=5, variant=variant)
+    orc = O.Oracle(variant)
+    want = [orc.lzencode(b) for b in blocks]
+    with api.Handle(variant, lib=gpulib) as h:
+        got = h.lzencode(blocks[:1], chain_ends=False) + h.lzencode(blocks[1:3], chain_ends=False) + h.lzencode(blocks[3:])
+        assert got == want
+        orc.reset_models()
+        h.reset_models()
+        assert h.lzencode(blocks[:1])[0] == orc.lzencode(blocks[0])
+
+
+def test_gpu_midchain_abort_is_loud(gpulib):
+    with api.Handle(api.ROLZ, lib=gpulib) as h:
+        with pytest.raises(api.CrgpuError) as e:
+            h.lzencode([b"abc", b"hello hello hello hello"])
+        assert e.value.code == -6

@@ -44,6 +44,11 @@ def _check(L, rc):
         raise CrgpuError(rc, L.crgpu_strerror(rc).decode())
 
 
+class Config(ctypes.Structure):
+    _fields_ = [("block_size", ctypes.c_uint32), ("filt", ctypes.c_int32), ("prec", ctypes.c_int32), ("flexible", ctypes.c_int32),
+                ("window_bytes", ctypes.c_uint64)]
+
+
 class Handle:
     """One crgpu_handle: the state a reference *process* holds in globals (models, dictionary, filter state)."""
 
@@ -85,6 +90,28 @@ class Handle:
             res.append(out.raw[p:p + osz[i]])
             p += osz[i]
         return res
+
+    def compress(self, data: bytes, block_size: int = 16 << 20, filt: bool = False, prec: bool = False, flexible: bool = False,
+                 window_bytes: int = 0) -> bytes:
+        """The container the reference CLI writes for `comprolz/comprop [-bN] [-F] [-p] e`."""
+        cfg = Config(block_size, int(filt), int(prec), int(flexible), window_bytes)
+        self.L.crgpu_compress_bound.restype = ctypes.c_uint64
+        cap = self.L.crgpu_compress_bound(ctypes.c_uint64(len(data)), ctypes.c_uint32(block_size))
+        out = ctypes.create_string_buffer(cap)
+        n = ctypes.c_uint64()
+        _check(self.L, self.L.crgpu_compress(self.h, ctypes.byref(cfg), data, ctypes.c_uint64(len(data)), out, ctypes.c_uint64(cap), ctypes.byref(n)))
+        return out.raw[:n.value]
+
+    def set_option(self, name, value):
+        _check(self.L, self.L.crgpu_set_option(self.h, name.encode(), ctypes.c_int64(int(value))))
+
+    def profile(self, enable=True):
+        _check(self.L, self.L.crgpu_profile(self.h, int(enable)))
+
+    def profile_report(self):
+        buf = ctypes.create_string_buffer(8192)
+        self.L.crgpu_profile_report(self.h, buf, ctypes.c_uint64(8192))
+        return {k: float(v) for k, v in (ln.split() for ln in buf.value.decode().splitlines())}
 
     def debug_fetch(self, what: str, dtype="uint8"):
         import numpy as np

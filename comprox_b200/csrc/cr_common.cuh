@@ -100,6 +100,40 @@ struct DevBuf {
     template <class T> T* as() const { return (T*)p; }
 };
 
+// ------------------------------------------------------------------ stage timer (CUDA events on the handle's stream)
+#include <string>
+#include <vector>
+struct StageTimer {
+    bool enabled = false;
+    cudaStream_t stream = 0;
+#ifndef CRGPU_SIM
+    std::vector<cudaEvent_t> ev;
+#endif
+    std::vector<std::string> names;
+    std::vector<std::pair<std::string, float>> result;
+    void begin(cudaStream_t s) { stream = s; names.clear(); if (enabled) mark("start"); }
+    void mark(const char* name) {
+        if (!enabled) return;
+#ifndef CRGPU_SIM
+        if (ev.size() <= names.size()) { cudaEvent_t e; cudaEventCreate(&e); ev.push_back(e); }
+        cudaEventRecord(ev[names.size()], stream);
+#endif
+        names.push_back(name);
+    }
+    void finish() {   // call after a stream synchronize
+        if (!enabled) return;
+#ifndef CRGPU_SIM
+        for (size_t i = 1; i < names.size(); i++) {
+            float ms = 0; cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+            bool found = false;
+            for (auto& r : result) if (r.first == names[i]) { r.second += ms; found = true; }
+            if (!found) result.push_back(std::make_pair(names[i], ms));
+        }
+#endif
+        names.clear();
+    }
+};
+
 // ------------------------------------------------------------------ small device helpers
 CR_HD uint32_t cr_ld32(const uint8_t* p) { return p[0] | p[1] << 8 | p[2] << 16 | (uint32_t)p[3] << 24; }
 CR_HD bool cr_is_lower(uint32_t c) { return c - 'a' < 26u; }

@@ -1,0 +1,278 @@
+// cr_container.cuh -- whole-container compression: what cr_main does between fopen and fclose
+// (src/main.c:137-218), restructured so that the GPU sees the whole input at once.
+//
+//   magic | u32 dict_len | lzencode(dic_lcp_encode(dicpick(file)))          <- chain 0, models reset after
+//         | { u32 len, u8 filt, u8 prec, payload }*                           <- chain 1, models carried (F2)
+// The serial per-block loop of the reference becomes: one dicpick pass over the file, then per WINDOW of
+// blocks: filters -> dictionary substitution -> lzencode chain (cr_lzchain.cuh).  The container bytes are
+// assembled on the device and leave with a single copy.
+#pragma once
+#include "cr_lzchain.cuh"
+#include "cr_dict.cuh"
+#include "cr_filter.cuh"
+#include "cr_hostdict.h"
+
+struct CrConfig {
+    uint32_t block_size;     // bytes, reference default 16 MiB (src/main.c:62)
+    int filt;                // -F
+    int prec;                // -p
+    int flexible;            // -f (ROLZ) -- not implemented on the GPU yet
+    uint64_t window_bytes;   // raw bytes per window (0 = default)
+};
+
+struct Compressor {
+    LzChain* chain = nullptr;
+    cudaStream_t stream = 0;
+    DevBuf d_raw, d_D, d_out, d_dic;
+    DevBuf t_key, t_count, t_first, t_stats, t_entries;          // dicpick table
+    DevBuf d_trie_next, d_trie_id;
+    DevBuf b_subs, b_hist, b_esc10, b_escmask, b_span, b_hit, b_segs, b_xt, b_entry, b_cnt, b_scan, b_chunk0, b_hdr, b_copy, b_segoff, b_seglen;
+    HdTrie trie;
+    FilterHost filt;
+    StageTimer* timer = nullptr;
+
+    void release() {
+        DevBuf* all[] = { &d_raw, &d_D, &d_out, &d_dic, &t_key, &t_count, &t_first, &t_stats, &t_entries, &d_trie_next, &d_trie_id, &b_subs, &b_hist,
+                          &b_esc10, &b_escmask, &b_span, &b_hit, &b_segs, &b_xt, &b_entry, &b_cnt, &b_scan, &b_chunk0, &b_hdr, &b_copy, &b_segoff, &b_seglen };
+        for (DevBuf* b : all) b->release();
+        filt.release();
+    }
+    template <class T> int upload(DevBuf& b, const std::vector<T>& v) { return chain->upload(b, v); }
+    template <class T> int download(std::vector<T>& v, const void* src, size_t n) { return chain->download(v, src, n); }
+
+    int dicpick(const uint8_t* h_in, const uint8_t* d_in, uint64_t n, std::string& text);
+    int load_dictionary(const std::string& text);
+    int dict_encode_window(const uint8_t* d_rawwin, const std::vector<uint64_t>& roff, const std::vector<uint32_t>& rsize, std::vector<BlockIO>& blk, size_t& dtotal);
+    int compress(const CrConfig& cfg, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_n);
+};
+
+// ------------------------------------------------------------------ dicpick (src/cr-dicpick.c:164-259)
+inline int Compressor::dicpick(const uint8_t* h_in, const uint8_t* d_in, uint64_t n, std::string& text) {
+    CR_TRY(t_key.reserve((size_t)DP_SLOTS * 8)); CR_TRY(t_count.reserve((size_t)DP_SLOTS * 4)); CR_TRY(t_first.reserve((size_t)DP_SLOTS * 4));
+    CR_TRY(t_stats.reserve(64)); CR_TRY(t_entries.reserve((size_t)DP_MAXWORDS * sizeof(DpEntry)));
+    CR_CUDA(cudaMemsetAsync(t_key.p, 0, (size_t)DP_SLOTS * 8, stream));
+    CR_CUDA(cudaMemsetAsync(t_count.p, 0, (size_t)DP_SLOTS * 4, stream));
+    CR_CUDA(cudaMemsetAsync(t_first.p, 0xFF, (size_t)DP_SLOTS * 4, stream));
+    CR_CUDA(cudaMemsetAsync(t_stats.p, 0, 64, stream));
+    DpTable T = { t_key.as<unsigned long long>(), t_count.as<uint32_t>(), t_first.as<uint32_t>(), t_stats.as<uint32_t>() };
+    const uint64_t step = 1ull << 30;
+    for (uint64_t x0 = 0; x0 < n; x0 += step) {
+        uint64_t x1 = x0 + step < n ? x0 + step : n;
+        CR_LAUNCH(k_dp_count, dim3(cr_div_up(x1 - x0, 256)), dim3(256), stream, d_in, n, x0, x1, T);
+    }
+    for (uint64_t x0 = 0; x0 < n; x0 += step) {
+        uint64_t x1 = x0 + step < n ? x0 + step : n;
+        CR_LAUNCH(k_dp_verify, dim3(cr_div_up(x1 - x0, 256)), dim3(256), stream, d_in, n, x0, x1, T);
+    }
+    CR_LAUNCH(k_dp_collect, dim3(DP_SLOTS / 256), dim3(256), stream, T, t_entries.as<DpEntry>(), DP_MAXWORDS);
+    std::vector<uint32_t> stats;
+    CR_TRY(download(stats, t_stats.p, 4));
+    if (stats[1] & 1u) return CRGPU_ERR_VOCAB_OVERFLOW;
+    if (stats[1] & 2u) return CRGPU_ERR_HASH_COLLISION;
+    std::vector<DpEntry> ent;
+    CR_TRY(download(ent, t_entries.p, stats[2]));
+    std::vector<HdWord> words(ent.size());
+    for (size_t i = 0; i < ent.size(); i++) { words[i].w = hd_word_at(h_in, n, ent[i].first); words[i].count = ent[i].count; }
+    text = hd_dictionary_text(words);
+    return CRGPU_OK;
+}
+
+inline int Compressor::load_dictionary(const std::string& text) {
+    trie.load(text.c_str());
+    CR_TRY(upload(d_trie_next, trie.next)); CR_TRY(upload(d_trie_id, trie.id));
+    return CRGPU_OK;
+}
+
+// ------------------------------------------------------------------ dictionary_encode for a window of blocks
+// (src/cr-diccode.c:142-221).  Produces the dictionary-coded blocks back to back (16-byte aligned) in d_D.
+inline int Compressor::dict_encode_window(const uint8_t* d_rawwin, const std::vector<uint64_t>& roff, const std::vector<uint32_t>& rsize,
+                                          std::vector<BlockIO>& blk, size_t& dtotal) {
+    const uint32_t nb = (uint32_t)rsize.size();
+    Prims& prims = chain->prims;
+    // ---- sub-chunks: pairs of up to 1 000 000 bytes (:173-180); the second of a pair may be empty
+    std::vector<DcSub> subs;
+    std::vector<uint32_t> first_sub(nb + 1);
+    uint32_t maxsize = 0;
+    for (uint32_t b = 0; b < nb; b++) {
+        first_sub[b] = (uint32_t)subs.size();
+        for (uint32_t pos = 0; pos < rsize[b];) {
+            for (int k = 0; k < 2; k++) {
+                uint32_t s = rsize[b] - pos < DC_SUB ? rsize[b] - pos : DC_SUB;
+                DcSub S; S.off = roff[b] + pos; S.size = s; S.block = b; S.out = 0;
+                subs.push_back(S);
+                pos += s;
+            }
+        }
+        if (rsize[b] > maxsize) maxsize = rsize[b];
+    }
+    first_sub[nb] = (uint32_t)subs.size();
+    const uint32_t nsub = (uint32_t)subs.size();
+    size_t rawtotal = 0;
+    for (uint32_t b = 0; b < nb; b++) if (roff[b] + rsize[b] > rawtotal) rawtotal = roff[b] + rsize[b];
+
+    // ---- the 10 rarest bytes of every raw block (:161-171)
+    CR_TRY(upload(b_segoff, roff)); CR_TRY(upload(b_seglen, rsize));
+    CR_TRY(b_hist.reserve((size_t)nb * 1024)); CR_TRY(b_esc10.reserve((size_t)nb * 10 + 16)); CR_TRY(b_escmask.reserve((size_t)nb * 32));
+    CR_CUDA(cudaMemsetAsync(b_hist.p, 0, (size_t)nb * 1024, stream));
+    if (maxsize) CR_LAUNCH(k_hist256, dim3(cr_div_up(maxsize, CR_HIST_TILE), nb), dim3(256), stream, d_rawwin, b_segoff.as<uint64_t>(), b_seglen.as<uint32_t>(), b_hist.as<uint32_t>());
+    CR_LAUNCH(k_pick_escapes, dim3(cr_div_up(nb, 64)), dim3(64), stream, b_hist.as<uint32_t>(), nb, b_esc10.as<uint8_t>(), (uint8_t*)nullptr);
+    CR_LAUNCH(k_dc_escmask, dim3(cr_div_up(nb, 64)), dim3(64), stream, b_esc10.as<uint8_t>(), nb, b_escmask.as<uint32_t>());
+
+    // ---- per-position trie walk, parse resolution, code sizes
+    std::vector<ChainSeg> segs(nsub);
+    for (uint32_t s = 0; s < nsub; s++) { segs[s].off = subs[s].off; segs[s].len = subs[s].size; segs[s].start = 0; }
+    const uint32_t nchunk = cr_chain_layout(segs.data(), nsub);
+    std::vector<uint32_t> chunk0(nsub + 1);
+    for (uint32_t s = 0; s < nsub; s++) chunk0[s] = segs[s].chunk0;
+    chunk0[nsub] = nchunk;
+    std::vector<uint32_t> hscan(nchunk + 1, 0);
+    DcTrie T = { d_trie_next.as<int32_t>(), d_trie_id.as<int32_t>(), trie.nentries, trie.level1() };
+    if (nsub) {
+        CR_TRY(upload(b_subs, subs)); CR_TRY(upload(b_segs, segs)); CR_TRY(upload(b_chunk0, chunk0));
+        CR_TRY(b_span.reserve(rawtotal + 16)); CR_TRY(b_hit.reserve(rawtotal * 4 + 16));
+        CR_TRY(b_xt.reserve((size_t)nchunk * 256 + 16)); CR_TRY(b_entry.reserve(nchunk + 16));
+        CR_TRY(b_cnt.reserve((size_t)(nchunk + 1) * 4)); CR_TRY(b_scan.reserve((size_t)(nchunk + 1) * 4));
+        CR_LAUNCH(k_dc_spans, dim3(cr_div_up(DC_SUB, 256), nsub), dim3(256), stream, d_rawwin, b_subs.as<DcSub>(), T, b_span.as<uint8_t>(), b_hit.as<uint32_t>());
+        CR_CUDA(cudaMemsetAsync(b_cnt.p, 0, (size_t)(nchunk + 1) * 4, stream));
+        if (nchunk) {
+            CR_LAUNCH(k_chain_exits, dim3(cr_div_up(nchunk, 64)), dim3(64), stream, b_span.as<uint8_t>(), b_segs.as<ChainSeg>(), nsub, nchunk, b_xt.as<uint8_t>());
+            CR_LAUNCH(k_chain_entries, dim3(cr_div_up(nsub, 32)), dim3(32), stream, b_segs.as<ChainSeg>(), nsub, b_xt.as<uint8_t>(), b_entry.as<uint8_t>());
+            DcCount f = { d_rawwin, b_subs.as<DcSub>(), b_span.as<uint8_t>(), b_hit.as<uint32_t>(), b_escmask.as<uint32_t>(), T.level1, b_cnt.as<uint32_t>() };
+            CR_LAUNCH(k_chain_walk<DcCount>, dim3(cr_div_up(nchunk, 64)), dim3(64), stream, b_span.as<uint8_t>(), b_segs.as<ChainSeg>(), nsub, nchunk, b_entry.as<uint8_t>(), f);
+        }
+        CR_TRY(cr_exclusive_sum(prims, b_cnt.as<uint32_t>(), b_scan.as<uint32_t>(), nchunk + 1));
+        CR_TRY(download(hscan, b_scan.p, nchunk + 1));
+    }
+    std::vector<uint8_t> hesc;
+    CR_TRY(download(hesc, b_esc10.p, (size_t)nb * 10));
+
+    // ---- layout: coded if smaller than raw, else raw + 0 (:208-217)
+    std::vector<HeaderDesc> hdrs; std::vector<CopyDesc> copies;
+    blk.assign(nb, BlockIO());
+    size_t pos = 0;
+    auto put_bytes = [&](uint64_t dst, const void* p, uint32_t len) { HeaderDesc h; memset(&h, 0, sizeof h); h.dst = dst; h.len = len; memcpy(h.bytes, p, len); hdrs.push_back(h); };
+    for (uint32_t b = 0; b < nb; b++) {
+        memset(&blk[b], 0, sizeof(BlockIO));
+        uint64_t coded = 11;
+        for (uint32_t s = first_sub[b]; s < first_sub[b + 1]; s += 2) coded += 8 + (hscan[chunk0[s + 1]] - hscan[chunk0[s]]) + 4 + (hscan[chunk0[s + 2]] - hscan[chunk0[s + 1]]) + 4;
+        blk[b].off = pos;
+        if (coded >= rsize[b]) {
+            blk[b].size = rsize[b] + 1;
+            if (rsize[b]) { CopyDesc c = { roff[b], pos, rsize[b], 0 }; copies.push_back(c); }
+            uint8_t z = 0; put_bytes(pos + rsize[b], &z, 1);
+            for (uint32_t s = first_sub[b]; s < first_sub[b + 1]; s++) subs[s].out = ~0ull;   // nothing to emit
+        } else {
+            blk[b].size = (uint32_t)coded;
+            uint64_t p = pos;
+            for (uint32_t s = first_sub[b]; s < first_sub[b + 1]; s += 2) {
+                uint32_t l1 = hscan[chunk0[s + 1]] - hscan[chunk0[s]] + 4, l2 = hscan[chunk0[s + 2]] - hscan[chunk0[s + 1]] + 4;
+                uint32_t pair[2] = { l1, l2 };
+                put_bytes(p, pair, 8); p += 8;
+                subs[s].out = p; p += l1 - 4; put_bytes(p, &subs[s].size, 4); p += 4;
+                subs[s + 1].out = p; p += l2 - 4; put_bytes(p, &subs[s + 1].size, 4); p += 4;
+            }
+            uint8_t tail[11]; memcpy(tail, &hesc[(size_t)b * 10], 10); tail[10] = 1;
+            put_bytes(p, tail, 11);
+        }
+        pos += ((size_t)blk[b].size + 15) & ~(size_t)15;
+    }
+    dtotal = pos;
+    CR_TRY(d_D.reserve(dtotal + 64));
+    // emit codes of the coded blocks (sub-chunks of raw blocks carry out = ~0 and emit nothing)
+    if (nsub && nchunk) {
+        CR_TRY(upload(b_subs, subs));
+        DcEmit f = { d_rawwin, b_subs.as<DcSub>(), b_span.as<uint8_t>(), b_hit.as<uint32_t>(), b_escmask.as<uint32_t>(), b_esc10.as<uint8_t>(),
+                     T.level1, T.nentries, b_scan.as<uint32_t>(), b_chunk0.as<uint32_t>(), d_D.as<uint8_t>() };
+        CR_LAUNCH(k_chain_walk<DcEmit>, dim3(cr_div_up(nchunk, 64)), dim3(64), stream, b_span.as<uint8_t>(), b_segs.as<ChainSeg>(), nsub, nchunk, b_entry.as<uint8_t>(), f);
+    }
+    if (!hdrs.empty()) { CR_TRY(upload(b_hdr, hdrs)); CR_LAUNCH(k_write_headers, dim3(cr_div_up(hdrs.size(), 64)), dim3(64), stream, b_hdr.as<HeaderDesc>(), (uint32_t)hdrs.size(), d_D.as<uint8_t>()); }
+    if (!copies.empty()) { CR_TRY(upload(b_copy, copies)); CR_LAUNCH(k_copy_segments, dim3(64, (unsigned)copies.size()), dim3(256), stream, b_copy.as<CopyDesc>(), d_rawwin, d_rawwin, d_D.as<uint8_t>()); }
+    return CRGPU_OK;
+}
+
+static inline const char* cr_magic(int variant) { return variant == CR_ROLZ ? "\x1f\x9d\x01\x01::0.11.0-comprolz" : "\x1f\x9d\x01\x01::0.11.0-comprop"; }
+static inline uint64_t cr_compress_bound(uint64_t n, uint32_t block_size) {
+    uint64_t nblocks = n / (block_size ? block_size : 1) + 2;
+    return 64 + (1u << 20) + n + nblocks * 64;
+}
+
+inline int Compressor::compress(const CrConfig& cfg, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_n) {
+    if (cfg.block_size == 0 || (n && !in) || !out || !out_n) return CRGPU_ERR_ARG;
+    if (cfg.flexible) return CRGPU_ERR_UNSUPPORTED;
+    stream = chain->stream;
+    StageTimer& tm = chain->timer;
+    const size_t mlen = strlen(cr_magic(chain->variant));
+    if (out_cap < cr_compress_bound(n, cfg.block_size)) return CRGPU_ERR_ARG;
+    memcpy(out, cr_magic(chain->variant), mlen);
+
+    // ---- whole input to HBM
+    CR_TRY(d_raw.reserve(n + 256));
+    if (n) CR_CUDA(cudaMemcpyAsync(d_raw.p, in, n, cudaMemcpyHostToDevice, stream));
+    CR_CUDA(cudaMemsetAsync(d_raw.as<uint8_t>() + n, 0, 128, stream));
+
+    // ---- static dictionary: build, load, emit as its own model chain (src/main.c:156-172)
+    std::string text;
+    CR_TRY(dicpick(in, d_raw.as<uint8_t>(), n, text));
+    CR_TRY(load_dictionary(text));
+    std::vector<uint8_t> lcp = hd_lcp_encode(text);
+    CR_TRY(upload(d_dic, lcp));
+    CR_TRY(chain->reset_models());
+    std::vector<BlockIO> dblk(1);
+    memset(&dblk[0], 0, sizeof(BlockIO)); dblk[0].size = (uint32_t)lcp.size();
+    size_t out_pos = 0, wrote = 0;
+    CR_TRY(chain->encode_window(d_dic.as<uint8_t>(), dblk, 0, true, d_out, out_pos, wrote));
+    out_pos += wrote;
+    CR_TRY(chain->reset_models());
+
+    // ---- data blocks, window by window.  A trailing empty block appears when n % block_size == 0 (F8).
+    const uint64_t nblocks = n / cfg.block_size + 1;
+    uint64_t wbytes = cfg.window_bytes ? cfg.window_bytes : (512ull << 20);
+    uint64_t per_window = wbytes / cfg.block_size; if (per_window == 0) per_window = 1;
+    filt.reset();
+    int filt_flag = 0;
+    for (uint64_t b0 = 0; b0 < nblocks; b0 += per_window) {
+        const uint64_t b1 = b0 + per_window < nblocks ? b0 + per_window : nblocks;
+        std::vector<uint64_t> roff; std::vector<uint32_t> rsize;
+        const uint64_t wbase = b0 * cfg.block_size;              // offsets below are relative to the window
+        uint8_t* d_win = d_raw.as<uint8_t>() + wbase;
+        for (uint64_t b = b0; b < b1; b++) {
+            uint64_t off = b * cfg.block_size;
+            roff.push_back(off - wbase);
+            rsize.push_back((uint32_t)(n - off < cfg.block_size ? n - off : cfg.block_size));
+        }
+        std::vector<uint8_t> filt_flags(rsize.size(), 0);
+        if (cfg.filt) CR_TRY(filt.run_window(*chain, in + wbase, d_win, n - wbase, roff, rsize, filt_flags, filt_flag));
+        std::vector<BlockIO> blk; size_t dtotal = 0;
+        CR_TRY(dict_encode_window(d_win, roff, rsize, blk, dtotal));
+        for (size_t i = 0; i < blk.size(); i++) { blk[i].filt = filt_flags[i]; blk[i].prec = (uint8_t)cfg.prec; }
+        const bool last = b1 == nblocks;
+        if (!cfg.prec) {
+            CR_TRY(chain->encode_window(d_D.as<uint8_t>(), blk, 1, last, d_out, out_pos, wrote));
+        } else {
+            // -p: the dictionary-coded block is the payload (src/main.c:191-195)
+            std::vector<HeaderDesc> hdrs; std::vector<CopyDesc> copies; size_t p = out_pos;
+            for (size_t i = 0; i < blk.size(); i++) {
+                HeaderDesc h; memset(&h, 0, sizeof h); h.dst = p; h.len = 6; memcpy(h.bytes, &blk[i].size, 4); h.bytes[4] = blk[i].filt; h.bytes[5] = 1; hdrs.push_back(h);
+                CopyDesc c = { blk[i].off, p + 6, blk[i].size, 0 }; copies.push_back(c);
+                p += 6 + blk[i].size;
+            }
+            wrote = p - out_pos;
+            if (d_out.cap < p) {
+                DevBuf nb2; CR_TRY(nb2.reserve(p + p / 4));
+                if (d_out.p && out_pos) CR_CUDA(cudaMemcpyAsync(nb2.p, d_out.p, out_pos, cudaMemcpyDeviceToDevice, stream));
+                CR_CUDA(cudaStreamSynchronize(stream));
+                d_out.release(); d_out = nb2;
+            }
+            CR_TRY(upload(b_hdr, hdrs)); CR_TRY(upload(b_copy, copies));
+            CR_LAUNCH(k_write_headers, dim3(cr_div_up(hdrs.size(), 64)), dim3(64), stream, b_hdr.as<HeaderDesc>(), (uint32_t)hdrs.size(), d_out.as<uint8_t>());
+            CR_LAUNCH(k_copy_segments, dim3(64, (unsigned)copies.size()), dim3(256), stream, b_copy.as<CopyDesc>(), d_D.as<uint8_t>(), d_D.as<uint8_t>(), d_out.as<uint8_t>());
+        }
+        out_pos += wrote;
+    }
+    if (mlen + out_pos > out_cap) return CRGPU_ERR_ARG;
+    CR_CUDA(cudaMemcpyAsync(out + mlen, d_out.p, out_pos, cudaMemcpyDeviceToHost, stream));
+    CR_CUDA(cudaStreamSynchronize(stream));
+    *out_n = mlen + out_pos;
+    (void)tm;
+    return CRGPU_OK;
+}

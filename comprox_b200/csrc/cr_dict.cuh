@@ -1,0 +1,178 @@
+// cr_dict.cuh -- static word dictionary on the GPU: word statistics (dicpick) and substitution (diccode).
+//
+// dicpick  replaces the tokenizer + hash map of src/cr-dicpick.c:164-216,95-146.  A word start is a local
+//          property of two neighbouring bytes, so every byte position is examined in parallel; accepted words
+//          are counted in a device-wide open-addressing table keyed by a 64-bit hash.  The host receives only
+//          the (first position, count) pairs with count > 5 and performs the tiny ordering step
+//          (src/cr-dicpick.c:218-257) there.  Counts are order independent as long as fewer than 325001 distinct
+//          words exist; beyond that the reference prunes in arrival order and we refuse loudly.
+// diccode  replaces dictionary_encode_imp (src/cr-diccode.c:285-362): the trie walk is evaluated at every word
+//          start in parallel, the serial "i = j" skip is resolved with cr_chain.cuh, output offsets come from a
+//          scan of the per-position code sizes.
+#pragma once
+#include "cr_common.cuh"
+
+// ------------------------------------------------------------------ dicpick
+#define DP_CHUNK      200000u            // fread granularity of the reference tokenizer (cr-dicpick.c:162)
+#define DP_SLOTS_LOG2 21
+#define DP_SLOTS      (1u << DP_SLOTS_LOG2)
+#define DP_MAXWORDS   325001u            // HASHMAP_MAXSIZE (cr-dicpick.c:34)
+#define DP_MINLEN     2u
+#define DP_MAXLEN     20u
+
+struct DpTable {
+    unsigned long long* key;   // [DP_SLOTS] 0 = empty
+    uint32_t* count;           // [DP_SLOTS]
+    uint32_t* first;           // [DP_SLOTS] smallest position at which the word starts
+    uint32_t* stats;           // [0] distinct words, [1] error flags, [2] number of selected entries
+};
+
+CR_HD uint32_t dp_byte(const uint8_t* in, uint64_t chunk0, uint32_t c, uint32_t flen) {
+    return c == flen - 1 ? 0u : in[chunk0 + c];                 // the last byte of every chunk reads as 0 (:192)
+}
+// If a word that the reference would count starts at file position x, returns its length (2..20), else 0.
+CR_HD uint32_t dp_word_at(const uint8_t* in, uint64_t n, uint64_t x, unsigned long long* hash_out) {
+    const uint64_t chunk0 = x / DP_CHUNK * DP_CHUNK;
+    const uint32_t c = (uint32_t)(x - chunk0);
+    const uint32_t flen = (uint32_t)(n - chunk0 < DP_CHUNK ? n - chunk0 : DP_CHUNK);
+    if (c == 0) return 0;
+    uint32_t b = dp_byte(in, chunk0, c, flen);
+    if (!cr_is_alpha(b) || cr_is_alpha(in[x - 1])) return 0;
+    unsigned long long h = 1469598103934665603ull;
+    h = (h ^ (b | 32)) * 1099511628211ull;
+    uint32_t y = c + 1;
+    while (y < flen) {
+        uint32_t v = dp_byte(in, chunk0, y, flen);
+        if (!cr_is_lower(v)) break;
+        if (y - c >= DP_MAXLEN) return 0;                          // longer than 20: rejected whatever follows
+        h = (h ^ v) * 1099511628211ull;
+        y++;
+    }
+    const uint32_t len = y - c;
+    if (len < DP_MINLEN || y >= flen) return 0;
+    const uint32_t s = dp_byte(in, chunk0, y, flen);
+    if (!(s == ' ' || s == ',' || s == '.' || s == ':' || s == ';')) return 0;
+    h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
+    if (h == 0) h = 1;
+    *hash_out = h;
+    return len;
+}
+
+// positions [x0, x1) of the file; the table persists across launches so a file can be fed in windows
+__global__ void k_dp_count(const uint8_t* __restrict__ in, uint64_t n, uint64_t x0, uint64_t x1, DpTable T) {
+    uint64_t x = x0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= x1) return;
+    unsigned long long h;
+    if (!dp_word_at(in, n, x, &h)) return;
+    uint32_t slot = (uint32_t)h & (DP_SLOTS - 1);
+    for (uint32_t probe = 0; probe < DP_SLOTS; probe++) {
+        unsigned long long prev = atomicCAS(&T.key[slot], 0ull, h);
+        if (prev == 0ull) {
+            if (atomicAdd(&T.stats[0], 1u) + 1 >= DP_MAXWORDS) atomicOr(&T.stats[1], 1u);
+            prev = h;
+        }
+        if (prev == h) { atomicAdd(&T.count[slot], 1u); atomicMin(&T.first[slot], (uint32_t)x); return; }
+        slot = (slot + 1) & (DP_SLOTS - 1);
+    }
+    atomicOr(&T.stats[1], 1u);
+}
+// every occurrence must spell the same word as the table entry's first occurrence (hash collisions are loud)
+__global__ void k_dp_verify(const uint8_t* __restrict__ in, uint64_t n, uint64_t x0, uint64_t x1, DpTable T) {
+    uint64_t x = x0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= x1) return;
+    unsigned long long h;
+    uint32_t len = dp_word_at(in, n, x, &h);
+    if (!len) return;
+    uint32_t slot = (uint32_t)h & (DP_SLOTS - 1);
+    for (uint32_t probe = 0; probe < DP_SLOTS && T.key[slot] != h; probe++) slot = (slot + 1) & (DP_SLOTS - 1);
+    const uint8_t* a = in + x; const uint8_t* b = in + T.first[slot];
+    bool same = true;
+    for (uint32_t i = 0; i < len; i++) same &= (a[i] | 32) == (b[i] | 32);
+    same &= !cr_is_lower(b[len]);
+    if (!same) atomicOr(&T.stats[1], 2u);
+}
+struct DpEntry { uint32_t first, count; };
+__global__ void k_dp_collect(DpTable T, DpEntry* __restrict__ out, uint32_t cap) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= DP_SLOTS || T.key[s] == 0ull || T.count[s] <= 5) return;      // WORD_MIN_FREQ (:221)
+    uint32_t i = atomicAdd(&T.stats[2], 1u);
+    if (i < cap) { out[i].first = T.first[s]; out[i].count = T.count[s]; }
+}
+
+// ------------------------------------------------------------------ diccode
+#define DC_SUB 1000000u                  // sub-chunk size (cr-diccode.c:177-180)
+
+struct DcTrie { const int32_t* next; const int32_t* id; int32_t nentries; int32_t level1; };
+struct DcSub {                           // one sub-chunk = one chain segment
+    uint64_t off;                        // offset of the sub-chunk in the raw window
+    uint32_t size;
+    uint32_t block;                      // owning block (for the escape set)
+    uint64_t out;                        // where its codes start in the dictionary-coded window (set after sizing)
+};
+#define DC_HIT 0x80000000u
+
+CR_HD bool dc_sentence_start(const uint8_t* s, uint32_t i) {     // M_check_reverse_case (cr-diccode.c:313)
+    return i >= 3 && s[i - 1] == ' ' && (s[i - 2] == '.' || (s[i - 2] == ' ' && s[i - 3] == '.'));
+}
+
+// span[g] and hit[g] for every raw position of the window (grid.y = sub-chunk)
+__global__ void k_dc_spans(const uint8_t* __restrict__ raw, const DcSub* __restrict__ subs, DcTrie T, uint8_t* __restrict__ span, uint32_t* __restrict__ hit) {
+    const DcSub S = subs[blockIdx.y];
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S.size) return;
+    const uint8_t* d = raw + S.off;
+    uint32_t sp = 1;
+    if (i > 0 && i + 40 < S.size && cr_is_alpha(d[i]) && !cr_is_alpha(d[i - 1])) {
+        uint32_t j = i; int32_t node = 0;
+        while (d[j] < 128 && (node = T.next[(size_t)node * 128 + d[j]]) != 0 && T.id[node] == -1) j++;
+        if (d[j] < 128 && node != 0) {
+            uint32_t rev = (uint32_t)cr_is_upper(d[i]) ^ (uint32_t)dc_sentence_start(d, i);
+            uint32_t tail = d[j] == ':' ? 4 : d[j] == ';' ? 3 : d[j] == ',' ? 2 : d[j] == '.' ? 1 : 0;
+            sp = j - i + 1;
+            hit[S.off + i] = DC_HIT | (uint32_t)T.id[node] | (rev * 5 + tail) << 24;
+        }
+    }
+    span[S.off + i] = (uint8_t)sp;
+}
+
+struct DcCount {
+    typedef uint32_t State;
+    const uint8_t* raw; const DcSub* subs; const uint8_t* span; const uint32_t* hit; const uint32_t* escmask;   // escmask[block*8 + w]
+    int32_t level1; uint32_t* cnt;
+    CR_D State begin(uint32_t, uint32_t) const { return 0; }
+    CR_D void visit(State& n, uint32_t s, uint32_t i, uint32_t sp) const {
+        const DcSub S = subs[s];
+        if (sp > 1) { uint32_t id = hit[S.off + i] & 0xFFFFFF; n += (int32_t)id < level1 ? 2 : 3; }
+        else { uint32_t b = raw[S.off + i]; n += (escmask[S.block * 8 + (b >> 5)] >> (b & 31) & 1) ? 3 : 1; }
+    }
+    CR_D void end(State& n, uint32_t c, uint32_t) const { cnt[c] = n; }
+};
+struct DcEmit {
+    typedef uint64_t State;
+    const uint8_t* raw; const DcSub* subs; const uint8_t* span; const uint32_t* hit; const uint32_t* escmask; const uint8_t* esc10;
+    int32_t level1, nentries; const uint32_t* scan; const uint32_t* sub_chunk0; uint8_t* out;
+    CR_D State begin(uint32_t c, uint32_t s) const { return subs[s].out == ~0ull ? ~0ull : subs[s].out + (scan[c] - scan[sub_chunk0[s]]); }
+    CR_D void visit(State& o, uint32_t s, uint32_t i, uint32_t sp) const {
+        if (o == ~0ull) return;                                   // block is stored raw: nothing to emit
+        const DcSub S = subs[s];
+        const uint32_t wide = 256 - level1;
+        if (sp > 1) {                                             // cr-diccode.c:327-336
+            uint32_t h = hit[S.off + i], id = h & 0xFFFFFF;
+            if ((int32_t)id < level1) out[o++] = (uint8_t)id;
+            else { out[o++] = (uint8_t)(id / wide); out[o++] = (uint8_t)(id % wide + level1); }
+            out[o++] = esc10[S.block * 10 + ((h >> 24) & 0x7F)];
+        } else {                                                  // cr-diccode.c:338-346
+            uint32_t b = raw[S.off + i];
+            if (escmask[S.block * 8 + (b >> 5)] >> (b & 31) & 1) { out[o++] = (uint8_t)(nentries / wide); out[o++] = (uint8_t)(nentries % wide + level1); }
+            out[o++] = (uint8_t)b;
+        }
+    }
+    CR_D void end(State&, uint32_t, uint32_t) const {}
+};
+__global__ void k_dc_escmask(const uint8_t* __restrict__ esc10, uint32_t nblocks, uint32_t* __restrict__ mask) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblocks) return;
+    uint32_t m[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = 0; k < 10; k++) { uint32_t e = esc10[b * 10 + k]; m[e >> 5] |= 1u << (e & 31); }
+    for (int w = 0; w < 8; w++) mask[b * 8 + w] = m[w];
+}

@@ -14,6 +14,7 @@
 #include "cr_lzp.cuh"
 #include "cr_ppm.cuh"
 #include "cr_rc.cuh"
+#include "cr_warp.cuh"
 
 enum { CR_ROLZ = 0, CR_LZP = 1 };
 
@@ -45,7 +46,8 @@ struct LzChain {
     // ---- sizes of the last window (for the debug/trace fetch used by the tests)
     uint32_t last_nev = 0, last_nside = 0, last_nesc = 0, last_nent = 0;
     size_t last_dtotal = 0;
-    float ms_match = 0, ms_model = 0, ms_rc = 0;
+    StageTimer timer;
+    bool scalar_models = false;   // GPU A/B switch: run the scalar (simulation-checked) model/coder kernels
 
     int init(int variant_, cudaStream_t s) {
         variant = variant_; stream = s; prims.stream = s;
@@ -119,6 +121,7 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
     const uint32_t hdr_size = variant == CR_ROLZ ? 16 : 20;
     const uint32_t prefix = prefix_mode == 0 ? 4 : prefix_mode == 1 ? 6 : 0;
 
+    timer.begin(stream);
     // ---- block table
     std::vector<LzBlock> hb(nb);
     std::vector<uint64_t> segoff(nb);
@@ -147,6 +150,7 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
     CR_LAUNCH(k_pick_escapes, dim3(cr_div_up(nb, 64)), dim3(64), stream, b_hist.as<uint32_t>(), nb, (uint8_t*)nullptr, b_esc1.as<uint8_t>());
     CR_LAUNCH(k_first_bytes, dim3(cr_div_up(nb, 64)), dim3(64), stream, dD, d_blocks, nb, b_first.as<uint8_t>());
 
+    timer.mark("hist_esc");
     // ---- per-position tokens
     CR_TRY(b_span.reserve(dtotal + 16)); CR_TRY(b_tidx.reserve(dtotal + 16));
     const int bbits = cr_bits_for(nb);
@@ -177,6 +181,7 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
         if (maxsize) CR_LAUNCH(k_lzp_tokens, dim3(cr_div_up(maxsize, 256), nb), dim3(256), stream, dD, d_blocks, cand, cand + nent, cand + 2 * (size_t)nent, b_span.as<uint8_t>());
     }
 
+    timer.mark("match");
     // ---- resolve the parse (cr_chain.cuh)
     std::vector<ChainSeg> segs(nb);
     for (uint32_t b = 0; b < nb; b++) {
@@ -202,6 +207,7 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
             CR_LAUNCH(k_chain_walk<LzpCount>, dim3(cr_div_up(nchunk, 64)), dim3(64), stream, b_span.as<uint8_t>(), d_segs, nb, nchunk, b_entry.as<uint8_t>(), f);
         }
     }
+    timer.mark("chain_count");
     for (int k = 0; k < 3; k++) CR_TRY(cr_exclusive_sum(prims, cnt + k * (nchunk + 1), scan + k * (nchunk + 1), nchunk + 1));
     std::vector<uint32_t> hscan; std::vector<uint8_t> hfirst, hesc;
     CR_TRY(download(hscan, scan, (size_t)(nchunk + 1) * 3));
@@ -232,6 +238,7 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
         CR_TRY(upload(b_ctxout, keep));
     }
 
+    timer.mark("events");
     // ---- model passes
     uint32_t nesc = 0;
     CR_TRY(b_esccount.reserve(16));
@@ -244,9 +251,15 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
         CR_LAUNCH(k_o3_keys, ge, te, stream, b_evctx.as<uint32_t>(), b_evsym.as<uint8_t>(), nev, b_k0.as<uint32_t>(), b_v0.as<uint32_t>());
         CR_TRY(cr_sort_pairs<uint32_t>(prims, b_k0.as<uint32_t>(), b_k1.as<uint32_t>(), b_v0.as<uint32_t>(), b_v1.as<uint32_t>(), nev, 0, 22));
         CR_LAUNCH(k_o3_pass, dim3(cr_div_up(nev, 128)), dim3(128), stream, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nev, st, b_pred.as<uint8_t>());
+    timer.mark("o3");
         CR_LAUNCH(k_o2_keys, ge, te, stream, b_evctx.as<uint32_t>(), b_evsym.as<uint8_t>(), b_pred.as<uint8_t>(), nev, b_k0.as<uint32_t>(), b_v0.as<uint32_t>());
         CR_TRY(cr_sort_pairs<uint32_t>(prims, b_k0.as<uint32_t>(), b_k1.as<uint32_t>(), b_v0.as<uint32_t>(), b_v1.as<uint32_t>(), nev, 0, 16));
+#ifndef CRGPU_SIM
+        if (!scalar_models) CR_LAUNCH(k_o2_pass_warp, dim3(65536 * 32 / 128), dim3(128), stream, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nev, st, b_T1.as<uint64_t>(), b_escrec.as<EscRec>(), b_esccount.as<uint32_t>());
+        else
+#endif
         CR_LAUNCH(k_o2_pass, dim3(cr_div_up(nev, 128)), dim3(128), stream, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nev, st, b_T1.as<uint64_t>(), b_escrec.as<EscRec>(), b_esccount.as<uint32_t>());
+    timer.mark("o2");
         std::vector<uint32_t> hc;
         CR_TRY(download(hc, b_esccount.p, 1));
         nesc = hc[0];
@@ -258,12 +271,24 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
             CR_TRY(cr_sort_pairs<uint64_t>(prims, b_k64a.as<uint64_t>(), b_k64b.as<uint64_t>(), b_v0.as<uint32_t>(), b_v1.as<uint32_t>(), nesc, 0, 32));
             CR_LAUNCH(k_o1_ordinals, gx, te, stream, b_v1.as<uint32_t>(), nesc, b_ord.as<uint32_t>());
             CR_TRY(cr_sort_pairs<uint64_t>(prims, b_k64a.as<uint64_t>(), b_k64b.as<uint64_t>(), b_v0.as<uint32_t>(), b_v1.as<uint32_t>(), nesc, 0, 40));
+#ifndef CRGPU_SIM
+            if (!scalar_models) CR_LAUNCH(k_o1_pass_warp, dim3(256 * 32 / 128), dim3(128), stream, b_k64b.as<uint64_t>(), b_v1.as<uint32_t>(), nesc, b_escrec.as<EscRec>(), b_ord.as<uint32_t>(), st, b_T2.as<uint64_t>());
+            else
+#endif
             CR_LAUNCH(k_o1_pass, dim3(cr_div_up(nesc, 64)), dim3(64), stream, b_k64b.as<uint64_t>(), b_v1.as<uint32_t>(), nesc, b_escrec.as<EscRec>(), b_ord.as<uint32_t>(), st, b_T2.as<uint64_t>());
         }
     }
+    timer.mark("o1");
     last_nesc = nesc;
-    if (nside) CR_LAUNCH(k_side_models, dim3(1), dim3(1), stream, b_side.as<uint16_t>(), nside, st, b_TS.as<uint64_t>());
+    if (nside) {
+#ifndef CRGPU_SIM
+        if (!scalar_models) CR_LAUNCH(k_side_models_warp, dim3(1), dim3(32), stream, b_side.as<uint16_t>(), nside, st, b_TS.as<uint64_t>());
+        else
+#endif
+        CR_LAUNCH(k_side_models, dim3(1), dim3(1), stream, b_side.as<uint16_t>(), nside, st, b_TS.as<uint64_t>());
+    }
 
+    timer.mark("side_models");
     // ---- dense triple streams
     CR_TRY(b_flag.reserve((size_t)(nev + 1) * 4 + 16)); CR_TRY(b_escord.reserve((size_t)(nev + 1) * 4 + 16));
     CR_TRY(b_dense.reserve(((size_t)nev + nesc) * sizeof(Tri) + 16)); CR_TRY(b_denseside.reserve((size_t)nside * sizeof(Tri) + 16));
@@ -273,6 +298,7 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
                        variant == CR_LZP ? b_tokend.as<uint8_t>() : (const uint8_t*)nullptr, nev, b_dense.as<Tri>());
     if (nside) CR_LAUNCH(k_expand_side, dim3(cr_div_up(nside, 256)), dim3(256), stream, b_TS.as<uint64_t>(), nside, b_denseside.as<Tri>());
 
+    timer.mark("expand");
     // ---- range coding: one serial coder per (block, stream)
     const uint32_t spb = variant == CR_ROLZ ? 2 : 1;
     std::vector<RcStream> streams((size_t)nb * spb);
@@ -295,8 +321,14 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
     }
     CR_TRY(upload(b_streams, streams));
     CR_TRY(b_rcres.reserve(streams.size() * sizeof(RcResult) + 16)); CR_TRY(b_rcout.reserve(rc_total + 16));
+#ifndef CRGPU_SIM
+    if (!scalar_models) CR_LAUNCH(k_range_encode_warp, dim3(cr_div_up(streams.size() * 32, 128)), dim3(128), stream, b_dense.as<Tri>(), b_denseside.as<Tri>(), b_escord.as<uint32_t>(),
+              b_streams.as<RcStream>(), (uint32_t)streams.size(), b_rcout.as<uint8_t>(), b_rcres.as<RcResult>());
+    else
+#endif
     CR_LAUNCH(k_range_encode, dim3(cr_div_up(streams.size(), 32)), dim3(32), stream, b_dense.as<Tri>(), b_denseside.as<Tri>(), b_escord.as<uint32_t>(),
               b_streams.as<RcStream>(), (uint32_t)streams.size(), b_rcout.as<uint8_t>(), b_rcres.as<RcResult>());
+    timer.mark("range_coder");
     std::vector<RcResult> res; std::vector<uint32_t> hctx;
     CR_TRY(download(res, b_rcres.p, streams.size()));
     CR_TRY(download(hctx, b_ctxout.p, 1)); chain_ctx = hctx[0];
@@ -348,5 +380,8 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
     CR_TRY(upload(b_copy, copies)); CR_TRY(upload(b_hdr, hdrs));
     CR_LAUNCH(k_write_headers, dim3(cr_div_up(nb, 64)), dim3(64), stream, b_hdr.as<HeaderDesc>(), nb, out.as<uint8_t>());
     if (!copies.empty()) CR_LAUNCH(k_copy_segments, dim3(64, (unsigned)copies.size()), dim3(256), stream, b_copy.as<CopyDesc>(), b_rcout.as<uint8_t>(), dD, out.as<uint8_t>());
+    timer.mark("assemble");
+    CR_CUDA(cudaStreamSynchronize(stream));
+    timer.finish();
     return CRGPU_OK;
 }

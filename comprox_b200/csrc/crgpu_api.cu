@@ -1,6 +1,7 @@
 // crgpu_api.cu -- the C ABI declared in include/crgpu.h.
 #include "../../include/crgpu.h"
 #include "cr_lzchain.cuh"
+#include "cr_container.cuh"
 #include <string>
 
 #ifdef CRGPU_SIM
@@ -13,6 +14,7 @@ struct crgpu_handle {
     cudaStream_t stream = 0;
     LzChain chain;
     DevBuf d_in, d_out;
+    Compressor comp;
 };
 
 extern "C" const char* crgpu_strerror(int code) {
@@ -54,7 +56,7 @@ extern "C" void crgpu_destroy(crgpu_handle* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
 #endif
-    h->chain.release(); h->d_in.release(); h->d_out.release();
+    h->chain.release(); h->d_in.release(); h->d_out.release(); h->comp.release();
     delete h;
 }
 
@@ -109,4 +111,40 @@ extern "C" int64_t crgpu_debug_fetch(crgpu_handle* h, const char* what, void* ds
         if (cudaStreamSynchronize(h->stream) != cudaSuccess) return CRGPU_ERR_CUDA;
     }
     return (int64_t)bytes;
+}
+
+extern "C" int crgpu_profile(crgpu_handle* h, int enable) {
+    if (!h) return CRGPU_ERR_ARG;
+    h->chain.timer.enabled = enable != 0;
+    h->chain.timer.result.clear();
+    return CRGPU_OK;
+}
+
+extern "C" int crgpu_profile_report(crgpu_handle* h, char* buf, uint64_t cap) {
+    if (!h || !buf || cap == 0) return CRGPU_ERR_ARG;
+    std::string s;
+    char line[128];
+    for (auto& r : h->chain.timer.result) { snprintf(line, sizeof line, "%s %.3f\n", r.first.c_str(), r.second); s += line; }
+    size_t n = s.size() < cap - 1 ? s.size() : cap - 1;
+    memcpy(buf, s.data(), n); buf[n] = 0;
+    return (int)n;
+}
+
+extern "C" int crgpu_set_option(crgpu_handle* h, const char* name, int64_t value) {
+    if (!h || !name) return CRGPU_ERR_ARG;
+    std::string n(name);
+    if (n == "scalar_models") { h->chain.scalar_models = value != 0; return CRGPU_OK; }
+    return CRGPU_ERR_ARG;
+}
+
+extern "C" uint64_t crgpu_compress_bound(uint64_t n, uint32_t block_size) { return cr_compress_bound(n, block_size); }
+
+extern "C" int crgpu_compress(crgpu_handle* h, const crgpu_config* cfg, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_n) {
+    if (!h || !cfg) return CRGPU_ERR_ARG;
+#ifndef CRGPU_SIM
+    CR_CUDA(cudaSetDevice(h->device));
+#endif
+    CrConfig c; c.block_size = cfg->block_size; c.filt = cfg->filt; c.prec = cfg->prec; c.flexible = cfg->flexible; c.window_bytes = cfg->window_bytes;
+    h->comp.chain = &h->chain;
+    return h->comp.compress(c, in, n, out, out_cap, out_n);
 }

@@ -54,11 +54,36 @@ int crgpu_reset_models(crgpu_handle* h);
 int crgpu_lzencode(crgpu_handle* h, const uint8_t* in, const uint32_t* sizes, uint32_t nblocks, int chain_ends,
                    uint8_t* out, uint64_t out_cap, uint32_t* out_sizes);
 
+/* Whole-container compression: everything cr_main does between write_magic and the last fwrite
+ * (src/main.c:153-206): dicpick over the file, dictionary payload, then per block filter_inplace (-F),
+ * dictionary_encode and lzencode (unless -p), framed with the 6-byte block headers.  `out` receives the bytes the
+ * reference CLI would have written to its output file for the same input and switches.
+ * out_cap must be >= crgpu_compress_bound(n, block_size). */
+typedef struct crgpu_config {
+    uint32_t block_size;    /* -b, in BYTES (reference default 16 MiB, src/main.c:62) */
+    int32_t  filt;          /* -F  cr_filt_enable */
+    int32_t  prec;          /* -p  cr_prec_enable */
+    int32_t  flexible;      /* -f  flexible parsing (ROLZ); not yet implemented: CRGPU_ERR_UNSUPPORTED */
+    uint64_t window_bytes;  /* raw bytes resident per window, 0 = default (512 MiB) */
+} crgpu_config;
+uint64_t crgpu_compress_bound(uint64_t n, uint32_t block_size);
+int crgpu_compress(crgpu_handle* h, const crgpu_config* cfg, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_n);
+
 /* Test / profiling aid: copies an intermediate array of the most recent lzencode window to the host.
  * what: "span" (u8 per position), "tidx" (u8 per position), "ev_ctx" (u32 per event), "ev_sym" (u8 per event),
  *       "pred" (u8 per event), "dense" (4 x u32 per main-stream triple), "dense_side" (4 x u32 per side triple).
  * Returns the number of BYTES available (copies min(cap, available)), or a negative error. */
 int64_t crgpu_debug_fetch(crgpu_handle* h, const char* what, void* dst, uint64_t cap);
+
+/* Tuning / test switches.  "scalar_models" = 1 runs the scalar model and coder kernels (the ones the CPU
+ * kernel-logic simulation checks) instead of the warp-cooperative ones; results are identical. */
+int crgpu_set_option(crgpu_handle* h, const char* name, int64_t value);
+
+/* Stage timing (CUDA events on the handle's stream, accumulated over calls until reset).
+ * crgpu_profile(h, 1) enables and clears, crgpu_profile(h, 0) disables.  crgpu_profile_report writes
+ * "stage_name milliseconds\n" lines into buf and returns the number of bytes written. */
+int crgpu_profile(crgpu_handle* h, int enable);
+int crgpu_profile_report(crgpu_handle* h, char* buf, uint64_t cap);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,76 @@
+"""GPU parity of crgpu_compress (whole container through the C ABI) against the CPU oracle and, where the
+reference binaries travelled with the repo (oracle/_ref), against the unmodified reference CLI itself,
+including a round trip through the REFERENCE decompressor."""
+import hashlib
+
+import pytest
+
+import oracle_ffi as O
+from comprox_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+MiB = 1 << 20
+BIN = {api.ROLZ: "comprolz", api.LZP: "comprop"}
+
+
+def _check(gpulib, variant, data, bs, flags=(), **kw):
+    with api.Handle(variant, lib=gpulib) as h:
+        got = h.compress(data, bs, **kw)
+    want = O.compress(data, variant, bs, int(kw.get("filt", False)), int(kw.get("prec", False)))
+    assert len(got) == len(want), "container size differs from oracle"
+    assert got == want, "container differs from oracle"
+    ref = O.ref_compress(data, BIN[variant], ["-b%d" % (bs // MiB), *flags]) if bs % MiB == 0 else None
+    if ref is not None:
+        assert got == ref, "container differs from the reference CLI"
+        assert O.ref_decompress(got, BIN[variant]) == data, "reference decompressor does not round-trip our container"
+    return got
+
+
+@pytest.mark.parametrize("variant", [api.ROLZ, api.LZP])
+def test_gpu_compress_text_8m_b1(gpulib, variant):
+    _check(gpulib, variant, synth.markov_text(8 * MiB + 4321, seed=42), MiB)
+
+
+@pytest.mark.parametrize("variant", [api.ROLZ, api.LZP])
+def test_gpu_compress_text_8m_b16(gpulib, variant):
+    _check(gpulib, variant, synth.markov_text(8 * MiB, seed=43), 16 * MiB)
+
+
+@pytest.mark.parametrize("variant", [api.ROLZ, api.LZP])
+def test_gpu_compress_trailing_empty_block(gpulib, variant):
+    _check(gpulib, variant, synth.markov_text(2 * MiB, seed=44), MiB)
+
+
+@pytest.mark.parametrize("variant", [api.ROLZ, api.LZP])
+@pytest.mark.parametrize("data", [b"", b"A", bytes(MiB), (b"The quick brown fox jumps over the lazy dog. " * 30000)[:1300000]],
+                         ids=["empty", "A", "zeros", "fox"])
+def test_gpu_compress_known_answers(gpulib, variant, data):
+    _check(gpulib, variant, data, 16 * MiB)
+
+
+def test_gpu_compress_survey_digests(gpulib):
+    """SURVEY.md App. E known answers of the reference build (sha256[:16] of the comprolz container)."""
+    kat = {b"": "87c0b28fce506b04", b"A": "a7b3209b72de7a3c", bytes(MiB): "8a20dfe0637804bc",
+           (b"The quick brown fox jumps over the lazy dog. " * 30000)[:1300000]: "67dc0831e1ad8791"}
+    with api.Handle(api.ROLZ, lib=gpulib) as h:
+        for data, digest in kat.items():
+            assert hashlib.sha256(h.compress(data)).hexdigest()[:16] == digest
+
+
+@pytest.mark.parametrize("variant", [api.ROLZ, api.LZP])
+def test_gpu_compress_prec(gpulib, variant):
+    _check(gpulib, variant, synth.markov_text(2 * MiB + 5, seed=45), MiB, flags=["-p"], prec=True)
+
+
+def test_gpu_compress_windows_carry_models(gpulib):
+    """Small windows: model state and PPM context must carry across windows exactly as across blocks."""
+    data = synth.markov_text(6 * MiB, seed=46)
+    with api.Handle(api.ROLZ, lib=gpulib) as h:
+        a = h.compress(data, MiB)
+    with api.Handle(api.ROLZ, lib=gpulib) as h:
+        b = h.compress(data, MiB, window_bytes=2 * MiB)
+    assert a == b == O.compress(data, api.ROLZ, MiB)
+
+
+def test_gpu_compress_binary_no_filter(gpulib):
+    _check(gpulib, api.ROLZ, synth.x86_corpus(4 * MiB, elf_bytes=MiB, pe_min=MiB // 2, pe_max=MiB), MiB)

@@ -42,10 +42,11 @@ def _diagnose(h, orc_variant, blocks, want, got):
     return "\n".join(msg)
 
 
-def _run(gpulib, variant, blocks):
+def _run(gpulib, variant, blocks, scalar=False):
     orc = O.Oracle(variant)
     want = [orc.lzencode(b) for b in blocks]
     with api.Handle(variant, lib=gpulib) as h:
+        h.set_option("scalar_models", scalar)
         got = h.lzencode(blocks)
         if got != want:
             pytest.fail("payload mismatch sizes want=%s got=%s\n%s" % ([len(w) for w in want], [len(g) for g in got],
@@ -62,6 +63,13 @@ def test_gpu_lzencode_matches_oracle(gpulib, variant, name):
 def test_gpu_lzencode_dict_coded_text_8m(gpulib, variant):
     """8 MiB of Markov text, dictionary-coded by the oracle, 1 MiB blocks -> 8 chained blocks; also 4-byte contexts."""
     _run(gpulib, variant, cases.dict_coded_text(8 << 20, 1 << 20, seed=21, variant=variant))
+
+
+@pytest.mark.parametrize("variant", [api.ROLZ, api.LZP])
+@pytest.mark.parametrize("name", ["rawtext", "x86", "fox", "short_tail"])
+def test_gpu_scalar_kernels_match_oracle(gpulib, variant, name):
+    """The scalar model/coder kernels (the family the CPU simulation checks) give the same bytes on the GPU."""
+    _run(gpulib, variant, cases.lz_cases()[name], scalar=True)
 
 
 def test_gpu_lzencode_ctx4_block(gpulib):

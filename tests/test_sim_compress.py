@@ -1,0 +1,30 @@
+"""CPU pre-flight (kernel-logic simulation, see cr_common.cuh) of the whole-container path against the oracle."""
+import pytest
+
+import oracle_ffi as O
+from comprox_b200 import api, synth
+
+MiB = 1 << 20
+
+
+def _cases():
+    text = synth.markov_text(MiB + MiB // 2 + 12345, seed=7)
+    return {
+        "text_b1": (text, MiB, 0),
+        "text_exact_multiple": (text[:MiB], MiB // 2, 0),        # trailing empty block
+        "empty": (b"", MiB, 0),
+        "single_byte": (b"A", MiB, 0),
+        "fox": ((b"The quick brown fox jumps over the lazy dog. " * 30000)[:1300000], MiB, 0),
+        "text_prec": (text[:MiB + 5], MiB, 1),
+    }
+
+
+@pytest.mark.parametrize("variant", [api.ROLZ, api.LZP])
+@pytest.mark.parametrize("name", sorted(_cases().keys()))
+def test_sim_compress_matches_oracle(simlib, variant, name):
+    data, bs, prec = _cases()[name]
+    want = O.compress(data, variant, bs, 0, prec)
+    with api.Handle(variant, lib=simlib) as h:
+        got = h.compress(data, bs, prec=bool(prec))
+    assert len(got) == len(want)
+    assert got == want

@@ -61,7 +61,8 @@ static inline const char* cudaGetErrorString(int) { return "sim"; }
 #else
 // ------------------------------------------------------------------ real CUDA
 #include <cuda_runtime.h>
-#define CR_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+extern unsigned long long g_cr_launches;   // kernels launched by this library (crgpu_launch_count)
+#define CR_LAUNCH(kernel, grid, block, stream, ...) do { g_cr_launches++; kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__); } while (0)
 #endif
 
 #define CR_HD __host__ __device__ __forceinline__
@@ -110,7 +111,7 @@ struct StageTimer {
     std::vector<cudaEvent_t> ev;
 #endif
     std::vector<std::string> names;
-    std::vector<std::pair<std::string, float>> result;
+    std::vector<std::pair<std::string, double>> result;
     void begin(cudaStream_t s) { stream = s; names.clear(); if (enabled) mark("start"); }
     void mark(const char* name) {
         if (!enabled) return;
@@ -120,6 +121,11 @@ struct StageTimer {
 #endif
         names.push_back(name);
     }
+    void count(const char* name, double v) {   // counters ride along in the report (names start with '#')
+        if (!enabled) return;
+        for (auto& r : result) if (r.first == name) { r.second += v; return; }
+        result.push_back(std::make_pair(std::string(name), v));
+    }
     void finish() {   // call after a stream synchronize
         if (!enabled) return;
 #ifndef CRGPU_SIM
@@ -127,7 +133,7 @@ struct StageTimer {
             float ms = 0; cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
             bool found = false;
             for (auto& r : result) if (r.first == names[i]) { r.second += ms; found = true; }
-            if (!found) result.push_back(std::make_pair(names[i], ms));
+            if (!found) result.push_back(std::make_pair(names[i], (double)ms));
         }
 #endif
         names.clear();

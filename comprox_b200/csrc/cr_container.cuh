@@ -29,7 +29,7 @@ struct Compressor {
     DevBuf b_subs, b_hist, b_esc10, b_escmask, b_span, b_hit, b_segs, b_xt, b_entry, b_cnt, b_scan, b_chunk0, b_hdr, b_copy, b_segoff, b_seglen;
     HdTrie trie;
     FilterHost filt;
-    StageTimer* timer = nullptr;
+    const uint8_t* staged_ptr = nullptr; uint64_t staged_n = 0;
 
     void release() {
         DevBuf* all[] = { &d_raw, &d_D, &d_out, &d_dic, &t_key, &t_count, &t_first, &t_stats, &t_entries, &d_trie_next, &d_trie_id, &b_subs, &b_hist,
@@ -40,6 +40,14 @@ struct Compressor {
     template <class T> int upload(DevBuf& b, const std::vector<T>& v) { return chain->upload(b, v); }
     template <class T> int download(std::vector<T>& v, const void* src, size_t n) { return chain->download(v, src, n); }
 
+    int stage(const uint8_t* in, uint64_t n) {
+        CR_TRY(d_raw.reserve(n + 256));
+        if (n) CR_CUDA(cudaMemcpyAsync(d_raw.p, in, n, cudaMemcpyHostToDevice, stream));
+        CR_CUDA(cudaMemsetAsync(d_raw.as<uint8_t>() + n, 0, 128, stream));
+        CR_CUDA(cudaStreamSynchronize(stream));
+        staged_ptr = in; staged_n = n;
+        return CRGPU_OK;
+    }
     int dicpick(const uint8_t* h_in, const uint8_t* d_in, uint64_t n, std::string& text);
     int load_dictionary(const std::string& text);
     int dict_encode_window(const uint8_t* d_rawwin, const std::vector<uint64_t>& roff, const std::vector<uint32_t>& rsize, std::vector<BlockIO>& blk, size_t& dtotal);
@@ -206,13 +214,20 @@ inline int Compressor::compress(const CrConfig& cfg, const uint8_t* in, uint64_t
     memcpy(out, cr_magic(chain->variant), mlen);
 
     // ---- whole input to HBM
-    CR_TRY(d_raw.reserve(n + 256));
-    if (n) CR_CUDA(cudaMemcpyAsync(d_raw.p, in, n, cudaMemcpyHostToDevice, stream));
-    CR_CUDA(cudaMemsetAsync(d_raw.as<uint8_t>() + n, 0, 128, stream));
+    const bool staged = staged_ptr == in && staged_n == n && d_raw.p != nullptr && !cfg.filt;   // filters modify d_raw in place
+    staged_ptr = nullptr;
+    if (!staged) {
+        CR_TRY(d_raw.reserve(n + 256));
+        if (n) CR_CUDA(cudaMemcpyAsync(d_raw.p, in, n, cudaMemcpyHostToDevice, stream));
+        CR_CUDA(cudaMemsetAsync(d_raw.as<uint8_t>() + n, 0, 128, stream));
+    }
 
     // ---- static dictionary: build, load, emit as its own model chain (src/main.c:156-172)
     std::string text;
+    tm.begin(stream);
     CR_TRY(dicpick(in, d_raw.as<uint8_t>(), n, text));
+    tm.mark("dicpick");
+    if (tm.enabled) { CR_CUDA(cudaStreamSynchronize(stream)); tm.finish(); }
     CR_TRY(load_dictionary(text));
     std::vector<uint8_t> lcp = hd_lcp_encode(text);
     CR_TRY(upload(d_dic, lcp));
@@ -241,9 +256,15 @@ inline int Compressor::compress(const CrConfig& cfg, const uint8_t* in, uint64_t
             rsize.push_back((uint32_t)(n - off < cfg.block_size ? n - off : cfg.block_size));
         }
         std::vector<uint8_t> filt_flags(rsize.size(), 0);
+        tm.begin(stream);
         if (cfg.filt) CR_TRY(filt.run_window(*chain, in + wbase, d_win, n - wbase, roff, rsize, filt_flags, filt_flag));
+        tm.mark("filters");
+        if (tm.enabled) { CR_CUDA(cudaStreamSynchronize(stream)); tm.finish(); }
         std::vector<BlockIO> blk; size_t dtotal = 0;
+        tm.begin(stream);
         CR_TRY(dict_encode_window(d_win, roff, rsize, blk, dtotal));
+        tm.mark("diccode");
+        if (tm.enabled) { CR_CUDA(cudaStreamSynchronize(stream)); tm.finish(); }
         for (size_t i = 0; i < blk.size(); i++) { blk[i].filt = filt_flags[i]; blk[i].prec = (uint8_t)cfg.prec; }
         const bool last = b1 == nblocks;
         if (!cfg.prec) {
@@ -273,6 +294,5 @@ inline int Compressor::compress(const CrConfig& cfg, const uint8_t* in, uint64_t
     CR_CUDA(cudaMemcpyAsync(out + mlen, d_out.p, out_pos, cudaMemcpyDeviceToHost, stream));
     CR_CUDA(cudaStreamSynchronize(stream));
     *out_n = mlen + out_pos;
-    (void)tm;
     return CRGPU_OK;
 }

@@ -1,9 +1,256 @@
-// cr_filter.cuh -- executable / bitmap pre-filters (src/cr-filter.c, filter_x86_elf.c, filter_x86_pe.c, filter_bmp.c).
+// cr_filter.cuh -- executable / bitmap pre-filters (the -F switch).
+//
+// Replaces filter_inplace (src/cr-filter.c:33-73) and its three sub-filters
+//   pe_i386_transform  src/filter_x86_pe.c:128-159      elf_i386_transform src/filter_x86_elf.c:131-156
+//   bmp_transform      src/filter_bmp.c:149-204         i386_e8e9          src/filter_x86opcode.h:38-62
+// Split of work:
+//   GPU  k_filter_scan      every byte position is tested for the 2/4-byte magics that can start an image
+//   host FilterHost::walk   the reference's tiny sticky state machine runs over those few candidates and the
+//                           image headers (a few dozen bytes per image) and emits a list of transform ops
+//   GPU  e8e9 ops           the E8/E9 skip automaton is resolved exactly with cr_chain.cuh (a hit skips its
+//                           4 operand bytes), then every live CALL/JMP operand is rewritten in parallel
+//   GPU  bmp ops            colour + left + up delta in closed form per byte from the untouched tile
+// State that the reference keeps in function-local statics (lastproc, flag/curr/imsz, BMP geometry) lives in
+// FilterHost and carries across blocks and windows exactly like the statics do.
 #pragma once
+#include <algorithm>
+#include <vector>
 #include "cr_common.cuh"
-struct LzChain;
+#include "cr_chain.cuh"
+#include "cr_rc.cuh"      // CopyDesc / k_copy_segments
+
+// ------------------------------------------------------------------ candidate scan
+__global__ void k_filter_scan(const uint8_t* __restrict__ d, uint64_t n, uint32_t* __restrict__ list, uint32_t cap, uint32_t* __restrict__ count) {
+    uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p + 1 >= n) return;
+    const uint32_t a = d[p], b = d[p + 1];
+    bool hit = (a == 'M' && b == 'Z') || (a == 'B' && b == 'M') || (a == 0x7F && b == 'E' && p + 3 < n && d[p + 2] == 'L' && d[p + 3] == 'F');
+    if (hit) { uint32_t i = atomicAdd(count, 1u); if (i < cap) list[i] = (uint32_t)p; }
+}
+
+// ------------------------------------------------------------------ E8/E9
+struct E8Op {
+    uint64_t off;        // window offset of the region's byte 0
+    uint32_t limit;      // region length the reference passes to i386_e8e9
+    uint32_t valid;      // bytes of the region that really exist in the block (the ELF detection call runs 52 bytes past it)
+    int32_t  ncur, nend;
+    uint64_t span_off;   // offset of the region in the op-local span array
+};
+CR_D uint32_t e8_byte(const uint8_t* d, const E8Op& o, uint32_t i) { return i < o.valid ? d[o.off + i] : 0u; }
+
+__global__ void k_e8e9_spans(const uint8_t* __restrict__ d, const E8Op* __restrict__ ops, uint8_t* __restrict__ span) {
+    const E8Op o = ops[blockIdx.y];
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= o.limit) return;
+    span[o.span_off + i] = (i < o.limit - 8 && (e8_byte(d, o, i) & 254) == 0xe8) ? 5 : 1;      // src/filter_x86opcode.h:41-42,58
+}
+struct E8Apply {
+    typedef int State;
+    uint8_t* d; const E8Op* ops; const uint8_t* span;
+    CR_D State begin(uint32_t, uint32_t) const { return 0; }
+    CR_D void visit(State&, uint32_t s, uint32_t i, uint32_t sp) const {
+        if (sp != 5) return;
+        const E8Op o = ops[s];
+        const uint32_t at = i + 1;                               // index of the operand (the reference's i after i++)
+        int32_t op = (int32_t)(e8_byte(d, o, at) | e8_byte(d, o, at + 1) << 8 | e8_byte(d, o, at + 2) << 16 | e8_byte(d, o, at + 3) << 24);
+        const int32_t pos = o.ncur + (int32_t)at;
+        if (op >= -pos && op < o.nend - pos) op = (int32_t)((uint32_t)op + (uint32_t)pos);          // :46-47
+        else if (op > 0 && op < o.nend) op = (int32_t)((uint32_t)op - (uint32_t)o.nend);            // :48-49
+        else return;
+        for (uint32_t k = 0; k < 4; k++) if (at + k < o.valid) d[o.off + at + k] = (uint8_t)((uint32_t)op >> (8 * k));
+    }
+    CR_D void end(State&, uint32_t, uint32_t) const {}
+};
+
+// ------------------------------------------------------------------ BMP
+struct BmpOp {
+    uint64_t off;        // window offset of the tile
+    uint64_t src_off;    // offset of the tile's untouched copy
+    uint32_t rows, width, row_size, bytes;   // bytes per pixel (3 or 4)
+};
+// colour-decorrelated value of byte xb of row y (src/filter_bmp.c:63-73)
+CR_D uint32_t bmp_c(const uint8_t* src, const BmpOp& o, uint32_t y, uint32_t xb) {
+    const uint32_t ch = xb % o.bytes;
+    const uint8_t* row = src + o.src_off + (uint64_t)y * o.row_size;
+    uint32_t v = row[xb];
+    if (ch == 0 || ch == 2) v -= row[xb - ch + 1];
+    return v;
+}
+__global__ void k_bmp_rows(const uint8_t* __restrict__ src, uint8_t* __restrict__ d, const BmpOp* __restrict__ ops) {
+    const BmpOp o = ops[blockIdx.y];
+    const uint32_t wb = o.width * o.bytes;
+    const uint64_t total = (uint64_t)o.rows * wb;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t y = (uint32_t)(t / wb), xb = (uint32_t)(t % wb);
+        uint32_t v = bmp_c(src, o, y, xb);
+        if (xb >= o.bytes) v -= bmp_c(src, o, y, xb - o.bytes);                                       // left delta  (:75-88)
+        if (y > 0) { v -= bmp_c(src, o, y - 1, xb); if (xb >= o.bytes) v += bmp_c(src, o, y - 1, xb - o.bytes); }   // up delta (:89-102)
+        d[o.off + (uint64_t)y * o.row_size + xb] = (uint8_t)v;
+    }
+}
+
+// ------------------------------------------------------------------ host state machine
 struct FilterHost {
-    void reset() {}
-    void release() {}
-    int run_window(LzChain&, const uint8_t*, uint8_t*, uint64_t, const std::vector<uint64_t>&, const std::vector<uint32_t>&, std::vector<uint8_t>&, int&) { return CRGPU_ERR_UNSUPPORTED; }
+    int lastproc = 0;                                   // 0 none, 1 pe, 2 elf, 3 bmp (src/cr-filter.c:41)
+    struct { int flag; uint32_t curr, imsz; } pe = {0, 0, 0}, elf = {0, 0, 0};
+    struct { int flag, curr, size, row_size, bpp, width, height, skip_size; } bmp = {0, 0, 0, 0, 0, 0, 0, 0};
+    std::vector<E8Op> e8ops; std::vector<BmpOp> bmpops;
+    DevBuf b_list, b_count, b_e8, b_bmp, b_span, b_segs, b_xt, b_entry, b_tmp, b_copy;
+
+    void reset() { lastproc = 0; pe = {0, 0, 0}; elf = {0, 0, 0}; bmp = {0, 0, 0, 0, 0, 0, 0, 0}; }
+    void release() { DevBuf* all[] = { &b_list, &b_count, &b_e8, &b_bmp, &b_span, &b_segs, &b_xt, &b_entry, &b_tmp, &b_copy }; for (DevBuf* b : all) b->release(); }
+
+    // view of one block for header parsing: bytes past the block read as 0 ("filter envelope")
+    struct View {
+        const uint8_t* p; uint32_t len;
+        uint32_t u8(uint32_t i) const { return i < len ? p[i] : 0; }
+        uint32_t u16(uint32_t i) const { return u8(i) | u8(i + 1) << 8; }
+        uint32_t u32(uint32_t i) const { return u16(i) | u16(i + 2) << 16; }
+    };
+    static uint32_t umin(uint32_t a, uint32_t b) { return a < b ? a : b; }
+
+    void push_e8(uint64_t off, uint32_t limit, uint32_t valid, uint32_t ncur, uint32_t nend) {
+        if (limit < 8) return;                          // the reference's loop bound wraps here (undefined); we transform nothing
+        E8Op o; o.off = off; o.limit = limit; o.valid = umin(valid, limit); o.ncur = (int32_t)ncur; o.nend = (int32_t)nend; o.span_off = 0;
+        e8ops.push_back(o);
+    }
+    uint32_t run_elf(const View& v, uint64_t woff) {                                              // src/filter_x86_elf.c:131-156
+        uint32_t size = umin(elf.imsz - elf.curr, v.len), start = 0;
+        if (!elf.flag) {
+            if (v.len < 52 || v.u32(0) != 0x464C457Fu || v.u16(18) != 3) return 0;
+            uint32_t shoff = v.u32(32), est = shoff - 52;
+            if (shoff < 52 || est >= (1u << 30)) return 0;
+            elf.imsz = est - 52; start = 52; size = umin(elf.imsz, v.len);
+        }
+        push_e8(woff + start, size, v.len > start ? v.len - start : 0, elf.curr, elf.imsz);
+        elf.curr += size; elf.flag = elf.curr < elf.imsz;
+        return size;
+    }
+    uint32_t run_pe(const View& v, uint64_t woff) {                                               // src/filter_x86_pe.c:75-159
+        uint32_t size = umin(pe.imsz - pe.curr, v.len), ret = size, start = 0;
+        if (!pe.flag) {
+            pe.curr = 0;
+            if (v.len < 0x3C + 4 || v.u16(0) != 0x5A4D) return 0;
+            uint32_t hdr = v.u32(0x3C);
+            if (hdr >= v.len || v.u32(hdr) != 0x00004550u || hdr == 0) return 0;
+            if (hdr + v.len < 24) return 0;
+            uint32_t machine = v.u16(hdr + 4), nsec = v.u16(hdr + 6), optsz = v.u16(hdr + 20), chars = v.u16(hdr + 22);
+            if (machine != 0x14c && (chars & 2)) return 0;
+            uint32_t sec_off = 24 + optsz, size_hdr = sec_off + nsec * 40, est = size_hdr;
+            if (hdr + v.len < size_hdr) return 0;
+            for (uint32_t i = 0; i < nsec; i++) est += v.u32(hdr + sec_off + i * 40 + 16);
+            if (est > (1u << 28)) return 0;
+            start = size_hdr; pe.imsz = est - size_hdr;
+            size = umin(pe.imsz, v.len - size_hdr);
+            ret = size + size_hdr;
+        }
+        push_e8(woff + start, size, v.len > start ? v.len - start : 0, pe.curr, pe.imsz);
+        pe.curr += size; pe.flag = pe.curr < pe.imsz;
+        return ret;
+    }
+    uint32_t run_bmp(const View& v, uint64_t woff) {                                              // src/filter_bmp.c:149-204
+        if (!bmp.flag) {
+            if (v.len < 54 || v.u16(0) != 0x4d42 || v.u16(26) != 1 || v.u32(30) != 0) return 0;
+            uint32_t fsize = v.u32(2), off = v.u32(10), isz = v.u32(34), bpp = v.u16(28);
+            if ((isz != 0 && off + isz != fsize) || (bpp != 24 && bpp != 32)) return 0;
+            int w = (int32_t)v.u32(18), h = (int32_t)v.u32(22);
+            bmp.width = w < 0 ? -w : w; bmp.height = h < 0 ? -h : h;
+            bmp.row_size = ((int)bpp * bmp.width + 31) / 32 * 4; bmp.bpp = (int)bpp;
+            if (bmp.width < 4 || bmp.height < 4 || bmp.width >= (1 << 20) || bmp.height >= (1 << 20)) return 0;
+            bmp.curr = (int)off; bmp.size = bmp.height * bmp.row_size; bmp.skip_size = 0; bmp.flag = 1;
+            return off;
+        }
+        if (bmp.skip_size > 0) { uint32_t t = umin((uint32_t)bmp.skip_size, v.len); bmp.curr += (int)t; bmp.skip_size -= (int)t; return t; }
+        uint32_t avail = umin(v.len, (uint32_t)(bmp.size - bmp.curr));
+        uint32_t rows = avail / (uint32_t)bmp.row_size, t = rows * (uint32_t)bmp.row_size;
+        if (rows) { BmpOp o; o.off = woff; o.src_off = 0; o.rows = rows; o.width = (uint32_t)bmp.width; o.row_size = (uint32_t)bmp.row_size; o.bytes = (uint32_t)bmp.bpp / 8; bmpops.push_back(o); }
+        bmp.curr += (int)t;
+        if (bmp.curr < bmp.size) bmp.skip_size = (int)umin((uint32_t)bmp.row_size, (uint32_t)(bmp.size - bmp.curr)); else bmp.flag = 0;
+        return t;
+    }
+    uint32_t run(int which, const View& v, uint64_t woff) { return which == 1 ? run_pe(v, woff) : which == 2 ? run_elf(v, woff) : run_bmp(v, woff); }
+
+    // filter_inplace over one block (src/cr-filter.c:50-71); cand = sorted candidate offsets (window relative)
+    int walk_block(const uint8_t* h_block, uint64_t boff, uint32_t len, const std::vector<uint32_t>& cand) {
+        int filt = 0;
+        size_t ci = std::lower_bound(cand.begin(), cand.end(), (uint32_t)boff) - cand.begin();
+        for (uint32_t pos = 0; pos < len;) {
+            View v = { h_block + pos, len - pos };
+            if (lastproc) {
+                uint32_t n = run(lastproc, v, boff + pos);
+                if ((int)n == 0) lastproc = 0; else { filt = 1; pos += n; continue; }
+            }
+            while (ci < cand.size() && cand[ci] < boff + pos) ci++;
+            if (ci >= cand.size() || cand[ci] >= boff + len) break;
+            pos = (uint32_t)(cand[ci] - boff);
+            v.p = h_block + pos; v.len = len - pos;
+            bool fired = false;
+            for (int k = 1; k <= 3 && !fired; k++) {
+                uint32_t n = run(k, v, boff + pos);
+                if ((int)n > 0) { filt = 1; lastproc = k; pos += n; fired = true; }
+            }
+            if (!fired) pos++;
+        }
+        return filt;
+    }
+
+    template <class Chain>
+    int run_window(Chain& C, const uint8_t* h_win, uint8_t* d_win, uint64_t nwin_total, const std::vector<uint64_t>& roff, const std::vector<uint32_t>& rsize,
+                   std::vector<uint8_t>& flags, int& filt_flag) {
+        cudaStream_t stream = C.stream;
+        uint64_t wlen = 0;
+        for (size_t b = 0; b < roff.size(); b++) if (roff[b] + rsize[b] > wlen) wlen = roff[b] + rsize[b];
+        (void)nwin_total;
+        // ---- candidates
+        std::vector<uint32_t> cand;
+        if (wlen >= 2) {
+            uint32_t cap = (uint32_t)(wlen / 64 + 4096);
+            for (;;) {
+                CR_TRY(b_list.reserve((size_t)cap * 4)); CR_TRY(b_count.reserve(16));
+                CR_CUDA(cudaMemsetAsync(b_count.p, 0, 4, stream));
+                CR_LAUNCH(k_filter_scan, dim3(cr_div_up(wlen, 256)), dim3(256), stream, d_win, wlen, b_list.as<uint32_t>(), cap, b_count.as<uint32_t>());
+                std::vector<uint32_t> cnt;
+                CR_TRY(C.download(cnt, b_count.p, 1));
+                if (cnt[0] <= cap) { CR_TRY(C.download(cand, b_list.p, cnt[0])); break; }
+                cap = cnt[0] + 16;
+            }
+            std::sort(cand.begin(), cand.end());
+        }
+        // ---- the reference's state machine, block by block
+        e8ops.clear(); bmpops.clear();
+        for (size_t b = 0; b < roff.size(); b++) { filt_flag = walk_block(h_win + roff[b], roff[b], rsize[b], cand); flags[b] = (uint8_t)filt_flag; }
+        // ---- E8/E9 regions
+        if (!e8ops.empty()) {
+            std::vector<ChainSeg> segs(e8ops.size());
+            uint64_t so = 0; uint32_t maxlimit = 0;
+            for (size_t i = 0; i < e8ops.size(); i++) {
+                e8ops[i].span_off = so;
+                segs[i].off = so; segs[i].len = e8ops[i].limit; segs[i].start = 0;
+                so += e8ops[i].limit; if (e8ops[i].limit > maxlimit) maxlimit = e8ops[i].limit;
+            }
+            const uint32_t nseg = (uint32_t)segs.size(), nchunk = cr_chain_layout(segs.data(), nseg);
+            CR_TRY(C.upload(b_e8, e8ops)); CR_TRY(C.upload(b_segs, segs));
+            CR_TRY(b_span.reserve(so + 16)); CR_TRY(b_xt.reserve((size_t)nchunk * 256 + 16)); CR_TRY(b_entry.reserve(nchunk + 16));
+            CR_LAUNCH(k_e8e9_spans, dim3(cr_div_up(maxlimit, 256), nseg), dim3(256), stream, d_win, b_e8.as<E8Op>(), b_span.as<uint8_t>());
+            CR_LAUNCH(k_chain_exits, dim3(cr_div_up(nchunk, 64)), dim3(64), stream, b_span.as<uint8_t>(), b_segs.as<ChainSeg>(), nseg, nchunk, b_xt.as<uint8_t>());
+            CR_LAUNCH(k_chain_entries, dim3(cr_div_up(nseg, 32)), dim3(32), stream, b_segs.as<ChainSeg>(), nseg, b_xt.as<uint8_t>(), b_entry.as<uint8_t>());
+            E8Apply f = { d_win, b_e8.as<E8Op>(), b_span.as<uint8_t>() };
+            CR_LAUNCH(k_chain_walk<E8Apply>, dim3(cr_div_up(nchunk, 64)), dim3(64), stream, b_span.as<uint8_t>(), b_segs.as<ChainSeg>(), nseg, nchunk, b_entry.as<uint8_t>(), f);
+        }
+        // ---- BMP tiles: snapshot the tiles, then transform from the snapshot
+        if (!bmpops.empty()) {
+            std::vector<CopyDesc> copies(bmpops.size());
+            uint64_t to = 0;
+            for (size_t i = 0; i < bmpops.size(); i++) {
+                uint64_t bytes = (uint64_t)bmpops[i].rows * bmpops[i].row_size;
+                bmpops[i].src_off = to;
+                CopyDesc c = { bmpops[i].off, to, (uint32_t)bytes, 0 }; copies[i] = c;
+                to += (bytes + 15) & ~15ull;
+            }
+            CR_TRY(b_tmp.reserve(to + 16)); CR_TRY(C.upload(b_copy, copies)); CR_TRY(C.upload(b_bmp, bmpops));
+            CR_LAUNCH(k_copy_segments, dim3(128, (unsigned)copies.size()), dim3(256), stream, b_copy.as<CopyDesc>(), d_win, d_win, b_tmp.as<uint8_t>());
+            CR_LAUNCH(k_bmp_rows, dim3(296, (unsigned)bmpops.size()), dim3(256), stream, b_tmp.as<uint8_t>(), d_win, b_bmp.as<BmpOp>());
+        }
+        return CRGPU_OK;
+    }
 };

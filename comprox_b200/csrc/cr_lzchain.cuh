@@ -280,6 +280,7 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
     }
     timer.mark("o1");
     last_nesc = nesc;
+    timer.count("#events", nev); timer.count("#triples", (double)nev + nesc + nside); timer.count("#escapes", nesc); timer.count("#side_symbols", nside);
     if (nside) {
 #ifndef CRGPU_SIM
         if (!scalar_models) CR_LAUNCH(k_side_models_warp, dim3(1), dim3(32), stream, b_side.as<uint16_t>(), nside, st, b_TS.as<uint64_t>());

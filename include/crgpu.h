@@ -69,6 +69,14 @@ typedef struct crgpu_config {
 uint64_t crgpu_compress_bound(uint64_t n, uint32_t block_size);
 int crgpu_compress(crgpu_handle* h, const crgpu_config* cfg, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_n);
 
+/* Copies `in` to HBM ahead of time.  A following crgpu_compress(h, cfg, in, n, ...) with the same pointer and
+ * length (and no -F, which rewrites the staged bytes in place) then skips its host-to-device copy; used by
+ * bench.py to time the device-resident path separately from the end-to-end path. */
+int crgpu_stage_input(crgpu_handle* h, const uint8_t* in, uint64_t n);
+
+/* Number of CUDA kernels this library has launched in this process (all handles). */
+uint64_t crgpu_launch_count(void);
+
 /* Test / profiling aid: copies an intermediate array of the most recent lzencode window to the host.
  * what: "span" (u8 per position), "tidx" (u8 per position), "ev_ctx" (u32 per event), "ev_sym" (u8 per event),
  *       "pred" (u8 per event), "dense" (4 x u32 per main-stream triple), "dense_side" (4 x u32 per side triple).

@@ -91,7 +91,7 @@ struct HdTrie {
         std::string cur;
         for (const char* s = text; *s; s++) {
             if (*s == '\n') {
-                if (!cur.empty() && (((unsigned char)cur.back() | 32) - 'a') < 26u) cur.push_back(' ');
+                if (!cur.empty() && (unsigned)(((unsigned char)cur.back() | 32) - 'a') < 26u) cur.push_back(' ');
                 entries.push_back(cur); cur.clear();
             } else cur.push_back(*s);
         }

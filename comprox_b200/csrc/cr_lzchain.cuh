@@ -42,6 +42,9 @@ struct LzChain {
     DevBuf b_segs, b_xt, b_entry, b_cnt, b_scan;
     DevBuf b_evctx, b_evsym, b_tokend, b_pred, b_T1, b_T2, b_TS, b_side;
     DevBuf b_escrec, b_esccount, b_k64a, b_k64b, b_ord, b_flag, b_escord;
+    DevBuf b_lensym, b_lenpos, b_idxsym, b_idxpos;
+    DevBuf b_o1info, b_o1ord, b_o1incl;
+    DevBuf b_qm, b_shm, b_bm, b_qs, b_shs, b_bs, b_stot, b_dsum, b_lsm, b_lss, b_rsm, b_rss, b_fb;
     DevBuf b_dense, b_denseside, b_streams, b_rcres, b_rcout, b_copy, b_hdr;
     // ---- sizes of the last window (for the debug/trace fetch used by the tests)
     uint32_t last_nev = 0, last_nside = 0, last_nesc = 0, last_nent = 0;
@@ -62,7 +65,7 @@ struct LzChain {
         DevBuf* all[] = { &s_o3b, &s_o3c, &s_o2, &s_o1, &s_m0, &b_blocks, &b_segoff, &b_seglen, &b_hist, &b_esc1, &b_first, &b_ctxout,
             &b_k0, &b_k1, &b_v0, &b_v1, &b_ks0, &b_M, &b_S, &b_span, &b_tidx, &b_segs, &b_xt, &b_entry, &b_cnt, &b_scan,
             &b_evctx, &b_evsym, &b_tokend, &b_pred, &b_T1, &b_T2, &b_TS, &b_side, &b_escrec, &b_esccount, &b_k64a, &b_k64b, &b_ord,
-            &b_flag, &b_escord, &b_dense, &b_denseside, &b_streams, &b_rcres, &b_rcout, &b_copy, &b_hdr, &prims.temp };
+            &b_flag, &b_escord, &b_lensym, &b_lenpos, &b_idxsym, &b_idxpos, &b_o1info, &b_o1ord, &b_o1incl, &b_qm, &b_shm, &b_bm, &b_qs, &b_shs, &b_bs, &b_stot, &b_dsum, &b_lsm, &b_lss, &b_rsm, &b_rss, &b_fb, &b_dense, &b_denseside, &b_streams, &b_rcres, &b_rcout, &b_copy, &b_hdr, &prims.temp };
         for (DevBuf* b : all) b->release();
         inited = false;
     }
@@ -222,9 +225,13 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
     // ---- events
     CR_TRY(b_evctx.reserve((size_t)nev * 4 + 16)); CR_TRY(b_evsym.reserve(nev + 16)); CR_TRY(b_tokend.reserve(nev + 16)); CR_TRY(b_pred.reserve(nev + 16));
     CR_TRY(b_T1.reserve((size_t)nev * 8 + 16)); CR_TRY(b_side.reserve((size_t)nside * 2 + 16)); CR_TRY(b_TS.reserve((size_t)nside * 8 + 16));
+    const uint32_t n_idxsym = variant == CR_ROLZ ? sc_a[nchunk] : 0, n_lensym = variant == CR_ROLZ ? sc_a[nchunk] + sc_b[nchunk] : 0;
+    CR_TRY(b_lensym.reserve(n_lensym + 16)); CR_TRY(b_lenpos.reserve((size_t)n_lensym * 4 + 16));
+    CR_TRY(b_idxsym.reserve(n_idxsym + 16)); CR_TRY(b_idxpos.reserve((size_t)n_idxsym * 4 + 16));
     if (nchunk) {
         if (variant == CR_ROLZ) {
-            RolzEmit f = { dD, d_blocks, b_tidx.as<uint8_t>(), scan, scan + (nchunk + 1), scan + 2 * (nchunk + 1), b_evctx.as<uint32_t>(), b_evsym.as<uint8_t>(), b_side.as<uint16_t>() };
+            RolzEmit f = { dD, d_blocks, b_tidx.as<uint8_t>(), scan, scan + (nchunk + 1), scan + 2 * (nchunk + 1), b_evctx.as<uint32_t>(), b_evsym.as<uint8_t>(), b_side.as<uint16_t>(),
+                           b_lensym.as<uint8_t>(), b_lenpos.as<uint32_t>(), b_idxsym.as<uint8_t>(), b_idxpos.as<uint32_t>() };
             CR_LAUNCH(k_chain_walk<RolzEmit>, dim3(cr_div_up(nchunk, 64)), dim3(64), stream, b_span.as<uint8_t>(), d_segs, nb, nchunk, b_entry.as<uint8_t>(), f);
         } else {
             CR_TRY(b_ord.reserve((size_t)(nchunk + 1) * 4 + 16));
@@ -272,8 +279,11 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
             CR_LAUNCH(k_o1_ordinals, gx, te, stream, b_v1.as<uint32_t>(), nesc, b_ord.as<uint32_t>());
             CR_TRY(cr_sort_pairs<uint64_t>(prims, b_k64a.as<uint64_t>(), b_k64b.as<uint64_t>(), b_v0.as<uint32_t>(), b_v1.as<uint32_t>(), nesc, 0, 40));
 #ifndef CRGPU_SIM
-            if (!scalar_models) CR_LAUNCH(k_o1_pass_warp, dim3(256 * 32 / 128), dim3(128), stream, b_k64b.as<uint64_t>(), b_v1.as<uint32_t>(), nesc, b_escrec.as<EscRec>(), b_ord.as<uint32_t>(), st, b_T2.as<uint64_t>());
-            else
+            if (!scalar_models) {
+                CR_TRY(b_o1info.reserve((size_t)nesc * 4 + 16)); CR_TRY(b_o1ord.reserve((size_t)nesc * 4 + 16)); CR_TRY(b_o1incl.reserve((size_t)nesc * 32 + 32));
+                CR_LAUNCH(k_o1_gather, gx, te, stream, b_v1.as<uint32_t>(), nesc, b_escrec.as<EscRec>(), b_ord.as<uint32_t>(), b_o1info.as<uint32_t>(), b_o1ord.as<uint32_t>(), b_o1incl.as<uint4>());
+                CR_LAUNCH(k_o1_pass_warp, dim3(256 * 32 / 128), dim3(128), stream, b_k64b.as<uint64_t>(), nesc, b_o1info.as<uint32_t>(), b_o1ord.as<uint32_t>(), b_o1incl.as<uint4>(), st, b_T2.as<uint64_t>());
+            } else
 #endif
             CR_LAUNCH(k_o1_pass, dim3(cr_div_up(nesc, 64)), dim3(64), stream, b_k64b.as<uint64_t>(), b_v1.as<uint32_t>(), nesc, b_escrec.as<EscRec>(), b_ord.as<uint32_t>(), st, b_T2.as<uint64_t>());
         }
@@ -283,7 +293,7 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
     timer.count("#events", nev); timer.count("#triples", (double)nev + nesc + nside); timer.count("#escapes", nesc); timer.count("#side_symbols", nside);
     if (nside) {
 #ifndef CRGPU_SIM
-        if (!scalar_models) CR_LAUNCH(k_side_models_warp, dim3(1), dim3(32), stream, b_side.as<uint16_t>(), nside, st, b_TS.as<uint64_t>());
+        if (!scalar_models) CR_LAUNCH(k_side_epochs, dim3(2), dim3(SE_THREADS), stream, b_lensym.as<uint8_t>(), b_lenpos.as<uint32_t>(), n_lensym, b_idxsym.as<uint8_t>(), b_idxpos.as<uint32_t>(), n_idxsym, st, b_TS.as<uint64_t>());
         else
 #endif
         CR_LAUNCH(k_side_models, dim3(1), dim3(1), stream, b_side.as<uint16_t>(), nside, st, b_TS.as<uint64_t>());
@@ -322,16 +332,68 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
     }
     CR_TRY(upload(b_streams, streams));
     CR_TRY(b_rcres.reserve(streams.size() * sizeof(RcResult) + 16)); CR_TRY(b_rcout.reserve(rc_total + 16));
+    std::vector<RcResult> res;
+    bool rc_done = false;
 #ifndef CRGPU_SIM
-    if (!scalar_models) CR_LAUNCH(k_range_encode_warp, dim3(cr_div_up(streams.size() * 32, 128)), dim3(128), stream, b_dense.as<Tri>(), b_denseside.as<Tri>(), b_escord.as<uint32_t>(),
-              b_streams.as<RcStream>(), (uint32_t)streams.size(), b_rcout.as<uint8_t>(), b_rcres.as<RcResult>());
-    else
+    if (!scalar_models) {
+        // split form (cr_warp.cuh): serial range chain, then the output bytes as a parallel big-number sum
+        const size_t ntm = (size_t)nev + nesc, nts = nside;
+        const uint32_t nstr = (uint32_t)streams.size();
+        CR_TRY(b_qm.reserve((ntm + 1) * 4 + 16)); CR_TRY(b_shm.reserve((ntm + 1) * 4 + 16)); CR_TRY(b_bm.reserve((ntm + 1) * 4 + 16));
+        CR_TRY(b_qs.reserve((nts + 1) * 4 + 16)); CR_TRY(b_shs.reserve((nts + 1) * 4 + 16)); CR_TRY(b_bs.reserve((nts + 1) * 4 + 16));
+        CR_TRY(b_stot.reserve((size_t)nstr * sizeof(StreamTotals) + 16));
+        CR_CUDA(cudaMemsetAsync(b_shm.as<uint32_t>() + ntm, 0, 4, stream));
+        CR_CUDA(cudaMemsetAsync(b_shs.as<uint32_t>() + nts, 0, 4, stream));
+        CR_LAUNCH(k_range_chain, dim3(cr_div_up((size_t)nstr * 32, 128)), dim3(128), stream, b_dense.as<Tri>(), b_denseside.as<Tri>(), b_escord.as<uint32_t>(),
+                  b_streams.as<RcStream>(), nstr, b_qm.as<uint32_t>(), b_shm.as<uint32_t>(), b_qs.as<uint32_t>(), b_shs.as<uint32_t>());
+        timer.mark("range_chain");
+        CR_TRY(cr_exclusive_sum(prims, b_shm.as<uint32_t>(), b_bm.as<uint32_t>(), ntm + 1));
+        CR_TRY(cr_exclusive_sum(prims, b_shs.as<uint32_t>(), b_bs.as<uint32_t>(), nts + 1));
+        CR_LAUNCH(k_stream_totals, dim3(cr_div_up(nstr, 64)), dim3(64), stream, b_streams.as<RcStream>(), nstr, b_escord.as<uint32_t>(), b_bm.as<uint32_t>(), b_bs.as<uint32_t>(), b_stot.as<StreamTotals>());
+        std::vector<StreamTotals> tot;
+        CR_TRY(download(tot, b_stot.p, nstr));
+        res.assign(nstr, RcResult());
+        std::vector<LowStream> lsm, lss; std::vector<RcStream> rsm, rss, fallback; std::vector<uint32_t> fb_index;
+        size_t dsum_total = 0; uint32_t maxlen = 0;
+        for (uint32_t i = 0; i < nstr; i++) {
+            const bool par = !streams[i].is_main || tot[i].shifts < streams[i].limit;      // bytes out <= shifts: no "cannot compress" possible
+            if (!par) { fallback.push_back(streams[i]); fb_index.push_back(i); continue; }
+            LowStream L; L.tri_begin = tot[i].tri_begin; L.tri_end = tot[i].tri_end; L.dsum_off = dsum_total; L.length = tot[i].shifts + 5; L.is_main = streams[i].is_main;
+            dsum_total += L.length; if (L.length > maxlen) maxlen = L.length;
+            if (L.length > streams[i].out_cap) return CRGPU_ERR_ARG;
+            if (streams[i].is_main) { lsm.push_back(L); rsm.push_back(streams[i]); } else { lss.push_back(L); rss.push_back(streams[i]); }
+            res[i].nbytes = L.length; res[i].aborted = 0;
+        }
+        CR_TRY(b_dsum.reserve(dsum_total * 4 + 16));
+        CR_CUDA(cudaMemsetAsync(b_dsum.p, 0, dsum_total * 4, stream));
+        if (!lsm.empty()) {
+            CR_TRY(upload(b_lsm, lsm)); CR_TRY(upload(b_rsm, rsm));
+            CR_LAUNCH(k_low_scatter, dim3(cr_div_up(ntm, 256)), dim3(256), stream, b_dense.as<Tri>(), b_qm.as<uint32_t>(), b_bm.as<uint32_t>(), b_lsm.as<LowStream>(), (uint32_t)lsm.size(), (uint64_t)ntm, b_dsum.as<uint32_t>());
+        }
+        if (!lss.empty()) {
+            CR_TRY(upload(b_lss, lss)); CR_TRY(upload(b_rss, rss));
+            CR_LAUNCH(k_low_scatter, dim3(cr_div_up(nts, 256)), dim3(256), stream, b_denseside.as<Tri>(), b_qs.as<uint32_t>(), b_bs.as<uint32_t>(), b_lss.as<LowStream>(), (uint32_t)lss.size(), (uint64_t)nts, b_dsum.as<uint32_t>());
+        }
+        if (!lsm.empty()) CR_LAUNCH(k_low_carry, dim3(cr_div_up(maxlen, 256), (unsigned)lsm.size()), dim3(256), stream, b_lsm.as<LowStream>(), b_dsum.as<uint32_t>(), b_rsm.as<RcStream>(), b_rcout.as<uint8_t>());
+        if (!lss.empty()) CR_LAUNCH(k_low_carry, dim3(cr_div_up(maxlen, 256), (unsigned)lss.size()), dim3(256), stream, b_lss.as<LowStream>(), b_dsum.as<uint32_t>(), b_rss.as<RcStream>(), b_rcout.as<uint8_t>());
+        if (!fallback.empty()) {                       // barely compressible streams: exact serial coder decides "cannot compress"
+            CR_TRY(upload(b_fb, fallback));
+            CR_LAUNCH(k_range_encode_warp, dim3(cr_div_up(fallback.size() * 32, 128)), dim3(128), stream, b_dense.as<Tri>(), b_denseside.as<Tri>(), b_escord.as<uint32_t>(),
+                      b_fb.as<RcStream>(), (uint32_t)fallback.size(), b_rcout.as<uint8_t>(), b_rcres.as<RcResult>());
+            std::vector<RcResult> fr;
+            CR_TRY(download(fr, b_rcres.p, fallback.size()));
+            for (size_t k = 0; k < fallback.size(); k++) res[fb_index[k]] = fr[k];
+        }
+        rc_done = true;
+    }
 #endif
-    CR_LAUNCH(k_range_encode, dim3(cr_div_up(streams.size(), 32)), dim3(32), stream, b_dense.as<Tri>(), b_denseside.as<Tri>(), b_escord.as<uint32_t>(),
-              b_streams.as<RcStream>(), (uint32_t)streams.size(), b_rcout.as<uint8_t>(), b_rcres.as<RcResult>());
+    if (!rc_done) {
+        CR_LAUNCH(k_range_encode, dim3(cr_div_up(streams.size(), 32)), dim3(32), stream, b_dense.as<Tri>(), b_denseside.as<Tri>(), b_escord.as<uint32_t>(),
+                  b_streams.as<RcStream>(), (uint32_t)streams.size(), b_rcout.as<uint8_t>(), b_rcres.as<RcResult>());
+    }
     timer.mark("range_coder");
-    std::vector<RcResult> res; std::vector<uint32_t> hctx;
-    CR_TRY(download(res, b_rcres.p, streams.size()));
+    std::vector<uint32_t> hctx;
+    if (!rc_done) CR_TRY(download(res, b_rcres.p, streams.size()));
     CR_TRY(download(hctx, b_ctxout.p, 1)); chain_ctx = hctx[0];
 
     // ---- payload layout + headers (src/rolzmain/cr-coder.c:241-262, src/ropmain/cr-coder.c:212-228)

@@ -58,15 +58,21 @@ __global__ void k_o3_pass(const uint32_t* __restrict__ K, const uint32_t* __rest
     const uint32_t slot = K[r] & 0x3fffff;
     if (r > 0 && (K[r - 1] & 0x3fffff) == slot) return;
     uint32_t byte = st.o3_byte[slot], conf = st.o3_conf[slot];
-    for (uint32_t i = r; i < n; i++) {
-        uint32_t k = K[i];
-        if ((k & 0x3fffff) != slot) break;
-        uint32_t sym = k >> 24;
-        pred[V[i]] = (uint8_t)byte;
-        if (sym == byte) conf += conf < 15;
-        else {
-            conf = (conf > 1) + (conf > 2) + (conf > 4) + (conf > 8);
-            if (conf == 0) { byte = sym; conf = 1; }
+    bool more = true;
+    for (uint32_t i = r; more && i < n; i += 8) {
+        uint32_t kk[8], vv[8];                       // 8 independent loads in flight per round trip
+#pragma unroll
+        for (int u = 0; u < 8; u++) { const uint32_t x = i + u < n ? i + u : n - 1; kk[u] = K[x]; vv[u] = V[x]; }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            if (!more || i + u >= n || (kk[u] & 0x3fffff) != slot) { more = false; continue; }
+            const uint32_t sym = kk[u] >> 24;
+            pred[vv[u]] = (uint8_t)byte;
+            if (sym == byte) conf += conf < 15;
+            else {
+                conf = (conf > 1) + (conf > 2) + (conf > 4) + (conf > 8);
+                if (conf == 0) { byte = sym; conf = 1; }
+            }
         }
     }
     st.o3_byte[slot] = (uint8_t)byte;

@@ -191,11 +191,13 @@ CR_HD uint32_t rz_ctx_at(const uint8_t* d, uint32_t t, uint32_t cin) {
 }
 
 struct RolzEmit {
-    typedef struct { uint32_t ev, side; } State;
+    typedef struct { uint32_t ev, side, nlen, nidx; } State;
     const uint8_t* D; const LzBlock* blocks; const uint8_t* tidx;
     const uint32_t *scan_ev, *scan_match, *scan_esclit;
     uint32_t* ev_ctx; uint8_t* ev_sym; uint16_t* side_sym;     // side symbol: value | model<<8 (0 = len model, 1 = idx model)
-    CR_D State begin(uint32_t c, uint32_t) const { State s = { scan_ev[c], 2 * scan_match[c] + scan_esclit[c] }; return s; }
+    // the same symbols split per model (k-th use of a model -> symbol, position in the side stream), for k_side_epochs
+    uint8_t* len_sym; uint32_t* len_pos; uint8_t* idx_sym; uint32_t* idx_pos;
+    CR_D State begin(uint32_t c, uint32_t) const { State s = { scan_ev[c], 2 * scan_match[c] + scan_esclit[c], scan_match[c] + scan_esclit[c], scan_match[c] }; return s; }
     CR_D void visit(State& s, uint32_t b, uint32_t t, uint32_t len) const {
         const LzBlock B = blocks[b];
         const uint8_t* d = D + B.off;
@@ -203,11 +205,13 @@ struct RolzEmit {
         ev_ctx[s.ev] = rz_ctx_at(d, t, B.cin);
         if (idx != 0xFF) {
             ev_sym[s.ev] = B.esc;
+            len_sym[s.nlen] = (uint8_t)len; len_pos[s.nlen++] = s.side;
             side_sym[s.side++] = (uint16_t)len;
+            idx_sym[s.nidx] = (uint8_t)idx; idx_pos[s.nidx++] = s.side;
             side_sym[s.side++] = (uint16_t)(idx | 0x100);
         } else {
             ev_sym[s.ev] = d[t];
-            if (d[t] == B.esc) side_sym[s.side++] = 0;
+            if (d[t] == B.esc) { len_sym[s.nlen] = 0; len_pos[s.nlen++] = s.side; side_sym[s.side++] = 0; }
         }
         s.ev++;
     }

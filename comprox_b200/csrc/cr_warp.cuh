@@ -131,10 +131,23 @@ __global__ void __launch_bounds__(128) k_o2_pass_warp(const uint32_t* __restrict
 }
 
 // ------------------------------------------------------------------ o1 pass, one warp per ctx8
-// lane l holds o1 counts of symbols 8l..8l+7 in (a0, a1).  Escapes arrive sorted by (ctx8, time).
-__global__ void __launch_bounds__(128) k_o1_pass_warp(const uint64_t* __restrict__ K, const uint32_t* __restrict__ V, uint32_t n, const EscRec* __restrict__ rec,
-                                                       const uint32_t* __restrict__ ord, PpmState st, uint64_t* __restrict__ T2) {
-    const uint32_t lane = threadIdx.x & 31;
+// Escapes arrive sorted by (ctx8, time).  k_o1_gather first makes that order physical, so the pass streams its
+// input: 32 records per batch, loaded one batch ahead and staged through shared memory.
+__global__ void k_o1_gather(const uint32_t* __restrict__ V, uint32_t n, const EscRec* __restrict__ rec, const uint32_t* __restrict__ ord,
+                            uint32_t* __restrict__ info_s, uint32_t* __restrict__ ord_s, uint4* __restrict__ incl_s) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t v = V[i];
+    info_s[i] = rec[v].info; ord_s[i] = ord[v];
+    const uint32_t* m = rec[v].incl;
+    incl_s[2 * (size_t)i] = make_uint4(m[0], m[1], m[2], m[3]);
+    incl_s[2 * (size_t)i + 1] = make_uint4(m[4], m[5], m[6], m[7]);
+}
+// lane l holds o1 counts of symbols 8l..8l+7 in (a0, a1).
+__global__ void __launch_bounds__(128) k_o1_pass_warp(const uint64_t* __restrict__ K, uint32_t n, const uint32_t* __restrict__ info_s, const uint32_t* __restrict__ ord_s,
+                                                       const uint4* __restrict__ incl_s, PpmState st, uint64_t* __restrict__ T2) {
+    __shared__ uint4 sincl[4][32][2];
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t c8 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (c8 >= 256) return;
     auto keyof = [](uint64_t k) { return (uint32_t)(k >> 32) & 0xffu; };
@@ -145,30 +158,42 @@ __global__ void __launch_bounds__(128) k_o1_pass_warp(const uint64_t* __restrict
     uint2 av = ((const uint2*)row)[lane];
     uint32_t a0 = av.x, a1 = av.y;
 
-    // software pipeline: the record fields of step i+1 are loaded while step i is computed
-    uint32_t vi = V[r0];
-    uint32_t n_info = rec[vi].info, n_bits = ((const uint8_t*)rec[vi].incl)[lane], n_ord = ord[vi];
-    for (uint32_t i = r0; i < r1; i++) {
-        const uint32_t info = n_info, bits = n_bits, o = n_ord;
-        if (i + 1 < r1) { vi = V[i + 1]; n_info = rec[vi].info; n_bits = ((const uint8_t*)rec[vi].incl)[lane]; n_ord = ord[vi]; }
-        const uint32_t sym = (info >> 8) & 255, own = sym >> 3, within = sym & 7;
-        // frequencies o1*8-7 of the included symbols of this lane
-        uint32_t sum = 0, cum = 0;
-#pragma unroll
-        for (uint32_t k = 0; k < 8; k++) {
-            const uint32_t c = ((k < 4 ? a0 : a1) >> (8 * (k & 3))) & 255;
-            const uint32_t fr = (bits >> k & 1u) ? c * 8 - 7 : 0u;
-            sum += fr;
-            if (lane < own || (lane == own && k < within)) cum += fr;
+    uint32_t n_info = 0, n_ord = 0; uint4 n_i0 = make_uint4(0, 0, 0, 0), n_i1 = n_i0;
+    if (r0 + lane < r1) { n_info = info_s[r0 + lane]; n_ord = ord_s[r0 + lane]; n_i0 = incl_s[2 * (size_t)(r0 + lane)]; n_i1 = incl_s[2 * (size_t)(r0 + lane) + 1]; }
+    for (uint32_t base = r0; base < r1; base += 32) {
+        const uint32_t c_info = n_info, c_ord = n_ord;
+        sincl[w][lane][0] = n_i0; sincl[w][lane][1] = n_i1;
+        __syncwarp();
+        if (base + 32 + lane < r1) {
+            const size_t x = base + 32 + lane;
+            n_info = info_s[x]; n_ord = ord_s[x]; n_i0 = incl_s[2 * x]; n_i1 = incl_s[2 * x + 1];
         }
-        sum = __reduce_add_sync(FULLMASK, sum);
-        cum = __reduce_add_sync(FULLMASK, cum);
-        const uint32_t mine = ((within < 4 ? a0 : a1) >> (8 * (within & 3))) & 255;
-        const uint32_t cs = __shfl_sync(FULLMASK, mine, own);
-        if (lane == 0) T2[o] = ppm_pack(cum, cs * 8 - 7, sum, 0);
-        // ppm_update_o1 (cr-ppm.c:90-97)
-        if (lane == own) { if (within < 4) a0 += 1u << (8 * within); else a1 += 1u << (8 * (within - 4)); }
-        if (cs + 1 >= 255) { a0 -= (a0 >> 1) & 0x7f7f7f7fu; a1 -= (a1 >> 1) & 0x7f7f7f7fu; }
+        const uint32_t cnt = r1 - base < 32 ? r1 - base : 32;
+        uint64_t mine = 0;
+        for (uint32_t j = 0; j < cnt; j++) {
+            const uint32_t info = __shfl_sync(FULLMASK, c_info, j);
+            const uint32_t bits = ((const uint8_t*)&sincl[w][j][0])[lane];
+            const uint32_t sym = (info >> 8) & 255, own = sym >> 3, within = sym & 7;
+            uint32_t sum = 0, cum = 0;
+#pragma unroll
+            for (uint32_t k = 0; k < 8; k++) {
+                const uint32_t c = ((k < 4 ? a0 : a1) >> (8 * (k & 3))) & 255;
+                const uint32_t fr = (bits >> k & 1u) ? c * 8 - 7 : 0u;      // M_freq_o1 (cr-ppm.c:98)
+                sum += fr;
+                if (lane < own || (lane == own && k < within)) cum += fr;
+            }
+            // one reduction for both: cum in the high half (sums stay below 2^20)
+            const unsigned long long both = ((unsigned long long)cum << 32) | sum;
+            const uint32_t lo = __reduce_add_sync(FULLMASK, (uint32_t)both), hi = __reduce_add_sync(FULLMASK, (uint32_t)(both >> 32));
+            const uint32_t mysym = ((within < 4 ? a0 : a1) >> (8 * (within & 3))) & 255;
+            const uint32_t cs = __shfl_sync(FULLMASK, mysym, own);
+            if (lane == j) mine = ppm_pack(hi, cs * 8 - 7, lo, 0);
+            // ppm_update_o1 (cr-ppm.c:90-97)
+            if (lane == own) { if (within < 4) a0 += 1u << (8 * within); else a1 += 1u << (8 * (within - 4)); }
+            if (cs + 1 >= 255) { a0 -= (a0 >> 1) & 0x7f7f7f7fu; a1 -= (a1 >> 1) & 0x7f7f7f7fu; }
+        }
+        if (lane < cnt) T2[c_ord] = mine;
+        __syncwarp();
     }
     ((uint2*)row)[lane] = make_uint2(a0, a1);
 }
@@ -226,6 +251,95 @@ __global__ void __launch_bounds__(32) k_side_models_warp(const uint16_t* __restr
     ((uint4*)(st.m0 + 256))[lane] = make_uint4(fb[0], fb[1], fb[2], fb[3]);
 }
 
+// ------------------------------------------------------------------ order-0 side models, epoch-parallel
+// One CTA per model (0 = len_model, 1 = idx_model).  Between two halvings ("epoch") the table is
+//   snapshot + 4 * (occurrences so far), and the halving instants depend only on how many symbols were coded,
+// so every cumulative frequency of an epoch is a snapshot value plus a rank:
+//   cum_i = snapcum[s_i] + 4 * #{j < i in epoch : s_j < s_i},  frq_i = snap[s_i] + 4 * #{j < i : s_j == s_i}.
+// 1024 symbols are ranked per step: per-warp histograms, a prefix over warps, a prefix over symbols, and a
+// 32-way comparison inside each warp.  Serial work left: one step per 1024 symbols plus one halving per epoch.
+#define SE_THREADS 1024
+__global__ void __launch_bounds__(SE_THREADS) k_side_epochs(const uint8_t* __restrict__ len_sym, const uint32_t* __restrict__ len_pos, uint32_t n_len,
+                                                            const uint8_t* __restrict__ idx_sym, const uint32_t* __restrict__ idx_pos, uint32_t n_idx,
+                                                            PpmState st, uint64_t* __restrict__ TS) {
+    const uint32_t m = blockIdx.x;                       // model
+    const uint8_t* sym = m == 0 ? len_sym : idx_sym;
+    const uint32_t* pos = m == 0 ? len_pos : idx_pos;
+    const uint32_t n = m == 0 ? n_len : n_idx;
+    uint16_t* state = st.m0 + m * 256;
+    __shared__ uint32_t cnt[256];                         // counts at the start of the current step
+    __shared__ uint32_t cumt[256];                        // exclusive prefix of cnt
+    __shared__ uint32_t s_total;
+    __shared__ __align__(4) uint16_t hist[32][256];       // per-warp histogram of the step -> exclusive prefix over warps
+    __shared__ uint16_t below[32][256];                   // per warp: exclusive prefix over symbols of its hist row
+    __shared__ uint16_t steptot[256];                     // occurrences of each symbol in the step
+    const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid < 256) cnt[tid] = state[tid];
+    __syncthreads();
+    uint32_t done = 0;
+    for (;;) {
+        // cumt / total from cnt: warp 0, 8 symbols per lane
+        if (w == 0) {
+            uint32_t v[8], sum = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { v[k] = cnt[lane * 8 + k]; sum += v[k]; }
+            uint32_t inc = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(FULLMASK, inc, d); if (lane >= d) inc += t; }
+            uint32_t run = inc - sum;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { cumt[lane * 8 + k] = run; run += v[k]; }
+            if (lane == 31) s_total = inc;
+        }
+        for (uint32_t i = tid; i < 32 * 128; i += SE_THREADS) ((uint32_t*)&hist[0][0])[i] = 0;
+        __syncthreads();
+        if (done >= n) break;
+        const uint32_t total = s_total;
+        // symbols up to and including the one whose update pushes the total past 32000 (cr-model.c:65)
+        const uint32_t to_rescale = (32000 - (total > 32000 ? 32000 : total)) / 4 + 1;
+        uint32_t step = n - done; if (step > SE_THREADS) step = SE_THREADS; if (step > to_rescale) step = to_rescale;
+        const bool active = tid < step;
+        const uint32_t s = active ? sym[done + tid] : 0xFFFFu;
+        if (active) atomicAdd((uint32_t*)&hist[w][0] + (s >> 1), (s & 1u) ? 0x10000u : 1u);
+        __syncthreads();
+        if (tid < 256) {                                   // exclusive prefix over warps, one symbol per thread
+            uint32_t run = 0;
+            for (int k = 0; k < 32; k++) { uint32_t h = hist[k][tid]; hist[k][tid] = (uint16_t)run; run += h; }
+            steptot[tid] = (uint16_t)run;
+        }
+        __syncthreads();
+        {                                                  // exclusive prefix over symbols, one row per warp
+            uint32_t v[8], sum = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { v[k] = hist[w][lane * 8 + k]; sum += v[k]; }
+            uint32_t inc = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(FULLMASK, inc, d); if (lane >= d) inc += t; }
+            uint32_t run = inc - sum;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { below[w][lane * 8 + k] = (uint16_t)run; run += v[k]; }
+        }
+        __syncwarp();
+        uint32_t lt = 0, eq = 0;                           // earlier lanes of this warp with a smaller / the same symbol
+#pragma unroll 8
+        for (uint32_t j = 0; j < 32; j++) { const uint32_t sj = __shfl_sync(FULLMASK, s, j); if (j < lane) { lt += sj < s; eq += sj == s; } }
+        if (active) {
+            const uint32_t cum = cumt[s] + 4 * ((uint32_t)below[w][s] + lt);
+            const uint32_t frq = cnt[s] + 4 * ((uint32_t)hist[w][s] + eq);
+            TS[pos[done + tid]] = ppm_pack(cum, frq, total + 4 * tid, 0);
+        }
+        __syncthreads();
+        if (tid < 256) {
+            uint32_t c = cnt[tid] + 4u * steptot[tid];
+            if (step == to_rescale) c = (c + 1) >> 1;      // halve, rounding up (cr-model.c:66-73)
+            cnt[tid] = c;
+        }
+        done += step;
+        __syncthreads();
+    }
+    if (tid < 256) state[tid] = (uint16_t)cnt[tid];
+}
+
 // ------------------------------------------------------------------ range coder, one warp per stream
 // All lanes stage triples through shared memory one batch ahead; lane 0 runs the serial recurrence.
 #define RC_BATCH 64
@@ -278,5 +392,112 @@ __global__ void __launch_bounds__(128) k_range_encode_warp(const Tri* __restrict
         res[s].nbytes = c.n;
         res[s].aborted = aborted;
     }
+}
+
+// ------------------------------------------------------------------ range coder, split form
+// The coder's two recurrences are independent:  range_{n+1} depends only on (range_n, sum_n, frq_n), while `low`
+// merely accumulates cum_n * (range_n / sum_n) at a byte offset given by the number of renormalisation shifts so
+// far.  So the only truly serial part is the range chain (k_range_chain: ~8 dependent integer ops per symbol);
+// the output bytes are the big-number sum  sum_n a_n * 256^-(B_n+4)  which k_low_scatter / k_low_carry evaluate
+// for all symbols and all output bytes in parallel (carry resolution by look-right over 0xFF runs).
+__global__ void __launch_bounds__(128) k_range_chain(const Tri* __restrict__ dense_main, const Tri* __restrict__ dense_side, const uint32_t* __restrict__ escord,
+                                                      const RcStream* __restrict__ streams, uint32_t nstreams,
+                                                      uint32_t* __restrict__ q_main, uint32_t* __restrict__ sh_main, uint32_t* __restrict__ q_side, uint32_t* __restrict__ sh_side) {
+    __shared__ uint4 stage[4][RC_BATCH];
+    __shared__ uint32_t oq[4][RC_BATCH], os[4][RC_BATCH];
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (s >= nstreams) return;
+    const RcStream S = streams[s];
+    const uint4* tri = (const uint4*)(S.is_main ? dense_main : dense_side);
+    uint32_t* qo = S.is_main ? q_main : q_side;
+    uint32_t* so = S.is_main ? sh_main : sh_side;
+    size_t i0 = S.ev_begin, i1 = S.ev_end;
+    if (S.is_main) { i0 += escord[S.ev_begin]; i1 += escord[S.ev_end]; }
+    uint32_t range = 0xFFFFFFFFu;
+    uint4 r0 = make_uint4(0, 1, 1, 0), r1 = r0;
+    if (i0 + lane < i1) r0 = tri[i0 + lane];
+    if (i0 + 32 + lane < i1) r1 = tri[i0 + 32 + lane];
+    for (size_t base = i0; base < i1; base += RC_BATCH) {
+        stage[w][lane] = r0; stage[w][lane + 32] = r1;
+        __syncwarp();
+        const size_t nb = base + RC_BATCH;
+        if (nb + lane < i1) r0 = tri[nb + lane];
+        if (nb + 32 + lane < i1) r1 = tri[nb + 32 + lane];
+        const uint32_t cnt = i1 - base < RC_BATCH ? (uint32_t)(i1 - base) : RC_BATCH;
+        if (lane == 0) {
+            uint4 t = stage[w][0];
+            for (uint32_t j = 0; j < cnt; j++) {
+                const uint4 tn = stage[w][j + 1 < RC_BATCH ? j + 1 : j];
+                uint32_t q = __umulhi(range, t.w);                  // range / sum  (cr-rangecoder.c:61) ...
+                if (range - q * t.z >= t.z) q++;                     // ... corrected: magic = floor(2^32/sum)
+                uint32_t r = q * (t.y & 0x7FFFFFFFu);                // range *= frq (:64)
+                const uint32_t sh = r < (1u << 8) ? 3u : r < (1u << 16) ? 2u : r < (1u << 24) ? 1u : 0u;   // while (range < 2^24) range <<= 8 (:65-68)
+                range = r << (8 * sh);
+                oq[w][j] = q; os[w][j] = sh;
+                t = tn;
+            }
+        }
+        __syncwarp();
+        if (lane < cnt) { qo[base + lane] = oq[w][lane]; so[base + lane] = os[w][lane]; }
+        if (lane + 32 < cnt) { qo[base + lane + 32] = oq[w][lane + 32]; so[base + lane + 32] = os[w][lane + 32]; }
+        __syncwarp();
+    }
+}
+
+struct LowStream {          // one stream in split form
+    uint64_t tri_begin, tri_end;   // dense triple range
+    uint64_t dsum_off;             // offset (in bytes == in uint32 digit slots) of the stream's output
+    uint32_t length;               // output bytes = shifts + 5
+    uint32_t is_main;
+};
+CR_D uint32_t low_find_stream(const LowStream* __restrict__ ls, uint32_t n, uint64_t i) {
+    uint32_t lo = 0, hi = n;
+    while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (ls[mid].tri_begin <= i) lo = mid; else hi = mid; }
+    return lo;
+}
+// digit sums: symbol n adds the 4 bytes of a_n = cum_n * q_n at output positions B_n+1 .. B_n+4 (cr-rangecoder.c:62-63)
+__global__ void k_low_scatter(const Tri* __restrict__ dense, const uint32_t* __restrict__ q, const uint32_t* __restrict__ bscan,
+                              const LowStream* __restrict__ ls, uint32_t nls, uint64_t ntri, uint32_t* __restrict__ dsum) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ntri) return;
+    const LowStream S = ls[low_find_stream(ls, nls, i)];
+    if (i < S.tri_begin || i >= S.tri_end) return;               // triple of a stream that runs the serial fallback
+    const uint32_t a = dense[i].cum * q[i];
+    if (a == 0) return;
+    uint32_t* d = dsum + S.dsum_off + (bscan[i] - bscan[S.tri_begin]) + 1;
+    if (a >> 24) atomicAdd(d, a >> 24);
+    if ((a >> 16) & 255) atomicAdd(d + 1, (a >> 16) & 255);
+    if ((a >> 8) & 255) atomicAdd(d + 2, (a >> 8) & 255);
+    if (a & 255) atomicAdd(d + 3, a & 255);
+}
+// value (0..258) of output position p after the digit sums have been spread to single bytes, before carries
+CR_D uint32_t low_digit(const uint32_t* __restrict__ d, uint32_t len, uint32_t p) {
+    auto D = [&](uint32_t x) { return x < len ? d[x] : 0u; };
+    auto E = [&](uint32_t x) { return (D(x) & 255) + ((D(x + 1) >> 8) & 255) + ((D(x + 2) >> 16) & 255) + (D(x + 3) >> 24); };
+    return (E(p) & 255) + (E(p + 1) >> 8);
+}
+__global__ void k_low_carry(const LowStream* __restrict__ ls, const uint32_t* __restrict__ dsum, const RcStream* __restrict__ streams_by_ls,
+                            uint8_t* __restrict__ outbuf) {
+    const LowStream S = ls[blockIdx.y];
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= S.length) return;
+    const uint32_t* d = dsum + S.dsum_off;
+    uint32_t v = low_digit(d, S.length, p);
+    uint32_t r = p + 1, carry = 0;
+    for (; r < S.length; r++) { uint32_t f = low_digit(d, S.length, r); if (f != 255) { carry = f >> 8; break; } }
+    outbuf[streams_by_ls[blockIdx.y].out_off + p] = (uint8_t)(v + carry);
+}
+
+struct StreamTotals { uint64_t tri_begin, tri_end; uint32_t shifts; uint32_t pad; };
+__global__ void k_stream_totals(const RcStream* __restrict__ streams, uint32_t nstreams, const uint32_t* __restrict__ escord,
+                                const uint32_t* __restrict__ bscan_main, const uint32_t* __restrict__ bscan_side, StreamTotals* __restrict__ out) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nstreams) return;
+    const RcStream S = streams[s];
+    uint64_t i0 = S.ev_begin, i1 = S.ev_end;
+    if (S.is_main) { i0 += escord[S.ev_begin]; i1 += escord[S.ev_end]; }
+    const uint32_t* b = S.is_main ? bscan_main : bscan_side;
+    out[s].tri_begin = i0; out[s].tri_end = i1; out[s].shifts = b[i1] - b[i0]; out[s].pad = 0;
 }
 #endif  // !CRGPU_SIM

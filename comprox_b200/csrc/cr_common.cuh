@@ -62,7 +62,16 @@ static inline const char* cudaGetErrorString(int) { return "sim"; }
 // ------------------------------------------------------------------ real CUDA
 #include <cuda_runtime.h>
 extern unsigned long long g_cr_launches;   // kernels launched by this library (crgpu_launch_count)
-#define CR_LAUNCH(kernel, grid, block, stream, ...) do { g_cr_launches++; kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__); } while (0)
+#define CR_LAUNCH(kernel, grid, block, stream, ...)                                             \
+    do {                                                                                        \
+        g_cr_launches++;                                                                        \
+        kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__);                                  \
+        cudaError_t le_ = cudaGetLastError();                                                   \
+        if (le_ != cudaSuccess) {                                                               \
+            fprintf(stderr, "crgpu: launch of %s failed: %s (%s:%d)\n", #kernel, cudaGetErrorString(le_), __FILE__, __LINE__); \
+            return CRGPU_ERR_CUDA;                                                              \
+        }                                                                                       \
+    } while (0)
 #endif
 
 #define CR_HD __host__ __device__ __forceinline__

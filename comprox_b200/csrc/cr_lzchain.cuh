@@ -43,13 +43,14 @@ struct LzChain {
     DevBuf b_evctx, b_evsym, b_tokend, b_pred, b_T1, b_T2, b_TS, b_side;
     DevBuf b_escrec, b_esccount, b_k64a, b_k64b, b_ord, b_flag, b_escord;
     DevBuf b_lensym, b_lenpos, b_idxsym, b_idxpos;
-    DevBuf b_o1info, b_o1ord, b_o1incl;
+    DevBuf b_o1info, b_o1ord, b_o1incl, b_bounds;
     DevBuf b_qm, b_shm, b_bm, b_qs, b_shs, b_bs, b_stot, b_dsum, b_lsm, b_lss, b_rsm, b_rss, b_fb;
     DevBuf b_dense, b_denseside, b_streams, b_rcres, b_rcout, b_copy, b_hdr;
     // ---- sizes of the last window (for the debug/trace fetch used by the tests)
     uint32_t last_nev = 0, last_nside = 0, last_nesc = 0, last_nent = 0;
     size_t last_dtotal = 0;
     StageTimer timer;
+    bool hot_contexts = true;      // hot o2 contexts run the rank-based CTA kernel (k_o2_pass_cta)
     bool scalar_models = false;   // GPU A/B switch: run the scalar (simulation-checked) model/coder kernels
 
     int init(int variant_, cudaStream_t s) {
@@ -65,7 +66,7 @@ struct LzChain {
         DevBuf* all[] = { &s_o3b, &s_o3c, &s_o2, &s_o1, &s_m0, &b_blocks, &b_segoff, &b_seglen, &b_hist, &b_esc1, &b_first, &b_ctxout,
             &b_k0, &b_k1, &b_v0, &b_v1, &b_ks0, &b_M, &b_S, &b_span, &b_tidx, &b_segs, &b_xt, &b_entry, &b_cnt, &b_scan,
             &b_evctx, &b_evsym, &b_tokend, &b_pred, &b_T1, &b_T2, &b_TS, &b_side, &b_escrec, &b_esccount, &b_k64a, &b_k64b, &b_ord,
-            &b_flag, &b_escord, &b_lensym, &b_lenpos, &b_idxsym, &b_idxpos, &b_o1info, &b_o1ord, &b_o1incl, &b_qm, &b_shm, &b_bm, &b_qs, &b_shs, &b_bs, &b_stot, &b_dsum, &b_lsm, &b_lss, &b_rsm, &b_rss, &b_fb, &b_dense, &b_denseside, &b_streams, &b_rcres, &b_rcout, &b_copy, &b_hdr, &prims.temp };
+            &b_flag, &b_escord, &b_lensym, &b_lenpos, &b_idxsym, &b_idxpos, &b_o1info, &b_o1ord, &b_o1incl, &b_bounds, &b_qm, &b_shm, &b_bm, &b_qs, &b_shs, &b_bs, &b_stot, &b_dsum, &b_lsm, &b_lss, &b_rsm, &b_rss, &b_fb, &b_dense, &b_denseside, &b_streams, &b_rcres, &b_rcout, &b_copy, &b_hdr, &prims.temp };
         for (DevBuf* b : all) b->release();
         inited = false;
     }
@@ -262,7 +263,13 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
         CR_LAUNCH(k_o2_keys, ge, te, stream, b_evctx.as<uint32_t>(), b_evsym.as<uint8_t>(), b_pred.as<uint8_t>(), nev, b_k0.as<uint32_t>(), b_v0.as<uint32_t>());
         CR_TRY(cr_sort_pairs<uint32_t>(prims, b_k0.as<uint32_t>(), b_k1.as<uint32_t>(), b_v0.as<uint32_t>(), b_v1.as<uint32_t>(), nev, 0, 16));
 #ifndef CRGPU_SIM
-        if (!scalar_models) CR_LAUNCH(k_o2_pass_warp, dim3(65536 * 32 / 128), dim3(128), stream, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nev, st, b_T1.as<uint64_t>(), b_escrec.as<EscRec>(), b_esccount.as<uint32_t>());
+        if (!scalar_models) {
+            const uint32_t hot_min = hot_contexts ? O2C_MIN : 0xFFFFFFFFu;
+            CR_TRY(b_bounds.reserve(65537 * 4 + 16));
+            CR_LAUNCH(k_o2_bounds, dim3(cr_div_up(65537, 256)), dim3(256), stream, b_k1.as<uint32_t>(), nev, b_bounds.as<uint32_t>());
+            if (hot_contexts) CR_LAUNCH(k_o2_pass_cta, dim3(65536), dim3(O2C_THREADS), stream, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nev, st, b_T1.as<uint64_t>(), b_escrec.as<EscRec>(), b_esccount.as<uint32_t>(), b_bounds.as<uint32_t>());
+            CR_LAUNCH(k_o2_pass_warp, dim3(65536 * 32 / 128), dim3(128), stream, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nev, st, b_T1.as<uint64_t>(), b_escrec.as<EscRec>(), b_esccount.as<uint32_t>(), hot_min, b_bounds.as<uint32_t>());
+        }
         else
 #endif
         CR_LAUNCH(k_o2_pass, dim3(cr_div_up(nev, 128)), dim3(128), stream, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nev, st, b_T1.as<uint64_t>(), b_escrec.as<EscRec>(), b_esccount.as<uint32_t>());
@@ -282,7 +289,8 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
             if (!scalar_models) {
                 CR_TRY(b_o1info.reserve((size_t)nesc * 4 + 16)); CR_TRY(b_o1ord.reserve((size_t)nesc * 4 + 16)); CR_TRY(b_o1incl.reserve((size_t)nesc * 32 + 32));
                 CR_LAUNCH(k_o1_gather, gx, te, stream, b_v1.as<uint32_t>(), nesc, b_escrec.as<EscRec>(), b_ord.as<uint32_t>(), b_o1info.as<uint32_t>(), b_o1ord.as<uint32_t>(), b_o1incl.as<uint4>());
-                CR_LAUNCH(k_o1_pass_warp, dim3(256 * 32 / 128), dim3(128), stream, b_k64b.as<uint64_t>(), nesc, b_o1info.as<uint32_t>(), b_o1ord.as<uint32_t>(), b_o1incl.as<uint4>(), st, b_T2.as<uint64_t>());
+                if (hot_contexts) CR_LAUNCH(k_o1_pass_cta, dim3(256), dim3(O1C_THREADS), stream, b_k64b.as<uint64_t>(), nesc, b_o1info.as<uint32_t>(), b_o1ord.as<uint32_t>(), b_o1incl.as<uint4>(), st, b_T2.as<uint64_t>());
+                CR_LAUNCH(k_o1_pass_warp, dim3(256 * 32 / 128), dim3(128), stream, b_k64b.as<uint64_t>(), nesc, b_o1info.as<uint32_t>(), b_o1ord.as<uint32_t>(), b_o1incl.as<uint4>(), st, b_T2.as<uint64_t>(), hot_contexts ? O1C_MIN : 0xFFFFFFFFu);
             } else
 #endif
             CR_LAUNCH(k_o1_pass, dim3(cr_div_up(nesc, 64)), dim3(64), stream, b_k64b.as<uint64_t>(), b_v1.as<uint32_t>(), nesc, b_escrec.as<EscRec>(), b_ord.as<uint32_t>(), st, b_T2.as<uint64_t>());
@@ -368,11 +376,11 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
         CR_CUDA(cudaMemsetAsync(b_dsum.p, 0, dsum_total * 4, stream));
         if (!lsm.empty()) {
             CR_TRY(upload(b_lsm, lsm)); CR_TRY(upload(b_rsm, rsm));
-            CR_LAUNCH(k_low_scatter, dim3(cr_div_up(ntm, 256)), dim3(256), stream, b_dense.as<Tri>(), b_qm.as<uint32_t>(), b_bm.as<uint32_t>(), b_lsm.as<LowStream>(), (uint32_t)lsm.size(), (uint64_t)ntm, b_dsum.as<uint32_t>());
+            if (ntm) CR_LAUNCH(k_low_scatter, dim3(cr_div_up(ntm, 256)), dim3(256), stream, b_dense.as<Tri>(), b_qm.as<uint32_t>(), b_bm.as<uint32_t>(), b_lsm.as<LowStream>(), (uint32_t)lsm.size(), (uint64_t)ntm, b_dsum.as<uint32_t>());
         }
         if (!lss.empty()) {
             CR_TRY(upload(b_lss, lss)); CR_TRY(upload(b_rss, rss));
-            CR_LAUNCH(k_low_scatter, dim3(cr_div_up(nts, 256)), dim3(256), stream, b_denseside.as<Tri>(), b_qs.as<uint32_t>(), b_bs.as<uint32_t>(), b_lss.as<LowStream>(), (uint32_t)lss.size(), (uint64_t)nts, b_dsum.as<uint32_t>());
+            if (nts) CR_LAUNCH(k_low_scatter, dim3(cr_div_up(nts, 256)), dim3(256), stream, b_denseside.as<Tri>(), b_qs.as<uint32_t>(), b_bs.as<uint32_t>(), b_lss.as<LowStream>(), (uint32_t)lss.size(), (uint64_t)nts, b_dsum.as<uint32_t>());
         }
         if (!lsm.empty()) CR_LAUNCH(k_low_carry, dim3(cr_div_up(maxlen, 256), (unsigned)lsm.size()), dim3(256), stream, b_lsm.as<LowStream>(), b_dsum.as<uint32_t>(), b_rsm.as<RcStream>(), b_rcout.as<uint8_t>());
         if (!lss.empty()) CR_LAUNCH(k_low_carry, dim3(cr_div_up(maxlen, 256), (unsigned)lss.size()), dim3(256), stream, b_lss.as<LowStream>(), b_dsum.as<uint32_t>(), b_rss.as<RcStream>(), b_rcout.as<uint8_t>());

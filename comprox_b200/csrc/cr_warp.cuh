@@ -28,17 +28,22 @@ template <class K, class F> CR_D uint32_t lower_bound_key(const K* __restrict__ 
     return lo;
 }
 
+// bounds[c] = first sorted rank whose 16-bit context is >= c (c = 0..65536): one binary search per context, done once
+__global__ void k_o2_bounds(const uint32_t* __restrict__ K, uint32_t n, uint32_t* __restrict__ bounds) {
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > 65536) return;
+    bounds[c] = lower_bound_key(K, n, c, [](uint32_t k) { return k & 0xffffu; });
+}
+
 // ------------------------------------------------------------------ o2 pass, one warp per ctx16
 // lane l holds the frequencies of symbols 8l..8l+7 in (f0, f1); flags 256/257 and the body total are uniform.
 __global__ void __launch_bounds__(128) k_o2_pass_warp(const uint32_t* __restrict__ K, const uint32_t* __restrict__ V, uint32_t n, PpmState st,
-                                                       uint64_t* __restrict__ T1, EscRec* __restrict__ esc_rec, uint32_t* __restrict__ esc_count) {
+                                                       uint64_t* __restrict__ T1, EscRec* __restrict__ esc_rec, uint32_t* __restrict__ esc_count, uint32_t hot_min, const uint32_t* __restrict__ bounds) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t c16 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (c16 >= 65536) return;
-    auto keyof = [](uint32_t k) { return k & 0xffffu; };
-    const uint32_t r0 = lower_bound_key(K, n, c16, keyof);
-    if (r0 >= n || (K[r0] & 0xffff) != c16) return;
-    const uint32_t r1 = lower_bound_key(K, n, c16 + 1, keyof);
+    const uint32_t r0 = bounds[c16], r1 = bounds[c16 + 1];
+    if (r0 == r1 || r1 - r0 >= hot_min) return;           // empty, or taken by k_o2_pass_cta                       // taken by k_o2_pass_cta
 
     uint8_t* row = st.o2 + (size_t)c16 * PPM_O2_STRIDE;
     uint2 fv = ((const uint2*)row)[lane];
@@ -130,6 +135,172 @@ __global__ void __launch_bounds__(128) k_o2_pass_warp(const uint32_t* __restrict
     if (lane == 0) { row[256] = (uint8_t)f256; row[257] = (uint8_t)f257; }
 }
 
+// ------------------------------------------------------------------ o2 pass for HOT contexts, one CTA per ctx16
+// The warp kernel above spends ~200 ns per event of a context; the hottest context of a text holds 3-4 % of all
+// events and was the longest serial chain of the encoder.  Between two rescales the o2 table only counts:
+//     f_x(i)   = f_x(0) + #{non-hit events j < i with symbol x}          (hits bump flag 256 instead, cr-ppm.c:124)
+//     body(i)  = body(0) + #non-hits before i,   f256(i) = f256(0) + #hits before i,
+//     f257(i)  = f257(0) + #escapes before i - #{counts that went 1 -> 2 before i}   (cr-ppm.c:136-138,146)
+// so every quantity of ppm_encode is a start-of-step value plus a rank, and 1024 events are evaluated at once
+// (per-warp histograms, prefix over warps / symbols, 32-way compare inside the warp -- as in k_side_epochs).
+// The first event whose update would rescale the table (cr-o2model.c:54) ends the step; everything after it is
+// recomputed in the next step from the rescaled table.
+#define O2C_THREADS 1024
+#define O2C_MIN     3072          // contexts with at least this many events in the window take this path
+__global__ void __launch_bounds__(O2C_THREADS) k_o2_pass_cta(const uint32_t* __restrict__ K, const uint32_t* __restrict__ V, uint32_t n, PpmState st,
+                                                             uint64_t* __restrict__ T1, EscRec* __restrict__ esc_rec, uint32_t* __restrict__ esc_count, const uint32_t* __restrict__ bounds) {
+    const uint32_t c16 = blockIdx.x;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const uint32_t r0 = bounds[c16], r1 = bounds[c16 + 1];
+    if (r1 - r0 < O2C_MIN) return;
+
+    __shared__ uint32_t cnt[256], cumt[256], zmask[8];
+    __shared__ uint32_t s_f256, s_f257, s_body, s_first;
+    __shared__ __align__(4) uint16_t hist[32][256];
+    __shared__ uint16_t below[32][256];
+    __shared__ uint32_t wtot[3][32];                      // per-warp totals: non-hits, escapes, 1->2 transitions -> exclusive prefixes
+    __shared__ uint16_t ssym[O2C_THREADS];                // symbol of each non-hit event (0x100 for hits) for the rare trigger-mask path
+    __shared__ uint8_t esc_sym[O2C_THREADS];
+    uint8_t* row = st.o2 + (size_t)c16 * PPM_O2_STRIDE;
+    if (tid < 256) cnt[tid] = row[tid];
+    if (tid == 0) { s_f256 = row[256]; s_f257 = row[257]; }
+    __syncthreads();
+
+    uint32_t pos = r0;
+    for (;;) {
+        // ---- derived tables from cnt: cumt, body, zero mask (warp 0); clear the histograms (all)
+        if (w == 0) {
+            uint32_t v[8], sum = 0, zb = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { v[k] = cnt[lane * 8 + k]; sum += v[k]; zb |= (uint32_t)(v[k] == 0) << k; }
+            uint32_t inc = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(FULLMASK, inc, d); if (lane >= d) inc += t; }
+            uint32_t run = inc - sum;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { cumt[lane * 8 + k] = run; run += v[k]; }
+            if (lane == 31) s_body = inc;
+            // zmask word q = symbols 32q..32q+31 = lanes 4q..4q+3
+            uint32_t z = zb << (8 * (lane & 3));
+            z |= __shfl_xor_sync(FULLMASK, z, 1); z |= __shfl_xor_sync(FULLMASK, z, 2);
+            if ((lane & 3) == 0) zmask[lane >> 2] = z;
+        }
+        for (uint32_t i = tid; i < 32 * 128; i += O2C_THREADS) ((uint32_t*)&hist[0][0])[i] = 0;
+        if (tid == 0) s_first = 0xFFFFFFFFu;
+        __syncthreads();
+        if (pos >= r1) break;
+        const uint32_t step = r1 - pos < O2C_THREADS ? r1 - pos : O2C_THREADS;
+        const bool active = tid < step;
+        uint32_t k = 0, ev = 0;
+        if (active) { k = K[pos + tid]; ev = V[pos + tid]; }
+        const uint32_t sym = k >> 24, pr = (k >> 16) & 255;
+        const bool hit = active && sym == pr, nonhit = active && sym != pr;
+        ssym[tid] = nonhit ? (uint16_t)sym : (uint16_t)0x100;
+        if (nonhit) atomicAdd((uint32_t*)&hist[w][0] + (sym >> 1), (sym & 1u) ? 0x10000u : 1u);
+        __syncthreads();
+        if (tid < 256) { uint32_t run = 0; for (int q = 0; q < 32; q++) { uint32_t h = hist[q][tid]; hist[q][tid] = (uint16_t)run; run += h; } }
+        __syncthreads();
+        {
+            uint32_t v[8], sum = 0;
+#pragma unroll
+            for (int q = 0; q < 8; q++) { v[q] = hist[w][lane * 8 + q]; sum += v[q]; }
+            uint32_t inc = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(FULLMASK, inc, d); if (lane >= d) inc += t; }
+            uint32_t run = inc - sum;
+#pragma unroll
+            for (int q = 0; q < 8; q++) { below[w][lane * 8 + q] = (uint16_t)run; run += v[q]; }
+        }
+        __syncwarp();
+        // ---- ranks inside the warp: earlier non-hit lanes with a smaller / the same symbol, or the predicted byte
+        const uint32_t code = nonhit ? sym : 0x1FFu;
+        uint32_t lt = 0, eq = 0, peq = 0;
+#pragma unroll 8
+        for (uint32_t j = 0; j < 32; j++) {
+            const uint32_t sj = __shfl_sync(FULLMASK, code, j);
+            if (j < lane) { lt += sj < sym; eq += sj == sym; peq += sj == pr; }
+        }
+        const uint32_t lanes_before = (1u << lane) - 1u;
+        const uint32_t b_nh = __ballot_sync(FULLMASK, nonhit);
+        uint32_t fs = 0, pf = 0;
+        if (active) { fs = cnt[sym] + hist[w][sym] + eq; pf = cnt[pr] + hist[w][pr] + peq; }
+        const bool esc = nonhit && fs == 0, two = nonhit && fs == 1;
+        const uint32_t b_es = __ballot_sync(FULLMASK, esc), b_tw = __ballot_sync(FULLMASK, two);
+        if (lane == 0) { wtot[0][w] = __popc(b_nh); wtot[1][w] = __popc(b_es); wtot[2][w] = __popc(b_tw); }
+        __syncthreads();
+        if (w < 3) {                                       // exclusive prefix of the three per-warp totals
+            uint32_t v = wtot[w][lane], inc = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(FULLMASK, inc, d); if (lane >= d) inc += t; }
+            wtot[w][lane] = inc - v;
+        }
+        __syncthreads();
+        const uint32_t A = wtot[0][w] + __popc(b_nh & lanes_before);          // non-hits before this event
+        const uint32_t ES = wtot[1][w] + __popc(b_es & lanes_before);         // escapes before
+        const uint32_t TW = wtot[2][w] + __popc(b_tw & lanes_before);         // 1->2 transitions before
+        const uint32_t f256 = s_f256 + (tid - A), f257 = s_f257 + ES - TW, body = s_body + A;
+        // ---- does this event's update rescale the table?
+        bool trig = false;
+        if (hit) trig = f256 + 1 > 250;
+        else if (esc) trig = f257 + 1 > 250;
+        else if (nonhit) trig = (fs + 1 > 250) || (fs == 1 && f257 == 0);
+        if (trig) atomicMin(&s_first, tid);
+        if (esc) esc_sym[ES] = (uint8_t)sym;
+        __syncthreads();
+        const uint32_t first = s_first;
+        const bool valid = active && tid <= first;
+        if (valid) {
+            const uint32_t sum = body + f256 + f257 - pf;
+            if (hit) T1[ev] = ppm_pack(body - pf, f256, sum, 0);
+            else if (!esc) T1[ev] = ppm_pack(cumt[sym] + below[w][sym] + lt - (sym >= pr ? pf : 0), fs, sum, 0);
+            else {
+                T1[ev] = ppm_pack(body + f256 - pf, f257, sum, 1);
+                uint32_t m[8];
+                if (trig) {
+                    // the escape update rescales BEFORE the mask is taken (cr-ppm.c:146-151): zero <=> count <= 1 now
+#pragma unroll
+                    for (int q = 0; q < 8; q++) m[q] = 0;
+                    for (uint32_t x = 0; x < 256; x++) {
+                        uint32_t c = cnt[x] + hist[w][x];
+                        for (uint32_t j = w * 32; j < tid && c < 2; j++) c += ssym[j] == x;
+                        if (c < 2) m[x >> 5] |= 1u << (x & 31);
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 8; q++) m[q] = zmask[q];
+                    for (uint32_t e = 0; e < ES; e++) { const uint32_t x = esc_sym[e]; m[x >> 5] &= ~(1u << (x & 31)); }
+                }
+                m[pr >> 5] &= ~(1u << (pr & 31));
+                EscRec* rec = esc_rec + atomicAdd(esc_count, 1u);
+                rec->e = ev; rec->info = (c16 & 0xff) | sym << 8;
+#pragma unroll
+                for (int q = 0; q < 8; q++) rec->incl[q] = m[q];
+            }
+        }
+        // ---- apply the step: counts of all valid non-hit events (an escape that rescaled does not enter its symbol)
+        if (valid && nonhit && !(esc && trig)) atomicAdd(&cnt[sym], 1u);
+        __syncthreads();
+        const uint32_t applied = first == 0xFFFFFFFFu ? step : first + 1;
+        // totals through the last applied event (thread `applied-1` owns them)
+        if (tid == applied - 1) {
+            const uint32_t hits_incl = (tid - A) + (hit ? 1 : 0);
+            if (first == 0xFFFFFFFFu) { s_f256 = s_f256 + hits_incl; s_f257 = f257 + (esc ? 1 : 0) - (two ? 1 : 0); }
+            else { s_f256 = (s_f256 + hits_incl + 1) >> 1; }                    // flag 256 -> (f+1)/2 (cr-o2model.c:67)
+        }
+        __syncthreads();
+        if (first != 0xFFFFFFFFu) {                                             // rescale: halve, count the ones (cr-o2model.c:55-68)
+            uint32_t one = 0;
+            if (tid < 256) { const uint32_t c = cnt[tid] >> 1; cnt[tid] = c; one = c == 1; }
+            const uint32_t ones = __syncthreads_count(one);
+            if (tid == 0) s_f257 = (1 + ones) & 255;
+        }
+        pos += applied;
+        __syncthreads();
+    }
+    if (tid < 256) row[tid] = (uint8_t)cnt[tid];
+    if (tid == 0) { row[256] = (uint8_t)s_f256; row[257] = (uint8_t)s_f257; }
+}
+
 // ------------------------------------------------------------------ o1 pass, one warp per ctx8
 // Escapes arrive sorted by (ctx8, time).  k_o1_gather first makes that order physical, so the pass streams its
 // input: 32 records per batch, loaded one batch ahead and staged through shared memory.
@@ -145,7 +316,7 @@ __global__ void k_o1_gather(const uint32_t* __restrict__ V, uint32_t n, const Es
 }
 // lane l holds o1 counts of symbols 8l..8l+7 in (a0, a1).
 __global__ void __launch_bounds__(128) k_o1_pass_warp(const uint64_t* __restrict__ K, uint32_t n, const uint32_t* __restrict__ info_s, const uint32_t* __restrict__ ord_s,
-                                                       const uint4* __restrict__ incl_s, PpmState st, uint64_t* __restrict__ T2) {
+                                                       const uint4* __restrict__ incl_s, PpmState st, uint64_t* __restrict__ T2, uint32_t hot_min) {
     __shared__ uint4 sincl[4][32][2];
     const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t c8 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -154,6 +325,7 @@ __global__ void __launch_bounds__(128) k_o1_pass_warp(const uint64_t* __restrict
     const uint32_t r0 = lower_bound_key(K, n, c8, keyof);
     if (r0 >= n || keyof(K[r0]) != c8) return;
     const uint32_t r1 = lower_bound_key(K, n, c8 + 1, keyof);
+    if (r1 - r0 >= hot_min) return;                       // taken by k_o1_pass_cta
     uint8_t* row = st.o1 + c8 * 256;
     uint2 av = ((const uint2*)row)[lane];
     uint32_t a0 = av.x, a1 = av.y;
@@ -196,6 +368,97 @@ __global__ void __launch_bounds__(128) k_o1_pass_warp(const uint64_t* __restrict
         __syncwarp();
     }
     ((uint2*)row)[lane] = make_uint2(a0, a1);
+}
+
+// ------------------------------------------------------------------ o1 pass for HOT ctx8 rows, one CTA per row
+// Same idea as k_o2_pass_cta: between two halvings an o1 row only counts occurrences, so for escape i
+//   count_x(i) = count_x(0) + #{j < i with symbol x},  and with its own exclusion mask M_i (from the o2 pass)
+//   sum_i = SUM_{x in M_i} (8 count_x(i) - 7),  cum_i = the same restricted to x < s_i      (cr-ppm.c:150-156).
+// Each thread evaluates its masked sums against a per-warp table "start-of-step count + occurrences in earlier
+// warps" and corrects for the earlier lanes of its own warp.  The first escape whose update halves the row
+// (++o1[c] >= 255, cr-ppm.c:91) ends the step.
+#define O1C_THREADS 512
+#define O1C_WARPS   (O1C_THREADS / 32)
+#define O1C_MIN     2048
+__global__ void __launch_bounds__(O1C_THREADS) k_o1_pass_cta(const uint64_t* __restrict__ K, uint32_t n, const uint32_t* __restrict__ info_s, const uint32_t* __restrict__ ord_s,
+                                                             const uint4* __restrict__ incl_s, PpmState st, uint64_t* __restrict__ T2) {
+    const uint32_t c8 = blockIdx.x;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    auto keyof = [](uint64_t k) { return (uint32_t)(k >> 32) & 0xffu; };
+    const uint32_t r0 = lower_bound_key(K, n, c8, keyof);
+    if (r0 >= n || keyof(K[r0]) != c8) return;
+    const uint32_t r1 = lower_bound_key(K, n, c8 + 1, keyof);
+    if (r1 - r0 < O1C_MIN) return;
+    __shared__ uint32_t cnt[256];
+    __shared__ __align__(4) uint16_t hist[O1C_WARPS][256];      // per-warp histogram -> exclusive prefix over warps
+    __shared__ uint16_t basew[O1C_WARPS][256];                   // 8 * (cnt + earlier warps) - 7
+    __shared__ uint32_t smask[O1C_THREADS][8];
+    __shared__ uint32_t s_first;
+    uint8_t* row = st.o1 + c8 * 256;
+    if (tid < 256) cnt[tid] = row[tid];
+    uint32_t pos = r0;
+    for (;;) {
+        for (uint32_t i = tid; i < O1C_WARPS * 128; i += O1C_THREADS) ((uint32_t*)&hist[0][0])[i] = 0;
+        if (tid == 0) s_first = 0xFFFFFFFFu;
+        __syncthreads();
+        if (pos >= r1) break;
+        const uint32_t step = r1 - pos < O1C_THREADS ? r1 - pos : O1C_THREADS;
+        const bool active = tid < step;
+        uint32_t sym = 0x1FF, ord = 0;
+        uint32_t m[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (active) {
+            const size_t x = pos + tid;
+            sym = (info_s[x] >> 8) & 255; ord = ord_s[x];
+            const uint4 a = incl_s[2 * x], b = incl_s[2 * x + 1];
+            m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w; m[4] = b.x; m[5] = b.y; m[6] = b.z; m[7] = b.w;
+            atomicAdd((uint32_t*)&hist[w][0] + (sym >> 1), (sym & 1u) ? 0x10000u : 1u);
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++) smask[tid][q] = m[q];
+        __syncthreads();
+        if (tid < 256) {
+            uint32_t run = 0;
+            for (int q = 0; q < O1C_WARPS; q++) { uint32_t h = hist[q][tid]; hist[q][tid] = (uint16_t)run; basew[q][tid] = (uint16_t)(8 * (cnt[tid] + run) - 7); run += h; }
+        }
+        __syncthreads();
+        // earlier lanes of this warp: same symbol / symbols inside my mask (and below my symbol)
+        uint32_t eq = 0, in_all = 0, in_lt = 0;
+#pragma unroll 8
+        for (uint32_t j = 0; j < 32; j++) {
+            const uint32_t sj = __shfl_sync(FULLMASK, sym, j);
+            if (j < lane && sj < 256) {
+                const uint32_t in = (smask[tid][sj >> 5] >> (sj & 31)) & 1u;
+                eq += sj == sym; in_all += in; in_lt += in & (uint32_t)(sj < sym);
+            }
+        }
+        uint32_t sum = 0, cum = 0, count_s = 0;
+        if (active) {
+#pragma unroll
+            for (uint32_t q = 0; q < 8; q++) {
+                const uint32_t mq = m[q];
+                for (uint32_t b = 0; b < 32; b++) {
+                    const uint32_t x = q * 32 + b;
+                    const uint32_t v = (mq >> b & 1u) ? (uint32_t)basew[w][x] : 0u;
+                    sum += v; cum += x < sym ? v : 0u;
+                }
+            }
+            sum += 8 * in_all; cum += 8 * in_lt;
+            count_s = cnt[sym] + hist[w][sym] + eq;
+            if (count_s + 1 >= 255) atomicMin(&s_first, tid);
+        }
+        __syncthreads();
+        const uint32_t first = s_first;
+        const bool valid = active && tid <= first;
+        if (valid) {
+            T2[ord] = ppm_pack(cum, 8 * count_s - 7, sum, 0);
+            atomicAdd(&cnt[sym], 1u);
+        }
+        __syncthreads();
+        if (first != 0xFFFFFFFFu && tid < 256) cnt[tid] -= cnt[tid] / 2;           // cr-ppm.c:92-94
+        pos += first == 0xFFFFFFFFu ? step : first + 1;
+        __syncthreads();
+    }
+    if (tid < 256) row[tid] = (uint8_t)cnt[tid];
 }
 
 // ------------------------------------------------------------------ order-0 side models, one warp
@@ -429,11 +692,17 @@ __global__ void __launch_bounds__(128) k_range_chain(const Tri* __restrict__ den
             uint4 t = stage[w][0];
             for (uint32_t j = 0; j < cnt; j++) {
                 const uint4 tn = stage[w][j + 1 < RC_BATCH ? j + 1 : j];
-                uint32_t q = __umulhi(range, t.w);                  // range / sum  (cr-rangecoder.c:61) ...
-                if (range - q * t.z >= t.z) q++;                     // ... corrected: magic = floor(2^32/sum)
-                uint32_t r = q * (t.y & 0x7FFFFFFFu);                // range *= frq (:64)
-                const uint32_t sh = r < (1u << 8) ? 3u : r < (1u << 16) ? 2u : r < (1u << 24) ? 1u : 0u;   // while (range < 2^24) range <<= 8 (:65-68)
-                range = r << (8 * sh);
+                // range / sum (cr-rangecoder.c:61): magic = floor(2^32/sum) gives q or q-1.  Both candidates for the new
+                // range are normalised speculatively so that the correction test runs beside, not inside, the chain.
+                const uint32_t q0 = __umulhi(range, t.w);
+                const uint32_t frq = t.y & 0x7FFFFFFFu;
+                const bool up = range - q0 * t.z >= t.z;
+                const uint32_t ra = q0 * frq, rb = ra + frq;                      // range *= frq (:64)
+                const uint32_t sa = __clz(ra) >> 3, sb = __clz(rb) >> 3;          // while (range < 2^24) range <<= 8 (:65-68)
+                const uint32_t na = ra << (8 * sa), nb2 = rb << (8 * sb);
+                const uint32_t q = up ? q0 + 1 : q0;
+                const uint32_t sh = up ? sb : sa;
+                range = up ? nb2 : na;
                 oq[w][j] = q; os[w][j] = sh;
                 t = tn;
             }

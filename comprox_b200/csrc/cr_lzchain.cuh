@@ -43,7 +43,7 @@ struct LzChain {
     DevBuf b_evctx, b_evsym, b_tokend, b_pred, b_T1, b_T2, b_TS, b_side;
     DevBuf b_escrec, b_esccount, b_k64a, b_k64b, b_ord, b_flag, b_escord;
     DevBuf b_lensym, b_lenpos, b_idxsym, b_idxpos;
-    DevBuf b_o1info, b_o1ord, b_o1incl, b_bounds;
+    DevBuf b_o1info, b_o1ord, b_o1incl, b_bounds, b_o3hot;
     DevBuf b_qm, b_shm, b_bm, b_qs, b_shs, b_bs, b_stot, b_dsum, b_lsm, b_lss, b_rsm, b_rss, b_fb;
     DevBuf b_dense, b_denseside, b_streams, b_rcres, b_rcout, b_copy, b_hdr;
     // ---- sizes of the last window (for the debug/trace fetch used by the tests)
@@ -66,7 +66,7 @@ struct LzChain {
         DevBuf* all[] = { &s_o3b, &s_o3c, &s_o2, &s_o1, &s_m0, &b_blocks, &b_segoff, &b_seglen, &b_hist, &b_esc1, &b_first, &b_ctxout,
             &b_k0, &b_k1, &b_v0, &b_v1, &b_ks0, &b_M, &b_S, &b_span, &b_tidx, &b_segs, &b_xt, &b_entry, &b_cnt, &b_scan,
             &b_evctx, &b_evsym, &b_tokend, &b_pred, &b_T1, &b_T2, &b_TS, &b_side, &b_escrec, &b_esccount, &b_k64a, &b_k64b, &b_ord,
-            &b_flag, &b_escord, &b_lensym, &b_lenpos, &b_idxsym, &b_idxpos, &b_o1info, &b_o1ord, &b_o1incl, &b_bounds, &b_qm, &b_shm, &b_bm, &b_qs, &b_shs, &b_bs, &b_stot, &b_dsum, &b_lsm, &b_lss, &b_rsm, &b_rss, &b_fb, &b_dense, &b_denseside, &b_streams, &b_rcres, &b_rcout, &b_copy, &b_hdr, &prims.temp };
+            &b_flag, &b_escord, &b_lensym, &b_lenpos, &b_idxsym, &b_idxpos, &b_o1info, &b_o1ord, &b_o1incl, &b_bounds, &b_o3hot, &b_qm, &b_shm, &b_bm, &b_qs, &b_shs, &b_bs, &b_stot, &b_dsum, &b_lsm, &b_lss, &b_rsm, &b_rss, &b_fb, &b_dense, &b_denseside, &b_streams, &b_rcres, &b_rcout, &b_copy, &b_hdr, &prims.temp };
         for (DevBuf* b : all) b->release();
         inited = false;
     }
@@ -258,7 +258,16 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
         const dim3 ge(cr_div_up(nev, 256)), te(256);
         CR_LAUNCH(k_o3_keys, ge, te, stream, b_evctx.as<uint32_t>(), b_evsym.as<uint8_t>(), nev, b_k0.as<uint32_t>(), b_v0.as<uint32_t>());
         CR_TRY(cr_sort_pairs<uint32_t>(prims, b_k0.as<uint32_t>(), b_k1.as<uint32_t>(), b_v0.as<uint32_t>(), b_v1.as<uint32_t>(), nev, 0, 22));
-        CR_LAUNCH(k_o3_pass, dim3(cr_div_up(nev, 128)), dim3(128), stream, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nev, st, b_pred.as<uint8_t>());
+#ifndef CRGPU_SIM
+        if (!scalar_models && hot_contexts) {
+            const uint32_t hot_cap = nev / O3_HANDOVER + 16;
+            CR_TRY(b_o3hot.reserve((size_t)hot_cap * sizeof(O3Hot) + 16));
+            CR_CUDA(cudaMemsetAsync(b_esccount.as<uint32_t>() + 1, 0, 4, stream));
+            CR_LAUNCH(k_o3_pass, dim3(cr_div_up(nev, 128)), dim3(128), stream, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nev, st, b_pred.as<uint8_t>(), b_o3hot.as<O3Hot>(), b_esccount.as<uint32_t>() + 1, hot_cap);
+            CR_LAUNCH(k_o3_hot, dim3(148), dim3(128), stream, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nev, st, b_pred.as<uint8_t>(), b_o3hot.as<O3Hot>(), b_esccount.as<uint32_t>() + 1, hot_cap);
+        } else
+#endif
+        CR_LAUNCH(k_o3_pass, dim3(cr_div_up(nev, 128)), dim3(128), stream, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nev, st, b_pred.as<uint8_t>(), (O3Hot*)nullptr, (uint32_t*)nullptr, 0u);
     timer.mark("o3");
         CR_LAUNCH(k_o2_keys, ge, te, stream, b_evctx.as<uint32_t>(), b_evsym.as<uint8_t>(), b_pred.as<uint8_t>(), nev, b_k0.as<uint32_t>(), b_v0.as<uint32_t>());
         CR_TRY(cr_sort_pairs<uint32_t>(prims, b_k0.as<uint32_t>(), b_k1.as<uint32_t>(), b_v0.as<uint32_t>(), b_v1.as<uint32_t>(), nev, 0, 16));

@@ -52,7 +52,10 @@ __global__ void k_o3_keys(const uint32_t* __restrict__ ev_ctx, const uint8_t* __
 
 // One thread per slot segment of the slot-sorted event list: replays ppm_update_o3 (cr-ppm.c:69-88) and
 // records the byte the predictor held BEFORE each event (predict_ch, cr-ppm.c:114).
-__global__ void k_o3_pass(const uint32_t* __restrict__ K, const uint32_t* __restrict__ V, uint32_t n, PpmState st, uint8_t* __restrict__ pred) {
+struct O3Hot { uint32_t slot, rank, byte, conf; };   // a long slot segment handed over to k_o3_hot (cr_warp.cuh)
+#define O3_HANDOVER 2048u
+__global__ void k_o3_pass(const uint32_t* __restrict__ K, const uint32_t* __restrict__ V, uint32_t n, PpmState st, uint8_t* __restrict__ pred,
+                          O3Hot* __restrict__ hot, uint32_t* __restrict__ hot_count, uint32_t hot_cap) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
     const uint32_t slot = K[r] & 0x3fffff;
@@ -60,6 +63,10 @@ __global__ void k_o3_pass(const uint32_t* __restrict__ K, const uint32_t* __rest
     uint32_t byte = st.o3_byte[slot], conf = st.o3_conf[slot];
     bool more = true;
     for (uint32_t i = r; more && i < n; i += 8) {
+        if (hot && i - r >= O3_HANDOVER) {             // long segment: a warp with staged input continues from here
+            uint32_t h = atomicAdd(hot_count, 1u);
+            if (h < hot_cap) { hot[h].slot = slot; hot[h].rank = i; hot[h].byte = byte; hot[h].conf = conf; return; }
+        }
         uint32_t kk[8], vv[8];                       // 8 independent loads in flight per round trip
 #pragma unroll
         for (int u = 0; u < 8; u++) { const uint32_t x = i + u < n ? i + u : n - 1; kk[u] = K[x]; vv[u] = V[x]; }

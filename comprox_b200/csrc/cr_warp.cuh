@@ -28,6 +28,55 @@ template <class K, class F> CR_D uint32_t lower_bound_key(const K* __restrict__ 
     return lo;
 }
 
+// ------------------------------------------------------------------ o3 pass, long slot segments
+// k_o3_pass (one thread per slot) hands segments longer than O3_HANDOVER events to this kernel: one warp per
+// segment, keys staged 64 at a time through shared memory one batch ahead, lane 0 runs the 12-bit state machine
+// (ppm_update_o3, cr-ppm.c:69-88), all lanes scatter the predicted bytes.
+__global__ void __launch_bounds__(128) k_o3_hot(const uint32_t* __restrict__ K, const uint32_t* __restrict__ V, uint32_t n, PpmState st, uint8_t* __restrict__ pred,
+                                                 const O3Hot* __restrict__ hot, const uint32_t* __restrict__ hot_count, uint32_t hot_cap) {
+    __shared__ uint32_t sk[4][64];
+    __shared__ uint8_t sp[4][64];
+    __shared__ uint32_t s_cnt[4];
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
+    uint32_t total = *hot_count; if (total > hot_cap) total = hot_cap;
+    for (uint32_t e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < total; e += nwarps) {
+        const O3Hot H = hot[e];
+        uint32_t byte = H.byte, conf = H.conf;
+        uint32_t k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu, v0 = 0, v1 = 0;
+        if (H.rank + lane < n) { k0 = K[H.rank + lane]; v0 = V[H.rank + lane]; }
+        if (H.rank + 32 + lane < n) { k1 = K[H.rank + 32 + lane]; v1 = V[H.rank + 32 + lane]; }
+        for (uint32_t base = H.rank;; base += 64) {
+            const uint32_t c0 = v0, c1 = v1;
+            sk[w][lane] = k0; sk[w][lane + 32] = k1;
+            __syncwarp();
+            const uint32_t nb = base + 64;
+            k0 = k1 = 0xFFFFFFFFu;
+            if (nb + lane < n) { k0 = K[nb + lane]; v0 = V[nb + lane]; }
+            if (nb + 32 + lane < n) { k1 = K[nb + 32 + lane]; v1 = V[nb + 32 + lane]; }
+            if (lane == 0) {
+                uint32_t j = 0;
+                for (; j < 64; j++) {
+                    const uint32_t k = sk[w][j];
+                    if (base + j >= n || (k & 0x3fffff) != H.slot) break;
+                    const uint32_t sym = k >> 24;
+                    sp[w][j] = (uint8_t)byte;
+                    if (sym == byte) conf += conf < 15;
+                    else { conf = (conf > 1) + (conf > 2) + (conf > 4) + (conf > 8); if (conf == 0) { byte = sym; conf = 1; } }
+                }
+                s_cnt[w] = j;
+            }
+            __syncwarp();
+            const uint32_t cnt = s_cnt[w];
+            if (lane < cnt) pred[c0] = sp[w][lane];
+            if (lane + 32 < cnt) pred[c1] = sp[w][lane + 32];
+            __syncwarp();
+            if (cnt < 64) break;
+        }
+        if (lane == 0) { st.o3_byte[H.slot] = (uint8_t)byte; st.o3_conf[H.slot] = (uint8_t)conf; }
+    }
+}
+
 // bounds[c] = first sorted rank whose 16-bit context is >= c (c = 0..65536): one binary search per context, done once
 __global__ void k_o2_bounds(const uint32_t* __restrict__ K, uint32_t n, uint32_t* __restrict__ bounds) {
     uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -697,9 +746,12 @@ __global__ void __launch_bounds__(128) k_range_chain(const Tri* __restrict__ den
                 const uint32_t q0 = __umulhi(range, t.w);
                 const uint32_t frq = t.y & 0x7FFFFFFFu;
                 const bool up = range - q0 * t.z >= t.z;
-                const uint32_t ra = q0 * frq, rb = ra + frq;                      // range *= frq (:64)
-                const uint32_t sa = __clz(ra) >> 3, sb = __clz(rb) >> 3;          // while (range < 2^24) range <<= 8 (:65-68)
-                const uint32_t na = ra << (8 * sa), nb2 = rb << (8 * sb);
+                const uint32_t ra = q0 * frq, rb = q0 * frq + frq;                // range *= frq (:64), for q0 and q0+1
+                // while (range < 2^24) range <<= 8 (:65-68) as a compare/select tree (no FLO on the dependent chain)
+                const uint32_t na = ra < (1u << 16) ? (ra < (1u << 8) ? ra << 24 : ra << 16) : (ra < (1u << 24) ? ra << 8 : ra);
+                const uint32_t nb2 = rb < (1u << 16) ? (rb < (1u << 8) ? rb << 24 : rb << 16) : (rb < (1u << 24) ? rb << 8 : rb);
+                const uint32_t sa = (ra < (1u << 24)) + (ra < (1u << 16)) + (ra < (1u << 8));
+                const uint32_t sb = (rb < (1u << 24)) + (rb < (1u << 16)) + (rb < (1u << 8));
                 const uint32_t q = up ? q0 + 1 : q0;
                 const uint32_t sh = up ? sb : sa;
                 range = up ? nb2 : na;

@@ -43,13 +43,14 @@ struct LzChain {
     DevBuf b_evctx, b_evsym, b_tokend, b_pred, b_T1, b_T2, b_TS, b_side;
     DevBuf b_escrec, b_esccount, b_k64a, b_k64b, b_ord, b_flag, b_escord;
     DevBuf b_lensym, b_lenpos, b_idxsym, b_idxpos;
-    DevBuf b_o1info, b_o1ord, b_o1incl, b_bounds, b_o3hot;
+    DevBuf b_o1info, b_o1ord, b_o1incl, b_bounds, b_o3hot, b_cinm, b_cins, b_segstart, b_segkey;
     DevBuf b_qm, b_shm, b_bm, b_qs, b_shs, b_bs, b_stot, b_dsum, b_lsm, b_lss, b_rsm, b_rss, b_fb;
     DevBuf b_dense, b_denseside, b_streams, b_rcres, b_rcout, b_copy, b_hdr;
     // ---- sizes of the last window (for the debug/trace fetch used by the tests)
     uint32_t last_nev = 0, last_nside = 0, last_nesc = 0, last_nent = 0;
     size_t last_dtotal = 0;
     StageTimer timer;
+    int rc_variant = 4;            // range-chain formulation (cr_warp.cuh: k_range_chain<1|2|3>)
     bool hot_contexts = true;      // hot o2 contexts run the rank-based CTA kernel (k_o2_pass_cta)
     bool scalar_models = false;   // GPU A/B switch: run the scalar (simulation-checked) model/coder kernels
 
@@ -66,7 +67,7 @@ struct LzChain {
         DevBuf* all[] = { &s_o3b, &s_o3c, &s_o2, &s_o1, &s_m0, &b_blocks, &b_segoff, &b_seglen, &b_hist, &b_esc1, &b_first, &b_ctxout,
             &b_k0, &b_k1, &b_v0, &b_v1, &b_ks0, &b_M, &b_S, &b_span, &b_tidx, &b_segs, &b_xt, &b_entry, &b_cnt, &b_scan,
             &b_evctx, &b_evsym, &b_tokend, &b_pred, &b_T1, &b_T2, &b_TS, &b_side, &b_escrec, &b_esccount, &b_k64a, &b_k64b, &b_ord,
-            &b_flag, &b_escord, &b_lensym, &b_lenpos, &b_idxsym, &b_idxpos, &b_o1info, &b_o1ord, &b_o1incl, &b_bounds, &b_o3hot, &b_qm, &b_shm, &b_bm, &b_qs, &b_shs, &b_bs, &b_stot, &b_dsum, &b_lsm, &b_lss, &b_rsm, &b_rss, &b_fb, &b_dense, &b_denseside, &b_streams, &b_rcres, &b_rcout, &b_copy, &b_hdr, &prims.temp };
+            &b_flag, &b_escord, &b_lensym, &b_lenpos, &b_idxsym, &b_idxpos, &b_o1info, &b_o1ord, &b_o1incl, &b_bounds, &b_o3hot, &b_cinm, &b_cins, &b_segstart, &b_segkey, &b_qm, &b_shm, &b_bm, &b_qs, &b_shs, &b_bs, &b_stot, &b_dsum, &b_lsm, &b_lss, &b_rsm, &b_rss, &b_fb, &b_dense, &b_denseside, &b_streams, &b_rcres, &b_rcout, &b_copy, &b_hdr, &prims.temp };
         for (DevBuf* b : all) b->release();
         inited = false;
     }
@@ -263,7 +264,20 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
             const uint32_t hot_cap = nev / O3_HANDOVER + 16;
             CR_TRY(b_o3hot.reserve((size_t)hot_cap * sizeof(O3Hot) + 16));
             CR_CUDA(cudaMemsetAsync(b_esccount.as<uint32_t>() + 1, 0, 4, stream));
-            CR_LAUNCH(k_o3_pass, dim3(cr_div_up(nev, 128)), dim3(128), stream, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nev, st, b_pred.as<uint8_t>(), b_o3hot.as<O3Hot>(), b_esccount.as<uint32_t>() + 1, hot_cap);
+            // list the slot segments, longest first
+            CR_TRY(b_flag.reserve((size_t)(nev + 1) * 4 + 16)); CR_TRY(b_escord.reserve((size_t)(nev + 1) * 4 + 16));
+            CR_LAUNCH(k_o3_headflags, dim3(cr_div_up(nev + 1, 256)), dim3(256), stream, b_k1.as<uint32_t>(), nev, b_flag.as<uint32_t>());
+            CR_TRY(cr_exclusive_sum(prims, b_flag.as<uint32_t>(), b_escord.as<uint32_t>(), nev + 1));
+            std::vector<uint32_t> hseg;
+            CR_TRY(download(hseg, b_escord.as<uint32_t>() + nev, 1));
+            const uint32_t nseg = hseg[0];
+            CR_TRY(b_segstart.reserve((size_t)(nseg + 1) * 4 + 16)); CR_TRY(b_segkey.reserve((size_t)nseg * 16 + 64));
+            uint32_t* sk0 = b_segkey.as<uint32_t>(); uint32_t* sk1 = sk0 + nseg; uint32_t* sv0 = sk1 + nseg; uint32_t* sv1 = sv0 + nseg;
+            CR_LAUNCH(k_o3_segstarts, dim3(cr_div_up(nev + 1, 256)), dim3(256), stream, b_flag.as<uint32_t>(), b_escord.as<uint32_t>(), nev, b_segstart.as<uint32_t>());
+            CR_LAUNCH(k_o3_seglen_keys, dim3(cr_div_up(nseg, 256)), dim3(256), stream, b_segstart.as<uint32_t>(), nseg, sk0, sv0);
+            CR_TRY(cr_sort_pairs<uint32_t>(prims, sk0, sk1, sv0, sv1, nseg, 0, 32));
+            CR_LAUNCH(k_o3_pass_sorted, dim3(cr_div_up(nseg, 128)), dim3(128), stream, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nev, b_segstart.as<uint32_t>(), sv1, nseg, st,
+                      b_pred.as<uint8_t>(), b_o3hot.as<O3Hot>(), b_esccount.as<uint32_t>() + 1, hot_cap);
             CR_LAUNCH(k_o3_hot, dim3(148), dim3(128), stream, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nev, st, b_pred.as<uint8_t>(), b_o3hot.as<O3Hot>(), b_esccount.as<uint32_t>() + 1, hot_cap);
         } else
 #endif
@@ -361,8 +375,22 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
         CR_TRY(b_stot.reserve((size_t)nstr * sizeof(StreamTotals) + 16));
         CR_CUDA(cudaMemsetAsync(b_shm.as<uint32_t>() + ntm, 0, 4, stream));
         CR_CUDA(cudaMemsetAsync(b_shs.as<uint32_t>() + nts, 0, 4, stream));
-        CR_LAUNCH(k_range_chain, dim3(cr_div_up((size_t)nstr * 32, 128)), dim3(128), stream, b_dense.as<Tri>(), b_denseside.as<Tri>(), b_escord.as<uint32_t>(),
-                  b_streams.as<RcStream>(), nstr, b_qm.as<uint32_t>(), b_shm.as<uint32_t>(), b_qs.as<uint32_t>(), b_shs.as<uint32_t>());
+        const dim3 gchain(cr_div_up((size_t)nstr * 32, 128));
+        if (rc_variant == 1) {
+            CR_LAUNCH(k_range_chain<1>, gchain, dim3(128), stream, (const uint4*)b_dense.p, (const uint4*)b_denseside.p, b_escord.as<uint32_t>(),
+                      b_streams.as<RcStream>(), nstr, b_qm.as<uint32_t>(), b_shm.as<uint32_t>(), b_qs.as<uint32_t>(), b_shs.as<uint32_t>());
+        } else {
+            CR_TRY(b_cinm.reserve((ntm + 1) * 16 + 16)); CR_TRY(b_cins.reserve((nts + 1) * 16 + 16));
+            if (ntm) CR_LAUNCH(k_chain_inputs, dim3(cr_div_up(ntm, 256)), dim3(256), stream, b_dense.as<Tri>(), (uint64_t)ntm, b_cinm.as<uint4>());
+            if (nts) CR_LAUNCH(k_chain_inputs, dim3(cr_div_up(nts, 256)), dim3(256), stream, b_denseside.as<Tri>(), (uint64_t)nts, b_cins.as<uint4>());
+            timer.mark("expand");
+            if (rc_variant == 2) CR_LAUNCH(k_range_chain<2>, gchain, dim3(128), stream, b_cinm.as<uint4>(), b_cins.as<uint4>(), b_escord.as<uint32_t>(),
+                      b_streams.as<RcStream>(), nstr, b_qm.as<uint32_t>(), b_shm.as<uint32_t>(), b_qs.as<uint32_t>(), b_shs.as<uint32_t>());
+            else if (rc_variant == 4) CR_LAUNCH(k_range_chain<4>, gchain, dim3(128), stream, b_cinm.as<uint4>(), b_cins.as<uint4>(), b_escord.as<uint32_t>(),
+                      b_streams.as<RcStream>(), nstr, b_qm.as<uint32_t>(), b_shm.as<uint32_t>(), b_qs.as<uint32_t>(), b_shs.as<uint32_t>());
+            else CR_LAUNCH(k_range_chain<3>, gchain, dim3(128), stream, b_cinm.as<uint4>(), b_cins.as<uint4>(), b_escord.as<uint32_t>(),
+                      b_streams.as<RcStream>(), nstr, b_qm.as<uint32_t>(), b_shm.as<uint32_t>(), b_qs.as<uint32_t>(), b_shs.as<uint32_t>());
+        }
         timer.mark("range_chain");
         CR_TRY(cr_exclusive_sum(prims, b_shm.as<uint32_t>(), b_bm.as<uint32_t>(), ntm + 1));
         CR_TRY(cr_exclusive_sum(prims, b_shs.as<uint32_t>(), b_bs.as<uint32_t>(), nts + 1));

@@ -28,6 +28,57 @@ template <class K, class F> CR_D uint32_t lower_bound_key(const K* __restrict__ 
     return lo;
 }
 
+// ------------------------------------------------------------------ o3 pass, balanced over slot segments
+// k_o3_pass (cr_ppm.cuh) gives one thread to every sorted rank and lets segment heads walk their segment: a warp
+// then runs as long as its longest segment.  Here the segments are listed, ordered by length (longest first) and
+// given one thread each, so the lanes of a warp have equally long walks; segments of O3_HANDOVER events or more
+// go to k_o3_hot.
+__global__ void k_o3_headflags(const uint32_t* __restrict__ K, uint32_t n, uint32_t* __restrict__ flag) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n) return;
+    flag[r] = (r < n && (r == 0 || (K[r - 1] & 0x3fffff) != (K[r] & 0x3fffff))) ? 1u : 0u;
+}
+__global__ void k_o3_segstarts(const uint32_t* __restrict__ flag, const uint32_t* __restrict__ hidx, uint32_t n, uint32_t* __restrict__ seg_start) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n) return;
+    if (r == n) seg_start[hidx[n]] = n;                 // sentinel after the last segment
+    else if (flag[r]) seg_start[hidx[r]] = r;
+}
+__global__ void k_o3_seglen_keys(const uint32_t* __restrict__ seg_start, uint32_t nseg, uint32_t* __restrict__ key, uint32_t* __restrict__ val) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nseg) return;
+    key[i] = 0xFFFFFFFFu - (seg_start[i + 1] - seg_start[i]);
+    val[i] = i;
+}
+__global__ void k_o3_pass_sorted(const uint32_t* __restrict__ K, const uint32_t* __restrict__ V, uint32_t n, const uint32_t* __restrict__ seg_start,
+                                 const uint32_t* __restrict__ order, uint32_t nseg, PpmState st, uint8_t* __restrict__ pred,
+                                 O3Hot* __restrict__ hot, uint32_t* __restrict__ hot_count, uint32_t hot_cap) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nseg) return;
+    const uint32_t seg = order[t];
+    const uint32_t r0 = seg_start[seg], r1 = seg_start[seg + 1];
+    const uint32_t slot = K[r0] & 0x3fffff;
+    uint32_t byte = st.o3_byte[slot], conf = st.o3_conf[slot];
+    if (r1 - r0 >= O3_HANDOVER) {
+        uint32_t h = atomicAdd(hot_count, 1u);
+        if (h < hot_cap) { hot[h].slot = slot; hot[h].rank = r0; hot[h].byte = byte; hot[h].conf = conf; return; }
+    }
+    for (uint32_t i = r0; i < r1; i += 8) {
+        uint32_t kk[8], vv[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) { const uint32_t x = i + u < r1 ? i + u : r1 - 1; kk[u] = K[x]; vv[u] = V[x]; }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            if (i + u >= r1) break;
+            const uint32_t sym = kk[u] >> 24;
+            pred[vv[u]] = (uint8_t)byte;
+            if (sym == byte) conf += conf < 15;
+            else { conf = (conf > 1) + (conf > 2) + (conf > 4) + (conf > 8); if (conf == 0) { byte = sym; conf = 1; } }
+        }
+    }
+    st.o3_byte[slot] = (uint8_t)byte; st.o3_conf[slot] = (uint8_t)conf;
+}
+
 // ------------------------------------------------------------------ o3 pass, long slot segments
 // k_o3_pass (one thread per slot) hands segments longer than O3_HANDOVER events to this kernel: one warp per
 // segment, keys staged 64 at a time through shared memory one batch ahead, lane 0 runs the 12-bit state machine
@@ -712,7 +763,24 @@ __global__ void __launch_bounds__(128) k_range_encode_warp(const Tri* __restrict
 // far.  So the only truly serial part is the range chain (k_range_chain: ~8 dependent integer ops per symbol);
 // the output bytes are the big-number sum  sum_n a_n * 256^-(B_n+4)  which k_low_scatter / k_low_carry evaluate
 // for all symbols and all output bytes in parallel (carry resolution by look-right over 0xFF runs).
-__global__ void __launch_bounds__(128) k_range_chain(const Tri* __restrict__ dense_main, const Tri* __restrict__ dense_side, const uint32_t* __restrict__ escord,
+// chain input: {frq, M_lo, M_hi, 0} with M = floor(2^63 / sum) + 1, for which  (n * M) >> 63 == n / sum  exactly
+// for every n < 2^32 and sum < 2^31 (error term n/2^63 < 1/sum).
+__global__ void k_chain_inputs(const Tri* __restrict__ dense, uint64_t n, uint4* __restrict__ cin) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Tri t = dense[i];
+    const unsigned long long M = (1ull << 63) / t.sum + 1ull;
+    cin[i] = make_uint4(t.frq & 0x7FFFFFFFu, (uint32_t)M, (uint32_t)(M >> 32), t.sum);
+}
+
+// VARIANT 1: 32-bit reciprocal + correction, both candidates normalised speculatively (input: Tri)
+// VARIANT 2: exact 64-bit reciprocal, FLO-based normalisation                          (input: k_chain_inputs)
+// VARIANT 3: exact 64-bit reciprocal, one compare/select for the common 0/1-byte shift, loop for the rest
+// VARIANT 4: as 2, but the range is never normalised explicitly: with r = q*frq (un-normalised) and k = leading zero
+//            bytes of r, the next quotient is ((r << 8k) * M) >> 63 == (r * M) >> (63 - 8k), so the multiply runs
+//            beside the leading-zero count instead of behind it (the count was ~1/4 of the dependent chain).
+template <int VARIANT>
+__global__ void __launch_bounds__(128) k_range_chain(const uint4* __restrict__ in_main, const uint4* __restrict__ in_side, const uint32_t* __restrict__ escord,
                                                       const RcStream* __restrict__ streams, uint32_t nstreams,
                                                       uint32_t* __restrict__ q_main, uint32_t* __restrict__ sh_main, uint32_t* __restrict__ q_side, uint32_t* __restrict__ sh_side) {
     __shared__ uint4 stage[4][RC_BATCH];
@@ -721,13 +789,14 @@ __global__ void __launch_bounds__(128) k_range_chain(const Tri* __restrict__ den
     const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (s >= nstreams) return;
     const RcStream S = streams[s];
-    const uint4* tri = (const uint4*)(S.is_main ? dense_main : dense_side);
+    const uint4* tri = S.is_main ? in_main : in_side;
     uint32_t* qo = S.is_main ? q_main : q_side;
     uint32_t* so = S.is_main ? sh_main : sh_side;
     size_t i0 = S.ev_begin, i1 = S.ev_end;
     if (S.is_main) { i0 += escord[S.ev_begin]; i1 += escord[S.ev_end]; }
     uint32_t range = 0xFFFFFFFFu;
-    uint4 r0 = make_uint4(0, 1, 1, 0), r1 = r0;
+    uint32_t msb = 31;                                   // VARIANT 4: index of the top set bit of the un-normalised range
+    uint4 r0 = make_uint4(1, 1, 1, 1), r1 = r0;
     if (i0 + lane < i1) r0 = tri[i0 + lane];
     if (i0 + 32 + lane < i1) r1 = tri[i0 + 32 + lane];
     for (size_t base = i0; base < i1; base += RC_BATCH) {
@@ -741,20 +810,37 @@ __global__ void __launch_bounds__(128) k_range_chain(const Tri* __restrict__ den
             uint4 t = stage[w][0];
             for (uint32_t j = 0; j < cnt; j++) {
                 const uint4 tn = stage[w][j + 1 < RC_BATCH ? j + 1 : j];
-                // range / sum (cr-rangecoder.c:61): magic = floor(2^32/sum) gives q or q-1.  Both candidates for the new
-                // range are normalised speculatively so that the correction test runs beside, not inside, the chain.
-                const uint32_t q0 = __umulhi(range, t.w);
-                const uint32_t frq = t.y & 0x7FFFFFFFu;
-                const bool up = range - q0 * t.z >= t.z;
-                const uint32_t ra = q0 * frq, rb = q0 * frq + frq;                // range *= frq (:64), for q0 and q0+1
-                // while (range < 2^24) range <<= 8 (:65-68) as a compare/select tree (no FLO on the dependent chain)
-                const uint32_t na = ra < (1u << 16) ? (ra < (1u << 8) ? ra << 24 : ra << 16) : (ra < (1u << 24) ? ra << 8 : ra);
-                const uint32_t nb2 = rb < (1u << 16) ? (rb < (1u << 8) ? rb << 24 : rb << 16) : (rb < (1u << 24) ? rb << 8 : rb);
-                const uint32_t sa = (ra < (1u << 24)) + (ra < (1u << 16)) + (ra < (1u << 8));
-                const uint32_t sb = (rb < (1u << 24)) + (rb < (1u << 16)) + (rb < (1u << 8));
-                const uint32_t q = up ? q0 + 1 : q0;
-                const uint32_t sh = up ? sb : sa;
-                range = up ? nb2 : na;
+                uint32_t q, sh;
+                if (VARIANT == 1) {
+                    // Tri: x = cum, y = frq|flag, z = sum, w = floor(2^32/sum): umulhi gives q or q-1 (cr-rangecoder.c:61)
+                    const uint32_t q0 = __umulhi(range, t.w);
+                    const uint32_t frq = t.y & 0x7FFFFFFFu;
+                    const bool up = range - q0 * t.z >= t.z;
+                    const uint32_t ra = q0 * frq, rb = ra + frq;                  // range *= frq (:64)
+                    const uint32_t sa = __clz(ra) >> 3, sb = __clz(rb) >> 3;      // while (range < 2^24) range <<= 8 (:65-68)
+                    const uint32_t na = ra << (8 * sa), nb2 = rb << (8 * sb);
+                    q = up ? q0 + 1 : q0; sh = up ? sb : sa; range = up ? nb2 : na;
+                } else if (VARIANT == 4) {
+                    const uint32_t ahi = __umulhi(range, t.y);
+                    const unsigned long long S2 = (unsigned long long)range * t.z + ahi;      // (range * M) >> 32
+                    q = (uint32_t)(S2 >> ((msb & 24u) | 7u));                               // >> (31 - 8 * leading zero bytes)
+                    range = q * t.x;                                                        // range *= frq, left un-normalised
+                    asm("bfind.u32 %0, %1;" : "=r"(msb) : "r"(range));
+                    sh = 3u - (msb >> 3);                                                   // renormalisation shifts after this symbol
+                } else {
+                    // x = frq, (y, z) = M: q = (range * M) >> 63, exact
+                    const uint32_t ahi = __umulhi(range, t.y);
+                    const unsigned long long S2 = (unsigned long long)range * t.z + ahi;
+                    q = (uint32_t)(S2 >> 31);
+                    uint32_t r = q * t.x;
+                    if (VARIANT == 2) { sh = __clz(r) >> 3; range = r << (8 * sh); }
+                    else {
+                        sh = r < (1u << 24);
+                        r = sh ? r << 8 : r;
+                        while (r < (1u << 24)) { r <<= 8; sh++; }
+                        range = r;
+                    }
+                }
                 oq[w][j] = q; os[w][j] = sh;
                 t = tn;
             }

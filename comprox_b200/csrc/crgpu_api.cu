@@ -136,6 +136,7 @@ extern "C" int crgpu_set_option(crgpu_handle* h, const char* name, int64_t value
     if (!h || !name) return CRGPU_ERR_ARG;
     std::string n(name);
     if (n == "scalar_models") { h->chain.scalar_models = value != 0; return CRGPU_OK; }
+    if (n == "rc_variant") { if (value < 1 || value > 4) return CRGPU_ERR_ARG; h->chain.rc_variant = (int)value; return CRGPU_OK; }
     if (n == "hot_contexts") { h->chain.hot_contexts = value != 0; return CRGPU_OK; }
     return CRGPU_ERR_ARG;
 }

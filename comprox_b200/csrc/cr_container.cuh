@@ -25,14 +25,14 @@ struct Compressor {
     cudaStream_t stream = 0;
     DevBuf d_raw, d_D, d_out, d_dic;
     DevBuf t_key, t_count, t_first, t_stats, t_entries;          // dicpick table
-    DevBuf d_trie_next, d_trie_id;
+    DevBuf d_trie_key, d_trie_val, d_trie_id;
     DevBuf b_subs, b_hist, b_esc10, b_escmask, b_span, b_hit, b_segs, b_xt, b_entry, b_cnt, b_scan, b_chunk0, b_hdr, b_copy, b_segoff, b_seglen;
     HdTrie trie;
     FilterHost filt;
     const uint8_t* staged_ptr = nullptr; uint64_t staged_n = 0;
 
     void release() {
-        DevBuf* all[] = { &d_raw, &d_D, &d_out, &d_dic, &t_key, &t_count, &t_first, &t_stats, &t_entries, &d_trie_next, &d_trie_id, &b_subs, &b_hist,
+        DevBuf* all[] = { &d_raw, &d_D, &d_out, &d_dic, &t_key, &t_count, &t_first, &t_stats, &t_entries, &d_trie_key, &d_trie_val, &d_trie_id, &b_subs, &b_hist,
                           &b_esc10, &b_escmask, &b_span, &b_hit, &b_segs, &b_xt, &b_entry, &b_cnt, &b_scan, &b_chunk0, &b_hdr, &b_copy, &b_segoff, &b_seglen };
         for (DevBuf* b : all) b->release();
         filt.release();
@@ -73,6 +73,7 @@ inline int Compressor::dicpick(const uint8_t* h_in, const uint8_t* d_in, uint64_
         CR_LAUNCH(k_dp_verify, dim3(cr_div_up(x1 - x0, 256)), dim3(256), stream, d_in, n, x0, x1, T);
     }
     CR_LAUNCH(k_dp_collect, dim3(DP_SLOTS / 256), dim3(256), stream, T, t_entries.as<DpEntry>(), DP_MAXWORDS);
+    chain->timer.mark("dp_kernels");
     std::vector<uint32_t> stats;
     CR_TRY(download(stats, t_stats.p, 4));
     if (stats[1] & 1u) return CRGPU_ERR_VOCAB_OVERFLOW;
@@ -82,12 +83,13 @@ inline int Compressor::dicpick(const uint8_t* h_in, const uint8_t* d_in, uint64_
     std::vector<HdWord> words(ent.size());
     for (size_t i = 0; i < ent.size(); i++) { words[i].w = hd_word_at(h_in, n, ent[i].first); words[i].count = ent[i].count; }
     text = hd_dictionary_text(words);
+    chain->timer.mark("dp_host");
     return CRGPU_OK;
 }
 
 inline int Compressor::load_dictionary(const std::string& text) {
     trie.load(text.c_str());
-    CR_TRY(upload(d_trie_next, trie.next)); CR_TRY(upload(d_trie_id, trie.id));
+    CR_TRY(upload(d_trie_key, trie.ekey)); CR_TRY(upload(d_trie_val, trie.eval)); CR_TRY(upload(d_trie_id, trie.id));
     return CRGPU_OK;
 }
 
@@ -134,7 +136,7 @@ inline int Compressor::dict_encode_window(const uint8_t* d_rawwin, const std::ve
     for (uint32_t s = 0; s < nsub; s++) chunk0[s] = segs[s].chunk0;
     chunk0[nsub] = nchunk;
     std::vector<uint32_t> hscan(nchunk + 1, 0);
-    DcTrie T = { d_trie_next.as<int32_t>(), d_trie_id.as<int32_t>(), trie.nentries, trie.level1() };
+    DcTrie T = { d_trie_key.as<uint32_t>(), d_trie_val.as<uint32_t>(), d_trie_id.as<int32_t>(), trie.mask, trie.nentries, trie.level1() };
     if (nsub) {
         CR_TRY(upload(b_subs, subs)); CR_TRY(upload(b_segs, segs)); CR_TRY(upload(b_chunk0, chunk0));
         CR_TRY(b_span.reserve(rawtotal + 16)); CR_TRY(b_hit.reserve(rawtotal * 4 + 16));
@@ -226,7 +228,6 @@ inline int Compressor::compress(const CrConfig& cfg, const uint8_t* in, uint64_t
     std::string text;
     tm.begin(stream);
     CR_TRY(dicpick(in, d_raw.as<uint8_t>(), n, text));
-    tm.mark("dicpick");
     if (tm.enabled) { CR_CUDA(cudaStreamSynchronize(stream)); tm.finish(); }
     CR_TRY(load_dictionary(text));
     std::vector<uint8_t> lcp = hd_lcp_encode(text);

@@ -102,7 +102,12 @@ __global__ void k_dp_collect(DpTable T, DpEntry* __restrict__ out, uint32_t cap)
 // ------------------------------------------------------------------ diccode
 #define DC_SUB 1000000u                  // sub-chunk size (cr-diccode.c:177-180)
 
-struct DcTrie { const int32_t* next; const int32_t* id; int32_t nentries; int32_t level1; };
+struct DcTrie { const uint32_t* ekey; const uint32_t* eval; const int32_t* id; uint32_t mask; int32_t nentries; int32_t level1; };
+// child of `node` along byte `ch` (0 = none); same table as HdTrie (cr_hostdict.h)
+CR_D uint32_t dc_child(const DcTrie& T, uint32_t node, uint32_t ch) {
+    const uint32_t key = ((node << 7) | ch) + 1;
+    for (uint32_t h = (key * 2654435761u) >> 8;; h++) { const uint32_t k = T.ekey[h & T.mask]; if (k == key) return T.eval[h & T.mask]; if (k == 0) return 0; }
+}
 struct DcSub {                           // one sub-chunk = one chain segment
     uint64_t off;                        // offset of the sub-chunk in the raw window
     uint32_t size;
@@ -123,8 +128,8 @@ __global__ void k_dc_spans(const uint8_t* __restrict__ raw, const DcSub* __restr
     const uint8_t* d = raw + S.off;
     uint32_t sp = 1;
     if (i > 0 && i + 40 < S.size && cr_is_alpha(d[i]) && !cr_is_alpha(d[i - 1])) {
-        uint32_t j = i; int32_t node = 0;
-        while (d[j] < 128 && (node = T.next[(size_t)node * 128 + d[j]]) != 0 && T.id[node] == -1) j++;
+        uint32_t j = i, node = 0;
+        while (d[j] < 128 && (node = dc_child(T, node, d[j])) != 0 && T.id[node] == -1) j++;
         if (d[j] < 128 && node != 0) {
             uint32_t rev = (uint32_t)cr_is_upper(d[i]) ^ (uint32_t)dc_sentence_start(d, i);
             uint32_t tail = d[j] == ':' ? 4 : d[j] == ';' ? 3 : d[j] == ',' ? 2 : d[j] == '.' ? 1 : 0;

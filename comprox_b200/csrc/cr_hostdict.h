@@ -66,42 +66,59 @@ static inline std::vector<uint8_t> hd_lcp_encode(const std::string& t) {
 
 // src/cr-diccode.c:47-120: entries get a trailing blank when they end in a letter; 128-ary trie with the
 // root's upper-case links ('A'..'Y', sic) and the ". , : ;" aliases of every blank edge.
+// The reference stores 128 child slots per node (516 B/node, tens of MB).  Only the edges that exist are kept
+// here, in an open-addressing table keyed by (parent node, byte): a few MB that stay resident in L2 and are
+// cheap to upload.  Lookup semantics are identical: a missing edge is child 0 (= the root, "no match").
 struct HdTrie {
-    std::vector<int32_t> next;   // nnode x 128
-    std::vector<int32_t> id;     // nnode; -1 = inner node
+    std::vector<uint32_t> ekey, eval;   // edge table: key = ((parent << 7) | byte) + 1, 0 = empty; value = child node
+    std::vector<int32_t> id;            // per node: word index, -1 = inner node, 0 for a fresh node (as the reference)
+    uint32_t mask = 0;
     int nentries = 0, nword = 0;
     int level1() const { return HD_LEVEL1(nentries); }
-    uint32_t new_node() { next.resize(next.size() + 128, 0); id.push_back(0); return (uint32_t)id.size() - 1; }
-    void add(const std::string& w) {
+    static uint32_t hash(uint32_t key) { return key * 2654435761u; }
+    uint32_t child(uint32_t node, uint32_t ch) const {
+        const uint32_t key = ((node << 7) | ch) + 1;
+        for (uint32_t h = hash(key) >> 8;; h++) { const uint32_t k = ekey[h & mask]; if (k == key) return eval[h & mask]; if (k == 0) return 0; }
+    }
+    void link(uint32_t node, uint32_t ch, uint32_t to) {
+        const uint32_t key = ((node << 7) | ch) + 1;
+        uint32_t h = hash(key) >> 8;
+        while (ekey[h & mask] != 0 && ekey[h & mask] != key) h++;
+        ekey[h & mask] = key; eval[h & mask] = to;
+    }
+    void add(const std::string& w) {                     // dictionary_add_word, :47-70
         uint32_t node = 0;
         for (unsigned char ch : w) {
-            if (next[(size_t)node * 128 + ch] == 0) {
-                uint32_t nn = new_node();
-                id[node] = -1;
-                next[(size_t)node * 128 + ch] = (int32_t)nn;
-            }
-            node = (uint32_t)next[(size_t)node * 128 + ch];
+            uint32_t nx = child(node, ch);
+            if (nx == 0) { nx = (uint32_t)id.size(); id.push_back(0); id[node] = -1; link(node, ch, nx); }
+            node = nx;
         }
         id[node] = nword++;
     }
     // `text` = dictionary text up to (not including) the NUL
     void load(const char* text) {
-        next.clear(); id.clear(); nentries = 0; nword = 0;
+        id.clear(); nentries = 0; nword = 0;
         std::vector<std::string> entries;
         std::string cur;
+        size_t chars = 0;
         for (const char* s = text; *s; s++) {
             if (*s == '\n') {
                 if (!cur.empty() && (unsigned)(((unsigned char)cur.back() | 32) - 'a') < 26u) cur.push_back(' ');
-                entries.push_back(cur); cur.clear();
+                chars += cur.size(); entries.push_back(cur); cur.clear();
             } else cur.push_back(*s);
         }
         nentries = (int)entries.size();
-        new_node();
+        uint32_t cap = 1024;
+        while (cap < 2 * (chars + 5 * entries.size() + 64)) cap <<= 1;      // edges <= chars, + 4 aliases per word, + root links
+        mask = cap - 1;
+        ekey.assign(cap, 0); eval.assign(cap, 0);
+        id.push_back(0);                                                     // root
         for (auto& e : entries) add(e);
-        for (int c = 'A'; c < 'Z'; c++) next[c] = next[c + 32];
-        for (size_t i = 0; i < id.size(); i++) {
-            int32_t* nx = &next[i * 128];
-            if (nx[' '] > 0) { for (char a : { '.', ',', ':', ';' }) if (!nx[(int)a]) nx[(int)a] = nx[' ']; }
+        for (int c = 'A'; c < 'Z'; c++) { uint32_t lo = child(0, (uint32_t)c + 32); if (lo || child(0, (uint32_t)c)) link(0, (uint32_t)c, lo); }   // :107-109
+        const uint32_t nnode = (uint32_t)id.size();
+        for (uint32_t i = 0; i < nnode; i++) {                               // :110-117
+            const uint32_t sp = child(i, ' ');
+            if (sp > 0) for (char a : { '.', ',', ':', ';' }) if (!child(i, (uint32_t)a)) link(i, (uint32_t)a, sp);
         }
     }
 };

@@ -278,7 +278,7 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
             CR_TRY(cr_sort_pairs<uint32_t>(prims, sk0, sk1, sv0, sv1, nseg, 0, 32));
             CR_LAUNCH(k_o3_pass_sorted, dim3(cr_div_up(nseg, 128)), dim3(128), stream, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nev, b_segstart.as<uint32_t>(), sv1, nseg, st,
                       b_pred.as<uint8_t>(), b_o3hot.as<O3Hot>(), b_esccount.as<uint32_t>() + 1, hot_cap);
-            CR_LAUNCH(k_o3_hot, dim3(148), dim3(128), stream, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nev, st, b_pred.as<uint8_t>(), b_o3hot.as<O3Hot>(), b_esccount.as<uint32_t>() + 1, hot_cap);
+            CR_LAUNCH(k_o3_hot_spec, dim3(296), dim3(O3S_THREADS), stream, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nev, b_segstart.as<uint32_t>(), st, b_pred.as<uint8_t>(), b_o3hot.as<O3Hot>(), b_esccount.as<uint32_t>() + 1, hot_cap);
         } else
 #endif
         CR_LAUNCH(k_o3_pass, dim3(cr_div_up(nev, 128)), dim3(128), stream, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nev, st, b_pred.as<uint8_t>(), (O3Hot*)nullptr, (uint32_t*)nullptr, 0u);
@@ -392,6 +392,10 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
                       b_streams.as<RcStream>(), nstr, b_qm.as<uint32_t>(), b_shm.as<uint32_t>(), b_qs.as<uint32_t>(), b_shs.as<uint32_t>());
         }
         timer.mark("range_chain");
+        if (rc_variant == 4) {
+            if (ntm) CR_LAUNCH(k_msb_to_shifts, dim3(cr_div_up(ntm, 256)), dim3(256), stream, b_shm.as<uint32_t>(), (uint64_t)ntm);
+            if (nts) CR_LAUNCH(k_msb_to_shifts, dim3(cr_div_up(nts, 256)), dim3(256), stream, b_shs.as<uint32_t>(), (uint64_t)nts);
+        }
         CR_TRY(cr_exclusive_sum(prims, b_shm.as<uint32_t>(), b_bm.as<uint32_t>(), ntm + 1));
         CR_TRY(cr_exclusive_sum(prims, b_shs.as<uint32_t>(), b_bs.as<uint32_t>(), nts + 1));
         CR_LAUNCH(k_stream_totals, dim3(cr_div_up(nstr, 64)), dim3(64), stream, b_streams.as<RcStream>(), nstr, b_escord.as<uint32_t>(), b_bm.as<uint32_t>(), b_bs.as<uint32_t>(), b_stot.as<StreamTotals>());

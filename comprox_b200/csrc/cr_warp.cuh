@@ -128,6 +128,69 @@ __global__ void __launch_bounds__(128) k_o3_hot(const uint32_t* __restrict__ K, 
     }
 }
 
+// ------------------------------------------------------------------ o3 pass, long slot segments, speculative
+// The o3 slot automaton (12 bits of state) forgets its past quickly: four misses in a row, or a run of hits that
+// saturates the confidence, bring any two states together.  So a long segment is cut into chunks of O3S_CHUNK
+// events; every chunk is replayed by its own thread from a GUESSED entry state (obtained by warming up over the
+// previous chunk), all chunks at once.  Thread 0 then walks the chunks in order: where the guess equals the true
+// entry state the speculative results stand, otherwise that chunk alone is replayed from the true state.
+// Exactness does not depend on the guess; only speed does.
+#define O3S_CHUNK   256u
+#define O3S_THREADS 256u
+CR_D void o3_step(uint32_t& byte, uint32_t& conf, uint32_t sym) {          // ppm_update_o3, cr-ppm.c:69-88
+    if (sym == byte) conf += conf < 15;
+    else { conf = (conf > 1) + (conf > 2) + (conf > 4) + (conf > 8); if (conf == 0) { byte = sym; conf = 1; } }
+}
+__global__ void __launch_bounds__(O3S_THREADS) k_o3_hot_spec(const uint32_t* __restrict__ K, const uint32_t* __restrict__ V, uint32_t n, const uint32_t* __restrict__ seg_start,
+                                                             PpmState st, uint8_t* __restrict__ pred, const O3Hot* __restrict__ hot, const uint32_t* __restrict__ hot_count, uint32_t hot_cap) {
+    __shared__ uint32_t s_guess[O3S_THREADS], s_end[O3S_THREADS];          // byte | conf << 8
+    __shared__ uint32_t s_true;
+    uint32_t total = *hot_count; if (total > hot_cap) total = hot_cap;
+    for (uint32_t e = blockIdx.x; e < total; e += gridDim.x) {
+        const O3Hot H = hot[e];
+        const uint32_t r0 = H.rank;
+        uint32_t r1 = r0;                                                  // end of the slot's segment
+        {   // the segment ends where the slot changes; segments are sorted, so gallop + binary search
+            uint32_t lo = r0, step = O3S_CHUNK;
+            while (lo + step < n && (K[lo + step] & 0x3fffff) == H.slot) { lo += step; step <<= 1; }
+            uint32_t hi = lo + step < n ? lo + step : n;                   // K[hi] differs (or hi == n)
+            while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if ((K[mid] & 0x3fffff) == H.slot) lo = mid; else hi = mid; }
+            r1 = hi;
+        }
+        if (threadIdx.x == 0) s_true = H.byte | H.conf << 8;
+        __syncthreads();
+        for (uint32_t pass0 = r0; pass0 < r1; pass0 += O3S_CHUNK * O3S_THREADS) {
+            const uint32_t c0 = pass0 + threadIdx.x * O3S_CHUNK;
+            const bool have = c0 < r1;
+            const uint32_t c1 = have ? (c0 + O3S_CHUNK < r1 ? c0 + O3S_CHUNK : r1) : c0;
+            uint32_t byte = 0, conf = 0;
+            if (have) {
+                if (threadIdx.x == 0) { byte = s_true & 255; conf = s_true >> 8; }           // exact entry of the pass
+                else for (uint32_t i = c0 - O3S_CHUNK; i < c0; i++) o3_step(byte, conf, K[i] >> 24);   // warm-up guess
+                s_guess[threadIdx.x] = byte | conf << 8;
+                for (uint32_t i = c0; i < c1; i++) { pred[V[i]] = (uint8_t)byte; o3_step(byte, conf, K[i] >> 24); }
+                s_end[threadIdx.x] = byte | conf << 8;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                uint32_t cur = s_true;
+                const uint32_t nch = (r1 - pass0 + O3S_CHUNK - 1) / O3S_CHUNK < O3S_THREADS ? (r1 - pass0 + O3S_CHUNK - 1) / O3S_CHUNK : O3S_THREADS;
+                for (uint32_t c = 0; c < nch; c++) {
+                    if (s_guess[c] == cur) { cur = s_end[c]; continue; }
+                    uint32_t b = cur & 255, cf = cur >> 8;                 // wrong guess: replay this chunk from the true state
+                    const uint32_t a0 = pass0 + c * O3S_CHUNK, a1 = a0 + O3S_CHUNK < r1 ? a0 + O3S_CHUNK : r1;
+                    for (uint32_t i = a0; i < a1; i++) { pred[V[i]] = (uint8_t)b; o3_step(b, cf, K[i] >> 24); }
+                    cur = b | cf << 8;
+                }
+                s_true = cur;
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) { st.o3_byte[H.slot] = (uint8_t)(s_true & 255); st.o3_conf[H.slot] = (uint8_t)(s_true >> 8); }
+        __syncthreads();
+    }
+}
+
 // bounds[c] = first sorted rank whose 16-bit context is >= c (c = 0..65536): one binary search per context, done once
 __global__ void k_o2_bounds(const uint32_t* __restrict__ K, uint32_t n, uint32_t* __restrict__ bounds) {
     uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -783,7 +846,7 @@ template <int VARIANT>
 __global__ void __launch_bounds__(128) k_range_chain(const uint4* __restrict__ in_main, const uint4* __restrict__ in_side, const uint32_t* __restrict__ escord,
                                                       const RcStream* __restrict__ streams, uint32_t nstreams,
                                                       uint32_t* __restrict__ q_main, uint32_t* __restrict__ sh_main, uint32_t* __restrict__ q_side, uint32_t* __restrict__ sh_side) {
-    __shared__ uint4 stage[4][RC_BATCH];
+    __shared__ uint4 stage[4][RC_BATCH + 1];          // +1: the look-ahead read of the last symbol needs no clamp
     __shared__ uint32_t oq[4][RC_BATCH], os[4][RC_BATCH];
     const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -796,6 +859,8 @@ __global__ void __launch_bounds__(128) k_range_chain(const uint4* __restrict__ i
     if (S.is_main) { i0 += escord[S.ev_begin]; i1 += escord[S.ev_end]; }
     uint32_t range = 0xFFFFFFFFu;
     uint32_t msb = 31;                                   // VARIANT 4: index of the top set bit of the un-normalised range
+    uint32_t c24 = 24, c7 = 7;
+    asm volatile("" : "+r"(c24), "+r"(c7));            // keep the LOP3 operands in registers
     uint4 r0 = make_uint4(1, 1, 1, 1), r1 = r0;
     if (i0 + lane < i1) r0 = tri[i0 + lane];
     if (i0 + 32 + lane < i1) r1 = tri[i0 + 32 + lane];
@@ -809,7 +874,7 @@ __global__ void __launch_bounds__(128) k_range_chain(const uint4* __restrict__ i
         if (lane == 0) {
             uint4 t = stage[w][0];
             for (uint32_t j = 0; j < cnt; j++) {
-                const uint4 tn = stage[w][j + 1 < RC_BATCH ? j + 1 : j];
+                const uint4 tn = stage[w][j + 1];
                 uint32_t q, sh;
                 if (VARIANT == 1) {
                     // Tri: x = cum, y = frq|flag, z = sum, w = floor(2^32/sum): umulhi gives q or q-1 (cr-rangecoder.c:61)
@@ -823,10 +888,12 @@ __global__ void __launch_bounds__(128) k_range_chain(const uint4* __restrict__ i
                 } else if (VARIANT == 4) {
                     const uint32_t ahi = __umulhi(range, t.y);
                     const unsigned long long S2 = (unsigned long long)range * t.z + ahi;      // (range * M) >> 32
-                    q = (uint32_t)(S2 >> ((msb & 24u) | 7u));                               // >> (31 - 8 * leading zero bytes)
+                    uint32_t amt;                                                           // 31 - 8 * leading zero bytes = (msb & 24) | 7
+                    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(amt) : "r"(msb), "r"(c24), "r"(c7));
+                    q = (uint32_t)(S2 >> amt);
                     range = q * t.x;                                                        // range *= frq, left un-normalised
                     asm("bfind.u32 %0, %1;" : "=r"(msb) : "r"(range));
-                    sh = 3u - (msb >> 3);                                                   // renormalisation shifts after this symbol
+                    sh = msb;                                                               // k_msb_to_shifts turns this into 3 - (msb >> 3)
                 } else {
                     // x = frq, (y, z) = M: q = (range * M) >> 63, exact
                     const uint32_t ahi = __umulhi(range, t.y);
@@ -850,6 +917,12 @@ __global__ void __launch_bounds__(128) k_range_chain(const uint4* __restrict__ i
         if (lane + 32 < cnt) { qo[base + lane + 32] = oq[w][lane + 32]; so[base + lane + 32] = os[w][lane + 32]; }
         __syncwarp();
     }
+}
+
+// VARIANT 4 stores the top-bit index of the un-normalised range; the renormalisation shift count is 3 - (msb >> 3)
+__global__ void k_msb_to_shifts(uint32_t* __restrict__ sh, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) sh[i] = 3u - (sh[i] >> 3);
 }
 
 struct LowStream {          // one stream in split form

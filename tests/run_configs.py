@@ -1,0 +1,46 @@
+"""Runs the larger BASELINE.json configurations end to end on the GPU and against the unmodified reference CLI
+(byte identity + reference-decoder round trip + timings).  Not part of pytest: too large for a unit test."""
+import argparse
+import hashlib
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import oracle_ffi as O  # noqa: E402
+from comprox_b200 import api, synth  # noqa: E402
+
+MiB = 1 << 20
+CONFIGS = {
+    "text-100M": dict(make=lambda n: synth.markov_text(n, seed=42), n=100 * MiB, variant=api.ROLZ, binary="comprolz", flags=[], filt=False),
+    "x86-256M": dict(make=lambda n: synth.x86_corpus(n, seed=43), n=256 * MiB, variant=api.ROLZ, binary="comprolz", flags=["-F"], filt=True),
+    "bmp-512M": dict(make=lambda n: synth.bmp_corpus(n, seed=44), n=512 * MiB, variant=api.LZP, binary="comprop", flags=["-F"], filt=True),
+}
+ap = argparse.ArgumentParser()
+ap.add_argument("names", nargs="*", default=list(CONFIGS))
+ap.add_argument("--scale", type=float, default=1.0, help="shrink the configs (1.0 = BASELINE sizes)")
+ap.add_argument("--no-ref", action="store_true")
+ap.add_argument("--out", default="gpurun_out/configs.jsonl")
+a = ap.parse_args()
+os.makedirs(os.path.dirname(a.out), exist_ok=True)
+for name in a.names:
+    c = CONFIGS[name]
+    n = int(c["n"] * a.scale) // MiB * MiB
+    t0 = time.time(); data = c["make"](n); tgen = time.time() - t0
+    rec = {"config": name, "bytes": len(data), "gen_s": round(tgen, 1)}
+    with api.Handle(c["variant"]) as h:
+        h.compress(data[:4 * MiB], 16 * MiB, filt=c["filt"])                 # warm-up (allocations, module load)
+        h.profile(True)
+        t0 = time.time(); out = h.compress(data, 16 * MiB, filt=c["filt"]); dt = time.time() - t0
+        rec.update(gpu_s=round(dt, 3), gpu_mibs=round(len(data) / MiB / dt, 1), container=len(out), sha=hashlib.sha256(out).hexdigest()[:16],
+                   stages_ms={k: round(v, 1) for k, v in h.profile_report().items()})
+    if not a.no_ref and O.ref_binary(c["binary"]):
+        t0 = time.time(); ref = O.ref_compress(data, c["binary"], ["-b16", *c["flags"]], tmpdir="/dev/shm"); dr = time.time() - t0
+        rec.update(ref_s=round(dr, 1), ref_mibs=round(len(data) / MiB / dr, 2), identical=(ref == out))
+        t0 = time.time(); back = O.ref_decompress(out, c["binary"], tmpdir="/dev/shm"); dd = time.time() - t0
+        rec.update(ref_decode_s=round(dd, 1), roundtrip=(back == data))
+    print(json.dumps(rec), flush=True)
+    with open(a.out, "a") as f:
+        f.write(json.dumps(rec) + "\n")

@@ -11,6 +11,7 @@
 #include "cr_dict.cuh"
 #include "cr_filter.cuh"
 #include "cr_hostdict.h"
+#include <chrono>
 
 struct CrConfig {
     uint32_t block_size;     // bytes, reference default 16 MiB (src/main.c:62)
@@ -74,15 +75,26 @@ inline int Compressor::dicpick(const uint8_t* h_in, const uint8_t* d_in, uint64_
     }
     CR_LAUNCH(k_dp_collect, dim3(DP_SLOTS / 256), dim3(256), stream, T, t_entries.as<DpEntry>(), DP_MAXWORDS);
     chain->timer.mark("dp_kernels");
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!getenv("CRGPU_TIMING")) return;
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "crgpu timing: %-16s %.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    };
     std::vector<uint32_t> stats;
     CR_TRY(download(stats, t_stats.p, 4));
     if (stats[1] & 1u) return CRGPU_ERR_VOCAB_OVERFLOW;
     if (stats[1] & 2u) return CRGPU_ERR_HASH_COLLISION;
+    lap("dp sync+stats");
     std::vector<DpEntry> ent;
     CR_TRY(download(ent, t_entries.p, stats[2]));
+    lap("dp entries d2h");
     std::vector<HdWord> words(ent.size());
-    for (size_t i = 0; i < ent.size(); i++) { words[i].w = hd_word_at(h_in, n, ent[i].first); words[i].count = ent[i].count; }
+    for (size_t i = 0; i < ent.size(); i++) { words[i].set(h_in, n, ent[i].first); words[i].count = ent[i].count; }
+    lap("dp words");
     text = hd_dictionary_text(words);
+    lap("dp text");
     chain->timer.mark("dp_host");
     return CRGPU_OK;
 }

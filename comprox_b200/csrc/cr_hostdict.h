@@ -16,31 +16,36 @@
 #define HD_TOTAL_WORDS 25000
 #define HD_LEVEL1(n)   ((65535 - (n)) / 255 - 1)
 
-struct HdWord { std::string w; uint32_t count; };
-
-// word text of a counted entry: the letters starting at `first`, lower-cased (copyword, cr-dicpick.c:88-94)
-static inline std::string hd_word_at(const uint8_t* in, uint64_t n, uint64_t first) {
-    std::string w;
-    w.push_back((char)(in[first] | 32));
-    for (uint64_t i = first + 1; i < n && in[i] >= 'a' && in[i] <= 'z' && w.size() < 20; i++) w.push_back((char)in[i]);
-    return w;
-}
+// a counted word: up to 20 lower-case letters, zero padded, kept as three big-endian 64-bit keys so that
+// comparing keys compares the strings (strcmp order) without touching memory twice
+struct HdWord {
+    uint64_t k[3]; uint32_t count; uint32_t len;
+    void set(const uint8_t* in, uint64_t n, uint64_t first) {       // copyword, cr-dicpick.c:88-94
+        char w[24] = {0};
+        w[0] = (char)(in[first] | 32); len = 1;
+        for (uint64_t i = first + 1; i < n && in[i] >= 'a' && in[i] <= 'z' && len < 20; i++) w[len++] = (char)in[i];
+        for (int q = 0; q < 3; q++) { uint64_t v = 0; for (int b = 0; b < 8; b++) v = v << 8 | (uint8_t)w[q * 8 + b]; k[q] = v; }
+    }
+    void append_to(std::string& t) const { for (uint32_t i = 0; i < len; i++) t.push_back((char)(k[i >> 3] >> (56 - 8 * (i & 7)))); }
+    bool word_less(const HdWord& o) const { return k[0] != o.k[0] ? k[0] < o.k[0] : k[1] != o.k[1] ? k[1] < o.k[1] : k[2] < o.k[2]; }
+};
 
 // src/cr-dicpick.c:218-257.  `words` = all words with count > 5.  Returns the dictionary text incl. the final NUL.
 static inline std::string hd_dictionary_text(std::vector<HdWord>& words) {
     std::sort(words.begin(), words.end(), [](const HdWord& a, const HdWord& b) {
         if (a.count != b.count) return a.count > b.count;          // count descending
-        return a.w > b.w;                                          // ties: word descending (:60-67)
+        return b.word_less(a);                                     // ties: word descending (:60-67)
     });
     int y = (int)words.size();
     if (y > HD_TOTAL_WORDS - 2) y = HD_TOTAL_WORDS - 2;
     if (y > HD_LEVEL1(y) - 2) {
         int x = HD_LEVEL1(y) - 2;
-        std::sort(words.begin() + x, words.begin() + y, [](const HdWord& a, const HdWord& b) { return a.w < b.w; });
+        std::sort(words.begin() + x, words.begin() + y, [](const HdWord& a, const HdWord& b) { return a.word_less(b); });
     }
     std::string t("\x20\x20\n" "http://www.\n");
+    t.reserve((size_t)y * 10 + 64);
     for (int x = 0; x < y; x++)
-        if (x < HD_LEVEL1(y) || words[x].w.size() >= 3) { t += words[x].w; t.push_back('\n'); }
+        if (x < HD_LEVEL1(y) || words[x].len >= 3) { words[x].append_to(t); t.push_back('\n'); }
     t.push_back('\0');
     return t;
 }

@@ -164,7 +164,13 @@ def pe_image(rng: np.random.Generator, nbytes: int) -> bytes:
     head[0x96:0x98] = (0x0102).to_bytes(2, "little")
     # filter_x86_pe.c:148-151 places the body at buf+size_hdr (e_lfanew not added) and consumes size+size_hdr
     body = nbytes - size_hdr
+
+    def clean(v):   # no E8/E9 byte: the reference rewrites "operands" inside the section table too (the body is taken to
+        return not any(((v >> (8 * k)) & 0xFE) == 0xE8 for k in range(4))   # start at buf+size_hdr), and its decoder re-reads it
+
     s0 = body // 2
+    while not (clean(s0) and clean(body - s0)):
+        s0 -= 4099
     for i, (nm, sz) in enumerate(((b".text\0\0\0", s0), (b".data\0\0\0", body - s0))):
         o = 0x80 + 24 + opt + i * 40
         head[o:o + 8] = nm

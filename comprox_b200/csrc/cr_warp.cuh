@@ -847,7 +847,7 @@ __global__ void __launch_bounds__(128) k_range_chain(const uint4* __restrict__ i
                                                       const RcStream* __restrict__ streams, uint32_t nstreams,
                                                       uint32_t* __restrict__ q_main, uint32_t* __restrict__ sh_main, uint32_t* __restrict__ q_side, uint32_t* __restrict__ sh_side) {
     __shared__ uint4 stage[4][RC_BATCH + 1];          // +1: the look-ahead read of the last symbol needs no clamp
-    __shared__ uint32_t oq[4][RC_BATCH], os[4][RC_BATCH];
+    __shared__ uint32_t oq[4][RC_BATCH], os[4][RC_BATCH + 1];   // VARIANT 4: os[j] = top-bit index BEFORE symbol j (stored late, off the chain)
     const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (s >= nstreams) return;
@@ -886,14 +886,17 @@ __global__ void __launch_bounds__(128) k_range_chain(const uint4* __restrict__ i
                     const uint32_t na = ra << (8 * sa), nb2 = rb << (8 * sb);
                     q = up ? q0 + 1 : q0; sh = up ? sb : sa; range = up ? nb2 : na;
                 } else if (VARIANT == 4) {
-                    const uint32_t ahi = __umulhi(range, t.y);
-                    const unsigned long long S2 = (unsigned long long)range * t.z + ahi;      // (range * M) >> 32
+                    const uint32_t ahi = __umulhi(range, t.y);                              // these two do not need msb: they run
+                    const unsigned long long S2 = (unsigned long long)range * t.z + ahi;      // while the FLO below is in flight
                     uint32_t amt;                                                           // 31 - 8 * leading zero bytes = (msb & 24) | 7
-                    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(amt) : "r"(msb), "r"(c24), "r"(c7));
+                    asm volatile("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(amt) : "r"(msb), "r"(c24), "r"(c7));
                     q = (uint32_t)(S2 >> amt);
+                    os[w][j] = msb;                                                         // top bit before this symbol = after the previous one
+                    oq[w][j] = q;
                     range = q * t.x;                                                        // range *= frq, left un-normalised
-                    asm("bfind.u32 %0, %1;" : "=r"(msb) : "r"(range));
-                    sh = msb;                                                               // k_msb_to_shifts turns this into 3 - (msb >> 3)
+                    asm volatile("bfind.u32 %0, %1;" : "=r"(msb) : "r"(range));
+                    t = tn;
+                    continue;
                 } else {
                     // x = frq, (y, z) = M: q = (range * M) >> 63, exact
                     const uint32_t ahi = __umulhi(range, t.y);
@@ -911,10 +914,12 @@ __global__ void __launch_bounds__(128) k_range_chain(const uint4* __restrict__ i
                 oq[w][j] = q; os[w][j] = sh;
                 t = tn;
             }
+            if (VARIANT == 4) os[w][cnt] = msb;
         }
         __syncwarp();
-        if (lane < cnt) { qo[base + lane] = oq[w][lane]; so[base + lane] = os[w][lane]; }
-        if (lane + 32 < cnt) { qo[base + lane + 32] = oq[w][lane + 32]; so[base + lane + 32] = os[w][lane + 32]; }
+        const uint32_t so_off = VARIANT == 4 ? 1u : 0u;                    // VARIANT 4 keeps the value after symbol j in slot j+1
+        if (lane < cnt) { qo[base + lane] = oq[w][lane]; so[base + lane] = os[w][lane + so_off]; }
+        if (lane + 32 < cnt) { qo[base + lane + 32] = oq[w][lane + 32]; so[base + lane + 32] = os[w][lane + 32 + so_off]; }
         __syncwarp();
     }
 }

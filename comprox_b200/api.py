@@ -102,6 +102,13 @@ class Handle:
         _check(self.L, self.L.crgpu_compress(self.h, ctypes.byref(cfg), data, ctypes.c_uint64(len(data)), out, ctypes.c_uint64(cap), ctypes.byref(n)))
         return out.raw[:n.value]
 
+    def decompress(self, container: bytes, out_cap: int) -> bytes:
+        """The bytes `comprolz/comprop d` would write for this container."""
+        out = ctypes.create_string_buffer(max(out_cap, 1))
+        n = ctypes.c_uint64()
+        _check(self.L, self.L.crgpu_decompress(self.h, container, ctypes.c_uint64(len(container)), out, ctypes.c_uint64(out_cap), ctypes.byref(n)))
+        return out.raw[:n.value]
+
     def set_option(self, name, value):
         _check(self.L, self.L.crgpu_set_option(self.h, name.encode(), ctypes.c_int64(int(value))))
 

@@ -1,0 +1,272 @@
+// cr_decode.cuh -- decompression (the inverse path): lzdecode, dictionary_decode, inverse filters.
+//
+// Replaces lzdecode (src/rolzmain/cr-coder.c:287-379, src/ropmain/cr-coder.c:231-292), ppm_decode
+// (src/cr-ppm.c:169-235), the decoder half of src/cr-rangecoder.c:81-104, dictionary_decode(_imp)
+// (src/cr-diccode.c:223-283,364-425) and filter_inplace(FILTER_DEC).
+//
+// Decoding one container is ONE serial chain: the context of every symbol depends on the
+// bytes decoded before it and the models carry across blocks, so -- unlike compression -- nothing can be replayed
+// per context.  k_lzdecode_serial therefore runs one thread per container; throughput comes only from decoding
+// many containers at once ("replicas only").  The stages after it are parallel again: one thread per 1 000 000-byte
+// sub-chunk for the (backwards) dictionary expansion, byte-parallel inverse filters.
+// The matcher tables are not cleared per block: every entry carries the ordinal of the block that wrote it.
+#pragma once
+#include "cr_common.cuh"
+#include "cr_ppm.cuh"
+#include "cr_rolz.cuh"
+#include "cr_lzp.cuh"
+
+struct DecBlock {
+    uint64_t in_off;      // payload (after the 6-byte block header) in the container buffer
+    uint32_t in_size;
+    uint32_t coded;       // 1 = lzencode'd payload with "compressed" set: run the serial decoder
+    uint64_t d_off;       // where the dictionary-coded block goes
+    uint32_t d_size;      // its size (original_size of the inner header)
+    uint32_t epoch;       // ordinal used to tag matcher table entries (> 0)
+};
+struct DecTables {        // matcher state of ONE container
+    uint32_t* rz_meta;    // [262144]  epoch << 16 | count << 8 | head
+    uint32_t* rz_items;   // [262144 * 64]
+    uint32_t* rz_short;   // [256 * 16]
+    unsigned long long* lzp8;   // [1 << 24]  epoch << 32 | position
+    unsigned long long* lzp4;   // [1 << 20]
+    unsigned long long* lzp2;   // [1 << 16]
+};
+
+// ------------------------------------------------------------------ range decoder (cr-rangecoder.c:81-104)
+struct RcDec {
+    uint32_t range, code;
+    const uint8_t* in;
+    CR_D void init(const uint8_t* p) { range = 0xFFFFFFFFu; code = 0; in = p; for (int i = 0; i < 5; i++) code = (code << 8) + *in++; }
+    CR_D uint32_t target(uint32_t sum) { range /= sum; return code / range; }
+    CR_D void consume(uint32_t cum, uint32_t frq) {
+        code -= cum * range; range *= frq;
+        while (range < (1u << 24)) { code = (code << 8) + *in++; range <<= 8; }
+    }
+};
+
+CR_D int dec_o2_bump(uint8_t* f, uint32_t s, int inc) {       // o2_model_update, cr-o2model.c:43-72
+    f[s] = (uint8_t)(f[s] + inc);
+    if (f[s] > 250) {
+        uint32_t ee = 1;
+        for (int i = 0; i < 256; i++) { f[i] >>= 1; ee += f[i] == 1; }
+        f[256] = (uint8_t)((f[256] + 1) / 2);
+        f[257] = (uint8_t)ee;
+        return 1;
+    }
+    return 0;
+}
+CR_D void dec_o3_update(PpmState& st, uint32_t slot, int c) {  // ppm_update_o3, cr-ppm.c:69-88
+    uint32_t f = st.o3_conf[slot];
+    if (c >= 0) { f = (f > 1) + (f > 2) + (f > 4) + (f > 8); if (f == 0) { st.o3_byte[slot] = (uint8_t)c; f = 1; } }
+    else f += f < 15;
+    st.o3_conf[slot] = (uint8_t)f;
+}
+// ppm_decode, cr-ppm.c:169-235
+CR_D uint32_t dec_ppm(PpmState& st, uint32_t ctx, RcDec& rc) {
+    uint8_t* f = st.o2 + (size_t)(ctx & 0xffff) * PPM_O2_STRIDE;
+    uint8_t* o1 = st.o1 + (ctx & 0xff) * 256;
+    const uint32_t slot = ppm_slot(ctx);
+    const uint32_t pred = st.o3_byte[slot];
+    uint32_t body = 0;
+    for (int i = 0; i < 256; i++) body += f[i];
+    const uint32_t pf = f[pred];
+    const uint32_t tgt = rc.target(body + f[256] + f[257] - pf);
+    uint32_t acc = 0, s = 0;
+    for (;; s++) { const uint32_t wgt = s == pred ? 0u : f[s]; if (acc + wgt > tgt || s == 257) break; acc += wgt; }
+    rc.consume(acc, f[s]);
+    const int rescaled = dec_o2_bump(f, s, 1);
+    if (s == 256) { dec_o3_update(st, slot, -1); return pred; }
+    if (s < 256) {
+        if (!rescaled && f[s] == 2) dec_o2_bump(f, 257, -1);
+        dec_o3_update(st, slot, (int)s);
+        return s;
+    }
+    uint32_t sum1 = 0, cum1 = 0, d = 0;
+    for (uint32_t i = 0; i < 256; i++) if (f[i] == 0 && i != pred) sum1 += (uint32_t)o1[i] * 8 - 7;
+    const uint32_t t1 = rc.target(sum1);
+    for (uint32_t i = 0; i < 256; i++)
+        if (f[i] == 0 && i != pred) { const uint32_t fr = (uint32_t)o1[i] * 8 - 7; if (cum1 + fr > t1) { d = i; break; } cum1 += fr; }
+    rc.consume(cum1, (uint32_t)o1[d] * 8 - 7);
+    if (++o1[d] >= 255) for (int j = 0; j < 256; j++) o1[j] -= o1[j] / 2;
+    if (!rescaled) dec_o2_bump(f, d, 1);
+    dec_o3_update(st, slot, (int)d);
+    return d;
+}
+// M_my_dec_ with increment 4 (cr-model.h:66-74, cr-model.c:55-77,98-115)
+CR_D uint32_t dec_m0(uint16_t* f, RcDec& rc) {
+    uint32_t total = 0;
+    for (int i = 0; i < 256; i++) total += f[i];
+    const uint32_t tgt = rc.target(total);
+    uint32_t acc = 0, s = 0;
+    while (s < 255 && acc + f[s] <= tgt) acc += f[s++];
+    rc.consume(acc, f[s]);
+    f[s] += 4;
+    if (total + 4 > 32000) for (int i = 0; i < 256; i++) f[i] = (uint16_t)((f[i] + 1) / 2);
+    return s;
+}
+
+// ------------------------------------------------------------------ ROLZ tables with block tags
+struct RzDec {
+    DecTables T; uint32_t epoch, bucket, short_bucket; int ctx4;
+    CR_D void begin(const DecTables& t, uint32_t ep, int c4) {
+        T = t; epoch = ep; bucket = 0; short_bucket = 0; ctx4 = c4;
+        for (int i = 0; i < 256 * 16; i++) T.rz_short[i] = 0;                  // cr-matcher.c:53
+    }
+    CR_D void insert(const uint8_t* d, uint32_t pos) {                         // matcher_update, cr-matcher.c:65-81
+        if (pos < 16) return;
+        uint32_t m = T.rz_meta[bucket];
+        if ((m >> 16) != epoch) m = epoch << 16;
+        const uint32_t head = ((m & 255) + 1) & 63;
+        uint32_t count = ((m >> 8) & 255) + 1; if (count > 64) count = 64;
+        T.rz_items[(size_t)bucket * 64 + head] = pos;
+        T.rz_meta[bucket] = epoch << 16 | count << 8 | head;
+        bucket = rz_hash(d + pos, ctx4);
+        uint32_t* s = T.rz_short + short_bucket * 16;
+        for (int i = 15; i > 0; i--) s[i] = s[i - 1];
+        s[0] = pos;
+        short_bucket = d[pos];
+    }
+    CR_D uint32_t getpos(uint32_t idx) const {                                 // matcher_getpos, cr-matcher.c:83-88
+        if (idx < 64) { const uint32_t m = T.rz_meta[bucket]; return T.rz_items[(size_t)bucket * 64 + (((m & 255) + 64 - idx) & 63)]; }
+        return T.rz_short[short_bucket * 16 + idx - 64];
+    }
+};
+struct LzpDec {
+    DecTables T; unsigned long long tag;
+    CR_D void begin(const DecTables& t, uint32_t ep) { T = t; tag = (unsigned long long)ep << 32; }
+    CR_D uint32_t get(const unsigned long long* tab, uint32_t h, uint32_t dflt) const { const unsigned long long v = tab[h]; return (v >> 32 << 32) == tag ? (uint32_t)v : dflt; }
+    CR_D uint32_t getpos(const uint8_t* d, uint32_t pos) const {               // matcher_getpos, ropmain/cr-matcher.c:59-73
+        const uint32_t a = get(T.lzp8, lzp_hash(d + pos - 8, 0), 8), b = get(T.lzp4, lzp_hash(d + pos - 4, 1), 4), c = get(T.lzp2, lzp_hash(d + pos - 2, 2), 2);
+        if (lzp_same(d + a - 8, d + pos - 8, 8)) return a;
+        if (lzp_same(d + b - 4, d + pos - 4, 4)) return b;
+        return c;
+    }
+    CR_D void insert(const uint8_t* d, uint32_t pos) {                         // matcher_update, :91-96
+        T.lzp8[lzp_hash(d + pos - 8, 0)] = tag | pos; T.lzp4[lzp_hash(d + pos - 4, 1)] = tag | pos; T.lzp2[lzp_hash(d + pos - 2, 2)] = tag | pos;
+    }
+};
+
+// One thread decodes all lz-coded blocks of one container in order.  ctx_io carries the PPM context in and out.
+__global__ void k_lzdecode_serial(int variant, const uint8_t* __restrict__ cont, const DecBlock* __restrict__ blocks, uint32_t nb,
+                                  PpmState st, DecTables tabs, uint32_t* __restrict__ ctx_io, uint8_t* __restrict__ D) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    uint32_t ctx = *ctx_io;
+    for (uint32_t b = 0; b < nb; b++) {
+        const DecBlock B = blocks[b];
+        if (!B.coded) continue;
+        const uint8_t* in = cont + B.in_off;
+        uint8_t* out = D + B.d_off;
+        const uint32_t orig = B.d_size;
+        if (variant == 0) {                                                    // src/rolzmain/cr-coder.c:287-379
+            const uint32_t esc = in[2], off_idx = cr_ld32(in + 12);
+            RcDec rc, side; rc.init(in + 16); side.init(in + off_idx);
+            RzDec m; m.begin(tabs, B.epoch, orig >= 4194304);
+            uint32_t n = 0;
+            out[n++] = in[0];
+            while (n < orig) {
+                uint32_t len = 1;
+                const uint32_t s = dec_ppm(st, ctx, rc);
+                if (s == esc) {
+                    const uint32_t l = dec_m0(st.m0, side);
+                    if (l == 0) out[n++] = (uint8_t)esc;
+                    else {
+                        const uint32_t idx = dec_m0(st.m0 + 256, side);
+                        const uint32_t q = m.getpos(idx);
+                        len = l;
+                        for (uint32_t i = 0; i < len; i++) { out[n] = out[q + i]; n++; }
+                    }
+                } else out[n++] = (uint8_t)s;
+                for (; len; len--) { const uint32_t p = n - len; m.insert(out, p); ctx = ctx << 8 | out[p]; }
+            }
+        } else {                                                               // src/ropmain/cr-coder.c:231-292
+            const uint32_t esc = in[8];
+            for (int i = 0; i < 9; i++) out[i] = in[9 + i];
+            RcDec rc; rc.init(in + 20);
+            LzpDec m; m.begin(tabs, B.epoch);
+            uint32_t n = 9;
+            while (n < orig) {
+                uint32_t len = 1;
+                const uint32_t s = dec_ppm(st, ctx, rc);
+                if (s != esc) out[n++] = (uint8_t)s;
+                else {
+                    ctx = ctx << 8 | esc;
+                    len = dec_ppm(st, ctx, rc);
+                    if (len == 0) { len = 1; out[n++] = (uint8_t)esc; }
+                    else { const uint32_t q = m.getpos(out, n); for (uint32_t i = 0; i < len; i++) { out[n] = out[q + i]; n++; } }
+                }
+                for (; len; len--) { const uint32_t p = n - len; ctx = ctx << 8 | out[p]; m.insert(out, p); }
+            }
+        }
+    }
+    *ctx_io = ctx;
+}
+
+// ------------------------------------------------------------------ dictionary_decode (cr-diccode.c:223-283)
+struct DdSub { uint64_t src; uint32_t size; uint32_t block; uint64_t dst; uint32_t orig; uint32_t pad; };   // one sub-chunk
+struct DdBlock { uint64_t d_off; uint32_t d_size; uint32_t first_sub; uint64_t raw_off; uint32_t raw_size; uint32_t nsub; };
+// Walks the pair framing of every dictionary-coded block (serial over a few hundred headers) and lays out the output.
+__global__ void k_dd_layout(const uint8_t* __restrict__ D, DdBlock* __restrict__ blocks, uint32_t nb, DdSub* __restrict__ subs, uint32_t sub_cap,
+                            uint64_t out_base, uint64_t* __restrict__ totals) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    uint64_t raw = out_base; uint32_t ns = 0;
+    for (uint32_t b = 0; b < nb; b++) {
+        DdBlock& B = blocks[b];
+        const uint8_t* d = D + B.d_off;
+        B.raw_off = raw; B.first_sub = ns; B.nsub = 0;
+        if (B.d_size == 0) { B.raw_size = 0; continue; }
+        if (d[B.d_size - 1] == 0) { B.raw_size = B.d_size - 1; raw += B.raw_size; continue; }      // stored (:237-241)
+        uint32_t size = 0;
+        for (uint32_t pos = 0; pos + 11 < B.d_size;) {
+            const uint32_t s1 = cr_ld32(d + pos), s2 = cr_ld32(d + pos + 4);
+            const uint32_t sz[2] = { s1, s2 }; uint64_t src = B.d_off + pos + 8;
+            for (int k = 0; k < 2; k++) {
+                const uint32_t orig = cr_ld32(D + src + sz[k] - 4);
+                if (ns < sub_cap) { DdSub S; S.src = src; S.size = sz[k]; S.block = b; S.dst = raw + size; S.orig = orig; S.pad = 0; subs[ns] = S; }
+                ns++; B.nsub++; size += orig; src += sz[k];
+            }
+            pos += 8 + s1 + s2;
+        }
+        B.raw_size = size; raw += size;
+    }
+    totals[0] = raw - out_base; totals[1] = ns;
+}
+struct DdDict { const char* words; const uint8_t* lens; int32_t nentries, level1; };   // words: [nentries][24]
+CR_HD bool dd_sentence_start(const uint8_t* s, uint32_t i) { return i >= 3 && s[i - 1] == ' ' && (s[i - 2] == '.' || (s[i - 2] == ' ' && s[i - 3] == '.')); }
+// dictionary_decode_imp (cr-diccode.c:364-425): each sub-chunk is expanded back to front by one thread
+__global__ void k_dd_subs(const uint8_t* __restrict__ D, const DdBlock* __restrict__ blocks, const DdSub* __restrict__ subs, uint32_t nsub, DdDict dic, uint8_t* __restrict__ out) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nsub) return;
+    const DdSub S = subs[t];
+    const DdBlock B = blocks[S.block];
+    const uint8_t* esc = D + B.d_off + B.d_size - 11;
+    uint8_t escmap[256];
+    for (int i = 0; i < 256; i++) escmap[i] = 0;
+    for (int i = 0; i < 10; i++) escmap[esc[i]] = (uint8_t)(i + 1);
+    const uint8_t* d = D + S.src;
+    uint8_t* o = out + S.dst;
+    const int L1 = dic.level1;
+    uint32_t src = S.orig, rev = 0xFFFFFFFFu; int dst = (int)S.size - 4;
+    while (src > 0) {
+        const uint32_t ch = d[--dst];
+        if (!escmap[ch]) { o[--src] = (uint8_t)ch; continue; }
+        int id = d[--dst];
+        if (id >= L1) {
+            id = d[--dst] * (256 - L1) + (id - L1);
+            if (id == dic.nentries) { o[--src] = (uint8_t)ch; continue; }
+        }
+        const uint32_t wl = dic.lens[id];
+        const char* w = dic.words + (size_t)id * 24;
+        src -= wl;
+        for (uint32_t i = 0; i < wl; i++) o[src + i] = (uint8_t)w[i];
+        const uint32_t e = escmap[ch];
+        if (e == 2 || e == 7) o[src + wl - 1] = '.';
+        else if (e == 3 || e == 8) o[src + wl - 1] = ',';
+        else if (e == 4 || e == 9) o[src + wl - 1] = ';';
+        else if (e == 5 || e == 10) o[src + wl - 1] = ':';
+        if (e >= 6) o[src] ^= 0x20;
+        if (rev != 0xFFFFFFFFu && dd_sentence_start(o, rev)) o[rev] ^= 0x20;
+        rev = src;
+    }
+    if (rev != 0xFFFFFFFFu && dd_sentence_start(o, rev)) o[rev] ^= 0x20;
+}

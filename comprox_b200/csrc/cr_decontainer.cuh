@@ -1,0 +1,160 @@
+// cr_decontainer.cuh -- whole-container decompression: cr_main's decode branch (src/main.c:220-302).
+#pragma once
+#include "cr_container.cuh"
+#include "cr_decode.cuh"
+
+struct Decompressor {
+    LzChain* chain = nullptr;
+    cudaStream_t stream = 0;
+    DevBuf d_cont, d_D, d_out, d_blocks, d_ctx, d_ddblocks, d_subs, d_totals, d_words, d_lens, d_copy;
+    DevBuf t_meta, t_items, t_short, t_l8, t_l4, t_l2;
+    FilterHost filt;
+    uint32_t epoch = 0;
+
+    void release() {
+        DevBuf* all[] = { &d_cont, &d_D, &d_out, &d_blocks, &d_ctx, &d_ddblocks, &d_subs, &d_totals, &d_words, &d_lens, &d_copy, &t_meta, &t_items, &t_short, &t_l8, &t_l4, &t_l2 };
+        for (DevBuf* b : all) b->release();
+        filt.release();
+    }
+    int tables(DecTables& T) {
+        if (chain->variant == CR_ROLZ) {
+            const bool fresh = t_meta.p == nullptr;
+            CR_TRY(t_meta.reserve((size_t)RZ_BUCKETS * 4)); CR_TRY(t_items.reserve((size_t)RZ_BUCKETS * 64 * 4)); CR_TRY(t_short.reserve(256 * 16 * 4));
+            if (fresh) { CR_CUDA(cudaMemsetAsync(t_meta.p, 0, (size_t)RZ_BUCKETS * 4, stream)); epoch = 0; }
+        } else {
+            const bool fresh = t_l8.p == nullptr;
+            CR_TRY(t_l8.reserve((size_t)8 << 24)); CR_TRY(t_l4.reserve((size_t)8 << 20)); CR_TRY(t_l2.reserve((size_t)8 << 16));
+            if (fresh) {
+                CR_CUDA(cudaMemsetAsync(t_l8.p, 0, (size_t)8 << 24, stream)); CR_CUDA(cudaMemsetAsync(t_l4.p, 0, (size_t)8 << 20, stream));
+                CR_CUDA(cudaMemsetAsync(t_l2.p, 0, (size_t)8 << 16, stream)); epoch = 0;
+            }
+        }
+        T.rz_meta = t_meta.as<uint32_t>(); T.rz_items = t_items.as<uint32_t>(); T.rz_short = t_short.as<uint32_t>();
+        T.lzp8 = t_l8.as<unsigned long long>(); T.lzp4 = t_l4.as<unsigned long long>(); T.lzp2 = t_l2.as<unsigned long long>();
+        return CRGPU_OK;
+    }
+    // lzdecode of `blk` (consecutive blocks of one model chain); fills D at blk[i].d_off
+    int lzdecode(const uint8_t* h_cont, std::vector<DecBlock>& blk) {
+        DecTables T; CR_TRY(tables(T));
+        std::vector<CopyDesc> copies;
+        const uint32_t hdr = chain->variant == CR_ROLZ ? 16 : 20;
+        for (auto& b : blk) {
+            if (epoch >= 65000 && t_meta.p) { CR_CUDA(cudaMemsetAsync(t_meta.p, 0, (size_t)RZ_BUCKETS * 4, stream)); epoch = 0; }   // ROLZ tags are 16 bit
+            b.epoch = ++epoch;
+            if (!b.coded && b.d_size) { CopyDesc c = { b.in_off + (b.in_size - b.d_size), b.d_off, b.d_size, 0 }; copies.push_back(c); }
+        }
+        (void)h_cont; (void)hdr;
+        CR_TRY(chain->upload(d_blocks, blk));
+        std::vector<uint32_t> c(1, chain->chain_ctx);
+        CR_TRY(chain->upload(d_ctx, c));
+        if (!copies.empty()) {
+            CR_TRY(chain->upload(d_copy, copies));
+            CR_LAUNCH(k_copy_segments, dim3(64, (unsigned)copies.size()), dim3(256), stream, d_copy.as<CopyDesc>(), d_cont.as<uint8_t>(), d_cont.as<uint8_t>(), d_D.as<uint8_t>());
+        }
+        CR_LAUNCH(k_lzdecode_serial, dim3(1), dim3(1), stream, chain->variant, d_cont.as<uint8_t>(), d_blocks.as<DecBlock>(), (uint32_t)blk.size(), chain->st, T, d_ctx.as<uint32_t>(), d_D.as<uint8_t>());
+        CR_TRY(chain->download(c, d_ctx.p, 1));
+        chain->chain_ctx = c[0];
+        return CRGPU_OK;
+    }
+    int decompress(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_n);
+};
+
+inline int Decompressor::decompress(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_n) {
+    stream = chain->stream;
+    const int variant = chain->variant;
+    const char* magic = cr_magic(variant);
+    const size_t mlen = strlen(magic);
+    const uint32_t hdr = variant == CR_ROLZ ? 16 : 20;
+    if (!in || !out_n || n < mlen + 4 || memcmp(in, magic, mlen) != 0) return CRGPU_ERR_ARG;     // check_magic, src/main.c:72-79
+    auto rd32 = [&](uint64_t o) { uint32_t v; memcpy(&v, in + o, 4); return v; };
+    // payload -> DecBlock: sizes come from the inner headers (src/rolzmain/cr-coder.c:63-71, src/ropmain/cr-coder.c:60-66)
+    auto describe = [&](uint64_t off, uint32_t size, int prec, uint64_t d_off, DecBlock& b) -> int {
+        memset(&b, 0, sizeof b);
+        b.in_off = off; b.in_size = size; b.d_off = d_off;
+        if (prec) { b.coded = 0; b.d_size = size; return CRGPU_OK; }
+        if (size < hdr) return CRGPU_ERR_ARG;
+        const int compressed = variant == CR_ROLZ ? in[off + 1] : in[off];
+        if (!compressed) { b.coded = 0; b.d_size = size - hdr; return CRGPU_OK; }
+        b.coded = 1; b.d_size = rd32(off + 4);
+        return CRGPU_OK;
+    };
+    CR_TRY(d_cont.reserve(n + 64));
+    CR_CUDA(cudaMemcpyAsync(d_cont.p, in, n, cudaMemcpyHostToDevice, stream));
+
+    // ---- static dictionary (src/main.c:244-259)
+    uint64_t p = mlen;
+    const uint32_t dict_len = rd32(p); p += 4;
+    if (p + dict_len > n) return CRGPU_ERR_ARG;
+    std::vector<DecBlock> dblk(1);
+    CR_TRY(describe(p, dict_len, 0, 0, dblk[0]));
+    p += dict_len;
+    CR_TRY(d_D.reserve((size_t)dblk[0].d_size + 64));
+    CR_TRY(chain->reset_models());
+    CR_TRY(lzdecode(in, dblk));
+    std::vector<uint8_t> lcp;
+    CR_TRY(chain->download(lcp, d_D.p, dblk[0].d_size));
+    CR_TRY(chain->reset_models());
+    const std::string text = hd_lcp_decode(lcp.data(), lcp.size());
+    const std::vector<std::string> entries = hd_entries(text.c_str());
+    std::vector<char> words(entries.size() * 24 + 24, 0); std::vector<uint8_t> lens(entries.size() + 1, 0);
+    for (size_t i = 0; i < entries.size(); i++) { lens[i] = (uint8_t)entries[i].size(); memcpy(&words[i * 24], entries[i].data(), entries[i].size() < 24 ? entries[i].size() : 24); }
+    CR_TRY(chain->upload(d_words, words)); CR_TRY(chain->upload(d_lens, lens));
+    DdDict dic = { d_words.as<char>(), d_lens.as<uint8_t>(), (int32_t)entries.size(), HD_LEVEL1((int)entries.size()) };
+
+    // ---- data blocks (src/main.c:263-292)
+    std::vector<DecBlock> blk; std::vector<uint8_t> filt_flags;
+    uint64_t dtotal = 0;
+    while (p + 6 <= n) {
+        const uint32_t size = rd32(p); const int f = in[p + 4], prec = in[p + 5];
+        p += 6;
+        if (p + size > n) return CRGPU_ERR_ARG;
+        DecBlock b; CR_TRY(describe(p, size, prec, dtotal, b));
+        blk.push_back(b); filt_flags.push_back((uint8_t)f);
+        dtotal += ((uint64_t)b.d_size + 15) & ~15ull;
+        p += size;
+    }
+    CR_TRY(d_D.reserve(dtotal + 64));
+    if (!blk.empty()) CR_TRY(lzdecode(in, blk));
+
+    // ---- dictionary_decode
+    const uint32_t nb = (uint32_t)blk.size();
+    std::vector<DdBlock> ddb(nb);
+    uint64_t sub_cap = 2 * nb + 16;
+    for (uint32_t b = 0; b < nb; b++) { memset(&ddb[b], 0, sizeof(DdBlock)); ddb[b].d_off = blk[b].d_off; ddb[b].d_size = blk[b].d_size; sub_cap += blk[b].d_size / 8 + 2; }
+    if (sub_cap > (1u << 24)) sub_cap = 1u << 24;
+    CR_TRY(chain->upload(d_ddblocks, ddb));
+    CR_TRY(d_subs.reserve(sub_cap * sizeof(DdSub))); CR_TRY(d_totals.reserve(64));
+    CR_LAUNCH(k_dd_layout, dim3(1), dim3(1), stream, d_D.as<uint8_t>(), d_ddblocks.as<DdBlock>(), nb, d_subs.as<DdSub>(), (uint32_t)sub_cap, (uint64_t)0, d_totals.as<uint64_t>());
+    std::vector<uint64_t> totals;
+    CR_TRY(chain->download(totals, d_totals.p, 2));
+    const uint64_t raw_total = totals[0]; const uint32_t nsub = (uint32_t)totals[1];
+    if (nsub > sub_cap) return CRGPU_ERR_ARG;
+    if (raw_total > out_cap) return CRGPU_ERR_ARG;
+    CR_TRY(chain->download(ddb, d_ddblocks.p, nb));
+    CR_TRY(d_out.reserve(raw_total + 256));
+    CR_CUDA(cudaMemsetAsync(d_out.as<uint8_t>() + raw_total, 0, 128, stream));
+    std::vector<CopyDesc> copies;
+    for (uint32_t b = 0; b < nb; b++) if (ddb[b].nsub == 0 && ddb[b].raw_size) { CopyDesc c = { ddb[b].d_off, ddb[b].raw_off, ddb[b].raw_size, 0 }; copies.push_back(c); }
+    if (!copies.empty()) {
+        CR_TRY(chain->upload(d_copy, copies));
+        CR_LAUNCH(k_copy_segments, dim3(64, (unsigned)copies.size()), dim3(256), stream, d_copy.as<CopyDesc>(), d_D.as<uint8_t>(), d_D.as<uint8_t>(), d_out.as<uint8_t>());
+    }
+    if (nsub) CR_LAUNCH(k_dd_subs, dim3(cr_div_up(nsub, 32)), dim3(32), stream, d_D.as<uint8_t>(), d_ddblocks.as<DdBlock>(), d_subs.as<DdSub>(), nsub, dic, d_out.as<uint8_t>());
+
+    // ---- inverse filters (src/main.c:284-286): the state machine needs the decoded headers on the host
+    bool any_filt = false;
+    for (uint8_t f : filt_flags) any_filt |= f != 0;
+    if (any_filt) {
+        CR_CUDA(cudaMemcpyAsync(out, d_out.p, raw_total, cudaMemcpyDeviceToHost, stream));
+        CR_CUDA(cudaStreamSynchronize(stream));
+        filt.reset();
+        std::vector<uint64_t> roff; std::vector<uint32_t> rsize;
+        for (uint32_t b = 0; b < nb; b++) if (filt_flags[b]) { roff.push_back(ddb[b].raw_off); rsize.push_back(ddb[b].raw_size); }
+        std::vector<uint8_t> ff(roff.size(), 0); int dummy = 0;
+        CR_TRY(filt.run_window(*chain, out, d_out.as<uint8_t>(), raw_total, roff, rsize, ff, dummy, /*decode=*/1));
+    }
+    CR_CUDA(cudaMemcpyAsync(out, d_out.p, raw_total, cudaMemcpyDeviceToHost, stream));
+    CR_CUDA(cudaStreamSynchronize(stream));
+    *out_n = raw_total;
+    return CRGPU_OK;
+}

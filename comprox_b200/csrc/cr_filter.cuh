@@ -46,7 +46,7 @@ __global__ void k_e8e9_spans(const uint8_t* __restrict__ d, const E8Op* __restri
 }
 struct E8Apply {
     typedef int State;
-    uint8_t* d; const E8Op* ops; const uint8_t* span;
+    uint8_t* d; const E8Op* ops; const uint8_t* span; int en_de;
     CR_D State begin(uint32_t, uint32_t) const { return 0; }
     CR_D void visit(State&, uint32_t s, uint32_t i, uint32_t sp) const {
         if (sp != 5) return;
@@ -54,9 +54,15 @@ struct E8Apply {
         const uint32_t at = i + 1;                               // index of the operand (the reference's i after i++)
         int32_t op = (int32_t)(e8_byte(d, o, at) | e8_byte(d, o, at + 1) << 8 | e8_byte(d, o, at + 2) << 16 | e8_byte(d, o, at + 3) << 24);
         const int32_t pos = o.ncur + (int32_t)at;
-        if (op >= -pos && op < o.nend - pos) op = (int32_t)((uint32_t)op + (uint32_t)pos);          // :46-47
-        else if (op > 0 && op < o.nend) op = (int32_t)((uint32_t)op - (uint32_t)o.nend);            // :48-49
-        else return;
+        if (en_de == 0) {
+            if (op >= -pos && op < o.nend - pos) op = (int32_t)((uint32_t)op + (uint32_t)pos);      // :46-47
+            else if (op > 0 && op < o.nend) op = (int32_t)((uint32_t)op - (uint32_t)o.nend);        // :48-49
+            else return;
+        } else {
+            if (op < 0) { if ((int32_t)((uint32_t)op + (uint32_t)pos) >= 0) op = (int32_t)((uint32_t)op + (uint32_t)o.nend); else return; }   // :51-53
+            else if (op < o.nend) op = (int32_t)((uint32_t)op - (uint32_t)pos);                      // :54-55
+            else return;
+        }
         for (uint32_t k = 0; k < 4; k++) if (at + k < o.valid) d[o.off + at + k] = (uint8_t)((uint32_t)op >> (8 * k));
     }
     CR_D void end(State&, uint32_t, uint32_t) const {}
@@ -86,6 +92,32 @@ __global__ void k_bmp_rows(const uint8_t* __restrict__ src, uint8_t* __restrict_
         if (xb >= o.bytes) v -= bmp_c(src, o, y, xb - o.bytes);                                       // left delta  (:75-88)
         if (y > 0) { v -= bmp_c(src, o, y - 1, xb); if (xb >= o.bytes) v += bmp_c(src, o, y - 1, xb - o.bytes); }   // up delta (:89-102)
         d[o.off + (uint64_t)y * o.row_size + xb] = (uint8_t)v;
+    }
+}
+
+// inverse (src/filter_bmp.c:104-145): horizontal prefix sums, vertical prefix sums, colour re-correlation, in place
+__global__ void k_bmp_dec_rows(uint8_t* __restrict__ d, const BmpOp* __restrict__ ops) {
+    const BmpOp o = ops[blockIdx.y];
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;             // (row, channel)
+    if (t >= o.rows * o.bytes) return;
+    uint8_t* p = d + o.off + (uint64_t)(t / o.bytes) * o.row_size + t % o.bytes;
+    uint32_t acc = p[0];
+    for (uint32_t x = 1; x < o.width; x++) { acc += p[(size_t)x * o.bytes]; p[(size_t)x * o.bytes] = (uint8_t)acc; }
+}
+__global__ void k_bmp_dec_cols(uint8_t* __restrict__ d, const BmpOp* __restrict__ ops) {
+    const BmpOp o = ops[blockIdx.y];
+    const uint32_t xb = blockIdx.x * blockDim.x + threadIdx.x;
+    if (xb >= o.width * o.bytes) return;
+    uint8_t* p = d + o.off + xb;
+    uint32_t acc = p[0];
+    for (uint32_t y = 1; y < o.rows; y++) { acc += p[(uint64_t)y * o.row_size]; p[(uint64_t)y * o.row_size] = (uint8_t)acc; }
+}
+__global__ void k_bmp_dec_colour(uint8_t* __restrict__ d, const BmpOp* __restrict__ ops) {
+    const BmpOp o = ops[blockIdx.y];
+    const uint64_t total = (uint64_t)o.rows * o.width;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+        uint8_t* p = d + o.off + (t / o.width) * o.row_size + (t % o.width) * o.bytes;
+        p[0] = (uint8_t)(p[0] + p[1]); p[2] = (uint8_t)(p[2] + p[1]);
     }
 }
 
@@ -196,7 +228,7 @@ struct FilterHost {
 
     template <class Chain>
     int run_window(Chain& C, const uint8_t* h_win, uint8_t* d_win, uint64_t nwin_total, const std::vector<uint64_t>& roff, const std::vector<uint32_t>& rsize,
-                   std::vector<uint8_t>& flags, int& filt_flag) {
+                   std::vector<uint8_t>& flags, int& filt_flag, int en_de = 0) {
         cudaStream_t stream = C.stream;
         uint64_t wlen = 0;
         for (size_t b = 0; b < roff.size(); b++) if (roff[b] + rsize[b] > wlen) wlen = roff[b] + rsize[b];
@@ -234,11 +266,18 @@ struct FilterHost {
             CR_LAUNCH(k_e8e9_spans, dim3(cr_div_up(maxlimit, 256), nseg), dim3(256), stream, d_win, b_e8.as<E8Op>(), b_span.as<uint8_t>());
             CR_LAUNCH(k_chain_exits, dim3(cr_div_up(nchunk, 64)), dim3(64), stream, b_span.as<uint8_t>(), b_segs.as<ChainSeg>(), nseg, nchunk, b_xt.as<uint8_t>());
             CR_LAUNCH(k_chain_entries, dim3(cr_div_up(nseg, 32)), dim3(32), stream, b_segs.as<ChainSeg>(), nseg, b_xt.as<uint8_t>(), b_entry.as<uint8_t>());
-            E8Apply f = { d_win, b_e8.as<E8Op>(), b_span.as<uint8_t>() };
+            E8Apply f = { d_win, b_e8.as<E8Op>(), b_span.as<uint8_t>(), en_de };
             CR_LAUNCH(k_chain_walk<E8Apply>, dim3(cr_div_up(nchunk, 64)), dim3(64), stream, b_span.as<uint8_t>(), b_segs.as<ChainSeg>(), nseg, nchunk, b_entry.as<uint8_t>(), f);
         }
         // ---- BMP tiles: snapshot the tiles, then transform from the snapshot
-        if (!bmpops.empty()) {
+        if (!bmpops.empty() && en_de) {
+            uint32_t maxrc = 0, maxwb = 0;
+            for (auto& o : bmpops) { if (o.rows * o.bytes > maxrc) maxrc = o.rows * o.bytes; if (o.width * o.bytes > maxwb) maxwb = o.width * o.bytes; }
+            CR_TRY(C.upload(b_bmp, bmpops));
+            CR_LAUNCH(k_bmp_dec_rows, dim3(cr_div_up(maxrc, 128), (unsigned)bmpops.size()), dim3(128), stream, d_win, b_bmp.as<BmpOp>());
+            CR_LAUNCH(k_bmp_dec_cols, dim3(cr_div_up(maxwb, 128), (unsigned)bmpops.size()), dim3(128), stream, d_win, b_bmp.as<BmpOp>());
+            CR_LAUNCH(k_bmp_dec_colour, dim3(296, (unsigned)bmpops.size()), dim3(256), stream, d_win, b_bmp.as<BmpOp>());
+        } else if (!bmpops.empty()) {
             std::vector<CopyDesc> copies(bmpops.size());
             uint64_t to = 0;
             for (size_t i = 0; i < bmpops.size(); i++) {

@@ -69,6 +69,36 @@ static inline std::vector<uint8_t> hd_lcp_encode(const std::string& t) {
     return o;
 }
 
+// src/cr-dicpick.c:307-346: inverse of hd_lcp_encode; returns the dictionary text without the final NUL
+static inline std::string hd_lcp_decode(const uint8_t* d, size_t n) {
+    std::string o;
+    size_t wi = 0, wo = 0;
+    while (wi < n && d[wi] != '\n') o.push_back((char)d[wi++]);
+    wi++; o.push_back('\n');
+    while (wi < n && d[wi] != 255) {
+        int lcp = d[wi++];
+        while (lcp-- > 0) o.push_back(o[wo++]);
+        while (wi < n && d[wi] != '\n') o.push_back((char)d[wi++]);
+        wi++; o.push_back('\n');
+        while (o[wo] != '\n') wo++;
+        wo++;
+    }
+    return o;
+}
+// the dictionary entries as dictionary_load stores them (src/cr-diccode.c:82-93): one per line, a blank appended
+// to entries that end in a letter
+static inline std::vector<std::string> hd_entries(const char* text) {
+    std::vector<std::string> entries;
+    std::string cur;
+    for (const char* s = text; *s; s++) {
+        if (*s == '\n') {
+            if (!cur.empty() && (unsigned)(((unsigned char)cur.back() | 32) - 'a') < 26u) cur.push_back(' ');
+            entries.push_back(cur); cur.clear();
+        } else cur.push_back(*s);
+    }
+    return entries;
+}
+
 // src/cr-diccode.c:47-120: entries get a trailing blank when they end in a letter; 128-ary trie with the
 // root's upper-case links ('A'..'Y', sic) and the ". , : ;" aliases of every blank edge.
 // The reference stores 128 child slots per node (516 B/node, tens of MB).  Only the edges that exist are kept

@@ -2,6 +2,7 @@
 #include "../../include/crgpu.h"
 #include "cr_lzchain.cuh"
 #include "cr_container.cuh"
+#include "cr_decontainer.cuh"
 #include <string>
 
 #ifdef CRGPU_SIM
@@ -17,6 +18,7 @@ struct crgpu_handle {
     LzChain chain;
     DevBuf d_in, d_out;
     Compressor comp;
+    Decompressor decomp;
 };
 
 extern "C" const char* crgpu_strerror(int code) {
@@ -58,7 +60,7 @@ extern "C" void crgpu_destroy(crgpu_handle* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
 #endif
-    h->chain.release(); h->d_in.release(); h->d_out.release(); h->comp.release();
+    h->chain.release(); h->d_in.release(); h->d_out.release(); h->comp.release(); h->decomp.release();
     delete h;
 }
 
@@ -170,4 +172,13 @@ extern "C" int crgpu_stage_input(crgpu_handle* h, const uint8_t* in, uint64_t n)
 #endif
     h->comp.chain = &h->chain; h->comp.stream = h->chain.stream;
     return h->comp.stage(in, n);
+}
+
+extern "C" int crgpu_decompress(crgpu_handle* h, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_n) {
+    if (!h) return CRGPU_ERR_ARG;
+#ifndef CRGPU_SIM
+    CR_CUDA(cudaSetDevice(h->device));
+#endif
+    h->decomp.chain = &h->chain;
+    return h->decomp.decompress(in, n, out, out_cap, out_n);
 }

@@ -76,11 +76,7 @@ int main(int argc, char** argv) {
     gettimeofday(&t0, NULL);
     if ((argc = process_arguments(argc, argv)) == 0) return -1;
     if (!(argc >= 2 && argc <= 4 && (!strcmp(argv[1], "e") || !strcmp(argv[1], "d")))) { usage(); return -1; }
-    if (!strcmp(argv[1], "d")) {
-        fprintf(stderr, "%s (B200 build): decompression is not part of this build yet; the container is the reference's, "
-                        "use the reference `%s d`.\n", NAME, NAME);
-        return -1;
-    }
+    const int decode = !strcmp(argv[1], "d");
     FILE* src = argc >= 3 ? fopen(argv[2], "rb") : stdin;
     FILE* dst = argc >= 4 ? fopen(argv[3], "wb") : stdout;
     if (!src || !dst) { perror("fopen()"); return -1; }
@@ -97,19 +93,28 @@ int main(int argc, char** argv) {
     if (!lib) { fprintf(stderr, "%s: cannot load %s: %s (no CPU fallback)\n", NAME, path, dlerror()); return -1; }
     int (*p_create)(crgpu_handle**, int, int, void*) = dlsym(lib, "crgpu_create");
     int (*p_compress)(crgpu_handle*, const crgpu_config*, const uint8_t*, uint64_t, uint8_t*, uint64_t, uint64_t*) = dlsym(lib, "crgpu_compress");
+    int (*p_decompress)(crgpu_handle*, const uint8_t*, uint64_t, uint8_t*, uint64_t, uint64_t*) = dlsym(lib, "crgpu_decompress");
     uint64_t (*p_bound)(uint64_t, uint32_t) = dlsym(lib, "crgpu_compress_bound");
     const char* (*p_err)(int) = dlsym(lib, "crgpu_strerror");
     void (*p_destroy)(crgpu_handle*) = dlsym(lib, "crgpu_destroy");
 
     uint64_t n = 0, out_n = 0;
     uint8_t* in = read_all(src, &n);
-    if (!quiet) fprintf(stderr, "compressing %s to %s, block_size = %uMB...\n", argc >= 3 ? argv[2] : "<stdin>", argc >= 4 ? argv[3] : "<stdout>", cr_split_size / 1048576);
+    if (!quiet && !decode) fprintf(stderr, "compressing %s to %s, block_size = %uMB...\n", argc >= 3 ? argv[2] : "<stdin>", argc >= 4 ? argv[3] : "<stdout>", cr_split_size / 1048576);
+    if (!quiet && decode) fprintf(stderr, "decompressing %s to %s...\n", argc >= 3 ? argv[2] : "<stdin>", argc >= 4 ? argv[3] : "<stdout>");
     crgpu_handle* h = NULL;
     int rc = p_create(&h, CR_VARIANT, getenv("CRGPU_DEVICE") ? atoi(getenv("CRGPU_DEVICE")) : 0, NULL);
     if (rc) { fprintf(stderr, "%s: %s\n", NAME, p_err(rc)); return -1; }
     crgpu_config cfg = { cr_split_size, cr_filt_enable, cr_prec_enable, flexible_parsing, 0 };
-    uint64_t cap = p_bound(n, cr_split_size);
+    uint64_t cap = decode ? 64 : p_bound(n, cr_split_size);
     uint8_t* out = malloc(cap);
+    if (decode) {                                   /* the container does not store the raw size: grow until it fits */
+        for (cap = n * 4 + (1u << 20);; cap *= 2) {
+            out = realloc(out, cap);
+            rc = p_decompress(h, in, n, out, cap, &out_n);
+            if (rc != CRGPU_ERR_ARG || cap > ((uint64_t)1 << 36)) break;
+        }
+    } else
     rc = p_compress(h, &cfg, in, n, out, cap, &out_n);
     if (rc) { fprintf(stderr, "%s: %s\n", NAME, p_err(rc)); return -1; }
     if (fwrite(out, 1, out_n, dst) != out_n) { perror("fwrite()"); return -1; }

@@ -69,6 +69,14 @@ typedef struct crgpu_config {
 uint64_t crgpu_compress_bound(uint64_t n, uint32_t block_size);
 int crgpu_compress(crgpu_handle* h, const crgpu_config* cfg, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_n);
 
+/* Whole-container decompression: cr_main's decode branch (src/main.c:220-302): check_magic, dictionary payload,
+ * then per block lzdecode (unless the block was written with -p), dictionary_decode and filter_inplace(FILTER_DEC).
+ * One container is one serial model chain, so this call runs the entropy stage on a single GPU thread: it is
+ * provided for completeness and for decoding MANY containers side by side (one handle each); a single container
+ * decodes faster on the host.  Returns CRGPU_ERR_ARG if the magic does not match the handle's variant or out_cap
+ * is too small. */
+int crgpu_decompress(crgpu_handle* h, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_n);
+
 /* Copies `in` to HBM ahead of time.  A following crgpu_compress(h, cfg, in, n, ...) with the same pointer and
  * length (and no -F, which rewrites the staged bytes in place) then skips its host-to-device copy; used by
  * bench.py to time the device-resident path separately from the end-to-end path. */

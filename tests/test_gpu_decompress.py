@@ -1,0 +1,57 @@
+"""GPU parity of crgpu_decompress: containers written by the unmodified reference CLI (oracle/_ref, when present),
+by the oracle, and by our own crgpu_compress must decode to the original bytes."""
+import pytest
+
+import oracle_ffi as O
+from comprox_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+MiB = 1 << 20
+BIN = {api.ROLZ: "comprolz", api.LZP: "comprop"}
+
+
+def _sources(variant, data, bs, flags, filt):
+    yield "oracle", O.compress(data, variant, bs, filt, 0)
+    ref = O.ref_compress(data, BIN[variant], ["-b%d" % (bs // MiB), *flags])
+    if ref is not None:
+        yield "reference", ref
+
+
+@pytest.mark.parametrize("variant", [api.ROLZ, api.LZP])
+def test_gpu_decompress_text(gpulib, variant):
+    data = synth.markov_text(3 * MiB + 4321, seed=42)
+    for who, container in _sources(variant, data, MiB, [], 0):
+        with api.Handle(variant, lib=gpulib) as h:
+            assert h.decompress(container, len(data) + 64) == data, who
+
+
+@pytest.mark.parametrize("variant", [api.ROLZ, api.LZP])
+@pytest.mark.parametrize("data", [b"", b"A", bytes(MiB), (b"The quick brown fox jumps over the lazy dog. " * 30000)[:1300000]],
+                         ids=["empty", "A", "zeros", "fox"])
+def test_gpu_decompress_known_answers(gpulib, variant, data):
+    for who, container in _sources(variant, data, 16 * MiB, [], 0):
+        with api.Handle(variant, lib=gpulib) as h:
+            assert h.decompress(container, len(data) + 64) == data, who
+
+
+def test_gpu_decompress_filtered_x86(gpulib):
+    data = synth.x86_corpus(3 * MiB, elf_bytes=MiB + 12345, pe_min=MiB // 2, pe_max=MiB)
+    for who, container in _sources(api.ROLZ, data, MiB, ["-F"], 1):
+        with api.Handle(api.ROLZ, lib=gpulib) as h:
+            assert h.decompress(container, len(data) + 64) == data, who
+
+
+def test_gpu_decompress_filtered_bmp(gpulib):
+    data = synth.bmp_corpus(3 * MiB, wmin=301, wmax=900, hmin=100, hmax=500)
+    for who, container in _sources(api.LZP, data, MiB, ["-F"], 1):
+        with api.Handle(api.LZP, lib=gpulib) as h:
+            assert h.decompress(container, len(data) + 64) == data, who
+
+
+@pytest.mark.parametrize("variant", [api.ROLZ, api.LZP])
+def test_gpu_roundtrip_own_container(gpulib, variant):
+    data = synth.markov_text(2 * MiB, seed=5) + synth.x86_corpus(MiB, elf_bytes=0, pe_min=MiB // 2, pe_max=MiB)
+    with api.Handle(variant, lib=gpulib) as h:
+        container = h.compress(data, MiB)
+    with api.Handle(variant, lib=gpulib) as h:
+        assert h.decompress(container, len(data) + 64) == data

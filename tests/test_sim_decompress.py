@@ -1,0 +1,36 @@
+"""CPU pre-flight (kernel-logic simulation) of crgpu_decompress: decodes containers written by the ORACLE."""
+import pytest
+
+import oracle_ffi as O
+from comprox_b200 import api, synth
+
+MiB = 1 << 20
+
+
+def _cases():
+    text = synth.markov_text(MiB + 12345, seed=7)
+    return {
+        "text": (text, MiB // 2, 0, 0),
+        "empty": (b"", MiB, 0, 0),
+        "single_byte": (b"A", MiB, 0, 0),
+        "fox": ((b"The quick brown fox jumps over the lazy dog. " * 30000)[:1300000], MiB, 0, 0),
+        "prec": (text[:MiB // 2], MiB, 0, 1),
+        "x86_filtered": (synth.x86_corpus(MiB, elf_bytes=MiB // 4 + 77, pe_min=MiB // 8, pe_max=MiB // 4), MiB // 2, 1, 0),
+        "bmp_filtered": (synth.bmp_corpus(MiB, wmin=201, wmax=500, hmin=60, hmax=300), MiB // 2, 1, 0),
+    }
+
+
+@pytest.mark.parametrize("variant", [api.ROLZ, api.LZP])
+@pytest.mark.parametrize("name", sorted(_cases().keys()))
+def test_sim_decompress_oracle_container(simlib, variant, name):
+    data, bs, filt, prec = _cases()[name]
+    container = O.compress(data, variant, bs, filt, prec)
+    with api.Handle(variant, lib=simlib) as h:
+        assert h.decompress(container, len(data) + 64) == data
+
+
+def test_sim_decompress_rejects_wrong_magic(simlib):
+    container = O.compress(b"hello hello hello", api.ROLZ)
+    with api.Handle(api.LZP, lib=simlib) as h:
+        with pytest.raises(api.CrgpuError):
+            h.decompress(container, 1024)

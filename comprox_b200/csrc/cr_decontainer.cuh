@@ -51,6 +51,10 @@ struct Decompressor {
             CR_TRY(chain->upload(d_copy, copies));
             CR_LAUNCH(k_copy_segments, dim3(64, (unsigned)copies.size()), dim3(256), stream, d_copy.as<CopyDesc>(), d_cont.as<uint8_t>(), d_cont.as<uint8_t>(), d_D.as<uint8_t>());
         }
+#ifndef CRGPU_SIM
+        if (!chain->scalar_models) CR_LAUNCH(k_lzdecode_warp, dim3(1), dim3(32), stream, chain->variant, d_cont.as<uint8_t>(), d_blocks.as<DecBlock>(), (uint32_t)blk.size(), chain->st, T, d_ctx.as<uint32_t>(), d_D.as<uint8_t>());
+        else
+#endif
         CR_LAUNCH(k_lzdecode_serial, dim3(1), dim3(1), stream, chain->variant, d_cont.as<uint8_t>(), d_blocks.as<DecBlock>(), (uint32_t)blk.size(), chain->st, T, d_ctx.as<uint32_t>(), d_D.as<uint8_t>());
         CR_TRY(chain->download(c, d_ctx.p, 1));
         chain->chain_ctx = c[0];

@@ -14,6 +14,7 @@
 #include "cr_common.cuh"
 #include "cr_ppm.cuh"
 #include "cr_rc.cuh"
+#include "cr_decode.cuh"
 
 #define FULLMASK 0xFFFFFFFFu
 
@@ -984,5 +985,257 @@ __global__ void k_stream_totals(const RcStream* __restrict__ streams, uint32_t n
     if (S.is_main) { i0 += escord[S.ev_begin]; i1 += escord[S.ev_end]; }
     const uint32_t* b = S.is_main ? bscan_main : bscan_side;
     out[s].tri_begin = i0; out[s].tri_end = i1; out[s].shifts = b[i1] - b[i0]; out[s].pad = 0;
+}
+
+// ------------------------------------------------------------------ warp-cooperative decoder (one warp per container)
+// Same serial chain as k_lzdecode_serial (cr_decode.cuh) -- decoding cannot be replayed per context -- but every
+// 256-wide loop of ppm_decode / model_get_decode_symbol runs across the lanes: lane l owns symbols 8l..8l+7 of the
+// current o2 row / o1 row / order-0 model, cumulative frequencies come from a warp scan, the symbol search is a
+// ballot.  The range decoder state is replicated in all lanes (uniform control flow, no divergence).
+struct WRc {
+    uint32_t range, code; const uint8_t* in;
+    CR_D void init(const uint8_t* p) { range = 0xFFFFFFFFu; code = 0; in = p; for (int i = 0; i < 5; i++) code = (code << 8) + __ldg(in++); }
+    CR_D uint32_t target(uint32_t sum) { range /= sum; return code / range; }
+    CR_D void consume(uint32_t cum, uint32_t frq) {
+        code -= cum * range; range *= frq;
+        while (range < (1u << 24)) { code = (code << 8) + __ldg(in++); range <<= 8; }
+    }
+};
+CR_D uint32_t wscan_incl(uint32_t v, uint32_t lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(FULLMASK, v, d); if (lane >= (uint32_t)d) v += t; }
+    return v;
+}
+CR_D uint32_t byte_of(uint32_t lo, uint32_t hi, uint32_t k) { return ((k < 4 ? lo : hi) >> (8 * (k & 3))) & 255u; }
+
+// ppm_decode (cr-ppm.c:169-235), warp form.  Returns the decoded symbol (uniform).
+CR_D uint32_t wdec_ppm(PpmState& st, uint32_t ctx, WRc& rc, uint32_t lane) {
+    uint8_t* row = st.o2 + (size_t)(ctx & 0xffff) * PPM_O2_STRIDE;
+    const uint32_t slot = ppm_slot(ctx);
+    uint2 fv = ((const uint2*)row)[lane];
+    uint32_t f0 = fv.x, f1 = fv.y;
+    const uint32_t fl = *(const uint16_t*)(row + 256);
+    uint32_t f256 = fl & 255, f257 = fl >> 8;
+    const uint32_t pred = st.o3_byte[slot];
+    uint32_t conf = st.o3_conf[slot];
+    const uint32_t pown = pred >> 3;
+    const uint32_t pf = __shfl_sync(FULLMASK, byte_of(f0, f1, pred & 7), pown);
+    const uint32_t lsum = wsum4(f0) + wsum4(f1);
+    uint32_t body = __reduce_add_sync(FULLMASK, lsum);
+    const uint32_t tgt = rc.target(body + f256 + f257 - pf);
+    const uint32_t ls = lsum - (lane == pown ? pf : 0u);
+    const uint32_t incl = wscan_incl(ls, lane);
+    const uint32_t hitmask = __ballot_sync(FULLMASK, incl > tgt);
+    uint32_t s, acc, frq;
+    if (hitmask) {
+        const uint32_t L = __ffs(hitmask) - 1;
+        acc = __shfl_sync(FULLMASK, incl - ls, L);
+        const uint32_t g0 = __shfl_sync(FULLMASK, f0, L), g1 = __shfl_sync(FULLMASK, f1, L);
+        uint32_t k = 0; frq = 0;
+        for (; k < 8; k++) { const uint32_t sy = L * 8 + k; frq = byte_of(g0, g1, k); const uint32_t wgt = sy == pred ? 0u : frq; if (acc + wgt > tgt) break; acc += wgt; }
+        s = L * 8 + k;
+    } else {
+        acc = body - pf;
+        if (tgt < acc + f256) { s = 256; frq = f256; } else { acc += f256; s = 257; frq = f257; }
+    }
+    rc.consume(acc, frq);
+    // ---- o2_model_update(s, +1) and its consequences
+    bool rescale = false, wrote_all = false;
+    uint32_t sym = s;
+    if (s == 256) { f256 = (f256 + 1) & 255; rescale = f256 > 250; sym = pred; }
+    else if (s < 256) {
+        if (lane == (s >> 3)) { const uint32_t k = s & 7; if (k < 4) f0 += 1u << (8 * k); else f1 += 1u << (8 * (k - 4)); }
+        body += 1;
+        if (frq + 1 > 250) rescale = true;
+        else if (frq + 1 == 2) { f257 = (f257 - 1) & 255; rescale = f257 > 250; }
+    } else {
+        f257 = (f257 + 1) & 255;
+        const bool resc257 = f257 > 250;
+        if (resc257) {
+            f0 = (f0 >> 1) & 0x7f7f7f7fu; f1 = (f1 >> 1) & 0x7f7f7f7fu;
+            const uint32_t ones = (__popc(__vcmpeq4(f0, 0x01010101u)) + __popc(__vcmpeq4(f1, 0x01010101u))) >> 3;
+            f257 = (1 + __reduce_add_sync(FULLMASK, ones)) & 255; f256 = (f256 + 1) >> 1;
+            wrote_all = true;
+        }
+        // o1 with exclusion (cr-ppm.c:208-227)
+        uint8_t* o1row = st.o1 + (ctx & 0xff) * 256;
+        uint2 av = ((const uint2*)o1row)[lane];
+        uint32_t a0 = av.x, a1 = av.y;
+        const uint32_t z0 = __vcmpeq4(f0, 0u), z1 = __vcmpeq4(f1, 0u);
+        uint32_t bits = ((z0 & 1u) | (z0 >> 7 & 2u) | (z0 >> 14 & 4u) | (z0 >> 21 & 8u)) | (((z1 & 1u) | (z1 >> 7 & 2u) | (z1 >> 14 & 4u) | (z1 >> 21 & 8u)) << 4);
+        if (lane == pown) bits &= ~(1u << (pred & 7));
+        uint32_t ls1 = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < 8; k++) if (bits >> k & 1u) ls1 += byte_of(a0, a1, k) * 8 - 7;
+        const uint32_t sum1 = __reduce_add_sync(FULLMASK, ls1);
+        const uint32_t t1 = rc.target(sum1);
+        const uint32_t incl1 = wscan_incl(ls1, lane);
+        const uint32_t hm = __ballot_sync(FULLMASK, incl1 > t1);
+        const uint32_t L = hm ? __ffs(hm) - 1 : 31;
+        uint32_t cum1 = __shfl_sync(FULLMASK, incl1 - ls1, L);
+        const uint32_t g0 = __shfl_sync(FULLMASK, a0, L), g1 = __shfl_sync(FULLMASK, a1, L), gb = __shfl_sync(FULLMASK, bits, L);
+        uint32_t k = 0, fr = 1;
+        for (; k < 8; k++) { if (!(gb >> k & 1u)) continue; fr = byte_of(g0, g1, k) * 8 - 7; if (cum1 + fr > t1) break; cum1 += fr; }
+        if (k == 8) k = 7;
+        const uint32_t d = L * 8 + k;
+        rc.consume(cum1, fr);
+        const uint32_t cd = (fr + 7) >> 3;                                   // o1[d] before the update
+        if (lane == L) { if (k < 4) a0 += 1u << (8 * k); else a1 += 1u << (8 * (k - 4)); }
+        if (cd + 1 >= 255) { a0 -= (a0 >> 1) & 0x7f7f7f7fu; a1 -= (a1 >> 1) & 0x7f7f7f7fu; ((uint2*)o1row)[lane] = make_uint2(a0, a1); }
+        else if (lane == L) ((uint2*)o1row)[lane] = make_uint2(a0, a1);
+        if (!resc257) { if (lane == (d >> 3)) { const uint32_t q = d & 7; if (q < 4) f0 += 1u << (8 * q); else f1 += 1u << (8 * (q - 4)); } }
+        sym = d;
+    }
+    if (rescale) {
+        f0 = (f0 >> 1) & 0x7f7f7f7fu; f1 = (f1 >> 1) & 0x7f7f7f7fu;
+        const uint32_t ones = (__popc(__vcmpeq4(f0, 0x01010101u)) + __popc(__vcmpeq4(f1, 0x01010101u))) >> 3;
+        f257 = (1 + __reduce_add_sync(FULLMASK, ones)) & 255; f256 = (f256 + 1) >> 1;
+        wrote_all = true;
+    }
+    if (wrote_all || lane == (sym >> 3)) ((uint2*)row)[lane] = make_uint2(f0, f1);
+    if (lane == 0) *(uint16_t*)(row + 256) = (uint16_t)(f256 | f257 << 8);
+    // ---- ppm_update_o3 (cr-ppm.c:69-88)
+    if (s == 256) conf += conf < 15;
+    else { conf = (conf > 1) + (conf > 2) + (conf > 4) + (conf > 8); if (conf == 0) { if (lane == 0) st.o3_byte[slot] = (uint8_t)sym; conf = 1; } }
+    if (lane == 0) st.o3_conf[slot] = (uint8_t)conf;
+    __syncwarp();
+    return sym;
+}
+// order-0 model in registers (8 x u16 per lane): M_my_dec_ with increment 4
+CR_D uint32_t wdec_m0(uint32_t (&f)[4], uint32_t& total, WRc& rc, uint32_t lane) {
+    const uint32_t tgt = rc.target(total);
+    const uint32_t ls = side_part(f, 8);
+    const uint32_t incl = wscan_incl(ls, lane);
+    const uint32_t hm = __ballot_sync(FULLMASK, incl > tgt);
+    const uint32_t L = hm ? __ffs(hm) - 1 : 31;
+    uint32_t acc = __shfl_sync(FULLMASK, incl - ls, L);
+    uint32_t g[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) g[q] = __shfl_sync(FULLMASK, f[q], L);
+    uint32_t k = 0, fr = 0;
+    for (; k < 8; k++) { fr = (g[k >> 1] >> (16 * (k & 1))) & 0xffff; if (acc + fr > tgt) break; acc += fr; }
+    if (k == 8) k = 7;
+    rc.consume(acc, fr);
+    if (lane == L) f[k >> 1] += 4u << (16 * (k & 1));
+    total += 4;
+    if (total > 32000) { for (int q = 0; q < 4; q++) f[q] = ((f[q] + 0x00010001u) >> 1) & 0x7fff7fffu; total = __reduce_add_sync(FULLMASK, side_part(f, 8)); }
+    return L * 8 + k;
+}
+// copy `len` bytes from out[q..] to out[n..] with the byte-serial semantics of the reference's copy loop
+CR_D void wcopy_match(uint8_t* out, uint32_t n, uint32_t q, uint32_t len, uint32_t lane) {
+    const uint32_t dist = n - q;
+    if (dist >= 32) { for (uint32_t b = 0; b < len; b += 32) { if (b + lane < len) out[n + b + lane] = out[q + b + lane]; __syncwarp(); } }
+    else { for (uint32_t b = 0; b < len; b += 32) if (b + lane < len) out[n + b + lane] = out[q + (b + lane) % dist]; __syncwarp(); }
+}
+
+__global__ void __launch_bounds__(32) k_lzdecode_warp(int variant, const uint8_t* __restrict__ cont, const DecBlock* __restrict__ blocks, uint32_t nb,
+                                                       PpmState st, DecTables T, uint32_t* __restrict__ ctx_io, uint8_t* __restrict__ D) {
+    if (blockIdx.x != 0) return;
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t ctx = *ctx_io;
+    uint32_t fa[4], fb[4];
+    { const uint4 v = ((const uint4*)(st.m0))[lane]; fa[0] = v.x; fa[1] = v.y; fa[2] = v.z; fa[3] = v.w;
+      const uint4 u = ((const uint4*)(st.m0 + 256))[lane]; fb[0] = u.x; fb[1] = u.y; fb[2] = u.z; fb[3] = u.w; }
+    uint32_t tota = __reduce_add_sync(FULLMASK, side_part(fa, 8)), totb = __reduce_add_sync(FULLMASK, side_part(fb, 8));
+    for (uint32_t b = 0; b < nb; b++) {
+        const DecBlock B = blocks[b];
+        if (!B.coded) continue;
+        const uint8_t* in = cont + B.in_off;
+        uint8_t* out = D + B.d_off;
+        const uint32_t orig = B.d_size;
+        if (variant == 0) {
+            const uint32_t esc = in[2], off_idx = cr_ld32(in + 12);
+            const int ctx4 = orig >= 4194304;
+            WRc rc, side; rc.init(in + 16); side.init(in + off_idx);
+            for (uint32_t i = lane; i < 256 * 16; i += 32) T.rz_short[i] = 0;
+            __syncwarp();
+            uint32_t bucket = 0, sbucket = 0, n = 0, hist = 0;                 // hist: last four bytes written
+            if (lane == 0) out[0] = in[0];
+            hist = in[0]; n = 1;
+            __syncwarp();
+            while (n < orig) {
+                uint32_t len = 1;
+                const uint32_t s = wdec_ppm(st, ctx, rc, lane);
+                if (s == esc) {
+                    const uint32_t l = wdec_m0(fa, tota, side, lane);
+                    if (l == 0) { if (lane == 0) out[n] = (uint8_t)esc; n++; }
+                    else {
+                        const uint32_t idx = wdec_m0(fb, totb, side, lane);
+                        uint32_t q;
+                        if (idx < 64) { const uint32_t m = T.rz_meta[bucket]; q = T.rz_items[(size_t)bucket * 64 + (((m & 255) + 64 - idx) & 63)]; }
+                        else q = T.rz_short[sbucket * 16 + idx - 64];
+                        len = l;
+                        wcopy_match(out, n, q, len, lane);
+                        n += len;
+                    }
+                } else { if (lane == 0) out[n] = (uint8_t)s; n++; }
+                __syncwarp();
+                for (uint32_t p = n - len; p < n; p++) {                        // matcher_update + ppm_update_context per byte
+                    const uint32_t byte = len == 1 ? (s == esc ? esc : s) : out[p];
+                    hist = hist << 8 | byte;
+                    if (p >= 16) {
+                        uint32_t m = T.rz_meta[bucket];
+                        if ((m >> 16) != B.epoch) m = B.epoch << 16;
+                        const uint32_t head = ((m & 255) + 1) & 63;
+                        uint32_t count = ((m >> 8) & 255) + 1; if (count > 64) count = 64;
+                        if (lane == 0) { T.rz_items[(size_t)bucket * 64 + head] = p; T.rz_meta[bucket] = B.epoch << 16 | count << 8 | head; }
+                        uint32_t h = (hist & 255) * 1313131u + (hist >> 8 & 255) * 13131u + (hist >> 16 & 255) * 131u;
+                        if (ctx4) h += hist >> 24;
+                        bucket = h & (RZ_BUCKETS - 1);
+                        uint32_t* srow = T.rz_short + sbucket * 16;
+                        const uint32_t v = lane < 16 ? srow[lane] : 0;
+                        __syncwarp();
+                        if (lane < 15) srow[lane + 1] = v;
+                        if (lane == 0) srow[0] = p;
+                        sbucket = byte;
+                        __syncwarp();
+                    }
+                    ctx = ctx << 8 | byte;
+                }
+            }
+        } else {
+            const uint32_t esc = in[8];
+            if (lane < 9) out[lane] = in[9 + lane];
+            __syncwarp();
+            WRc rc; rc.init(in + 20);
+            const unsigned long long tag = (unsigned long long)B.epoch << 32;
+            unsigned long long h8 = 0;                                          // last eight bytes written (most recent in the top byte)
+            for (int i = 1; i < 9; i++) h8 = h8 >> 8 | (unsigned long long)in[9 + i] << 56;
+            uint32_t n = 9;
+            while (n < orig) {
+                uint32_t len = 1;
+                const uint32_t s = wdec_ppm(st, ctx, rc, lane);
+                uint32_t lit = s;
+                if (s == esc) {
+                    ctx = ctx << 8 | esc;
+                    len = wdec_ppm(st, ctx, rc, lane);
+                    if (len == 0) { len = 1; lit = esc; if (lane == 0) out[n] = (uint8_t)esc; n++; }
+                    else {
+                        LzpDec m; m.T = T; m.tag = tag;
+                        const uint32_t q = m.getpos(out, n);
+                        wcopy_match(out, n, q, len, lane);
+                        n += len;
+                    }
+                } else { if (lane == 0) out[n] = (uint8_t)s; n++; }
+                __syncwarp();
+                for (uint32_t p = n - len; p < n; p++) {
+                    const uint32_t byte = len == 1 ? lit : out[p];
+                    // hashes of the 8 / 4 / 2 bytes in front of p (src/ropmain/cr-matcher.c:31-33): h8 holds bytes p-8..p-1 little endian
+                    if (lane == 0) {
+                        const uint32_t x4 = (uint32_t)(h8 >> 32), x2 = (uint32_t)(h8 >> 48);
+                        T.lzp8[(uint32_t)((h8 ^ h8 >> 20 ^ h8 >> 40) & 0xffffff)] = tag | p;
+                        T.lzp4[(x4 ^ x4 >> 6 ^ x4 >> 12) & 0xfffff] = tag | p;
+                        T.lzp2[x2] = tag | p;
+                    }
+                    h8 = h8 >> 8 | (unsigned long long)byte << 56;
+                    ctx = ctx << 8 | byte;
+                }
+                __syncwarp();
+            }
+        }
+    }
+    ((uint4*)(st.m0))[lane] = make_uint4(fa[0], fa[1], fa[2], fa[3]);
+    ((uint4*)(st.m0 + 256))[lane] = make_uint4(fb[0], fb[1], fb[2], fb[3]);
+    if (lane == 0) *ctx_io = ctx;
 }
 #endif  // !CRGPU_SIM

@@ -55,3 +55,13 @@ def test_gpu_roundtrip_own_container(gpulib, variant):
         container = h.compress(data, MiB)
     with api.Handle(variant, lib=gpulib) as h:
         assert h.decompress(container, len(data) + 64) == data
+
+
+@pytest.mark.parametrize("variant", [api.ROLZ, api.LZP])
+def test_gpu_decompress_scalar_kernel(gpulib, variant):
+    """The single-thread decoder (the one the CPU simulation checks) agrees with the warp decoder on the GPU."""
+    data = synth.markov_text(300000, seed=8)
+    container = O.compress(data, variant, MiB)
+    with api.Handle(variant, lib=gpulib) as h:
+        h.set_option("scalar_models", 1)
+        assert h.decompress(container, len(data) + 64) == data

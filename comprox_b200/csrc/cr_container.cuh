@@ -220,7 +220,7 @@ static inline uint64_t cr_compress_bound(uint64_t n, uint32_t block_size) {
 
 inline int Compressor::compress(const CrConfig& cfg, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_n) {
     if (cfg.block_size == 0 || (n && !in) || !out || !out_n) return CRGPU_ERR_ARG;
-    if (cfg.flexible) return CRGPU_ERR_UNSUPPORTED;
+    if (cfg.flexible && chain->variant != CR_ROLZ) return CRGPU_ERR_ARG;     // comprop has no -f (src/ropmain/main.c)
     stream = chain->stream;
     StageTimer& tm = chain->timer;
     const size_t mlen = strlen(cr_magic(chain->variant));
@@ -244,6 +244,7 @@ inline int Compressor::compress(const CrConfig& cfg, const uint8_t* in, uint64_t
     CR_TRY(load_dictionary(text));
     std::vector<uint8_t> lcp = hd_lcp_encode(text);
     CR_TRY(upload(d_dic, lcp));
+    chain->flexible = cfg.flexible != 0;       // flexible_parsing is a process-wide switch: it also applies to the dictionary payload
     CR_TRY(chain->reset_models());
     std::vector<BlockIO> dblk(1);
     memset(&dblk[0], 0, sizeof(BlockIO)); dblk[0].size = (uint32_t)lcp.size();

@@ -43,13 +43,14 @@ struct LzChain {
     DevBuf b_evctx, b_evsym, b_tokend, b_pred, b_T1, b_T2, b_TS, b_side;
     DevBuf b_escrec, b_esccount, b_k64a, b_k64b, b_ord, b_flag, b_escord;
     DevBuf b_lensym, b_lenpos, b_idxsym, b_idxpos;
-    DevBuf b_o1info, b_o1ord, b_o1incl, b_bounds, b_o3hot, b_cinm, b_cins, b_segstart, b_segkey;
+    DevBuf b_o1info, b_o1ord, b_o1incl, b_bounds, b_o3hot, b_cinm, b_cins, b_segstart, b_segkey, b_rank, b_flexlen;
     DevBuf b_qm, b_shm, b_bm, b_qs, b_shs, b_bs, b_stot, b_dsum, b_lsm, b_lss, b_rsm, b_rss, b_fb;
     DevBuf b_dense, b_denseside, b_streams, b_rcres, b_rcout, b_copy, b_hdr;
     // ---- sizes of the last window (for the debug/trace fetch used by the tests)
     uint32_t last_nev = 0, last_nside = 0, last_nesc = 0, last_nent = 0;
     size_t last_dtotal = 0;
     StageTimer timer;
+    bool flexible = false;         // -f flexible parsing (ROLZ)
     int rc_variant = 4;            // range-chain formulation (cr_warp.cuh: k_range_chain<1|2|3>)
     bool hot_contexts = true;      // hot o2 contexts run the rank-based CTA kernel (k_o2_pass_cta)
     bool scalar_models = false;   // GPU A/B switch: run the scalar (simulation-checked) model/coder kernels
@@ -67,7 +68,7 @@ struct LzChain {
         DevBuf* all[] = { &s_o3b, &s_o3c, &s_o2, &s_o1, &s_m0, &b_blocks, &b_segoff, &b_seglen, &b_hist, &b_esc1, &b_first, &b_ctxout,
             &b_k0, &b_k1, &b_v0, &b_v1, &b_ks0, &b_M, &b_S, &b_span, &b_tidx, &b_segs, &b_xt, &b_entry, &b_cnt, &b_scan,
             &b_evctx, &b_evsym, &b_tokend, &b_pred, &b_T1, &b_T2, &b_TS, &b_side, &b_escrec, &b_esccount, &b_k64a, &b_k64b, &b_ord,
-            &b_flag, &b_escord, &b_lensym, &b_lenpos, &b_idxsym, &b_idxpos, &b_o1info, &b_o1ord, &b_o1incl, &b_bounds, &b_o3hot, &b_cinm, &b_cins, &b_segstart, &b_segkey, &b_qm, &b_shm, &b_bm, &b_qs, &b_shs, &b_bs, &b_stot, &b_dsum, &b_lsm, &b_lss, &b_rsm, &b_rss, &b_fb, &b_dense, &b_denseside, &b_streams, &b_rcres, &b_rcout, &b_copy, &b_hdr, &prims.temp };
+            &b_flag, &b_escord, &b_lensym, &b_lenpos, &b_idxsym, &b_idxpos, &b_o1info, &b_o1ord, &b_o1incl, &b_bounds, &b_o3hot, &b_cinm, &b_cins, &b_segstart, &b_segkey, &b_rank, &b_flexlen, &b_qm, &b_shm, &b_bm, &b_qs, &b_shs, &b_bs, &b_stot, &b_dsum, &b_lsm, &b_lss, &b_rsm, &b_rss, &b_fb, &b_dense, &b_denseside, &b_streams, &b_rcres, &b_rcout, &b_copy, &b_hdr, &prims.temp };
         for (DevBuf* b : all) b->release();
         inited = false;
     }
@@ -167,11 +168,14 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
         if (nent) {
             CR_LAUNCH(k_rolz_keys, dim3(cr_div_up(maxsize, 256), nb), dim3(256), stream, dD, d_blocks, b_k0.as<uint32_t>(), b_ks0.as<uint32_t>(), b_v0.as<uint32_t>());
             CR_TRY(cr_sort_pairs<uint32_t>(prims, b_k0.as<uint32_t>(), b_k1.as<uint32_t>(), b_v0.as<uint32_t>(), b_v1.as<uint32_t>(), nent, 0, RZ_BUCKET_BITS + bbits));
-            CR_LAUNCH(k_rolz_match_main, dim3(cr_div_up(nent, 128)), dim3(128), stream, dD, d_blocks, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nent, b_M.as<uint16_t>());
+            if (flexible) { CR_TRY(b_rank.reserve((size_t)nent * 4 + 16)); CR_TRY(b_flexlen.reserve(nent + 16)); }
+            CR_LAUNCH(k_rolz_match_main, dim3(cr_div_up(nent, 128)), dim3(128), stream, dD, d_blocks, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nent, b_M.as<uint16_t>(),
+                      flexible ? b_rank.as<uint32_t>() : (uint32_t*)nullptr);
+            if (flexible) CR_LAUNCH(k_rolz_flex, dim3(cr_div_up(maxsize, 128), nb), dim3(128), stream, dD, d_blocks, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), b_rank.as<uint32_t>(), b_M.as<uint16_t>(), b_flexlen.as<uint8_t>());
             CR_TRY(cr_sort_pairs<uint32_t>(prims, b_ks0.as<uint32_t>(), b_k1.as<uint32_t>(), b_v0.as<uint32_t>(), b_v1.as<uint32_t>(), nent, 0, 8 + bbits));
             CR_LAUNCH(k_rolz_match_short, dim3(cr_div_up(nent, 128)), dim3(128), stream, dD, d_blocks, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nent, b_M.as<uint16_t>(), b_S.as<uint16_t>());
         }
-        if (maxsize) CR_LAUNCH(k_rolz_tokens, dim3(cr_div_up(maxsize, 256), nb), dim3(256), stream, d_blocks, b_M.as<uint16_t>(), b_S.as<uint16_t>(), nent, b_span.as<uint8_t>(), b_tidx.as<uint8_t>());
+        if (maxsize) CR_LAUNCH(k_rolz_tokens, dim3(cr_div_up(maxsize, 256), nb), dim3(256), stream, d_blocks, b_M.as<uint16_t>(), b_S.as<uint16_t>(), nent, b_span.as<uint8_t>(), b_tidx.as<uint8_t>(), flexible ? b_flexlen.as<uint8_t>() : (const uint8_t*)nullptr);
     } else {
         CR_LAUNCH(k_lzp_finish_blocks, dim3(cr_div_up(nb, 64)), dim3(64), stream, d_blocks, nb, b_esc1.as<uint8_t>());
         CR_TRY(b_k0.reserve((size_t)nent * 4 + 16)); CR_TRY(b_k1.reserve((size_t)nent * 4 + 16));

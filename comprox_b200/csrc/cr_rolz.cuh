@@ -56,11 +56,12 @@ __global__ void k_rolz_keys(const uint8_t* __restrict__ D, const LzBlock* __rest
 // for v = 0..4 = "table as of time p - v".
 __global__ void k_rolz_match_main(const uint8_t* __restrict__ D, const LzBlock* __restrict__ blocks,
                                   const uint32_t* __restrict__ K, const uint32_t* __restrict__ V, uint32_t n,
-                                  uint16_t* __restrict__ M) {
+                                  uint16_t* __restrict__ M, uint32_t* __restrict__ rank_of) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
     const uint32_t key = K[r], p = V[r];
     const LzBlock B = blocks[key >> RZ_BUCKET_BITS];
+    if (rank_of) rank_of[B.eoff + p - 16] = r;               // -f only: k_rolz_flex looks positions up in the sorted order
     if (p + (RZ_LOOKAHEAD - 4) >= B.size) return;            // never looked up (lazy look-ahead reaches pos+4)
     const uint8_t* d = D + B.off;
     const uint8_t* dp = d + p;
@@ -140,10 +141,46 @@ CR_HD uint32_t rz_price(uint32_t m) {                          // M_price, cr-ma
     return m ? ((m & 255) - 1) * 3 * RZ_WAYS - 3 * (m >> 8) : 9 * RZ_WAYS;
 }
 
+// Flexible parsing (-f, cr-matcher.c:142-162).  For a position t with a main-table match of length L the
+// reference prices match(t+i) for i = 1..L against the table AS OF TIME t and may shorten the match.  In sorted
+// order that is: the candidates of p = t+i, minus the leading ones that were inserted at or after t.
+__global__ void k_rolz_flex(const uint8_t* __restrict__ D, const LzBlock* __restrict__ blocks, const uint32_t* __restrict__ K, const uint32_t* __restrict__ V,
+                            const uint32_t* __restrict__ rank_of, const uint16_t* __restrict__ M0, uint8_t* __restrict__ flexlen) {
+    const LzBlock B = blocks[blockIdx.y];
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < 16 || t + RZ_LOOKAHEAD >= B.size) return;
+    const uint32_t e = B.eoff + t - 16;
+    const uint32_t m = M0[e];
+    if (m == 0) return;
+    const uint8_t* d = D + B.off;
+    const uint32_t len0 = m & 255, idx0 = m >> 8;
+    uint32_t prices[256];
+    for (uint32_t i = 1; i <= len0; i++) {
+        const uint32_t p = t + i, rp = rank_of[e + i], key = K[rp];
+        const uint8_t* dp = d + p;
+        uint32_t best = RZ_MINLEN - 1, idx = 0, taken = 0;
+        for (uint32_t c = 0; c < rp && taken < RZ_WAYS && best < RZ_MAXLEN; c++) {
+            if (K[rp - 1 - c] != key) break;
+            const uint32_t q = V[rp - 1 - c];
+            if (q >= t) continue;                                  // not yet in the table at time t
+            const uint8_t* dq = d + q;
+            if (dq[0] == dp[0] && dq[best] == dp[best]) { const uint32_t l = cr_cpl(dp, dq, RZ_MAXLEN); if (l > best) { best = l; idx = taken; } }
+            taken++;
+        }
+        prices[i] = rz_price(best >= RZ_MINLEN ? (best | idx << 8) : 0u);
+    }
+    uint32_t len = len0, maxprice = rz_price(m) + prices[len0];
+    for (uint32_t i = len0 - 1; i >= 1; i--) {
+        const uint32_t pi = (i >= RZ_MINLEN ? (i - 1) * 3 * RZ_WAYS - 3 * idx0 : 9 * RZ_WAYS) + prices[i];
+        if (pi > maxprice) { len = i; maxprice = pi; }
+    }
+    flexlen[e] = (uint8_t)len;
+}
+
 // Token that the serial parse would emit IF it stood at position t: span[g] = length, tidx[g] = ROLZ index
 // (0xFF = literal).  matcher_lookup's selection + lazy rule, cr-matcher.c:139-141,165-195.
 __global__ void k_rolz_tokens(const LzBlock* __restrict__ blocks, const uint16_t* __restrict__ M, const uint16_t* __restrict__ S,
-                              uint32_t n, uint8_t* __restrict__ span, uint8_t* __restrict__ tidx) {
+                              uint32_t n, uint8_t* __restrict__ span, uint8_t* __restrict__ tidx, const uint8_t* __restrict__ flexlen) {
     const LzBlock B = blocks[blockIdx.y];
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= B.size) return;
@@ -151,7 +188,11 @@ __global__ void k_rolz_tokens(const LzBlock* __restrict__ blocks, const uint16_t
     if (t >= 16 && t + RZ_LOOKAHEAD < B.size) {
         uint32_t e = B.eoff + t - 16;
         uint32_t m = M[e];
-        if (m == 0) m = S[e];
+        if (flexlen && m != 0) {                              // -f: shortened main match, no lazy rule (cr-matcher.c:143,186)
+            const uint32_t fl = flexlen[e];
+            if (fl >= RZ_MINLEN) { len = fl; idx = m >> 8; }
+            m = 0;
+        } else if (m == 0) m = S[e];
         if (m != 0) {
             bool keep = true;
             for (uint32_t i = 1; i < RZ_MINLEN; i++) {

@@ -63,7 +63,7 @@ typedef struct crgpu_config {
     uint32_t block_size;    /* -b, in BYTES (reference default 16 MiB, src/main.c:62) */
     int32_t  filt;          /* -F  cr_filt_enable */
     int32_t  prec;          /* -p  cr_prec_enable */
-    int32_t  flexible;      /* -f  flexible parsing (ROLZ); not yet implemented: CRGPU_ERR_UNSUPPORTED */
+    int32_t  flexible;      /* -f  flexible parsing (comprolz only, src/rolzmain/cr-matcher.c:143-162) */
     uint64_t window_bytes;  /* raw bytes resident per window, 0 = default (512 MiB) */
 } crgpu_config;
 uint64_t crgpu_compress_bound(uint64_t n, uint32_t block_size);

@@ -16,7 +16,7 @@ BIN = {api.ROLZ: "comprolz", api.LZP: "comprop"}
 def _check(gpulib, variant, data, bs, flags=(), **kw):
     with api.Handle(variant, lib=gpulib) as h:
         got = h.compress(data, bs, **kw)
-    want = O.compress(data, variant, bs, int(kw.get("filt", False)), int(kw.get("prec", False)))
+    want = O.compress(data, variant, bs, int(kw.get("filt", False)), int(kw.get("prec", False)), int(kw.get("flexible", False)))
     assert len(got) == len(want), "container size differs from oracle"
     assert got == want, "container differs from oracle"
     ref = O.ref_compress(data, BIN[variant], ["-b%d" % (bs // MiB), *flags]) if bs % MiB == 0 else None
@@ -74,3 +74,8 @@ def test_gpu_compress_windows_carry_models(gpulib):
 
 def test_gpu_compress_binary_no_filter(gpulib):
     _check(gpulib, api.ROLZ, synth.x86_corpus(4 * MiB, elf_bytes=MiB, pe_min=MiB // 2, pe_max=MiB), MiB)
+
+
+def test_gpu_compress_flexible_parsing(gpulib):
+    data = synth.markov_text(2 * MiB, seed=47) * 2 + synth.x86_corpus(2 * MiB, elf_bytes=0, pe_min=MiB, pe_max=2 * MiB)
+    _check(gpulib, api.ROLZ, data, MiB, flags=["-f"], flexible=True)

@@ -28,3 +28,15 @@ def test_sim_compress_matches_oracle(simlib, variant, name):
         got = h.compress(data, bs, prec=bool(prec))
     assert len(got) == len(want)
     assert got == want
+
+
+def test_sim_flexible_parsing(simlib):
+    """-f (comprolz only): shortened matches priced against the table as of the parse point."""
+    data = synth.markov_text(MiB // 2, seed=3) * 2 + synth.x86_corpus(MiB // 2, elf_bytes=0, pe_min=MiB // 4, pe_max=MiB // 2)
+    want = O.compress(data, api.ROLZ, MiB // 2, 0, 0, 1)
+    assert want != O.compress(data, api.ROLZ, MiB // 2)
+    with api.Handle(api.ROLZ, lib=simlib) as h:
+        assert h.compress(data, MiB // 2, flexible=True) == want
+    with api.Handle(api.LZP, lib=simlib) as h:
+        with pytest.raises(api.CrgpuError):
+            h.compress(data, MiB // 2, flexible=True)

@@ -158,7 +158,7 @@ inline int Compressor::dict_encode_window(const uint8_t* d_rawwin, const std::ve
         CR_CUDA(cudaMemsetAsync(b_cnt.p, 0, (size_t)(nchunk + 1) * 4, stream));
         if (nchunk) {
             CR_LAUNCH(k_chain_exits, dim3(cr_div_up(nchunk, 64)), dim3(64), stream, b_span.as<uint8_t>(), b_segs.as<ChainSeg>(), nsub, nchunk, b_xt.as<uint8_t>());
-            CR_LAUNCH(k_chain_entries, dim3(cr_div_up(nsub, 32)), dim3(32), stream, b_segs.as<ChainSeg>(), nsub, b_xt.as<uint8_t>(), b_entry.as<uint8_t>());
+            CR_TRY(cr_chain_run_entries(*chain, chain->b_chainwork, segs, b_segs.as<ChainSeg>(), nchunk, b_xt.as<uint8_t>(), b_entry.as<uint8_t>()));
             DcCount f = { d_rawwin, b_subs.as<DcSub>(), b_span.as<uint8_t>(), b_hit.as<uint32_t>(), b_escmask.as<uint32_t>(), T.level1, b_cnt.as<uint32_t>() };
             CR_LAUNCH(k_chain_walk<DcCount>, dim3(cr_div_up(nchunk, 64)), dim3(64), stream, b_span.as<uint8_t>(), b_segs.as<ChainSeg>(), nsub, nchunk, b_entry.as<uint8_t>(), f);
         }

@@ -265,7 +265,7 @@ struct FilterHost {
             CR_TRY(b_span.reserve(so + 16)); CR_TRY(b_xt.reserve((size_t)nchunk * 256 + 16)); CR_TRY(b_entry.reserve(nchunk + 16));
             CR_LAUNCH(k_e8e9_spans, dim3(cr_div_up(maxlimit, 256), nseg), dim3(256), stream, d_win, b_e8.as<E8Op>(), b_span.as<uint8_t>());
             CR_LAUNCH(k_chain_exits, dim3(cr_div_up(nchunk, 64)), dim3(64), stream, b_span.as<uint8_t>(), b_segs.as<ChainSeg>(), nseg, nchunk, b_xt.as<uint8_t>());
-            CR_LAUNCH(k_chain_entries, dim3(cr_div_up(nseg, 32)), dim3(32), stream, b_segs.as<ChainSeg>(), nseg, b_xt.as<uint8_t>(), b_entry.as<uint8_t>());
+            CR_TRY(cr_chain_run_entries(C, C.b_chainwork, segs, b_segs.as<ChainSeg>(), nchunk, b_xt.as<uint8_t>(), b_entry.as<uint8_t>()));
             E8Apply f = { d_win, b_e8.as<E8Op>(), b_span.as<uint8_t>(), en_de };
             CR_LAUNCH(k_chain_walk<E8Apply>, dim3(cr_div_up(nchunk, 64)), dim3(64), stream, b_span.as<uint8_t>(), b_segs.as<ChainSeg>(), nseg, nchunk, b_entry.as<uint8_t>(), f);
         }

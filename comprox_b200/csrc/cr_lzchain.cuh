@@ -39,7 +39,7 @@ struct LzChain {
     // ---- window work buffers (kept between calls)
     DevBuf b_blocks, b_segoff, b_seglen, b_hist, b_esc1, b_first, b_ctxout;
     DevBuf b_k0, b_k1, b_v0, b_v1, b_ks0, b_M, b_S, b_span, b_tidx;
-    DevBuf b_segs, b_xt, b_entry, b_cnt, b_scan;
+    DevBuf b_segs, b_xt, b_entry, b_cnt, b_scan, b_chainwork;
     DevBuf b_evctx, b_evsym, b_tokend, b_pred, b_T1, b_T2, b_TS, b_side;
     DevBuf b_escrec, b_esccount, b_k64a, b_k64b, b_ord, b_flag, b_escord;
     DevBuf b_lensym, b_lenpos, b_idxsym, b_idxpos;
@@ -66,7 +66,7 @@ struct LzChain {
     }
     void release() {
         DevBuf* all[] = { &s_o3b, &s_o3c, &s_o2, &s_o1, &s_m0, &b_blocks, &b_segoff, &b_seglen, &b_hist, &b_esc1, &b_first, &b_ctxout,
-            &b_k0, &b_k1, &b_v0, &b_v1, &b_ks0, &b_M, &b_S, &b_span, &b_tidx, &b_segs, &b_xt, &b_entry, &b_cnt, &b_scan,
+            &b_k0, &b_k1, &b_v0, &b_v1, &b_ks0, &b_M, &b_S, &b_span, &b_tidx, &b_segs, &b_xt, &b_entry, &b_cnt, &b_scan, &b_chainwork,
             &b_evctx, &b_evsym, &b_tokend, &b_pred, &b_T1, &b_T2, &b_TS, &b_side, &b_escrec, &b_esccount, &b_k64a, &b_k64b, &b_ord,
             &b_flag, &b_escord, &b_lensym, &b_lenpos, &b_idxsym, &b_idxpos, &b_o1info, &b_o1ord, &b_o1incl, &b_bounds, &b_o3hot, &b_cinm, &b_cins, &b_segstart, &b_segkey, &b_rank, &b_flexlen, &b_qm, &b_shm, &b_bm, &b_qs, &b_shs, &b_bs, &b_stot, &b_dsum, &b_lsm, &b_lss, &b_rsm, &b_rss, &b_fb, &b_dense, &b_denseside, &b_streams, &b_rcres, &b_rcout, &b_copy, &b_hdr, &prims.temp };
         for (DevBuf* b : all) b->release();
@@ -207,7 +207,7 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
     CR_CUDA(cudaMemsetAsync(cnt, 0, (size_t)(nchunk + 1) * 4 * 3, stream));
     if (nchunk) {
         CR_LAUNCH(k_chain_exits, dim3(cr_div_up(nchunk, 64)), dim3(64), stream, b_span.as<uint8_t>(), d_segs, nb, nchunk, b_xt.as<uint8_t>());
-        CR_LAUNCH(k_chain_entries, dim3(cr_div_up(nb, 32)), dim3(32), stream, d_segs, nb, b_xt.as<uint8_t>(), b_entry.as<uint8_t>());
+        CR_TRY(cr_chain_run_entries(*this, b_chainwork, segs, d_segs, nchunk, b_xt.as<uint8_t>(), b_entry.as<uint8_t>()));
         if (variant == CR_ROLZ) {
             RolzCount f = { dD, d_blocks, b_tidx.as<uint8_t>(), cnt, cnt + (nchunk + 1), cnt + 2 * (nchunk + 1) };
             CR_LAUNCH(k_chain_walk<RolzCount>, dim3(cr_div_up(nchunk, 64)), dim3(64), stream, b_span.as<uint8_t>(), d_segs, nb, nchunk, b_entry.as<uint8_t>(), f);

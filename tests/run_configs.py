@@ -22,6 +22,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("names", nargs="*", default=list(CONFIGS))
 ap.add_argument("--scale", type=float, default=1.0, help="shrink the configs (1.0 = BASELINE sizes)")
 ap.add_argument("--no-ref", action="store_true")
+ap.add_argument("--full-warmup", action="store_true", help="warm up with the full input so that the timed run does no allocation")
 ap.add_argument("--out", default="gpurun_out/configs.jsonl")
 a = ap.parse_args()
 os.makedirs(os.path.dirname(a.out), exist_ok=True)
@@ -31,7 +32,7 @@ for name in a.names:
     t0 = time.time(); data = c["make"](n); tgen = time.time() - t0
     rec = {"config": name, "bytes": len(data), "gen_s": round(tgen, 1)}
     with api.Handle(c["variant"]) as h:
-        h.compress(data[:4 * MiB], 16 * MiB, filt=c["filt"])                 # warm-up (allocations, module load)
+        h.compress(data if a.full_warmup else data[:4 * MiB], 16 * MiB, filt=c["filt"])   # warm-up (allocations, module load)
         h.profile(True)
         t0 = time.time(); out = h.compress(data, 16 * MiB, filt=c["filt"]); dt = time.time() - t0
         rec.update(gpu_s=round(dt, 3), gpu_mibs=round(len(data) / MiB / dt, 1), container=len(out), sha=hashlib.sha256(out).hexdigest()[:16],

@@ -52,8 +52,11 @@ __global__ void k_rolz_keys(const uint8_t* __restrict__ D, const LzBlock* __rest
     val[e] = p;
 }
 
-// Main-table search.  One thread per sorted rank.  Output M[v*n + e] = len | idx<<8 (0 = no match >= 5)
-// for v = 0..4 = "table as of time p - v".
+// Main-table search.  One thread per sorted rank.  Output M[e] = len | idx<<8 (0 = no match >= 5) for the table as of
+// time p.  The lazy rule also needs the result as of time p-1..p-4; those differ only when one of the four previous
+// positions shares p's bucket, so they are stored (M[v*n + e], v = 1..4) only then and flagged with bit 15 of M[e].
+// The common case therefore scatters 2 bytes per position into one block's 32 MB slice, which stays in L2.
+#define RZ_VARIANTS 0x8000u
 __global__ void k_rolz_match_main(const uint8_t* __restrict__ D, const LzBlock* __restrict__ blocks,
                                   const uint32_t* __restrict__ K, const uint32_t* __restrict__ V, uint32_t n,
                                   uint16_t* __restrict__ M, uint32_t* __restrict__ rank_of) {
@@ -79,9 +82,7 @@ __global__ void k_rolz_match_main(const uint8_t* __restrict__ D, const LzBlock* 
             uint32_t l = cr_cpl(dp, dq, RZ_MAXLEN);
             if (l > best) { best = l; idx = c; }
         }
-        uint16_t out = best >= RZ_MINLEN ? (uint16_t)(best | idx << 8) : (uint16_t)0;
-#pragma unroll
-        for (int v = 0; v < 5; v++) M[(size_t)v * n + e] = out;
+        M[e] = best >= RZ_MINLEN ? (uint16_t)(best | idx << 8) : (uint16_t)0;
         return;
     }
     uint32_t best[5], idx[5], skip[5];
@@ -104,8 +105,9 @@ __global__ void k_rolz_match_main(const uint8_t* __restrict__ D, const LzBlock* 
 #pragma unroll
         for (int v = 0; v < 5; v++) if (use[v] && l > best[v]) { best[v] = l; idx[v] = c - skip[v]; }
     }
+    M[e] = (uint16_t)((best[0] >= RZ_MINLEN ? (best[0] | idx[0] << 8) : 0u) | RZ_VARIANTS);
 #pragma unroll
-    for (int v = 0; v < 5; v++) M[(size_t)v * n + e] = best[v] >= RZ_MINLEN ? (uint16_t)(best[v] | idx[v] << 8) : (uint16_t)0;
+    for (int v = 1; v < 5; v++) M[(size_t)v * n + e] = best[v] >= RZ_MINLEN ? (uint16_t)(best[v] | idx[v] << 8) : (uint16_t)0;
 }
 
 // Order-1 ("short") table, consulted only where the main table found nothing (cr-matcher.c:165-179).
@@ -119,7 +121,7 @@ __global__ void k_rolz_match_short(const uint8_t* __restrict__ D, const LzBlock*
     const LzBlock B = blocks[key >> 8];
     if (p + RZ_LOOKAHEAD >= B.size) return;
     const uint32_t e = B.eoff + p - 16;
-    if (M0[e] != 0) return;
+    if ((M0[e] & ~RZ_VARIANTS) != 0) return;
     const uint8_t* d = D + B.off;
     const uint8_t* dp = d + p;
     uint32_t best = RZ_MINLEN - 1, idx = 0, c = 0;
@@ -150,7 +152,7 @@ __global__ void k_rolz_flex(const uint8_t* __restrict__ D, const LzBlock* __rest
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < 16 || t + RZ_LOOKAHEAD >= B.size) return;
     const uint32_t e = B.eoff + t - 16;
-    const uint32_t m = M0[e];
+    const uint32_t m = M0[e] & ~RZ_VARIANTS;
     if (m == 0) return;
     const uint8_t* d = D + B.off;
     const uint32_t len0 = m & 255, idx0 = m >> 8;
@@ -187,7 +189,7 @@ __global__ void k_rolz_tokens(const LzBlock* __restrict__ blocks, const uint16_t
     uint32_t len = 1, idx = 0xFF;
     if (t >= 16 && t + RZ_LOOKAHEAD < B.size) {
         uint32_t e = B.eoff + t - 16;
-        uint32_t m = M[e];
+        uint32_t m = M[e] & ~RZ_VARIANTS;
         if (flexlen && m != 0) {                              // -f: shortened main match, no lazy rule (cr-matcher.c:143,186)
             const uint32_t fl = flexlen[e];
             if (fl >= RZ_MINLEN) { len = fl; idx = m >> 8; }
@@ -196,7 +198,8 @@ __global__ void k_rolz_tokens(const LzBlock* __restrict__ blocks, const uint16_t
         if (m != 0) {
             bool keep = true;
             for (uint32_t i = 1; i < RZ_MINLEN; i++) {
-                uint32_t m2 = M[(size_t)i * n + e + i];
+                uint32_t m2 = M[e + i];                      // as of time t = (t+i) - i: stored separately only when it differs
+                m2 = (m2 & RZ_VARIANTS) ? M[(size_t)i * n + e + i] : m2;
                 if (rz_price(m2) > rz_price(m) + i * RZ_WAYS) { keep = false; break; }
             }
             if (keep) { len = m & 255; idx = m >> 8; }

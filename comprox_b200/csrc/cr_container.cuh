@@ -257,6 +257,7 @@ inline int Compressor::compress(const CrConfig& cfg, const uint8_t* in, uint64_t
     const uint64_t nblocks = n / cfg.block_size + 1;
     uint64_t wbytes = cfg.window_bytes ? cfg.window_bytes : (512ull << 20);
     uint64_t per_window = wbytes / cfg.block_size; if (per_window == 0) per_window = 1;
+    if (chain->variant == CR_ROLZ && per_window > RZ_MAX_BLOCKS) per_window = RZ_MAX_BLOCKS;
     filt.reset();
     int filt_flag = 0;
     for (uint64_t b0 = 0; b0 < nblocks; b0 += per_window) {

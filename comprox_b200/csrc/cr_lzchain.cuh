@@ -124,6 +124,7 @@ static inline int cr_bits_for(uint32_t n) { int b = 0; while ((1u << b) < n) b++
 inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, int prefix_mode, bool chain_ends, DevBuf& out, size_t out_base, size_t& out_total) {
     const uint32_t nb = (uint32_t)blk.size();
     if (nb == 0) { out_total = 0; return CRGPU_OK; }
+    if (variant == CR_ROLZ && nb > RZ_MAX_BLOCKS) return CRGPU_ERR_ARG;            // callers split (sort key layout, cr_rolz.cuh)
     const uint32_t hdr_size = variant == CR_ROLZ ? 16 : 20;
     const uint32_t prefix = prefix_mode == 0 ? 4 : prefix_mode == 1 ? 6 : 0;
 

@@ -18,6 +18,9 @@
 #define RZ_SHORT       16u
 #define RZ_MINLEN      5u
 #define RZ_MAXLEN      255u
+#define RZ_TAG_SHIFT   24
+#define RZ_KEY_MASK    0x00FFFFFFu
+#define RZ_MAX_BLOCKS  64u     // blocks per window: 6 block bits + 18 bucket bits below the tag
 #define RZ_LOOKAHEAD   1024u   // look-ups only while pos + 1024 < size (src/rolzmain/cr-coder.c:118)
 
 struct LzBlock {
@@ -47,8 +50,10 @@ __global__ void k_rolz_keys(const uint8_t* __restrict__ D, const LzBlock* __rest
     uint32_t e = B.eoff + p - 16;
     uint32_t bucket = p == 16 ? 0 : rz_hash(d + p - 1, B.ctx4);
     uint32_t sb = p == 16 ? 0 : d[p - 1];
-    kmain[e] = (blockIdx.y << RZ_BUCKET_BITS) | bucket;
-    kshort[e] = (blockIdx.y << 8) | sb;
+    // bits 24..31 carry the byte AT p (the reference's m_hash, cr-matcher.h:51): candidates whose first byte differs are
+    // rejected from the key alone, without touching the data.  Needs block index < 64 (main) -- callers split windows.
+    kmain[e] = (uint32_t)d[p] << RZ_TAG_SHIFT | (blockIdx.y << RZ_BUCKET_BITS) | bucket;
+    kshort[e] = (uint32_t)d[p] << RZ_TAG_SHIFT | (blockIdx.y << 8) | sb;
     val[e] = p;
 }
 
@@ -62,23 +67,25 @@ __global__ void k_rolz_match_main(const uint8_t* __restrict__ D, const LzBlock* 
                                   uint16_t* __restrict__ M, uint32_t* __restrict__ rank_of) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
-    const uint32_t key = K[r], p = V[r];
+    const uint32_t key = K[r] & RZ_KEY_MASK, p = V[r];
     const LzBlock B = blocks[key >> RZ_BUCKET_BITS];
     if (rank_of) rank_of[B.eoff + p - 16] = r;               // -f only: k_rolz_flex looks positions up in the sorted order
     if (p + (RZ_LOOKAHEAD - 4) >= B.size) return;            // never looked up (lazy look-ahead reaches pos+4)
     const uint8_t* d = D + B.off;
     const uint8_t* dp = d + p;
     const uint32_t e = B.eoff + p - 16;
-    const uint8_t first = dp[0];
+    const uint32_t first = K[r] >> RZ_TAG_SHIFT;
 
-    const bool simple = (r == 0) || K[r - 1] != key || V[r - 1] + 4 < p;
+    const bool simple = (r == 0) || (K[r - 1] & RZ_KEY_MASK) != key || V[r - 1] + 4 < p;
     if (simple) {
         // no candidate lies in [p-4, p): all five variants see the same list
         uint32_t best = RZ_MINLEN - 1, idx = 0;
         for (uint32_t c = 0; c < RZ_WAYS && c < r && best < RZ_MAXLEN; c++) {
-            if (K[r - 1 - c] != key) break;
+            const uint32_t kc = K[r - 1 - c];
+            if ((kc & RZ_KEY_MASK) != key) break;
+            if ((kc >> RZ_TAG_SHIFT) != first) continue;
             const uint8_t* dq = d + V[r - 1 - c];
-            if (dq[0] != first || dq[best] != dp[best]) continue;
+            if (dq[best] != dp[best]) continue;
             uint32_t l = cr_cpl(dp, dq, RZ_MAXLEN);
             if (l > best) { best = l; idx = c; }
         }
@@ -89,7 +96,8 @@ __global__ void k_rolz_match_main(const uint8_t* __restrict__ D, const LzBlock* 
 #pragma unroll
     for (int v = 0; v < 5; v++) { best[v] = RZ_MINLEN - 1; idx[v] = 0; skip[v] = 0; }
     for (uint32_t c = 0; c < RZ_WAYS + 4 && c < r; c++) {
-        if (K[r - 1 - c] != key) break;
+        const uint32_t kc = K[r - 1 - c];
+        if ((kc & RZ_KEY_MASK) != key) break;
         uint32_t q = V[r - 1 - c];
         bool use[5], any = false;
 #pragma unroll
@@ -100,7 +108,7 @@ __global__ void k_rolz_match_main(const uint8_t* __restrict__ D, const LzBlock* 
             any |= use[v];
         }
         if (!any) { if (c >= skip[4] + RZ_WAYS) break; continue; }
-        if (d[q] != first) continue;
+        if ((kc >> RZ_TAG_SHIFT) != first) continue;
         uint32_t l = cr_cpl(dp, d + q, RZ_MAXLEN);
 #pragma unroll
         for (int v = 0; v < 5; v++) if (use[v] && l > best[v]) { best[v] = l; idx[v] = c - skip[v]; }
@@ -117,7 +125,7 @@ __global__ void k_rolz_match_short(const uint8_t* __restrict__ D, const LzBlock*
                                    const uint16_t* __restrict__ M0, uint16_t* __restrict__ S) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
-    const uint32_t key = K[r], p = V[r];
+    const uint32_t key = K[r] & RZ_KEY_MASK, p = V[r], first = K[r] >> RZ_TAG_SHIFT;
     const LzBlock B = blocks[key >> 8];
     if (p + RZ_LOOKAHEAD >= B.size) return;
     const uint32_t e = B.eoff + p - 16;
@@ -126,7 +134,9 @@ __global__ void k_rolz_match_short(const uint8_t* __restrict__ D, const LzBlock*
     const uint8_t* dp = d + p;
     uint32_t best = RZ_MINLEN - 1, idx = 0, c = 0;
     for (; c < RZ_SHORT && c < r; c++) {
-        if (K[r - 1 - c] != key) break;
+        const uint32_t kc = K[r - 1 - c];
+        if ((kc & RZ_KEY_MASK) != key) break;
+        if ((kc >> RZ_TAG_SHIFT) != first) continue;               // a match of 5+ bytes needs an equal first byte
         const uint8_t* dq = d + V[r - 1 - c];
         if (dq[best] != dp[best]) continue;
         uint32_t l = cr_cpl(dp, dq, RZ_MAXLEN);
@@ -158,11 +168,11 @@ __global__ void k_rolz_flex(const uint8_t* __restrict__ D, const LzBlock* __rest
     const uint32_t len0 = m & 255, idx0 = m >> 8;
     uint32_t prices[256];
     for (uint32_t i = 1; i <= len0; i++) {
-        const uint32_t p = t + i, rp = rank_of[e + i], key = K[rp];
+        const uint32_t p = t + i, rp = rank_of[e + i], key = K[rp] & RZ_KEY_MASK;
         const uint8_t* dp = d + p;
         uint32_t best = RZ_MINLEN - 1, idx = 0, taken = 0;
         for (uint32_t c = 0; c < rp && taken < RZ_WAYS && best < RZ_MAXLEN; c++) {
-            if (K[rp - 1 - c] != key) break;
+            if ((K[rp - 1 - c] & RZ_KEY_MASK) != key) break;
             const uint32_t q = V[rp - 1 - c];
             if (q >= t) continue;                                  // not yet in the table at time t
             const uint8_t* dq = d + q;

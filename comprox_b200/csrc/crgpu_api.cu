@@ -75,24 +75,31 @@ extern "C" int crgpu_lzencode(crgpu_handle* h, const uint8_t* in, const uint32_t
 #ifndef CRGPU_SIM
     CR_CUDA(cudaSetDevice(h->device));
 #endif
-    std::vector<BlockIO> blk(nblocks);
-    size_t total = 0;
-    for (uint32_t b = 0; b < nblocks; b++) {
-        memset(&blk[b], 0, sizeof(BlockIO));
-        blk[b].off = total; blk[b].size = sizes[b];
-        total += ((size_t)sizes[b] + 15) & ~(size_t)15;          // keep blocks 16-byte aligned in the window
+    // windows of at most RZ_MAX_BLOCKS consecutive blocks; model state carries from window to window
+    size_t src = 0, written = 0;
+    for (uint32_t b0 = 0; b0 < nblocks || (nblocks == 0 && b0 == 0); b0 += RZ_MAX_BLOCKS) {
+        const uint32_t b1 = b0 + RZ_MAX_BLOCKS < nblocks ? b0 + RZ_MAX_BLOCKS : nblocks;
+        std::vector<BlockIO> blk(b1 - b0);
+        size_t total = 0;
+        for (uint32_t b = b0; b < b1; b++) {
+            memset(&blk[b - b0], 0, sizeof(BlockIO));
+            blk[b - b0].off = total; blk[b - b0].size = sizes[b];
+            total += ((size_t)sizes[b] + 15) & ~(size_t)15;      // keep blocks 16-byte aligned in the window
+        }
+        CR_TRY(h->d_in.reserve(total + 64));
+        for (uint32_t b = b0; b < b1; b++) {
+            CR_CUDA(cudaMemcpyAsync(h->d_in.as<uint8_t>() + blk[b - b0].off, in + src, sizes[b], cudaMemcpyHostToDevice, h->stream));
+            src += sizes[b];
+        }
+        size_t out_total = 0;
+        CR_TRY(h->chain.encode_window(h->d_in.as<uint8_t>(), blk, 2, chain_ends != 0 && b1 == nblocks, h->d_out, 0, out_total));
+        if (written + out_total > out_cap) return CRGPU_ERR_ARG;
+        CR_CUDA(cudaMemcpyAsync(out + written, h->d_out.p, out_total, cudaMemcpyDeviceToHost, h->stream));
+        CR_CUDA(cudaStreamSynchronize(h->stream));
+        written += out_total;
+        for (uint32_t b = b0; b < b1; b++) out_sizes[b] = blk[b - b0].out_size;
+        if (nblocks == 0) break;
     }
-    CR_TRY(h->d_in.reserve(total + 64));
-    for (uint32_t b = 0; b < nblocks; b++) {
-        size_t src = 0; for (uint32_t k = 0; k < b; k++) src += sizes[k];
-        CR_CUDA(cudaMemcpyAsync(h->d_in.as<uint8_t>() + blk[b].off, in + src, sizes[b], cudaMemcpyHostToDevice, h->stream));
-    }
-    size_t out_total = 0;
-    CR_TRY(h->chain.encode_window(h->d_in.as<uint8_t>(), blk, 2, chain_ends != 0, h->d_out, 0, out_total));
-    if (out_total > out_cap) return CRGPU_ERR_ARG;
-    CR_CUDA(cudaMemcpyAsync(out, h->d_out.p, out_total, cudaMemcpyDeviceToHost, h->stream));
-    CR_CUDA(cudaStreamSynchronize(h->stream));
-    for (uint32_t b = 0; b < nblocks; b++) out_sizes[b] = blk[b].out_size;
     return CRGPU_OK;
 }
 

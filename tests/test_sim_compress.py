@@ -40,3 +40,16 @@ def test_sim_flexible_parsing(simlib):
     with api.Handle(api.LZP, lib=simlib) as h:
         with pytest.raises(api.CrgpuError):
             h.compress(data, MiB // 2, flexible=True)
+
+
+def test_sim_more_blocks_than_one_window(simlib):
+    """ROLZ windows hold at most 64 blocks (sort-key layout); models must carry across the split."""
+    data = synth.markov_text(67 * 4096, seed=12)
+    want = O.compress(data, api.ROLZ, 4096)
+    with api.Handle(api.ROLZ, lib=simlib) as h:
+        assert h.compress(data, 4096) == want
+    blocks = [data[i:i + 3000] for i in range(0, 66 * 3000, 3000)]
+    orc = O.Oracle(api.ROLZ)
+    want_payloads = [orc.lzencode(b) for b in blocks]
+    with api.Handle(api.ROLZ, lib=simlib) as h:
+        assert h.lzencode(blocks) == want_payloads

@@ -31,6 +31,10 @@ struct LzChain {
     cudaStream_t stream = 0;
     Prims prims;
     int variant = CR_ROLZ;
+#ifndef CRGPU_SIM
+    cudaStream_t side_stream = 0;       // the order-0 side-model chain runs beside the PPM passes
+    cudaEvent_t ev_side_go = 0, ev_side_done = 0;
+#endif
     // ---- persistent model state (the reference's file-scope `m`, src/rolzmain/cr-coder.c:52-56)
     DevBuf s_o3b, s_o3c, s_o2, s_o1, s_m0;
     PpmState st;
@@ -61,6 +65,13 @@ struct LzChain {
         CR_TRY(s_o2.reserve((size_t)65536 * PPM_O2_STRIDE)); CR_TRY(s_o1.reserve(65536)); CR_TRY(s_m0.reserve(2 * 256 * 2));
         st.o3_byte = s_o3b.as<uint8_t>(); st.o3_conf = s_o3c.as<uint8_t>(); st.o2 = s_o2.as<uint8_t>();
         st.o1 = s_o1.as<uint8_t>(); st.m0 = s_m0.as<uint16_t>();
+#ifndef CRGPU_SIM
+        if (!side_stream) {
+            CR_CUDA(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
+            CR_CUDA(cudaEventCreateWithFlags(&ev_side_go, cudaEventDisableTiming));
+            CR_CUDA(cudaEventCreateWithFlags(&ev_side_done, cudaEventDisableTiming));
+        }
+#endif
         inited = true;
         return reset_models();
     }
@@ -70,6 +81,9 @@ struct LzChain {
             &b_evctx, &b_evsym, &b_tokend, &b_pred, &b_T1, &b_T2, &b_TS, &b_side, &b_escrec, &b_esccount, &b_k64a, &b_k64b, &b_ord,
             &b_flag, &b_escord, &b_lensym, &b_lenpos, &b_idxsym, &b_idxpos, &b_o1info, &b_o1ord, &b_o1incl, &b_bounds, &b_o3hot, &b_cinm, &b_cins, &b_segstart, &b_segkey, &b_rank, &b_flexlen, &b_qm, &b_shm, &b_bm, &b_qs, &b_shs, &b_bs, &b_stot, &b_dsum, &b_lsm, &b_lss, &b_rsm, &b_rss, &b_fb, &b_dense, &b_denseside, &b_streams, &b_rcres, &b_rcout, &b_copy, &b_hdr, &prims.temp };
         for (DevBuf* b : all) b->release();
+#ifndef CRGPU_SIM
+        if (side_stream) { cudaStreamDestroy(side_stream); cudaEventDestroy(ev_side_go); cudaEventDestroy(ev_side_done); side_stream = 0; }
+#endif
         inited = false;
     }
     // reset_models(): src/rolzmain/cr-coder.c:78-96 / src/ropmain/cr-coder.c:73-83
@@ -253,6 +267,19 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
     }
 
     timer.mark("events");
+    // ---- order-0 side models (len / idx) are independent of the PPM passes: run them on their own stream
+    bool side_async = false;
+#ifndef CRGPU_SIM
+    if (nside && !scalar_models) {
+        CR_TRY(b_denseside.reserve((size_t)nside * sizeof(Tri) + 16));
+        CR_CUDA(cudaEventRecord(ev_side_go, stream));
+        CR_CUDA(cudaStreamWaitEvent(side_stream, ev_side_go, 0));
+        CR_LAUNCH(k_side_epochs, dim3(2), dim3(SE_THREADS), side_stream, b_lensym.as<uint8_t>(), b_lenpos.as<uint32_t>(), n_lensym, b_idxsym.as<uint8_t>(), b_idxpos.as<uint32_t>(), n_idxsym, st, b_TS.as<uint64_t>());
+        CR_LAUNCH(k_expand_side, dim3(cr_div_up(nside, 256)), dim3(256), side_stream, b_TS.as<uint64_t>(), nside, b_denseside.as<Tri>());
+        CR_CUDA(cudaEventRecord(ev_side_done, side_stream));
+        side_async = true;
+    }
+#endif
     // ---- model passes
     uint32_t nesc = 0;
     CR_TRY(b_esccount.reserve(16));
@@ -327,7 +354,7 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
     timer.mark("o1");
     last_nesc = nesc;
     timer.count("#events", nev); timer.count("#triples", (double)nev + nesc + nside); timer.count("#escapes", nesc); timer.count("#side_symbols", nside);
-    if (nside) {
+    if (nside && !side_async) {
 #ifndef CRGPU_SIM
         if (!scalar_models) CR_LAUNCH(k_side_epochs, dim3(2), dim3(SE_THREADS), stream, b_lensym.as<uint8_t>(), b_lenpos.as<uint32_t>(), n_lensym, b_idxsym.as<uint8_t>(), b_idxpos.as<uint32_t>(), n_idxsym, st, b_TS.as<uint64_t>());
         else
@@ -343,7 +370,10 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
     CR_TRY(cr_exclusive_sum(prims, b_flag.as<uint32_t>(), b_escord.as<uint32_t>(), nev + 1));
     if (nev) CR_LAUNCH(k_expand_main, dim3(cr_div_up(nev, 256)), dim3(256), stream, b_T1.as<uint64_t>(), b_T2.as<uint64_t>(), b_escord.as<uint32_t>(),
                        variant == CR_LZP ? b_tokend.as<uint8_t>() : (const uint8_t*)nullptr, nev, b_dense.as<Tri>());
-    if (nside) CR_LAUNCH(k_expand_side, dim3(cr_div_up(nside, 256)), dim3(256), stream, b_TS.as<uint64_t>(), nside, b_denseside.as<Tri>());
+    if (nside && !side_async) CR_LAUNCH(k_expand_side, dim3(cr_div_up(nside, 256)), dim3(256), stream, b_TS.as<uint64_t>(), nside, b_denseside.as<Tri>());
+#ifndef CRGPU_SIM
+    if (side_async) CR_CUDA(cudaStreamWaitEvent(stream, ev_side_done, 0));
+#endif
 
     timer.mark("expand");
     // ---- range coding: one serial coder per (block, stream)

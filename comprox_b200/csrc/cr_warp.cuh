@@ -309,7 +309,8 @@ __global__ void __launch_bounds__(128) k_o2_pass_warp(const uint32_t* __restrict
 // (per-warp histograms, prefix over warps / symbols, 32-way compare inside the warp -- as in k_side_epochs).
 // The first event whose update would rescale the table (cr-o2model.c:54) ends the step; everything after it is
 // recomputed in the next step from the rescaled table.
-#define O2C_THREADS 1024
+#define O2C_THREADS 256           // steps are cut by rescales every ~250 events (flag 256 grows with every hit): small CTAs, cheap steps
+#define O2C_WARPS   (O2C_THREADS / 32)
 #define O2C_MIN     3072          // contexts with at least this many events in the window take this path
 __global__ void __launch_bounds__(O2C_THREADS) k_o2_pass_cta(const uint32_t* __restrict__ K, const uint32_t* __restrict__ V, uint32_t n, PpmState st,
                                                              uint64_t* __restrict__ T1, EscRec* __restrict__ esc_rec, uint32_t* __restrict__ esc_count, const uint32_t* __restrict__ bounds) {
@@ -320,8 +321,8 @@ __global__ void __launch_bounds__(O2C_THREADS) k_o2_pass_cta(const uint32_t* __r
 
     __shared__ uint32_t cnt[256], cumt[256], zmask[8];
     __shared__ uint32_t s_f256, s_f257, s_body, s_first;
-    __shared__ __align__(4) uint16_t hist[32][256];
-    __shared__ uint16_t below[32][256];
+    __shared__ __align__(4) uint16_t hist[O2C_WARPS][256];
+    __shared__ uint16_t below[O2C_WARPS][256];
     __shared__ uint32_t wtot[3][32];                      // per-warp totals: non-hits, escapes, 1->2 transitions -> exclusive prefixes
     __shared__ uint16_t ssym[O2C_THREADS];                // symbol of each non-hit event (0x100 for hits) for the rare trigger-mask path
     __shared__ uint8_t esc_sym[O2C_THREADS];
@@ -349,7 +350,8 @@ __global__ void __launch_bounds__(O2C_THREADS) k_o2_pass_cta(const uint32_t* __r
             z |= __shfl_xor_sync(FULLMASK, z, 1); z |= __shfl_xor_sync(FULLMASK, z, 2);
             if ((lane & 3) == 0) zmask[lane >> 2] = z;
         }
-        for (uint32_t i = tid; i < 32 * 128; i += O2C_THREADS) ((uint32_t*)&hist[0][0])[i] = 0;
+        for (uint32_t i = tid; i < O2C_WARPS * 128; i += O2C_THREADS) ((uint32_t*)&hist[0][0])[i] = 0;
+        if (tid < 96) (&wtot[0][0])[tid] = 0;
         if (tid == 0) s_first = 0xFFFFFFFFu;
         __syncthreads();
         if (pos >= r1) break;
@@ -362,7 +364,7 @@ __global__ void __launch_bounds__(O2C_THREADS) k_o2_pass_cta(const uint32_t* __r
         ssym[tid] = nonhit ? (uint16_t)sym : (uint16_t)0x100;
         if (nonhit) atomicAdd((uint32_t*)&hist[w][0] + (sym >> 1), (sym & 1u) ? 0x10000u : 1u);
         __syncthreads();
-        if (tid < 256) { uint32_t run = 0; for (int q = 0; q < 32; q++) { uint32_t h = hist[q][tid]; hist[q][tid] = (uint16_t)run; run += h; } }
+        if (tid < 256) { uint32_t run = 0; for (int q = 0; q < (int)O2C_WARPS; q++) { uint32_t h = hist[q][tid]; hist[q][tid] = (uint16_t)run; run += h; } }
         __syncthreads();
         {
             uint32_t v[8], sum = 0;

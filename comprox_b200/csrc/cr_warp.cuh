@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(128) k_o2_pass_warp(const uint32_t* __restrict
 // (per-warp histograms, prefix over warps / symbols, 32-way compare inside the warp -- as in k_side_epochs).
 // The first event whose update would rescale the table (cr-o2model.c:54) ends the step; everything after it is
 // recomputed in the next step from the rescaled table.
-#define O2C_THREADS 256           // steps are cut by rescales every ~250 events (flag 256 grows with every hit): small CTAs, cheap steps
+#define O2C_THREADS 1024          // upper bound of a step; the step width adapts (256..1024) to how often rescales cut it
 #define O2C_WARPS   (O2C_THREADS / 32)
 #define O2C_MIN     3072          // contexts with at least this many events in the window take this path
 __global__ void __launch_bounds__(O2C_THREADS) k_o2_pass_cta(const uint32_t* __restrict__ K, const uint32_t* __restrict__ V, uint32_t n, PpmState st,
@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(O2C_THREADS) k_o2_pass_cta(const uint32_t* __r
     if (tid == 0) { s_f256 = row[256]; s_f257 = row[257]; }
     __syncthreads();
 
-    uint32_t pos = r0;
+    uint32_t pos = r0, cap = 256;                           // events attempted per step; grows while steps complete, shrinks when rescales cut them
     for (;;) {
         // ---- derived tables from cnt: cumt, body, zero mask (warp 0); clear the histograms (all)
         if (w == 0) {
@@ -350,12 +350,13 @@ __global__ void __launch_bounds__(O2C_THREADS) k_o2_pass_cta(const uint32_t* __r
             z |= __shfl_xor_sync(FULLMASK, z, 1); z |= __shfl_xor_sync(FULLMASK, z, 2);
             if ((lane & 3) == 0) zmask[lane >> 2] = z;
         }
-        for (uint32_t i = tid; i < O2C_WARPS * 128; i += O2C_THREADS) ((uint32_t*)&hist[0][0])[i] = 0;
+        const uint32_t step = r1 - pos < cap ? r1 - pos : cap;
+        const uint32_t nw = (step + 31) >> 5;                 // warps that hold events in this step
+        if (w < nw) for (uint32_t i = lane; i < 128; i += 32) ((uint32_t*)&hist[w][0])[i] = 0;
         if (tid < 96) (&wtot[0][0])[tid] = 0;
         if (tid == 0) s_first = 0xFFFFFFFFu;
         __syncthreads();
         if (pos >= r1) break;
-        const uint32_t step = r1 - pos < O2C_THREADS ? r1 - pos : O2C_THREADS;
         const bool active = tid < step;
         uint32_t k = 0, ev = 0;
         if (active) { k = K[pos + tid]; ev = V[pos + tid]; }
@@ -364,9 +365,9 @@ __global__ void __launch_bounds__(O2C_THREADS) k_o2_pass_cta(const uint32_t* __r
         ssym[tid] = nonhit ? (uint16_t)sym : (uint16_t)0x100;
         if (nonhit) atomicAdd((uint32_t*)&hist[w][0] + (sym >> 1), (sym & 1u) ? 0x10000u : 1u);
         __syncthreads();
-        if (tid < 256) { uint32_t run = 0; for (int q = 0; q < (int)O2C_WARPS; q++) { uint32_t h = hist[q][tid]; hist[q][tid] = (uint16_t)run; run += h; } }
+        if (tid < 256) { uint32_t run = 0; for (uint32_t q = 0; q < nw; q++) { uint32_t h = hist[q][tid]; hist[q][tid] = (uint16_t)run; run += h; } }
         __syncthreads();
-        {
+        if (w < nw) {
             uint32_t v[8], sum = 0;
 #pragma unroll
             for (int q = 0; q < 8; q++) { v[q] = hist[w][lane * 8 + q]; sum += v[q]; }
@@ -461,6 +462,7 @@ __global__ void __launch_bounds__(O2C_THREADS) k_o2_pass_cta(const uint32_t* __r
             if (tid == 0) s_f257 = (1 + ones) & 255;
         }
         pos += applied;
+        cap = applied < step ? (2 * applied < 256 ? 256u : (2 * applied > O2C_THREADS ? O2C_THREADS : 2 * applied)) : (2 * cap > O2C_THREADS ? O2C_THREADS : 2 * cap);
         __syncthreads();
     }
     if (tid < 256) row[tid] = (uint8_t)cnt[tid];

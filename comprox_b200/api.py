@@ -102,6 +102,14 @@ class Handle:
         _check(self.L, self.L.crgpu_compress(self.h, ctypes.byref(cfg), data, ctypes.c_uint64(len(data)), out, ctypes.c_uint64(cap), ctypes.byref(n)))
         return out.raw[:n.value]
 
+    def dicpick(self, data: bytes) -> bytes:
+        """dicpick(): the dictionary text (with the final NUL) built from the whole input."""
+        cap = 25000 * 24 + 64
+        out = ctypes.create_string_buffer(cap)
+        n = ctypes.c_uint64()
+        _check(self.L, self.L.crgpu_dicpick(self.h, data, ctypes.c_uint64(len(data)), out, ctypes.c_uint64(cap), ctypes.byref(n)))
+        return out.raw[:n.value]
+
     def decompress(self, container: bytes, out_cap: int) -> bytes:
         """The bytes `comprolz/comprop d` would write for this container."""
         out = ctypes.create_string_buffer(max(out_cap, 1))

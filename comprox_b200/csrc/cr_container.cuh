@@ -50,6 +50,7 @@ struct Compressor {
         return CRGPU_OK;
     }
     int dicpick(const uint8_t* h_in, const uint8_t* d_in, uint64_t n, std::string& text);
+    int dicpick_epochs(const uint8_t* d_in, uint64_t n);
     int load_dictionary(const std::string& text);
     int dict_encode_window(const uint8_t* d_rawwin, const std::vector<uint64_t>& roff, const std::vector<uint32_t>& rsize, std::vector<BlockIO>& blk, size_t& dtotal);
     int compress(const CrConfig& cfg, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_n);
@@ -84,8 +85,12 @@ inline int Compressor::dicpick(const uint8_t* h_in, const uint8_t* d_in, uint64_
     };
     std::vector<uint32_t> stats;
     CR_TRY(download(stats, t_stats.p, 4));
-    if (stats[1] & 1u) return CRGPU_ERR_VOCAB_OVERFLOW;
-    if (stats[1] & 2u) return CRGPU_ERR_HASH_COLLISION;
+    if (stats[1] & 1u) {
+        // more than 325000 distinct words: replay the reference's prune epochs exactly (cr_dict.cuh)
+        CR_TRY(dicpick_epochs(d_in, n));
+        CR_TRY(download(stats, t_stats.p, 4));
+        if (stats[1] & 4u) return CRGPU_ERR_VOCAB_OVERFLOW;          // more distinct words in one window than the table holds
+    }
     lap("dp sync+stats");
     std::vector<DpEntry> ent;
     CR_TRY(download(ent, t_entries.p, stats[2]));
@@ -97,6 +102,71 @@ inline int Compressor::dicpick(const uint8_t* h_in, const uint8_t* d_in, uint64_
     lap("dp text");
     chain->timer.mark("dp_host");
     return CRGPU_OK;
+}
+
+// Exact vocabulary-overflow path.  Leaves the final table in t_key/t_count/t_first and the selected
+// entries in t_entries / stats[2], like the fast path.
+inline int Compressor::dicpick_epochs(const uint8_t* d_in, uint64_t n) {
+    DevBuf k2, c2, f2, list, small;
+    CR_TRY(k2.reserve((size_t)DP_SLOTS * 8)); CR_TRY(c2.reserve((size_t)DP_SLOTS * 4)); CR_TRY(f2.reserve((size_t)DP_SLOTS * 4));
+    CR_TRY(list.reserve((size_t)DP_SLOTS * 4)); CR_TRY(small.reserve(64));
+    auto clear = [&](DevBuf& k, DevBuf& c, DevBuf& f) -> int {
+        CR_CUDA(cudaMemsetAsync(k.p, 0, (size_t)DP_SLOTS * 8, stream)); CR_CUDA(cudaMemsetAsync(c.p, 0, (size_t)DP_SLOTS * 4, stream));
+        CR_CUDA(cudaMemsetAsync(f.p, 0xFF, (size_t)DP_SLOTS * 4, stream));
+        return CRGPU_OK;
+    };
+    DevBuf *ka = &t_key, *ca = &t_count, *fa = &t_first, *kb = &k2, *cb = &c2, *fb = &f2;
+    CR_TRY(clear(*ka, *ca, *fa));
+    CR_CUDA(cudaMemsetAsync(t_stats.p, 0, 64, stream));
+    uint32_t alive = 0;
+    const uint64_t window = 64ull << 20;
+    int rc = CRGPU_OK;
+    for (uint64_t pos = 0; pos < n && rc == CRGPU_OK;) {
+        DpTable T = { ka->as<unsigned long long>(), ca->as<uint32_t>(), fa->as<uint32_t>(), t_stats.as<uint32_t>() };
+        const uint64_t wend = pos + window < n ? pos + window : n;
+        CR_LAUNCH(k_dp_first, dim3(cr_div_up(wend - pos, 256)), dim3(256), stream, d_in, n, pos, wend, T);
+        CR_CUDA(cudaMemsetAsync(small.p, 0, 8, stream));
+        CR_LAUNCH(k_dp_list_new, dim3(DP_SLOTS / 256), dim3(256), stream, T, (uint32_t)pos, list.as<uint32_t>(), DP_SLOTS, small.as<uint32_t>());
+        std::vector<uint32_t> cnt, st;
+        CR_TRY(download(cnt, small.p, 1));
+        CR_TRY(download(st, t_stats.p, 4));
+        if (st[1] & 4u) break;                                           // table full: reported by the caller
+        const uint32_t n_new = cnt[0], need = DP_MAXWORDS - alive;
+        if (n_new < need) {                                              // no prune inside this window
+            CR_LAUNCH(k_dp_count, dim3(cr_div_up(wend - pos, 256)), dim3(256), stream, d_in, n, pos, wend, T);
+            alive += n_new; pos = wend;
+            continue;
+        }
+        std::vector<uint32_t> firsts;
+        CR_TRY(download(firsts, list.p, n_new));
+        std::nth_element(firsts.begin(), firsts.begin() + (need - 1), firsts.end());
+        const uint64_t X = firsts[need - 1];                             // the word starting here is the 325001st
+        CR_LAUNCH(k_dp_count, dim3(cr_div_up(X + 1 - pos, 256)), dim3(256), stream, d_in, n, pos, X + 1, T);
+        CR_CUDA(cudaMemsetAsync(small.p, 0xFF, 4, stream));
+        CR_LAUNCH(k_dp_min_count, dim3(DP_SLOTS / 256), dim3(256), stream, T, small.as<uint32_t>());
+        std::vector<uint32_t> mn;
+        CR_TRY(download(mn, small.p, 1));
+        CR_TRY(clear(*kb, *cb, *fb));
+        CR_CUDA(cudaMemsetAsync(t_stats.p, 0, 4, stream));
+        DpTable B = { kb->as<unsigned long long>(), cb->as<uint32_t>(), fb->as<uint32_t>(), t_stats.as<uint32_t>() };
+        CR_LAUNCH(k_dp_rebuild, dim3(DP_SLOTS / 256), dim3(256), stream, T, B, mn[0] + 5);
+        CR_TRY(download(st, t_stats.p, 1));
+        alive = st[0];
+        std::swap(ka, kb); std::swap(ca, cb); std::swap(fa, fb);
+        pos = X + 1;
+    }
+    // the final table must live in t_key/t_count/t_first
+    if (ka != &t_key) {
+        CR_CUDA(cudaMemcpyAsync(t_key.p, ka->p, (size_t)DP_SLOTS * 8, cudaMemcpyDeviceToDevice, stream));
+        CR_CUDA(cudaMemcpyAsync(t_count.p, ca->p, (size_t)DP_SLOTS * 4, cudaMemcpyDeviceToDevice, stream));
+        CR_CUDA(cudaMemcpyAsync(t_first.p, fa->p, (size_t)DP_SLOTS * 4, cudaMemcpyDeviceToDevice, stream));
+    }
+    DpTable T = { t_key.as<unsigned long long>(), t_count.as<uint32_t>(), t_first.as<uint32_t>(), t_stats.as<uint32_t>() };
+    CR_CUDA(cudaMemsetAsync(t_stats.as<uint32_t>() + 2, 0, 4, stream));
+    CR_LAUNCH(k_dp_collect, dim3(DP_SLOTS / 256), dim3(256), stream, T, t_entries.as<DpEntry>(), DP_MAXWORDS);
+    CR_CUDA(cudaStreamSynchronize(stream));
+    k2.release(); c2.release(); f2.release(); list.release(); small.release();
+    return rc;
 }
 
 inline int Compressor::load_dictionary(const std::string& text) {

@@ -91,6 +91,51 @@ __global__ void k_dp_verify(const uint8_t* __restrict__ in, uint64_t n, uint64_t
     same &= !cr_is_lower(b[len]);
     if (!same) atomicOr(&T.stats[1], 2u);
 }
+// ---- exact handling of vocabulary overflow (cr-dicpick.c:115-144).  When the 325001st distinct word
+// arrives the reference drops every word whose count is <= (smallest count) + 5 and carries on, so the result
+// depends on WHEN each word first appeared.  That moment is found without a serial pass: list the first position
+// of every word that is not yet in the table, take the k-th smallest (k = free places left), count everything up
+// to and including that position, prune, continue behind it.  One "epoch" per prune.
+// k_dp_first: like k_dp_count but only records first positions; new keys enter with count 0 ("candidates").
+__global__ void k_dp_first(const uint8_t* __restrict__ in, uint64_t n, uint64_t x0, uint64_t x1, DpTable T) {
+    uint64_t x = x0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= x1) return;
+    unsigned long long h;
+    if (!dp_word_at(in, n, x, &h)) return;
+    uint32_t slot = (uint32_t)h & (DP_SLOTS - 1);
+    for (uint32_t probe = 0; probe < DP_SLOTS; probe++) {
+        unsigned long long prev = atomicCAS(&T.key[slot], 0ull, h);
+        if (prev == 0ull) { atomicAdd(&T.stats[0], 1u); prev = h; }
+        if (prev == h) { atomicMin(&T.first[slot], (uint32_t)x); return; }
+        slot = (slot + 1) & (DP_SLOTS - 1);
+    }
+    atomicOr(&T.stats[1], 4u);                                   // table full
+}
+// first positions (>= x0) of all candidates (count == 0)
+__global__ void k_dp_list_new(DpTable T, uint32_t x0, uint32_t* __restrict__ list, uint32_t cap, uint32_t* __restrict__ n_new) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= DP_SLOTS || T.key[s] == 0ull || T.count[s] != 0 || T.first[s] < x0) return;
+    uint32_t i = atomicAdd(n_new, 1u);
+    if (i < cap) list[i] = T.first[s];
+}
+__global__ void k_dp_min_count(DpTable T, uint32_t* __restrict__ mn) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= DP_SLOTS || T.key[s] == 0ull || T.count[s] == 0) return;
+    atomicMin(mn, T.count[s]);
+}
+// survivors (count > threshold) move to a fresh table; candidates and pruned words vanish
+__global__ void k_dp_rebuild(DpTable A, DpTable B, uint32_t threshold) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= DP_SLOTS || A.key[s] == 0ull || A.count[s] <= threshold) return;
+    const unsigned long long h = A.key[s];
+    uint32_t slot = (uint32_t)h & (DP_SLOTS - 1);
+    for (;;) {
+        unsigned long long prev = atomicCAS(&B.key[slot], 0ull, h);
+        if (prev == 0ull) { B.count[slot] = A.count[s]; B.first[slot] = A.first[s]; atomicAdd(&B.stats[0], 1u); return; }
+        slot = (slot + 1) & (DP_SLOTS - 1);
+    }
+}
+
 struct DpEntry { uint32_t first, count; };
 __global__ void k_dp_collect(DpTable T, DpEntry* __restrict__ out, uint32_t cap) {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;

@@ -47,6 +47,7 @@ struct LzChain {
     DevBuf b_evctx, b_evsym, b_tokend, b_pred, b_T1, b_T2, b_TS, b_side;
     DevBuf b_escrec, b_esccount, b_k64a, b_k64b, b_ord, b_flag, b_escord;
     DevBuf b_lensym, b_lenpos, b_idxsym, b_idxpos;
+    DevBuf b_hits;
     DevBuf b_o1info, b_o1ord, b_o1incl, b_bounds, b_o3hot, b_cinm, b_cins, b_segstart, b_segkey, b_rank, b_flexlen;
     DevBuf b_qm, b_shm, b_bm, b_qs, b_shs, b_bs, b_stot, b_dsum, b_lsm, b_lss, b_rsm, b_rss, b_fb;
     DevBuf b_dense, b_denseside, b_streams, b_rcres, b_rcout, b_copy, b_hdr;
@@ -79,7 +80,7 @@ struct LzChain {
         DevBuf* all[] = { &s_o3b, &s_o3c, &s_o2, &s_o1, &s_m0, &b_blocks, &b_segoff, &b_seglen, &b_hist, &b_esc1, &b_first, &b_ctxout,
             &b_k0, &b_k1, &b_v0, &b_v1, &b_ks0, &b_M, &b_S, &b_span, &b_tidx, &b_segs, &b_xt, &b_entry, &b_cnt, &b_scan, &b_chainwork,
             &b_evctx, &b_evsym, &b_tokend, &b_pred, &b_T1, &b_T2, &b_TS, &b_side, &b_escrec, &b_esccount, &b_k64a, &b_k64b, &b_ord,
-            &b_flag, &b_escord, &b_lensym, &b_lenpos, &b_idxsym, &b_idxpos, &b_o1info, &b_o1ord, &b_o1incl, &b_bounds, &b_o3hot, &b_cinm, &b_cins, &b_segstart, &b_segkey, &b_rank, &b_flexlen, &b_qm, &b_shm, &b_bm, &b_qs, &b_shs, &b_bs, &b_stot, &b_dsum, &b_lsm, &b_lss, &b_rsm, &b_rss, &b_fb, &b_dense, &b_denseside, &b_streams, &b_rcres, &b_rcout, &b_copy, &b_hdr, &prims.temp };
+            &b_flag, &b_escord, &b_lensym, &b_lenpos, &b_idxsym, &b_idxpos, &b_hits, &b_o1info, &b_o1ord, &b_o1incl, &b_bounds, &b_o3hot, &b_cinm, &b_cins, &b_segstart, &b_segkey, &b_rank, &b_flexlen, &b_qm, &b_shm, &b_bm, &b_qs, &b_shs, &b_bs, &b_stot, &b_dsum, &b_lsm, &b_lss, &b_rsm, &b_rss, &b_fb, &b_dense, &b_denseside, &b_streams, &b_rcres, &b_rcout, &b_copy, &b_hdr, &prims.temp };
         for (DevBuf* b : all) b->release();
 #ifndef CRGPU_SIM
         if (side_stream) { cudaStreamDestroy(side_stream); cudaEventDestroy(ev_side_go); cudaEventDestroy(ev_side_done); side_stream = 0; }
@@ -322,7 +323,13 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
             const uint32_t hot_min = hot_contexts ? O2C_MIN : 0xFFFFFFFFu;
             CR_TRY(b_bounds.reserve(65537 * 4 + 16));
             CR_LAUNCH(k_o2_bounds, dim3(cr_div_up(65537, 256)), dim3(256), stream, b_k1.as<uint32_t>(), nev, b_bounds.as<uint32_t>());
-            if (hot_contexts) CR_LAUNCH(k_o2_pass_cta, dim3(65536), dim3(O2C_THREADS), stream, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nev, st, b_T1.as<uint64_t>(), b_escrec.as<EscRec>(), b_esccount.as<uint32_t>(), b_bounds.as<uint32_t>());
+            if (hot_contexts) {
+                CR_TRY(b_hits.reserve(65536 * 4));
+                CR_CUDA(cudaMemsetAsync(b_hits.p, 0, 65536 * 4, stream));
+                CR_LAUNCH(k_o2_hits, dim3(cr_div_up(nev, 256)), dim3(256), stream, b_k1.as<uint32_t>(), nev, b_hits.as<uint32_t>());
+                CR_LAUNCH(k_o2_pass_cta<256>, dim3(65536), dim3(256), stream, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nev, st, b_T1.as<uint64_t>(), b_escrec.as<EscRec>(), b_esccount.as<uint32_t>(), b_bounds.as<uint32_t>(), b_hits.as<uint32_t>());
+                CR_LAUNCH(k_o2_pass_cta<1024>, dim3(65536), dim3(1024), stream, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nev, st, b_T1.as<uint64_t>(), b_escrec.as<EscRec>(), b_esccount.as<uint32_t>(), b_bounds.as<uint32_t>(), b_hits.as<uint32_t>());
+            }
             CR_LAUNCH(k_o2_pass_warp, dim3(65536 * 32 / 128), dim3(128), stream, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nev, st, b_T1.as<uint64_t>(), b_escrec.as<EscRec>(), b_esccount.as<uint32_t>(), hot_min, b_bounds.as<uint32_t>());
         }
         else

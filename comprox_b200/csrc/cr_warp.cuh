@@ -309,15 +309,26 @@ __global__ void __launch_bounds__(128) k_o2_pass_warp(const uint32_t* __restrict
 // (per-warp histograms, prefix over warps / symbols, 32-way compare inside the warp -- as in k_side_epochs).
 // The first event whose update would rescale the table (cr-o2model.c:54) ends the step; everything after it is
 // recomputed in the next step from the rescaled table.
-#define O2C_THREADS 1024          // upper bound of a step; the step width adapts (256..1024) to how often rescales cut it
-#define O2C_WARPS   (O2C_THREADS / 32)
+// Two instantiations: 256-thread CTAs for contexts whose steps are cut early (flag 256 grows with every o3 hit, so a
+// context with hit rate h rescales about every 188/h events), 1024-thread CTAs for the others.  k_o2_hits counts the
+// hits per context; a context is "narrow" when 188 * events / hits < 512.
+__global__ void k_o2_hits(const uint32_t* __restrict__ K, uint32_t n, uint32_t* __restrict__ hits) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t k = K[i];
+    if ((k >> 24) == ((k >> 16) & 255)) atomicAdd(&hits[k & 0xffff], 1u);
+}
+CR_D bool o2_is_narrow(uint32_t events, uint32_t hits) { return (unsigned long long)hits * 512ull > (unsigned long long)events * 188ull; }
 #define O2C_MIN     3072          // contexts with at least this many events in the window take this path
+template <int O2C_THREADS>
 __global__ void __launch_bounds__(O2C_THREADS) k_o2_pass_cta(const uint32_t* __restrict__ K, const uint32_t* __restrict__ V, uint32_t n, PpmState st,
-                                                             uint64_t* __restrict__ T1, EscRec* __restrict__ esc_rec, uint32_t* __restrict__ esc_count, const uint32_t* __restrict__ bounds) {
+                                                             uint64_t* __restrict__ T1, EscRec* __restrict__ esc_rec, uint32_t* __restrict__ esc_count, const uint32_t* __restrict__ bounds, const uint32_t* __restrict__ hits) {
+    constexpr int O2C_WARPS = O2C_THREADS / 32;
     const uint32_t c16 = blockIdx.x;
     const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const uint32_t r0 = bounds[c16], r1 = bounds[c16 + 1];
     if (r1 - r0 < O2C_MIN) return;
+    if (o2_is_narrow(r1 - r0, hits[c16]) != (O2C_THREADS == 256)) return;      // the other instantiation takes this context
 
     __shared__ uint32_t cnt[256], cumt[256], zmask[8];
     __shared__ uint32_t s_f256, s_f257, s_body, s_first;
@@ -327,11 +338,11 @@ __global__ void __launch_bounds__(O2C_THREADS) k_o2_pass_cta(const uint32_t* __r
     __shared__ uint16_t ssym[O2C_THREADS];                // symbol of each non-hit event (0x100 for hits) for the rare trigger-mask path
     __shared__ uint8_t esc_sym[O2C_THREADS];
     uint8_t* row = st.o2 + (size_t)c16 * PPM_O2_STRIDE;
-    if (tid < 256) cnt[tid] = row[tid];
+    for (uint32_t i = tid; i < 256; i += O2C_THREADS) cnt[i] = row[i];
     if (tid == 0) { s_f256 = row[256]; s_f257 = row[257]; }
     __syncthreads();
 
-    uint32_t pos = r0, cap = 256;                           // events attempted per step; grows while steps complete, shrinks when rescales cut them
+    uint32_t pos = r0, cap = O2C_THREADS;                           // events attempted per step; grows while steps complete, shrinks when rescales cut them
     for (;;) {
         // ---- derived tables from cnt: cumt, body, zero mask (warp 0); clear the histograms (all)
         if (w == 0) {
@@ -462,7 +473,7 @@ __global__ void __launch_bounds__(O2C_THREADS) k_o2_pass_cta(const uint32_t* __r
             if (tid == 0) s_f257 = (1 + ones) & 255;
         }
         pos += applied;
-        cap = applied < step ? (2 * applied < 256 ? 256u : (2 * applied > O2C_THREADS ? O2C_THREADS : 2 * applied)) : (2 * cap > O2C_THREADS ? O2C_THREADS : 2 * cap);
+        cap = O2C_THREADS;
         __syncthreads();
     }
     if (tid < 256) row[tid] = (uint8_t)cnt[tid];

@@ -189,3 +189,19 @@ extern "C" int crgpu_decompress(crgpu_handle* h, const uint8_t* in, uint64_t n, 
     h->decomp.chain = &h->chain;
     return h->decomp.decompress(in, n, out, out_cap, out_n);
 }
+
+// dicpick(fp, dic_block): the dictionary text (NUL terminated) the reference builds from the whole input.
+extern "C" int crgpu_dicpick(crgpu_handle* h, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_n) {
+    if (!h || (n && !in) || !out || !out_n) return CRGPU_ERR_ARG;
+#ifndef CRGPU_SIM
+    CR_CUDA(cudaSetDevice(h->device));
+#endif
+    h->comp.chain = &h->chain; h->comp.stream = h->chain.stream;
+    CR_TRY(h->comp.stage(in, n));
+    std::string text;
+    CR_TRY(h->comp.dicpick(in, h->comp.d_raw.as<uint8_t>(), n, text));
+    if (text.size() > out_cap) return CRGPU_ERR_ARG;
+    memcpy(out, text.data(), text.size());
+    *out_n = text.size();
+    return CRGPU_OK;
+}

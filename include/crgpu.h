@@ -69,6 +69,11 @@ typedef struct crgpu_config {
 uint64_t crgpu_compress_bound(uint64_t n, uint32_t block_size);
 int crgpu_compress(crgpu_handle* h, const crgpu_config* cfg, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_n);
 
+/* dicpick(fp, dic_block)  -- src/cr-dicpick.h:40, src/cr-dicpick.c:164-259: word statistics of the whole input ->
+ * dictionary text ("\x20\x20\n" "http://www.\n" word\n ... NUL).  Stage-level entry point (crgpu_compress calls the
+ * same code); exact also beyond 325000 distinct words, where the reference prunes in arrival order. */
+int crgpu_dicpick(crgpu_handle* h, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_n);
+
 /* Whole-container decompression: cr_main's decode branch (src/main.c:220-302): check_magic, dictionary payload,
  * then per block lzdecode (unless the block was written with -p), dictionary_decode and filter_inplace(FILTER_DEC).
  * One container is one serial model chain, so this call runs the entropy stage on a single GPU thread: it is

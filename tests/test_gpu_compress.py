@@ -79,3 +79,11 @@ def test_gpu_compress_binary_no_filter(gpulib):
 def test_gpu_compress_flexible_parsing(gpulib):
     data = synth.markov_text(2 * MiB, seed=47) * 2 + synth.x86_corpus(2 * MiB, elf_bytes=0, pe_min=MiB, pe_max=2 * MiB)
     _check(gpulib, api.ROLZ, data, MiB, flags=["-f"], flexible=True)
+
+
+def test_gpu_dicpick_vocabulary_overflow(gpulib):
+    from vocab_overflow_input import overflow_text
+    data = overflow_text()
+    with api.Handle(api.LZP, lib=gpulib) as h:
+        assert h.dicpick(data) == O.dicpick(data)
+        assert h.compress(data, 16 * MiB) == O.compress(data, api.LZP, 16 * MiB)

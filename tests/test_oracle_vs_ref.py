@@ -61,3 +61,11 @@ def test_oracle_stage_traces_are_consistent():
     assert (tr[:, 3] == 0).sum() >= len(ev)
     assert payload[1] == 1
     assert toks == O.rolz_parse(data)
+
+
+@pytest.mark.skipif(O.ref_binary("comprop") is None, reason="oracle/_ref not built")
+def test_oracle_prune_matches_reference_cli():
+    """More than 325 000 distinct words: the oracle's restatement of the order-dependent prune (cr-dicpick.c:115-144)."""
+    from vocab_overflow_input import overflow_text
+    data = overflow_text()
+    assert O.compress(data, 1, 16 << 20) == O.ref_compress(data, "comprop", [])

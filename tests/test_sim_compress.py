@@ -53,3 +53,16 @@ def test_sim_more_blocks_than_one_window(simlib):
     want_payloads = [orc.lzencode(b) for b in blocks]
     with api.Handle(api.ROLZ, lib=simlib) as h:
         assert h.lzencode(blocks) == want_payloads
+
+
+def test_sim_dicpick_vocabulary_overflow(simlib):
+    """> 325 000 distinct words: the prune epochs are replayed exactly (the oracle's prune is pinned to the reference
+    CLI in tests/test_oracle_vs_ref.py)."""
+    from vocab_overflow_input import overflow_text
+    data = overflow_text()
+    want = O.dicpick(data)
+    with api.Handle(api.ROLZ, lib=simlib) as h:
+        assert h.dicpick(data) == want
+    text = synth.markov_text(300000, seed=2)
+    with api.Handle(api.LZP, lib=simlib) as h:
+        assert h.dicpick(text) == O.dicpick(text)

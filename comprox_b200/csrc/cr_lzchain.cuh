@@ -324,11 +324,16 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
             CR_TRY(b_bounds.reserve(65537 * 4 + 16));
             CR_LAUNCH(k_o2_bounds, dim3(cr_div_up(65537, 256)), dim3(256), stream, b_k1.as<uint32_t>(), nev, b_bounds.as<uint32_t>());
             if (hot_contexts) {
-                CR_TRY(b_hits.reserve(65536 * 4));
-                CR_CUDA(cudaMemsetAsync(b_hits.p, 0, 65536 * 4, stream));
+                CR_TRY(b_hits.reserve(64));
+                CR_CUDA(cudaMemsetAsync(b_hits.p, 0, 4, stream));
                 CR_LAUNCH(k_o2_hits, dim3(cr_div_up(nev, 256)), dim3(256), stream, b_k1.as<uint32_t>(), nev, b_hits.as<uint32_t>());
-                CR_LAUNCH(k_o2_pass_cta<256>, dim3(65536), dim3(256), stream, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nev, st, b_T1.as<uint64_t>(), b_escrec.as<EscRec>(), b_esccount.as<uint32_t>(), b_bounds.as<uint32_t>(), b_hits.as<uint32_t>());
-                CR_LAUNCH(k_o2_pass_cta<1024>, dim3(65536), dim3(1024), stream, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nev, st, b_T1.as<uint64_t>(), b_escrec.as<EscRec>(), b_esccount.as<uint32_t>(), b_bounds.as<uint32_t>(), b_hits.as<uint32_t>());
+                std::vector<uint32_t> hh;
+                CR_TRY(download(hh, b_hits.p, 1));
+                timer.count("#o3_hits", hh[0]);
+                if ((double)hh[0] > 0.25 * (double)nev)
+                    CR_LAUNCH(k_o2_pass_cta<256>, dim3(65536), dim3(256), stream, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nev, st, b_T1.as<uint64_t>(), b_escrec.as<EscRec>(), b_esccount.as<uint32_t>(), b_bounds.as<uint32_t>());
+                else
+                    CR_LAUNCH(k_o2_pass_cta<1024>, dim3(65536), dim3(1024), stream, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nev, st, b_T1.as<uint64_t>(), b_escrec.as<EscRec>(), b_esccount.as<uint32_t>(), b_bounds.as<uint32_t>());
             }
             CR_LAUNCH(k_o2_pass_warp, dim3(65536 * 32 / 128), dim3(128), stream, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nev, st, b_T1.as<uint64_t>(), b_escrec.as<EscRec>(), b_esccount.as<uint32_t>(), hot_min, b_bounds.as<uint32_t>());
         }

@@ -309,26 +309,25 @@ __global__ void __launch_bounds__(128) k_o2_pass_warp(const uint32_t* __restrict
 // (per-warp histograms, prefix over warps / symbols, 32-way compare inside the warp -- as in k_side_epochs).
 // The first event whose update would rescale the table (cr-o2model.c:54) ends the step; everything after it is
 // recomputed in the next step from the rescaled table.
-// Two instantiations: 256-thread CTAs for contexts whose steps are cut early (flag 256 grows with every o3 hit, so a
-// context with hit rate h rescales about every 188/h events), 1024-thread CTAs for the others.  k_o2_hits counts the
-// hits per context; a context is "narrow" when 188 * events / hits < 512.
+// Two instantiations: 256-thread CTAs when steps are cut early (flag 256 grows with every o3 hit, so a context with hit
+// rate h rescales about every 188/h events), 1024-thread CTAs otherwise.  The host picks one per window from the overall
+// hit rate (k_o2_hits).
+// total number of o3 hits among the events (one atomic per CTA)
 __global__ void k_o2_hits(const uint32_t* __restrict__ K, uint32_t n, uint32_t* __restrict__ hits) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t k = K[i];
-    if ((k >> 24) == ((k >> 16) & 255)) atomicAdd(&hits[k & 0xffff], 1u);
+    const uint32_t k = i < n ? K[i] : 0x01000000u;
+    const int c = __syncthreads_count((k >> 24) == ((k >> 16) & 255));
+    if (threadIdx.x == 0 && c) atomicAdd(hits, (uint32_t)c);
 }
-CR_D bool o2_is_narrow(uint32_t events, uint32_t hits) { return (unsigned long long)hits * 512ull > (unsigned long long)events * 188ull; }
 #define O2C_MIN     3072          // contexts with at least this many events in the window take this path
 template <int O2C_THREADS>
 __global__ void __launch_bounds__(O2C_THREADS) k_o2_pass_cta(const uint32_t* __restrict__ K, const uint32_t* __restrict__ V, uint32_t n, PpmState st,
-                                                             uint64_t* __restrict__ T1, EscRec* __restrict__ esc_rec, uint32_t* __restrict__ esc_count, const uint32_t* __restrict__ bounds, const uint32_t* __restrict__ hits) {
+                                                             uint64_t* __restrict__ T1, EscRec* __restrict__ esc_rec, uint32_t* __restrict__ esc_count, const uint32_t* __restrict__ bounds) {
     constexpr int O2C_WARPS = O2C_THREADS / 32;
     const uint32_t c16 = blockIdx.x;
     const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const uint32_t r0 = bounds[c16], r1 = bounds[c16 + 1];
     if (r1 - r0 < O2C_MIN) return;
-    if (o2_is_narrow(r1 - r0, hits[c16]) != (O2C_THREADS == 256)) return;      // the other instantiation takes this context
 
     __shared__ uint32_t cnt[256], cumt[256], zmask[8];
     __shared__ uint32_t s_f256, s_f257, s_body, s_first;

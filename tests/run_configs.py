@@ -16,6 +16,7 @@ MiB = 1 << 20
 CONFIGS = {
     "text-100M": dict(make=lambda n: synth.markov_text(n, seed=42), n=100 * MiB, variant=api.ROLZ, binary="comprolz", flags=[], filt=False),
     "x86-256M": dict(make=lambda n: synth.x86_corpus(n, seed=43), n=256 * MiB, variant=api.ROLZ, binary="comprolz", flags=["-F"], filt=True),
+    "mixed-192M": dict(make=lambda n: synth.mixed_corpus(n, seed=45, segment=64 * MiB), n=192 * MiB, variant=api.ROLZ, binary="comprolz", flags=["-F"], filt=True),
     "bmp-512M": dict(make=lambda n: synth.bmp_corpus(n, seed=44), n=512 * MiB, variant=api.LZP, binary="comprop", flags=["-F"], filt=True),
 }
 ap = argparse.ArgumentParser()
@@ -24,6 +25,7 @@ ap.add_argument("--scale", type=float, default=1.0, help="shrink the configs (1.
 ap.add_argument("--no-ref", action="store_true")
 ap.add_argument("--full-warmup", action="store_true", help="warm up with the full input so that the timed run does no allocation")
 ap.add_argument("--out", default="gpurun_out/configs.jsonl")
+ap.add_argument("--window-mb", type=int, default=0, help="raw bytes per window (0 = library default)")
 a = ap.parse_args()
 os.makedirs(os.path.dirname(a.out), exist_ok=True)
 for name in a.names:
@@ -34,7 +36,7 @@ for name in a.names:
     with api.Handle(c["variant"]) as h:
         h.compress(data if a.full_warmup else data[:4 * MiB], 16 * MiB, filt=c["filt"])   # warm-up (allocations, module load)
         h.profile(True)
-        t0 = time.time(); out = h.compress(data, 16 * MiB, filt=c["filt"]); dt = time.time() - t0
+        t0 = time.time(); out = h.compress(data, 16 * MiB, filt=c["filt"], window_bytes=a.window_mb * MiB); dt = time.time() - t0
         rec.update(gpu_s=round(dt, 3), gpu_mibs=round(len(data) / MiB / dt, 1), container=len(out), sha=hashlib.sha256(out).hexdigest()[:16],
                    stages_ms={k: round(v, 1) for k, v in h.profile_report().items()})
     if not a.no_ref and O.ref_binary(c["binary"]):

@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcrgpu.so")
 
 ROLZ, LZP = 0, 1
+OWN_STREAM = 1   # pass as `stream`: private stream per handle (several handles then overlap on one GPU)
 
 _lib = None
 

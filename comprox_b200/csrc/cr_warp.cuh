@@ -555,7 +555,7 @@ __global__ void __launch_bounds__(128) k_o1_pass_warp(const uint64_t* __restrict
 // Each thread evaluates its masked sums against a per-warp table "start-of-step count + occurrences in earlier
 // warps" and corrects for the earlier lanes of its own warp.  The first escape whose update halves the row
 // (++o1[c] >= 255, cr-ppm.c:91) ends the step.
-#define O1C_THREADS 256
+#define O1C_THREADS 512
 #define O1C_WARPS   (O1C_THREADS / 32)
 #define O1C_MIN     2048
 __global__ void __launch_bounds__(O1C_THREADS) k_o1_pass_cta(const uint64_t* __restrict__ K, uint32_t n, const uint32_t* __restrict__ info_s, const uint32_t* __restrict__ ord_s,
@@ -571,8 +571,6 @@ __global__ void __launch_bounds__(O1C_THREADS) k_o1_pass_cta(const uint64_t* __r
     __shared__ __align__(4) uint16_t hist[O1C_WARPS][256];      // per-warp histogram -> exclusive prefix over warps
     __shared__ uint16_t basew[O1C_WARPS][256];                   // 8 * (cnt + earlier warps) - 7
     __shared__ uint32_t smask[O1C_THREADS][8];
-    __shared__ uint32_t cumw[O1C_WARPS][256];                    // exclusive prefix of basew[w][.] over symbols
-    __shared__ uint32_t totw[O1C_WARPS];
     __shared__ uint32_t s_first;
     uint8_t* row = st.o1 + c8 * 256;
     if (tid < 256) cnt[tid] = row[tid];
@@ -601,19 +599,6 @@ __global__ void __launch_bounds__(O1C_THREADS) k_o1_pass_cta(const uint64_t* __r
             for (int q = 0; q < O1C_WARPS; q++) { uint32_t h = hist[q][tid]; hist[q][tid] = (uint16_t)run; basew[q][tid] = (uint16_t)(8 * (cnt[tid] + run) - 7); run += h; }
         }
         __syncthreads();
-        {   // per warp: prefix of its table over symbols, so that masked sums can be taken over the (few) EXCLUDED symbols
-            uint32_t v[8], sum = 0;
-#pragma unroll
-            for (int q = 0; q < 8; q++) { v[q] = basew[w][lane * 8 + q]; sum += v[q]; }
-            uint32_t inc = sum;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(FULLMASK, inc, d); if (lane >= d) inc += t; }
-            uint32_t run = inc - sum;
-#pragma unroll
-            for (int q = 0; q < 8; q++) { cumw[w][lane * 8 + q] = run; run += v[q]; }
-            if (lane == 31) totw[w] = inc;
-        }
-        __syncwarp();
         // earlier lanes of this warp: same symbol / symbols inside my mask (and below my symbol)
         uint32_t eq = 0, in_all = 0, in_lt = 0;
 #pragma unroll 8
@@ -626,18 +611,16 @@ __global__ void __launch_bounds__(O1C_THREADS) k_o1_pass_cta(const uint64_t* __r
         }
         uint32_t sum = 0, cum = 0, count_s = 0;
         if (active) {
-            // sum over included symbols = total - sum over excluded ones (symbols present in the o2 context + predicted byte)
-            uint32_t sumex = 0, cumex = 0;
 #pragma unroll
             for (uint32_t q = 0; q < 8; q++) {
-                uint32_t ex = ~m[q];
-                while (ex) {
-                    const uint32_t bpos = __ffs(ex) - 1; ex &= ex - 1;
-                    const uint32_t x = q * 32 + bpos, v = basew[w][x];
-                    sumex += v; cumex += x < sym ? v : 0u;
+                const uint32_t mq = m[q];
+                for (uint32_t b = 0; b < 32; b++) {
+                    const uint32_t x = q * 32 + b;
+                    const uint32_t v = (mq >> b & 1u) ? (uint32_t)basew[w][x] : 0u;
+                    sum += v; cum += x < sym ? v : 0u;
                 }
             }
-            sum = totw[w] - sumex + 8 * in_all; cum = cumw[w][sym] - cumex + 8 * in_lt;
+            sum += 8 * in_all; cum += 8 * in_lt;
             count_s = cnt[sym] + hist[w][sym] + eq;
             if (count_s + 1 >= 255) atomicMin(&s_first, tid);
         }

@@ -19,6 +19,7 @@ struct crgpu_handle {
     DevBuf d_in, d_out;
     Compressor comp;
     Decompressor decomp;
+    bool owns_stream = false;
 };
 
 extern "C" const char* crgpu_strerror(int code) {
@@ -48,6 +49,15 @@ extern "C" int crgpu_create(crgpu_handle** out, int variant, int device, void* s
 #endif
     crgpu_handle* h = new crgpu_handle();
     h->device = device; h->variant = variant; h->stream = (cudaStream_t)stream;
+#ifndef CRGPU_SIM
+    if (stream == CRGPU_OWN_STREAM) {            // private stream: several handles can then work side by side on one GPU
+        cudaStream_t own;
+        if (cudaStreamCreateWithFlags(&own, cudaStreamNonBlocking) != cudaSuccess) { delete h; return CRGPU_ERR_CUDA; }
+        h->stream = own; h->owns_stream = true;
+    }
+#else
+    if (stream == CRGPU_OWN_STREAM) h->stream = 0;
+#endif
     int rc = h->chain.init(variant, h->stream);
     if (rc != CRGPU_OK) { delete h; return rc; }
     *out = h;
@@ -61,6 +71,9 @@ extern "C" void crgpu_destroy(crgpu_handle* h) {
     cudaStreamSynchronize(h->stream);
 #endif
     h->chain.release(); h->d_in.release(); h->d_out.release(); h->comp.release(); h->decomp.release();
+#ifndef CRGPU_SIM
+    if (h->owns_stream) cudaStreamDestroy(h->stream);
+#endif
     delete h;
 }
 

@@ -34,8 +34,10 @@ extern "C" {
 typedef struct crgpu_handle crgpu_handle;
 
 /* Creates a handle on CUDA device `device`.  `stream` is a cudaStream_t passed as void* (NULL = the legacy
- * default stream); all work of the handle is enqueued on it.  `variant` selects the lzencode implementation
+ * default stream, CRGPU_OWN_STREAM = a private stream so that several handles overlap on one GPU); all work of the
+ * handle is enqueued on it.  `variant` selects the lzencode implementation
  * exactly as linking src/rolzmain or src/ropmain does in the reference (Makefile:12-27). */
+#define CRGPU_OWN_STREAM ((void*)1)   /* pass as `stream`: the handle creates (and owns) a private non-blocking stream */
 int  crgpu_create(crgpu_handle** out, int variant, int device, void* stream);
 void crgpu_destroy(crgpu_handle* h);
 const char* crgpu_strerror(int code);

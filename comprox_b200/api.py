@@ -129,6 +129,27 @@ class Handle:
         self.L.crgpu_profile_report(self.h, buf, ctypes.c_uint64(8192))
         return {k: float(v) for k, v in (ln.split() for ln in buf.value.decode().splitlines())}
 
+    def debug_sort(self, keys, vals, begin_bit=0, end_bit=None):
+        """Stable device radix sort of (keys, vals) on key bits [begin_bit, end_bit) (cr_sort.cuh); returns (keys, vals)."""
+        import numpy as np
+        keys = np.ascontiguousarray(keys); vals = np.ascontiguousarray(vals, dtype=np.uint32)
+        kb = keys.dtype.itemsize
+        assert kb in (4, 8) and len(keys) == len(vals)
+        ko = np.empty_like(keys); vo = np.empty_like(vals)
+        _check(self.L, self.L.crgpu_debug_sort(self.h, keys.ctypes.data_as(ctypes.c_void_p), vals.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint64(len(keys)),
+                                               kb, int(begin_bit), int(kb * 8 if end_bit is None else end_bit),
+                                               ko.ctypes.data_as(ctypes.c_void_p), vo.ctypes.data_as(ctypes.c_void_p)))
+        return ko, vo
+
+    def debug_scan(self, vals):
+        """Exclusive prefix sum (mod 2^32) of uint32 values through the device scan (cr_sort.cuh)."""
+        import numpy as np
+        vals = np.ascontiguousarray(vals, dtype=np.uint32)
+        vo = np.empty_like(vals)
+        _check(self.L, self.L.crgpu_debug_sort(self.h, None, vals.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint64(len(vals)), 0, 0, 0,
+                                               None, vo.ctypes.data_as(ctypes.c_void_p)))
+        return vo
+
     def debug_fetch(self, what: str, dtype="uint8"):
         import numpy as np
         n = self.L.crgpu_debug_fetch(self.h, what.encode(), None, ctypes.c_uint64(0))

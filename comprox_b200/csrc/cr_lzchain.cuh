@@ -80,8 +80,9 @@ struct LzChain {
         DevBuf* all[] = { &s_o3b, &s_o3c, &s_o2, &s_o1, &s_m0, &b_blocks, &b_segoff, &b_seglen, &b_hist, &b_esc1, &b_first, &b_ctxout,
             &b_k0, &b_k1, &b_v0, &b_v1, &b_ks0, &b_M, &b_S, &b_span, &b_tidx, &b_segs, &b_xt, &b_entry, &b_cnt, &b_scan, &b_chainwork,
             &b_evctx, &b_evsym, &b_tokend, &b_pred, &b_T1, &b_T2, &b_TS, &b_side, &b_escrec, &b_esccount, &b_k64a, &b_k64b, &b_ord,
-            &b_flag, &b_escord, &b_lensym, &b_lenpos, &b_idxsym, &b_idxpos, &b_hits, &b_o1info, &b_o1ord, &b_o1incl, &b_bounds, &b_o3hot, &b_cinm, &b_cins, &b_segstart, &b_segkey, &b_rank, &b_flexlen, &b_qm, &b_shm, &b_bm, &b_qs, &b_shs, &b_bs, &b_stot, &b_dsum, &b_lsm, &b_lss, &b_rsm, &b_rss, &b_fb, &b_dense, &b_denseside, &b_streams, &b_rcres, &b_rcout, &b_copy, &b_hdr, &prims.temp };
+            &b_flag, &b_escord, &b_lensym, &b_lenpos, &b_idxsym, &b_idxpos, &b_hits, &b_o1info, &b_o1ord, &b_o1incl, &b_bounds, &b_o3hot, &b_cinm, &b_cins, &b_segstart, &b_segkey, &b_rank, &b_flexlen, &b_qm, &b_shm, &b_bm, &b_qs, &b_shs, &b_bs, &b_stot, &b_dsum, &b_lsm, &b_lss, &b_rsm, &b_rss, &b_fb, &b_dense, &b_denseside, &b_streams, &b_rcres, &b_rcout, &b_copy, &b_hdr };
         for (DevBuf* b : all) b->release();
+        prims.release();
 #ifndef CRGPU_SIM
         if (side_stream) { cudaStreamDestroy(side_stream); cudaEventDestroy(ev_side_go); cudaEventDestroy(ev_side_done); side_stream = 0; }
 #endif

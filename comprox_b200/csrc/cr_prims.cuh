@@ -1,58 +1,7 @@
-// cr_prims.cuh -- device-wide building blocks: stable radix sort, exclusive scan, byte histograms.
-//
-// Sort and scan are plumbing between the hot kernels.  Round 1 calls CUB (shipped with the CUDA toolkit,
-// counts as a library call like cuBLAS); the hot operators themselves (match search, model replay, range
-// coder, dictionary substitution, filters, histograms) are hand-written in the other cr_*.cuh files.
+// cr_prims.cuh -- device-wide building blocks: byte histograms and escape selection (sort / scan live in cr_sort.cuh).
 #pragma once
 #include "cr_common.cuh"
-#ifndef CRGPU_SIM
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
-#endif
-
-struct Prims {
-    cudaStream_t stream = 0;
-    DevBuf temp;
-};
-
-// Stable sort of (key, value) pairs on key bits [begin_bit, end_bit).  Full keys travel with the pairs.
-template <class K>
-static int cr_sort_pairs(Prims& P, const K* kin, K* kout, const uint32_t* vin, uint32_t* vout, size_t n, int begin_bit, int end_bit) {
-    if (n == 0) return CRGPU_OK;
-#ifdef CRGPU_SIM
-    std::vector<uint32_t> order(n);
-    for (size_t i = 0; i < n; i++) order[i] = (uint32_t)i;
-    const K mask = (end_bit - begin_bit >= (int)(8 * sizeof(K))) ? ~(K)0 : ((((K)1) << (end_bit - begin_bit)) - 1);
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
-        return ((kin[a] >> begin_bit) & mask) < ((kin[b] >> begin_bit) & mask);
-    });
-    for (size_t i = 0; i < n; i++) { kout[i] = kin[order[i]]; vout[i] = vin[order[i]]; }
-    (void)P;
-    return CRGPU_OK;
-#else
-    size_t bytes = 0;
-    CR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int64_t)n, begin_bit, end_bit, P.stream));
-    CR_TRY(P.temp.reserve(bytes));
-    CR_CUDA(cub::DeviceRadixSort::SortPairs(P.temp.p, bytes, kin, kout, vin, vout, (int64_t)n, begin_bit, end_bit, P.stream));
-    return CRGPU_OK;
-#endif
-}
-
-static int cr_exclusive_sum(Prims& P, const uint32_t* in, uint32_t* out, size_t n) {
-    if (n == 0) return CRGPU_OK;
-#ifdef CRGPU_SIM
-    uint32_t acc = 0;
-    for (size_t i = 0; i < n; i++) { uint32_t v = in[i]; out[i] = acc; acc += v; }
-    (void)P;
-    return CRGPU_OK;
-#else
-    size_t bytes = 0;
-    CR_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, (int64_t)n, P.stream));
-    CR_TRY(P.temp.reserve(bytes));
-    CR_CUDA(cub::DeviceScan::ExclusiveSum(P.temp.p, bytes, in, out, (int64_t)n, P.stream));
-    return CRGPU_OK;
-#endif
-}
+#include "cr_sort.cuh"
 
 // ------------------------------------------------------------------ segmented byte histogram
 // One 256-bin histogram per segment (a raw block or a dictionary-coded block).

@@ -137,6 +137,34 @@ extern "C" int64_t crgpu_debug_fetch(crgpu_handle* h, const char* what, void* ds
     return (int64_t)bytes;
 }
 
+extern "C" int crgpu_debug_sort(crgpu_handle* h, const void* keys, const uint32_t* vals, uint64_t n, int key_bytes, int begin_bit, int end_bit,
+                                void* keys_out, uint32_t* vals_out) {
+    if (!h || !vals || !vals_out || (key_bytes != 0 && key_bytes != 4 && key_bytes != 8) || (key_bytes && (!keys || !keys_out))) return CRGPU_ERR_ARG;
+    if (n == 0) return CRGPU_OK;
+    LzChain& c = h->chain;
+    DevBuf ki, ko, vi, vo;
+    int rc = CRGPU_OK;
+    auto run = [&]() -> int {
+        CR_TRY(vi.reserve(n * 4 + 16)); CR_TRY(vo.reserve(n * 4 + 16));
+        CR_CUDA(cudaMemcpyAsync(vi.p, vals, n * 4, cudaMemcpyHostToDevice, h->stream));
+        if (key_bytes == 0) {
+            CR_TRY(cr_exclusive_sum(c.prims, vi.as<uint32_t>(), vo.as<uint32_t>(), n));
+        } else {
+            CR_TRY(ki.reserve(n * key_bytes + 16)); CR_TRY(ko.reserve(n * key_bytes + 16));
+            CR_CUDA(cudaMemcpyAsync(ki.p, keys, n * key_bytes, cudaMemcpyHostToDevice, h->stream));
+            if (key_bytes == 4) CR_TRY(cr_sort_pairs<uint32_t>(c.prims, ki.as<uint32_t>(), ko.as<uint32_t>(), vi.as<uint32_t>(), vo.as<uint32_t>(), n, begin_bit, end_bit));
+            else CR_TRY(cr_sort_pairs<uint64_t>(c.prims, ki.as<uint64_t>(), ko.as<uint64_t>(), vi.as<uint32_t>(), vo.as<uint32_t>(), n, begin_bit, end_bit));
+            CR_CUDA(cudaMemcpyAsync(keys_out, ko.p, n * key_bytes, cudaMemcpyDeviceToHost, h->stream));
+        }
+        CR_CUDA(cudaMemcpyAsync(vals_out, vo.p, n * 4, cudaMemcpyDeviceToHost, h->stream));
+        CR_CUDA(cudaStreamSynchronize(h->stream));
+        return CRGPU_OK;
+    };
+    rc = run();
+    ki.release(); ko.release(); vi.release(); vo.release();
+    return rc;
+}
+
 extern "C" int crgpu_profile(crgpu_handle* h, int enable) {
     if (!h) return CRGPU_ERR_ARG;
     h->chain.timer.enabled = enable != 0;

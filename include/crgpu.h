@@ -98,6 +98,12 @@ uint64_t crgpu_launch_count(void);
  * Returns the number of BYTES available (copies min(cap, available)), or a negative error. */
 int64_t crgpu_debug_fetch(crgpu_handle* h, const char* what, void* dst, uint64_t cap);
 
+/* Test aid for the device-wide primitives (cr_sort.cuh).  key_bytes = 4 or 8: stable radix sort of n (key, value)
+ * pairs on key bits [begin_bit, end_bit); key_bytes = 0: exclusive prefix sum of the n uint32 in `vals` (keys unused).
+ * Host arrays in, host arrays out (keys_out may be NULL for the scan). */
+int crgpu_debug_sort(crgpu_handle* h, const void* keys, const uint32_t* vals, uint64_t n, int key_bytes, int begin_bit, int end_bit,
+                     void* keys_out, uint32_t* vals_out);
+
 /* Tuning / test switches.  "scalar_models" = 1 runs the scalar model and coder kernels (the ones the CPU
  * kernel-logic simulation checks) instead of the warp-cooperative ones; results are identical. */
 int crgpu_set_option(crgpu_handle* h, const char* name, int64_t value);

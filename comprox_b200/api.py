@@ -45,6 +45,22 @@ def _check(L, rc):
         raise CrgpuError(rc, L.crgpu_strerror(rc).decode())
 
 
+def decompress_batch(handles, containers, out_caps):
+    """crgpu_decompress_batch: containers[i] is decoded with handles[i]; all in flight at once (one warp each)."""
+    k = len(handles)
+    assert k == len(containers) == len(out_caps) and k > 0
+    L = handles[0].L
+    outs = [ctypes.create_string_buffer(max(int(c), 1)) for c in out_caps]
+    hs = (ctypes.c_void_p * k)(*[h.h for h in handles])
+    ins = (ctypes.c_char_p * k)(*containers)
+    in_lens = (ctypes.c_uint64 * k)(*[len(c) for c in containers])
+    outp = (ctypes.c_void_p * k)(*[ctypes.addressof(o) for o in outs])
+    caps = (ctypes.c_uint64 * k)(*[int(c) for c in out_caps])
+    lens = (ctypes.c_uint64 * k)()
+    _check(L, L.crgpu_decompress_batch(hs, ctypes.c_uint32(k), ins, in_lens, outp, caps, lens))
+    return [outs[i].raw[:lens[i]] for i in range(k)]
+
+
 class Config(ctypes.Structure):
     _fields_ = [("block_size", ctypes.c_uint32), ("filt", ctypes.c_int32), ("prec", ctypes.c_int32), ("flexible", ctypes.c_int32),
                 ("window_bytes", ctypes.c_uint64)]

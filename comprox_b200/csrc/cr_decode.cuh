@@ -33,6 +33,13 @@ struct DecTables {        // matcher state of ONE container
     unsigned long long* lzp2;   // [1 << 16]
 };
 
+struct DecJob {           // everything one decode chain (the consecutive blocks of one container) needs
+    int variant; uint32_t nb;
+    const uint8_t* cont; const DecBlock* blocks;
+    PpmState st; DecTables T;
+    uint32_t* ctx_io; uint8_t* D;
+};
+
 // ------------------------------------------------------------------ range decoder (cr-rangecoder.c:81-104)
 struct RcDec {
     uint32_t range, code;
@@ -234,10 +241,7 @@ __global__ void k_dd_layout(const uint8_t* __restrict__ D, DdBlock* __restrict__
 struct DdDict { const char* words; const uint8_t* lens; int32_t nentries, level1; };   // words: [nentries][24]
 CR_HD bool dd_sentence_start(const uint8_t* s, uint32_t i) { return i >= 3 && s[i - 1] == ' ' && (s[i - 2] == '.' || (s[i - 2] == ' ' && s[i - 3] == '.')); }
 // dictionary_decode_imp (cr-diccode.c:364-425): each sub-chunk is expanded back to front by one thread
-__global__ void k_dd_subs(const uint8_t* __restrict__ D, const DdBlock* __restrict__ blocks, const DdSub* __restrict__ subs, uint32_t nsub, DdDict dic, uint8_t* __restrict__ out) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nsub) return;
-    const DdSub S = subs[t];
+CR_D void dd_sub_body(const uint8_t* __restrict__ D, const DdBlock* __restrict__ blocks, const DdSub S, const DdDict dic, uint8_t* __restrict__ out) {
     const DdBlock B = blocks[S.block];
     const uint8_t* esc = D + B.d_off + B.d_size - 11;
     uint8_t escmap[256];
@@ -269,4 +273,19 @@ __global__ void k_dd_subs(const uint8_t* __restrict__ D, const DdBlock* __restri
         rev = src;
     }
     if (rev != 0xFFFFFFFFu && dd_sentence_start(o, rev)) o[rev] ^= 0x20;
+}
+__global__ void k_dd_subs(const uint8_t* __restrict__ D, const DdBlock* __restrict__ blocks, const DdSub* __restrict__ subs, uint32_t nsub, DdDict dic, uint8_t* __restrict__ out) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nsub) return;
+    dd_sub_body(D, blocks, subs[t], dic, out);
+}
+// the same over the sub-chunks of many containers (crgpu_decompress_batch): first[j] = index of job j's first sub-chunk
+struct DdJob { const uint8_t* D; const DdBlock* blocks; const DdSub* subs; DdDict dic; uint8_t* out; };
+__global__ void k_dd_subs_jobs(const DdJob* __restrict__ jobs, const uint32_t* __restrict__ first, uint32_t njobs, uint32_t nsub) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nsub) return;
+    uint32_t lo = 0, hi = njobs;
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (first[mid] <= t) lo = mid; else hi = mid; }
+    const DdJob J = jobs[lo];
+    dd_sub_body(J.D, J.blocks, J.subs[t - first[lo]], J.dic, J.out);
 }

@@ -6,13 +6,13 @@
 struct Decompressor {
     LzChain* chain = nullptr;
     cudaStream_t stream = 0;
-    DevBuf d_cont, d_D, d_out, d_blocks, d_ctx, d_ddblocks, d_subs, d_totals, d_words, d_lens, d_copy;
+    DevBuf d_cont, d_D, d_out, d_blocks, d_ctx, d_ddblocks, d_subs, d_totals, d_words, d_lens, d_copy, d_jobs, d_first;
     DevBuf t_meta, t_items, t_short, t_l8, t_l4, t_l2;
     FilterHost filt;
     uint32_t epoch = 0;
 
     void release() {
-        DevBuf* all[] = { &d_cont, &d_D, &d_out, &d_blocks, &d_ctx, &d_ddblocks, &d_subs, &d_totals, &d_words, &d_lens, &d_copy, &t_meta, &t_items, &t_short, &t_l8, &t_l4, &t_l2 };
+        DevBuf* all[] = { &d_cont, &d_D, &d_out, &d_blocks, &d_ctx, &d_ddblocks, &d_subs, &d_totals, &d_words, &d_lens, &d_copy, &d_jobs, &d_first, &t_meta, &t_items, &t_short, &t_l8, &t_l4, &t_l2 };
         for (DevBuf* b : all) b->release();
         filt.release();
     }
@@ -33,17 +33,17 @@ struct Decompressor {
         T.lzp8 = t_l8.as<unsigned long long>(); T.lzp4 = t_l4.as<unsigned long long>(); T.lzp2 = t_l2.as<unsigned long long>();
         return CRGPU_OK;
     }
-    // lzdecode of `blk` (consecutive blocks of one model chain); fills D at blk[i].d_off
-    int lzdecode(const uint8_t* h_cont, std::vector<DecBlock>& blk) {
+    // lzdecode of `blk` (consecutive blocks of one model chain); fills D at blk[i].d_off.
+    // lz_prepare() uploads the descriptors and fills `job`; the caller launches the chain (alone or in a batch); lz_finish() reads the context back.
+    DecJob job;
+    int lz_prepare(std::vector<DecBlock>& blk) {
         DecTables T; CR_TRY(tables(T));
         std::vector<CopyDesc> copies;
-        const uint32_t hdr = chain->variant == CR_ROLZ ? 16 : 20;
         for (auto& b : blk) {
             if (epoch >= 65000 && t_meta.p) { CR_CUDA(cudaMemsetAsync(t_meta.p, 0, (size_t)RZ_BUCKETS * 4, stream)); epoch = 0; }   // ROLZ tags are 16 bit
             b.epoch = ++epoch;
             if (!b.coded && b.d_size) { CopyDesc c = { b.in_off + (b.in_size - b.d_size), b.d_off, b.d_size, 0 }; copies.push_back(c); }
         }
-        (void)h_cont; (void)hdr;
         CR_TRY(chain->upload(d_blocks, blk));
         std::vector<uint32_t> c(1, chain->chain_ctx);
         CR_TRY(chain->upload(d_ctx, c));
@@ -51,76 +51,117 @@ struct Decompressor {
             CR_TRY(chain->upload(d_copy, copies));
             CR_LAUNCH(k_copy_segments, dim3(64, (unsigned)copies.size()), dim3(256), stream, d_copy.as<CopyDesc>(), d_cont.as<uint8_t>(), d_cont.as<uint8_t>(), d_D.as<uint8_t>());
         }
+        job.variant = chain->variant; job.nb = (uint32_t)blk.size();
+        job.cont = d_cont.as<uint8_t>(); job.blocks = d_blocks.as<DecBlock>();
+        job.st = chain->st; job.T = T; job.ctx_io = d_ctx.as<uint32_t>(); job.D = d_D.as<uint8_t>();
+        return CRGPU_OK;
+    }
+    int lz_launch() {
+        if (job.nb == 0) return CRGPU_OK;
 #ifndef CRGPU_SIM
-        if (!chain->scalar_models) CR_LAUNCH(k_lzdecode_warp, dim3(1), dim3(32), stream, chain->variant, d_cont.as<uint8_t>(), d_blocks.as<DecBlock>(), (uint32_t)blk.size(), chain->st, T, d_ctx.as<uint32_t>(), d_D.as<uint8_t>());
+        if (!chain->scalar_models) CR_LAUNCH(k_lzdecode_warp, dim3(1), dim3(32), stream, job.variant, job.cont, job.blocks, job.nb, job.st, job.T, job.ctx_io, job.D);
         else
 #endif
-        CR_LAUNCH(k_lzdecode_serial, dim3(1), dim3(1), stream, chain->variant, d_cont.as<uint8_t>(), d_blocks.as<DecBlock>(), (uint32_t)blk.size(), chain->st, T, d_ctx.as<uint32_t>(), d_D.as<uint8_t>());
+        CR_LAUNCH(k_lzdecode_serial, dim3(1), dim3(1), stream, job.variant, job.cont, job.blocks, job.nb, job.st, job.T, job.ctx_io, job.D);
+        return CRGPU_OK;
+    }
+    int lz_finish() {
+        std::vector<uint32_t> c;
         CR_TRY(chain->download(c, d_ctx.p, 1));
         chain->chain_ctx = c[0];
         return CRGPU_OK;
     }
-    int decompress(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_n);
+    // one container in three phases; between the phases the decode chain `job` must have run (lz_launch() or a batched launch)
+    const uint8_t* c_in = nullptr; uint64_t c_n = 0; uint8_t* c_out = nullptr; uint64_t c_out_cap = 0; uint64_t* c_out_n = nullptr;
+    uint64_t c_p = 0;
+    std::vector<DecBlock> c_dblk, c_blk; std::vector<uint8_t> c_filt; DdDict c_dic;
+    int describe(uint64_t off, uint32_t size, int prec, uint64_t d_off, DecBlock& b);
+    int begin(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_n);   // -> job = dictionary payload
+    int middle();                                                                                  // -> job = data blocks (nb may be 0)
+    int finish_layout();                                                                           // -> ddjob = the sub-chunks to expand
+    int dd_launch();
+    int finish_output();                                                                           // inverse filters, copy out
+    DdJob ddjob; uint32_t dd_nsub = 0; std::vector<DdBlock> c_ddb; uint64_t c_raw_total = 0;
+    int decompress(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_n) {
+        CR_TRY(begin(in, n, out, out_cap, out_n)); CR_TRY(lz_launch());
+        CR_TRY(middle()); CR_TRY(lz_launch());
+        CR_TRY(finish_layout()); CR_TRY(dd_launch());
+        return finish_output();
+    }
 };
 
-inline int Decompressor::decompress(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_n) {
-    stream = chain->stream;
+// payload -> DecBlock: sizes come from the inner headers (src/rolzmain/cr-coder.c:63-71, src/ropmain/cr-coder.c:60-66)
+inline int Decompressor::describe(uint64_t off, uint32_t size, int prec, uint64_t d_off, DecBlock& b) {
     const int variant = chain->variant;
-    const char* magic = cr_magic(variant);
-    const size_t mlen = strlen(magic);
     const uint32_t hdr = variant == CR_ROLZ ? 16 : 20;
+    memset(&b, 0, sizeof b);
+    b.in_off = off; b.in_size = size; b.d_off = d_off;
+    if (prec) { b.coded = 0; b.d_size = size; return CRGPU_OK; }
+    if (size < hdr) return CRGPU_ERR_ARG;
+    const int compressed = variant == CR_ROLZ ? c_in[off + 1] : c_in[off];
+    if (!compressed) { b.coded = 0; b.d_size = size - hdr; return CRGPU_OK; }
+    b.coded = 1; memcpy(&b.d_size, c_in + off + 4, 4);
+    return CRGPU_OK;
+}
+
+inline int Decompressor::begin(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_n) {
+    stream = chain->stream;
+    const char* magic = cr_magic(chain->variant);
+    const size_t mlen = strlen(magic);
     if (!in || !out_n || n < mlen + 4 || memcmp(in, magic, mlen) != 0) return CRGPU_ERR_ARG;     // check_magic, src/main.c:72-79
-    auto rd32 = [&](uint64_t o) { uint32_t v; memcpy(&v, in + o, 4); return v; };
-    // payload -> DecBlock: sizes come from the inner headers (src/rolzmain/cr-coder.c:63-71, src/ropmain/cr-coder.c:60-66)
-    auto describe = [&](uint64_t off, uint32_t size, int prec, uint64_t d_off, DecBlock& b) -> int {
-        memset(&b, 0, sizeof b);
-        b.in_off = off; b.in_size = size; b.d_off = d_off;
-        if (prec) { b.coded = 0; b.d_size = size; return CRGPU_OK; }
-        if (size < hdr) return CRGPU_ERR_ARG;
-        const int compressed = variant == CR_ROLZ ? in[off + 1] : in[off];
-        if (!compressed) { b.coded = 0; b.d_size = size - hdr; return CRGPU_OK; }
-        b.coded = 1; b.d_size = rd32(off + 4);
-        return CRGPU_OK;
-    };
+    c_in = in; c_n = n; c_out = out; c_out_cap = out_cap; c_out_n = out_n;
     CR_TRY(d_cont.reserve(n + 64));
     CR_CUDA(cudaMemcpyAsync(d_cont.p, in, n, cudaMemcpyHostToDevice, stream));
-
     // ---- static dictionary (src/main.c:244-259)
     uint64_t p = mlen;
-    const uint32_t dict_len = rd32(p); p += 4;
+    uint32_t dict_len; memcpy(&dict_len, in + p, 4); p += 4;
     if (p + dict_len > n) return CRGPU_ERR_ARG;
-    std::vector<DecBlock> dblk(1);
-    CR_TRY(describe(p, dict_len, 0, 0, dblk[0]));
-    p += dict_len;
-    CR_TRY(d_D.reserve((size_t)dblk[0].d_size + 64));
+    c_dblk.assign(1, DecBlock());
+    CR_TRY(describe(p, dict_len, 0, 0, c_dblk[0]));
+    c_p = p + dict_len;
+    // the data blocks are parsed here too, so that every device buffer of the call is sized before any chain runs
+    c_blk.clear(); c_filt.clear();
+    uint64_t dtotal = 0;
+    p = c_p;
+    while (p + 6 <= n) {
+        uint32_t size; memcpy(&size, in + p, 4); const int f = in[p + 4], prec = in[p + 5];
+        p += 6;
+        if (p + size > n) return CRGPU_ERR_ARG;
+        DecBlock b; CR_TRY(describe(p, size, prec, dtotal, b));
+        c_blk.push_back(b); c_filt.push_back((uint8_t)f);
+        dtotal += ((uint64_t)b.d_size + 15) & ~15ull;
+        p += size;
+    }
+    CR_TRY(d_D.reserve((dtotal > c_dblk[0].d_size ? dtotal : (uint64_t)c_dblk[0].d_size) + 64));
     CR_TRY(chain->reset_models());
-    CR_TRY(lzdecode(in, dblk));
+    return lz_prepare(c_dblk);
+}
+
+inline int Decompressor::middle() {
+    CR_TRY(lz_finish());
     std::vector<uint8_t> lcp;
-    CR_TRY(chain->download(lcp, d_D.p, dblk[0].d_size));
+    CR_TRY(chain->download(lcp, d_D.p, c_dblk[0].d_size));
     CR_TRY(chain->reset_models());
     const std::string text = hd_lcp_decode(lcp.data(), lcp.size());
     const std::vector<std::string> entries = hd_entries(text.c_str());
     std::vector<char> words(entries.size() * 24 + 24, 0); std::vector<uint8_t> lens(entries.size() + 1, 0);
     for (size_t i = 0; i < entries.size(); i++) { lens[i] = (uint8_t)entries[i].size(); memcpy(&words[i * 24], entries[i].data(), entries[i].size() < 24 ? entries[i].size() : 24); }
     CR_TRY(chain->upload(d_words, words)); CR_TRY(chain->upload(d_lens, lens));
-    DdDict dic = { d_words.as<char>(), d_lens.as<uint8_t>(), (int32_t)entries.size(), HD_LEVEL1((int)entries.size()) };
-
+    c_dic = DdDict{ d_words.as<char>(), d_lens.as<uint8_t>(), (int32_t)entries.size(), HD_LEVEL1((int)entries.size()) };
     // ---- data blocks (src/main.c:263-292)
-    std::vector<DecBlock> blk; std::vector<uint8_t> filt_flags;
-    uint64_t dtotal = 0;
-    while (p + 6 <= n) {
-        const uint32_t size = rd32(p); const int f = in[p + 4], prec = in[p + 5];
-        p += 6;
-        if (p + size > n) return CRGPU_ERR_ARG;
-        DecBlock b; CR_TRY(describe(p, size, prec, dtotal, b));
-        blk.push_back(b); filt_flags.push_back((uint8_t)f);
-        dtotal += ((uint64_t)b.d_size + 15) & ~15ull;
-        p += size;
-    }
-    CR_TRY(d_D.reserve(dtotal + 64));
-    if (!blk.empty()) CR_TRY(lzdecode(in, blk));
+    job.nb = 0;
+    if (!c_blk.empty()) CR_TRY(lz_prepare(c_blk));
+    return CRGPU_OK;
+}
 
+inline int Decompressor::finish_layout() {
+    std::vector<DecBlock>& blk = c_blk;
+    uint8_t* out = c_out;
+    if (!blk.empty()) CR_TRY(lz_finish());
     // ---- dictionary_decode
+    const DdDict dic = c_dic;
+    const std::vector<uint8_t>& filt_flags = c_filt;
+    const uint64_t out_cap = c_out_cap;
     const uint32_t nb = (uint32_t)blk.size();
     std::vector<DdBlock> ddb(nb);
     uint64_t sub_cap = 2 * nb + 16;
@@ -143,7 +184,23 @@ inline int Decompressor::decompress(const uint8_t* in, uint64_t n, uint8_t* out,
         CR_TRY(chain->upload(d_copy, copies));
         CR_LAUNCH(k_copy_segments, dim3(64, (unsigned)copies.size()), dim3(256), stream, d_copy.as<CopyDesc>(), d_D.as<uint8_t>(), d_D.as<uint8_t>(), d_out.as<uint8_t>());
     }
-    if (nsub) CR_LAUNCH(k_dd_subs, dim3(cr_div_up(nsub, 32)), dim3(32), stream, d_D.as<uint8_t>(), d_ddblocks.as<DdBlock>(), d_subs.as<DdSub>(), nsub, dic, d_out.as<uint8_t>());
+    c_ddb = ddb; c_raw_total = raw_total;
+    ddjob = DdJob{ d_D.as<uint8_t>(), d_ddblocks.as<DdBlock>(), d_subs.as<DdSub>(), dic, d_out.as<uint8_t>() };
+    dd_nsub = nsub;
+    return CRGPU_OK;
+}
+
+inline int Decompressor::dd_launch() {
+    if (dd_nsub) CR_LAUNCH(k_dd_subs, dim3(cr_div_up(dd_nsub, 32)), dim3(32), stream, ddjob.D, ddjob.blocks, ddjob.subs, dd_nsub, ddjob.dic, ddjob.out);
+    return CRGPU_OK;
+}
+
+inline int Decompressor::finish_output() {
+    const std::vector<DdBlock>& ddb = c_ddb;
+    const uint64_t raw_total = c_raw_total;
+    const std::vector<uint8_t>& filt_flags = c_filt;
+    const uint32_t nb = (uint32_t)c_blk.size();
+    uint8_t* out = c_out;
 
     // ---- inverse filters (src/main.c:284-286): the state machine needs the decoded headers on the host
     bool any_filt = false;
@@ -159,6 +216,6 @@ inline int Decompressor::decompress(const uint8_t* in, uint64_t n, uint8_t* out,
     }
     CR_CUDA(cudaMemcpyAsync(out, d_out.p, raw_total, cudaMemcpyDeviceToHost, stream));
     CR_CUDA(cudaStreamSynchronize(stream));
-    *out_n = raw_total;
+    *c_out_n = raw_total;
     return CRGPU_OK;
 }

@@ -1142,9 +1142,8 @@ CR_D void wcopy_match(uint8_t* out, uint32_t n, uint32_t q, uint32_t len, uint32
     else { for (uint32_t b = 0; b < len; b += 32) if (b + lane < len) out[n + b + lane] = out[q + (b + lane) % dist]; __syncwarp(); }
 }
 
-__global__ void __launch_bounds__(32) k_lzdecode_warp(int variant, const uint8_t* __restrict__ cont, const DecBlock* __restrict__ blocks, uint32_t nb,
-                                                       PpmState st, DecTables T, uint32_t* __restrict__ ctx_io, uint8_t* __restrict__ D) {
-    if (blockIdx.x != 0) return;
+__device__ __forceinline__ void lzdecode_warp_body(int variant, const uint8_t* __restrict__ cont, const DecBlock* __restrict__ blocks, uint32_t nb,
+                                                   PpmState st, DecTables T, uint32_t* __restrict__ ctx_io, uint8_t* __restrict__ D) {
     const uint32_t lane = threadIdx.x & 31;
     uint32_t ctx = *ctx_io;
     uint32_t fa[4], fb[4];
@@ -1251,5 +1250,18 @@ __global__ void __launch_bounds__(32) k_lzdecode_warp(int variant, const uint8_t
     ((uint4*)(st.m0))[lane] = make_uint4(fa[0], fa[1], fa[2], fa[3]);
     ((uint4*)(st.m0 + 256))[lane] = make_uint4(fb[0], fb[1], fb[2], fb[3]);
     if (lane == 0) *ctx_io = ctx;
+}
+__global__ void __launch_bounds__(32) k_lzdecode_warp(int variant, const uint8_t* __restrict__ cont, const DecBlock* __restrict__ blocks, uint32_t nb,
+                                                       PpmState st, DecTables T, uint32_t* __restrict__ ctx_io, uint8_t* __restrict__ D) {
+    if (blockIdx.x != 0) return;
+    lzdecode_warp_body(variant, cont, blocks, nb, st, T, ctx_io, D);
+}
+// Many containers in flight: one warp per container, every container with its own model state and
+// matcher tables.  The chains are independent, so the grid is simply the list of jobs.
+__global__ void __launch_bounds__(32) k_lzdecode_jobs(const DecJob* __restrict__ jobs, uint32_t njobs) {
+    if (blockIdx.x >= njobs) return;
+    const DecJob j = jobs[blockIdx.x];
+    if (j.nb == 0) return;
+    lzdecode_warp_body(j.variant, j.cont, j.blocks, j.nb, j.st, j.T, j.ctx_io, j.D);
 }
 #endif  // !CRGPU_SIM

@@ -231,6 +231,53 @@ extern "C" int crgpu_decompress(crgpu_handle* h, const uint8_t* in, uint64_t n, 
     return h->decomp.decompress(in, n, out, out_cap, out_n);
 }
 
+extern "C" int crgpu_decompress_batch(crgpu_handle* const* hs, uint32_t count, const uint8_t* const* ins, const uint64_t* in_lens,
+                                      uint8_t* const* outs, const uint64_t* out_caps, uint64_t* out_lens) {
+    if (!hs || !ins || !in_lens || !outs || !out_caps || !out_lens) return CRGPU_ERR_ARG;
+    if (count == 0) return CRGPU_OK;
+    for (uint32_t i = 0; i < count; i++) {
+        if (!hs[i] || hs[i]->device != hs[0]->device || hs[i]->variant != hs[0]->variant || hs[i]->stream != hs[0]->stream) return CRGPU_ERR_ARG;
+        for (uint32_t k = 0; k < i; k++) if (hs[k] == hs[i]) return CRGPU_ERR_ARG;
+        hs[i]->decomp.chain = &hs[i]->chain;
+    }
+#ifdef CRGPU_SIM
+    for (uint32_t i = 0; i < count; i++) CR_TRY(hs[i]->decomp.decompress(ins[i], in_lens[i], outs[i], out_caps[i], &out_lens[i]));
+    return CRGPU_OK;
+#else
+    CR_CUDA(cudaSetDevice(hs[0]->device));
+    if (hs[0]->chain.scalar_models) {
+        for (uint32_t i = 0; i < count; i++) CR_TRY(hs[i]->decomp.decompress(ins[i], in_lens[i], outs[i], out_caps[i], &out_lens[i]));
+        return CRGPU_OK;
+    }
+    cudaStream_t stream = hs[0]->stream;
+    DevBuf& d_jobs = hs[0]->decomp.d_jobs;
+    std::vector<DecJob> jobs(count);
+    auto launch = [&]() -> int {
+        for (uint32_t i = 0; i < count; i++) jobs[i] = hs[i]->decomp.job;
+        CR_TRY(hs[0]->chain.upload(d_jobs, jobs));
+        CR_LAUNCH(k_lzdecode_jobs, dim3(count), dim3(32), stream, d_jobs.as<DecJob>(), count);
+        return CRGPU_OK;
+    };
+    for (uint32_t i = 0; i < count; i++) CR_TRY(hs[i]->decomp.begin(ins[i], in_lens[i], outs[i], out_caps[i], &out_lens[i]));
+    CR_TRY(launch());
+    for (uint32_t i = 0; i < count; i++) CR_TRY(hs[i]->decomp.middle());
+    CR_TRY(launch());
+    // dictionary_decode: the sub-chunks of all containers in one launch (each is a serial back-to-front expansion)
+    std::vector<DdJob> ddjobs(count); std::vector<uint32_t> first(count + 1, 0);
+    for (uint32_t i = 0; i < count; i++) {
+        CR_TRY(hs[i]->decomp.finish_layout());
+        ddjobs[i] = hs[i]->decomp.ddjob; first[i + 1] = first[i] + hs[i]->decomp.dd_nsub;
+    }
+    if (first[count]) {
+        DevBuf& d_first = hs[0]->decomp.d_first;
+        CR_TRY(hs[0]->chain.upload(d_jobs, ddjobs)); CR_TRY(hs[0]->chain.upload(d_first, first));
+        CR_LAUNCH(k_dd_subs_jobs, dim3(cr_div_up(first[count], 32)), dim3(32), stream, d_jobs.as<DdJob>(), d_first.as<uint32_t>(), count, first[count]);
+    }
+    for (uint32_t i = 0; i < count; i++) CR_TRY(hs[i]->decomp.finish_output());
+    return CRGPU_OK;
+#endif
+}
+
 // dicpick(fp, dic_block): the dictionary text (NUL terminated) the reference builds from the whole input.
 extern "C" int crgpu_dicpick(crgpu_handle* h, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_n) {
     if (!h || (n && !in) || !out || !out_n) return CRGPU_ERR_ARG;

@@ -84,6 +84,14 @@ int crgpu_dicpick(crgpu_handle* h, const uint8_t* in, uint64_t n, uint8_t* out, 
  * is too small. */
 int crgpu_decompress(crgpu_handle* h, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_n);
 
+/* Many containers in flight.  `count` containers are decoded side by side, one warp each, by
+ * ONE launch per phase (dictionary payloads, then data blocks); hs[i] supplies the model state, matcher tables and
+ * buffers of container i, so the number of handles is the number of containers in flight.  All handles must have been
+ * created for the same variant and device and on the SAME stream (not CRGPU_OWN_STREAM).  out_lens[i] receives the
+ * decoded size.  Returns the first error (outputs are then undefined). */
+int crgpu_decompress_batch(crgpu_handle* const* hs, uint32_t count, const uint8_t* const* ins, const uint64_t* in_lens,
+                           uint8_t* const* outs, const uint64_t* out_caps, uint64_t* out_lens);
+
 /* Copies `in` to HBM ahead of time.  A following crgpu_compress(h, cfg, in, n, ...) with the same pointer and
  * length (and no -F, which rewrites the staged bytes in place) then skips its host-to-device copy; used by
  * bench.py to time the device-resident path separately from the end-to-end path. */

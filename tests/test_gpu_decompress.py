@@ -65,3 +65,40 @@ def test_gpu_decompress_scalar_kernel(gpulib, variant):
     with api.Handle(variant, lib=gpulib) as h:
         h.set_option("scalar_models", 1)
         assert h.decompress(container, len(data) + 64) == data
+
+
+@pytest.mark.parametrize("variant", [api.ROLZ, api.LZP])
+def test_gpu_decompress_batch(gpulib, variant):
+    """Many containers in flight: one launch decodes all of them (one warp each); ragged, empty, filtered and -p members."""
+    inputs = [
+        (synth.markov_text(MiB + 777, seed=11), MiB, 0, 0),
+        (b"", 16 * MiB, 0, 0),
+        (synth.markov_text(2 * MiB, seed=12), MiB // 2, 0, 0),
+        (synth.x86_corpus(2 * MiB, elf_bytes=MiB, pe_min=MiB // 2, pe_max=MiB) if variant == api.ROLZ
+         else synth.bmp_corpus(2 * MiB, wmin=301, wmax=900, hmin=100, hmax=500), MiB, 1, 0),
+        (b"A", 16 * MiB, 0, 0),
+        (synth.markov_text(MiB, seed=13), MiB, 0, 1),
+        (bytes(300000), MiB, 0, 0),
+    ]
+    containers = [O.compress(d, variant, bs, filt, prec) for d, bs, filt, prec in inputs]
+    handles = [api.Handle(variant, lib=gpulib) for _ in inputs]
+    try:
+        for _ in range(2):                       # the second call reuses tables and model memory of the first
+            outs = api.decompress_batch(handles, containers, [len(d) + 64 for d, *_ in inputs])
+            for i, (d, *_r) in enumerate(inputs):
+                assert outs[i] == d, i
+        # a batch is the same as one call per container
+        assert handles[0].decompress(containers[2], 2 * MiB + 64) == inputs[2][0]
+    finally:
+        for h in handles:
+            h.close()
+
+
+def test_gpu_decompress_batch_rejects_mixed_handles(gpulib):
+    a, b = api.Handle(api.ROLZ, lib=gpulib), api.Handle(api.LZP, lib=gpulib)
+    c = O.compress(b"abc", api.ROLZ, MiB, 0, 0)
+    with pytest.raises(api.CrgpuError):
+        api.decompress_batch([a, b], [c, c], [64, 64])
+    with pytest.raises(api.CrgpuError):
+        api.decompress_batch([a, a], [c, c], [64, 64])
+    a.close(); b.close()

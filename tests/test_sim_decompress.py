@@ -34,3 +34,18 @@ def test_sim_decompress_rejects_wrong_magic(simlib):
     with api.Handle(api.LZP, lib=simlib) as h:
         with pytest.raises(api.CrgpuError):
             h.decompress(container, 1024)
+
+
+def test_sim_decompress_batch_host_flow(simlib):
+    """crgpu_decompress_batch: argument checks and the per-container phases (begin / middle / finish) on the simulation."""
+    datas = [synth.markov_text(200000 + 999 * i, seed=20 + i) for i in range(3)] + [b""]
+    conts = [O.compress(d, api.ROLZ, MiB // 4, 0, 0) for d in datas]
+    hs = [api.Handle(api.ROLZ, lib=simlib) for _ in datas]
+    try:
+        outs = api.decompress_batch(hs, conts, [len(d) + 64 for d in datas])
+        assert outs == datas
+        with pytest.raises(api.CrgpuError):
+            api.decompress_batch([hs[0], hs[0]], conts[:2], [1 << 20, 1 << 20])
+    finally:
+        for h in hs:
+            h.close()

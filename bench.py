@@ -268,6 +268,24 @@ def main():
                               "roundtrip_ok": back == dsample}
     except Exception as e:  # keep the compress line even if the decode leg fails
         line["decompress"] = {"error": str(e)}
+    # the scalable decode mode: many independent containers in flight, one warp each, one launch per phase
+    try:
+        K, per = 296, MiB
+        parts = [raw[i * 4096:i * 4096 + per] for i in range(K)]
+        with api.Handle(api.ROLZ, device=local_rank, stream=stream.cuda_stream) as hc:
+            conts = [hc.compress(p, BLOCK) for p in parts]
+        hs = [api.Handle(api.ROLZ, device=local_rank, stream=stream.cuda_stream) for _ in range(K)]
+        try:
+            api.decompress_batch(hs, conts, [per + 64] * K)
+            t0 = time.perf_counter(); backs = api.decompress_batch(hs, conts, [per + 64] * K); dt = time.perf_counter() - t0
+        finally:
+            for hh in hs:
+                hh.close()
+        line["decompress_batch"] = {"value": round(K * per / MiB / dt, 1), "unit": "MiB/s", "containers_in_flight": K,
+                                    "sample": "%d text containers of 1 MiB through crgpu_decompress_batch, host buffers in and out" % K,
+                                    "roundtrip_ok": backs == parts}
+    except Exception as e:
+        line["decompress_batch"] = {"error": str(e)}
     if not args.no_cpu_baseline and world == 1:
         sample = raw[:REF_SAMPLE]
         sec, cores, kind = time_reference(sample, 1, 0)

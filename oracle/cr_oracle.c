@@ -244,6 +244,8 @@ struct cro_ctx {
     int variant, flexible, tracing;
     ppm_t ppm;
     m0_t idx_model, len_model;
+    m0_t x_len, x_spos, x_pos[6];   /* LZ77 (comprox): src/roxmain/cr-coder.c:55-60 */
+    uint32_t match_limit;           /* -m, src/roxmain/cr-matcher.c:38 */
     dict_t dic;
     int last_filter;            /* 0 none, 1 pe, 2 elf, 3 bmp  (src/cr-filter.c:41) */
     x86_state pe, elf;
@@ -264,6 +266,7 @@ static void trace_token(cro_ctx* c, uint32_t pos, uint32_t len, uint32_t idx) {
 cro_ctx* cro_new(int variant) {
     cro_ctx* c = calloc(1, sizeof *c);
     c->variant = variant;
+    c->match_limit = 40;
     ppm_alloc(&c->ppm);
     c->dic.word = calloc(DIC_MAXWORDS, DIC_WORDBUF);
     cro_reset_models(c);
@@ -284,7 +287,15 @@ void cro_reset_models(cro_ctx* c) {
         c->len_model.frq[i] = (i == 0 || i >= 5);
     }
     m0_recount(&c->idx_model); m0_recount(&c->len_model);
+    /* src/roxmain/cr-coder.c:88-103 */
+    for (int i = 0; i < 5; i++) {
+        for (int k = 0; k < 256; k++) c->x_pos[i].frq[k] = (i == 0 && k % 8 == 0) || (i > 0 && (i < 2 || k < 128));
+        m0_recount(&c->x_pos[i]);
+    }
+    for (int k = 0; k < 256; k++) { c->x_pos[5].frq[k] = 1; c->x_spos.frq[k] = 1; c->x_len.frq[k] = (k >= 6) || (k == 0); }
+    m0_recount(&c->x_pos[5]); m0_recount(&c->x_spos); m0_recount(&c->x_len);
 }
+void cro_set_match_limit(cro_ctx* c, uint32_t limit) { c->match_limit = limit; }
 void cro_set_flexible(cro_ctx* c, int on) { c->flexible = on; }
 void cro_trace_enable(cro_ctx* c, int on) { c->tracing = on; }
 void cro_trace_clear(cro_ctx* c) { c->tokens.n = c->events.n = c->triples.n = 0; }
@@ -594,11 +605,212 @@ static void lzp_decode(cro_ctx* c, const uint8_t* in, uint32_t n, cro_buf* out) 
     lzp_free(&m);
 }
 
+/* ================================================================== LZ77 (src/roxmain, the `comprox` binary) */
+#define X_MAXLEN   255u
+#define X_MIN_NEAR 6u
+#define X_NONE     0xFFFFFFFFu
+typedef struct {
+    uint32_t* next;             /* previous position with the same (hash1 % 20, hash2 % bucketsize2), X_NONE = end */
+    uint32_t* short_cache;      /* [65536] most recent position per 6-byte hash */
+    uint32_t  last_match;       /* distance of the most recent match (the one parse-dependent scalar) */
+    uint32_t  match_min, limit;
+} x_t;
+typedef struct { uint32_t pos, len; } x_ret;
+
+static uint32_t x_hashn(const uint8_t* s, uint32_t k) { uint32_t h = 0; for (uint32_t i = 0; i < k; i++) h = (h * 123456791u) ^ s[i]; return h; }   /* cr-matcher.c:44-52,196-204 */
+/* matcher_init, cr-matcher.c:89-147.  The reference threads positions through two bucket passes; the result is:
+ * next[p] = the largest q < p with the same (hash1 % 20, hash2 % bucketsize2), for p <= len - 256. */
+static void x_init(x_t* m, const uint8_t* d, uint32_t len, uint32_t match_min, uint32_t limit) {
+    const uint32_t b2 = 20 + len / 25;
+    m->next = malloc(((size_t)len + 1) * 4); m->short_cache = calloc(65536, 4);
+    m->last_match = 0; m->match_min = match_min; m->limit = limit;
+    memset(m->next, 0xFF, ((size_t)len + 1) * 4);
+    if (len < X_MAXLEN + 1) return;
+    uint32_t* head = malloc((size_t)20 * b2 * 4);
+    memset(head, 0xFF, (size_t)20 * b2 * 4);
+    for (uint32_t p = 0; p + X_MAXLEN < len; p++) {
+        size_t k = (size_t)((d[p] + d[p + 1]) % 20) * b2 + x_hashn(d + p, match_min) % b2;
+        m->next[p] = head[k]; head[k] = p;
+    }
+    free(head);
+}
+static void x_free(x_t* m) { free(m->next); free(m->short_cache); }
+/* match(), cr-matcher.c:156-194 */
+static x_ret x_match(const x_t* m, const uint8_t* d, uint32_t pos, uint32_t min, uint32_t limit, uint32_t lazy) {
+    x_ret r = { 0, min - 1 };
+    uint32_t node = m->next[pos];
+    for (uint32_t i = 0; i < limit && node != X_NONE; i++) {
+        uint32_t nl = r.len;
+        while (nl < X_MAXLEN && d[node + nl] == d[pos + nl]) nl++;
+        uint32_t price = 0, dist = pos - node, best = pos - r.pos;
+        price += dist / 1048576 > best; price += dist / 4096 > best; price += dist / 64 > best;
+        if (nl > r.len + price && memcmp(d + pos, d + node, r.len) == 0) {
+            r.pos = node; r.len = nl;
+            if ((lazy && lazy < r.pos) || r.len == X_MAXLEN) return r;
+        }
+        node = m->next[node];
+    }
+    if (r.len < min) { r.pos = X_NONE; r.len = 1; }
+    return r;
+}
+static int x_log2(uint32_t x) { int l = -1; while (x) { l++; x >>= 1; } return l; }   /* fast_log2, cr-matcher.c:211-228: floor(log2 x), 0 -> -1 */
+/* matcher_lookup, cr-matcher.c:230-340 */
+static x_ret x_lookup(x_t* m, const uint8_t* d, uint32_t pos, int flexible) {
+    x_ret t1 = { pos - m->last_match, 0 }, ret;
+    const uint32_t mm = m->match_min;
+    if (t1.pos < pos) while (t1.len < X_MAXLEN && d[pos + t1.len] == d[t1.pos + t1.len]) t1.len++;
+    if (flexible) {
+        /* the reference caches match() results between calls (m_ret_cache); match() is pure, so we recompute */
+        x_ret r0 = x_match(m, d, pos, mm, m->limit, 0);
+        ret = r0;
+        if (r0.len >= mm) {
+#define XP(i, l) ((l) >= mm ? (int)(((l) - 1) * 3) - (x_log2(pos - (i)) * 4 / 5) : 9)
+            uint32_t n = r0.len;
+            x_ret* rs = malloc((n + 1) * sizeof *rs);
+            rs[0] = r0;
+            for (uint32_t i = 1; i <= n; i++) rs[i] = x_match(m, d, pos + i, mm, m->limit, 0);
+            uint32_t maxprice = (uint32_t)(XP(rs[0].pos, rs[0].len) + XP(rs[n].pos, rs[n].len));
+            for (uint32_t i = n - 1; i >= 1; i--) {
+                uint32_t pr = (uint32_t)(XP(ret.pos, i) + XP(rs[i].pos, rs[i].len));
+                if (maxprice < pr) { ret.len = i; maxprice = pr; }
+            }
+            free(rs);
+#undef XP
+            if (ret.len < mm) { ret.pos = X_NONE; ret.len = 1; }
+        }
+    } else {
+        ret = x_match(m, d, pos, mm, m->limit, 0);
+        if (ret.len >= mm) {
+            x_ret t2 = x_match(m, d, pos + 1, ret.len + 1, m->limit / 4, 1);
+            if (t2.len > ret.len + (t2.pos < ret.pos) ||
+                x_match(m, d, pos + 2, ret.len + 1, m->limit / 8, 1).len > 1 ||
+                x_match(m, d, pos + 3, ret.len + 2, m->limit / 8, 1).len > 1 ||
+                x_match(m, d, pos + 4, ret.len + 2, m->limit / 8, 1).len > 1 ||
+                x_match(m, d, pos + 5, ret.len + 2, m->limit / 8, 1).len > 1 ||
+                x_match(m, d, pos + 6, ret.len + 3, m->limit / 8, 1).len > 1) { ret.pos = X_NONE; ret.len = 1; }
+        }
+    }
+    if (ret.pos != X_NONE && ret.len < t1.len + 3 + (ret.pos + 64 < pos) + (ret.pos + 4096 < pos) + (ret.pos + 1048576 < pos)) ret = t1;
+    if (ret.len < X_MIN_NEAR) {
+        ret.pos = m->short_cache[x_hashn(d + pos, X_MIN_NEAR) % 65536]; ret.len = 0;
+        if (ret.pos < pos && ret.pos + 256 > pos) { uint32_t i = 0; while (i < X_MAXLEN && d[ret.pos + i] == d[pos + i]) i++; ret.len = i; }
+    }
+    if (ret.len < X_MIN_NEAR || (ret.len < mm && ret.pos + 256 <= pos)) { ret.pos = X_NONE; ret.len = 1; }
+    else m->last_match = pos - ret.pos;
+    return ret;
+}
+/* lzmatch_thread, cr-coder.c:116-142: the token list (the helper thread only runs ahead; the order of lookups is the serial one) */
+size_t cro_lz77_parse(const uint8_t* d, uint32_t n, int flexible, uint32_t match_limit, cro_token** out) {
+    vec_t v = {0};
+    x_t m; x_init(&m, d, n, 10 + (n > 16777216), match_limit);
+    for (uint32_t pos = 0; pos < n;) {
+        x_ret r = { X_NONE, 1 };
+        if (pos + 1024 < n) {
+            r = x_lookup(&m, d, pos, flexible);
+            for (uint32_t i = 0; i < r.len; i++) m.short_cache[x_hashn(d + pos + i, X_MIN_NEAR) % 65536] = pos + i;
+        }
+        cro_token* t = vec_grow(&v, sizeof *t); t->pos = pos; t->len = r.len; t->idx = r.pos;
+        pos += r.len;
+    }
+    x_free(&m);
+    *out = v.p;
+    return v.n;
+}
+static void x_code(cro_ctx* c, rc_t* r, m0_t* m, int s, int inc, uint32_t stream, cro_buf* o) {   /* M_my_enc_, cr-model.h:58-64 */
+    emit(c, r, m0_cum(m, s), m->frq[s], m->total, stream, o);
+    m0_update(m, s, inc);
+}
+#define X_INC(i) (1 << (i) << (i))
+/* lzencode, src/roxmain/cr-coder.c:144-318.  Streams: 0 = ppm, 1 = spos, 2 = pos, 3 = len. */
+static void lz77_encode(cro_ctx* c, const uint8_t* d, uint32_t n, cro_buf* out) {
+    cro_token* tok; size_t nt = cro_lz77_parse(d, n, c->flexible, c->match_limit, &tok);
+    cro_buf spos = {0}, posb = {0}, lenb = {0};
+    rc_t rc, rc_spos, rc_pos, rc_len; rc_enc_init(&rc); rc_enc_init(&rc_spos); rc_enc_init(&rc_pos); rc_enc_init(&rc_len);
+    const uint8_t esc = rarest_byte(d, n);
+    const uint32_t mm = 10 + (n > 16777216);
+    uint32_t n_spos = 0, n_pos = 0, n_len = 0, last = 0; int aborted = 0;
+    out->size = 0; buf_reserve(out, 32); memset(out->data, 0, 32); out->size = 32;
+    for (size_t k = 0; k < nt; k++) {
+        const uint32_t pos = tok[k].pos, len = tok[k].len; uint32_t mp = tok[k].idx;
+        trace_token(c, pos, len, mp);
+        if (mp != X_NONE) {
+            ppm_encode(c, &c->ppm, &rc, esc, out);
+            if (pos - mp == last) mp = pos;
+            x_code(c, &rc_len, &c->x_len, (int)len, 30, 3, &lenb); n_len++;
+            if (len < mm) { x_code(c, &rc_spos, &c->x_spos, (int)(pos - mp), 1, 1, &spos); n_spos++; }
+            else {
+                uint32_t j = (pos - mp) * 8; int i = 0;
+                while (j >= 128 && i < 2) { x_code(c, &rc_pos, &c->x_pos[i], (int)(j % 128 + 128), X_INC(i), 2, &posb); i++; j /= 128; }
+                if (i >= 2) while (j >= 64 && i < 5) { x_code(c, &rc_pos, &c->x_pos[i], (int)(j % 64 + 64), X_INC(i), 2, &posb); i++; j /= 64; }
+                x_code(c, &rc_pos, &c->x_pos[i], (int)j, X_INC(i), 2, &posb); n_pos++;
+            }
+            last = pos - mp;
+        } else {
+            ppm_encode(c, &c->ppm, &rc, d[pos], out);
+            if (d[pos] == esc) { x_code(c, &rc_len, &c->x_len, 0, 30, 3, &lenb); n_len++; }
+        }
+        for (uint32_t i = 0; i < len; i++) c->ppm.ctx = c->ppm.ctx << 8 | d[pos + i];
+        if (out->size >= n) { aborted = 1; break; }
+    }
+    free(tok);
+    if (aborted) { store_raw(d, n, 32, out); cro_buf_free(&spos); cro_buf_free(&posb); cro_buf_free(&lenb); return; }
+    rc_flush(&rc, out); rc_flush(&rc_spos, &spos); rc_flush(&rc_pos, &posb); rc_flush(&rc_len, &lenb);
+    /* block_header, cr-coder.c:68-80: u8 compressed, u8 match_min, u8 esc, pad, then 7 x u32 */
+    out->data[0] = 1; out->data[1] = (uint8_t)mm; out->data[2] = esc; out->data[3] = 0;
+    wr32(out->data + 4, n); wr32(out->data + 8, n_spos); wr32(out->data + 12, n_pos); wr32(out->data + 16, n_len);
+    wr32(out->data + 20, (uint32_t)out->size); wr32(out->data + 24, (uint32_t)(out->size + spos.size)); wr32(out->data + 28, (uint32_t)(out->size + spos.size + posb.size));
+    buf_append(out, spos.data, spos.size); buf_append(out, posb.data, posb.size); buf_append(out, lenb.data, lenb.size);
+    cro_buf_free(&spos); cro_buf_free(&posb); cro_buf_free(&lenb);
+}
+static int x_decode_sym(rc_t* r, m0_t* m, int inc, const uint8_t** in) {               /* M_my_dec_, cr-model.h:66-74 */
+    uint32_t target = rc_dec_cum(r, m->total), acc = 0; int s = 0;
+    while (acc + m->frq[s] <= target) acc += m->frq[s++];
+    rc_dec_consume(r, acc, m->frq[s], in);
+    m0_update(m, s, inc);
+    return s;
+}
+/* lzdecode, src/roxmain/cr-coder.c:388-526 (the queue threads only pre-decode; per-stream symbol order is unchanged) */
+static void lz77_decode(cro_ctx* c, const uint8_t* in, uint32_t n, cro_buf* out) {
+    if (!in[0]) { buf_append(out, in + 32, n - 32); return; }
+    const uint32_t mm = in[1], esc = in[2], orig = rd32(in + 4);
+    const uint8_t *pm = in + 32, *ps = in + rd32(in + 20), *pp = in + rd32(in + 24), *pl = in + rd32(in + 28);
+    rc_t rc, rc_spos, rc_pos, rc_len; rc_dec_init(&rc, &pm); rc_dec_init(&rc_spos, &ps); rc_dec_init(&rc_pos, &pp); rc_dec_init(&rc_len, &pl);
+    size_t base = out->size; uint32_t last = 0;
+    buf_reserve(out, base + orig + 300);
+    while (out->size - base < orig) {
+        uint32_t len = 1, from = 0;
+        int s = ppm_decode(&c->ppm, &rc, &pm);
+        if ((uint32_t)s == esc) {
+            uint32_t l = (uint32_t)x_decode_sym(&rc_len, &c->x_len, 30, &pl);
+            if (l == 0) { s = (int)esc; }
+            else {
+                uint32_t dist;
+                if (l < mm) dist = (uint32_t)x_decode_sym(&rc_spos, &c->x_spos, 1, &ps);
+                else {
+                    uint32_t j = 0, v = 0, sym = 0;
+                    while (j < 2 && (sym = (uint32_t)x_decode_sym(&rc_pos, &c->x_pos[j], X_INC(j), &pp)) >= 128) { v += (sym - 128) * (1u << (7 * j)); j++; }
+                    if (j < 2) dist = (v + sym * (1u << (7 * j))) / 8;
+                    else {
+                        while (j < 5 && (sym = (uint32_t)x_decode_sym(&rc_pos, &c->x_pos[j], X_INC(j), &pp)) >= 64) { v += (sym - 64) * (1u << (6 * j + 2)); j++; }
+                        dist = (v + sym * (1u << (6 * j + 2))) / 8;
+                    }
+                }
+                len = l;
+                if (len > 1) { if (dist == 0) dist = last; from = (uint32_t)(out->size - base) - dist; last = dist; }
+            }
+        }
+        buf_reserve(out, out->size + len);
+        if (len > 1) for (uint32_t i = 0; i < len; i++) { uint8_t b = out->data[base + from + i]; out->data[out->size++] = b; }
+        else out->data[out->size++] = (uint8_t)s;
+        for (uint32_t i = 0; i < len; i++) c->ppm.ctx = c->ppm.ctx << 8 | out->data[out->size - len + i];
+    }
+}
+
 void cro_lzencode(cro_ctx* c, const uint8_t* in, uint32_t n, cro_buf* out) {
-    if (c->variant == CRO_ROLZ) rolz_encode(c, in, n, out); else lzp_encode(c, in, n, out);
+    if (c->variant == CRO_ROLZ) rolz_encode(c, in, n, out); else if (c->variant == CRO_LZP) lzp_encode(c, in, n, out); else lz77_encode(c, in, n, out);
 }
 void cro_lzdecode(cro_ctx* c, const uint8_t* in, uint32_t n, cro_buf* out) {
-    if (c->variant == CRO_ROLZ) rolz_decode(c, in, n, out); else lzp_decode(c, in, n, out);
+    if (c->variant == CRO_ROLZ) rolz_decode(c, in, n, out); else if (c->variant == CRO_LZP) lzp_decode(c, in, n, out); else lz77_decode(c, in, n, out);
 }
 
 /* ================================================================== dicpick (src/cr-dicpick.c) */
@@ -964,12 +1176,15 @@ int cro_filter_inplace(cro_ctx* c, uint8_t* buf, uint32_t len, int en_de) {
 }
 
 /* ================================================================== container (src/main.c) */
-static const char* magic_of(int variant) { return variant == CRO_ROLZ ? "\x1f\x9d\x01\x01::0.11.0-comprolz" : "\x1f\x9d\x01\x01::0.11.0-comprop"; }
+static const char* magic_of(int variant) {
+    return variant == CRO_ROLZ ? "\x1f\x9d\x01\x01::0.11.0-comprolz" : variant == CRO_LZP ? "\x1f\x9d\x01\x01::0.11.0-comprop" : "\x1f\x9d\x01\x01::0.11.0-comprox";
+}
 
 /* src/main.c:137-218 */
 int cro_compress(const cro_config* cfg, const uint8_t* in, size_t n, cro_buf* out) {
     cro_ctx* c = cro_new(cfg->variant);
     c->flexible = cfg->flexible;
+    if (cfg->match_limit) c->match_limit = cfg->match_limit;
     cro_buf dic = {0}, tmp = {0}, pay = {0};
     int filt = 0;
     out->size = 0;

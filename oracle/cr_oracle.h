@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-enum { CRO_ROLZ = 0, CRO_LZP = 1 };
+enum { CRO_ROLZ = 0, CRO_LZP = 1, CRO_LZ77 = 2 };   /* comprolz, comprop, comprox */
 
 typedef struct cro_buf { uint8_t* data; size_t size, cap; } cro_buf;
 void cro_buf_free(cro_buf* b);
@@ -38,6 +38,7 @@ cro_ctx* cro_new(int variant);
 void     cro_free(cro_ctx* c);
 void     cro_reset_models(cro_ctx* c);               /* src/<variant>/cr-coder.c reset_models()             */
 void     cro_set_flexible(cro_ctx* c, int on);       /* src/rolzmain/cr-matcher.c:31                         */
+void     cro_set_match_limit(cro_ctx* c, uint32_t limit); /* -m, src/roxmain/cr-matcher.c:38 (LZ77 only)       */
 void     cro_trace_enable(cro_ctx* c, int on);
 void     cro_trace_clear(cro_ctx* c);
 size_t   cro_trace_tokens(cro_ctx* c, const cro_token** out);
@@ -60,13 +61,17 @@ size_t cro_rolz_parse(const uint8_t* data, uint32_t n, int flexible, cro_token**
 /* LZP parse only. src/ropmain/cr-coder.c:95-118 */
 size_t cro_lzp_parse(const uint8_t* data, uint32_t n, cro_token** out);
 
+/* LZ77 parse only: idx = match position (0xFFFFFFFF for literals). src/roxmain/cr-coder.c:116-142 */
+size_t cro_lz77_parse(const uint8_t* data, uint32_t n, int flexible, uint32_t match_limit, cro_token** out);
+
 /* ---- container API: what cr_main does between fopen and fclose. src/main.c:137-218 / 220-302 ---- */
 typedef struct cro_config {
     int      variant;       /* CRO_ROLZ (comprolz) or CRO_LZP (comprop) */
     uint32_t block_size;    /* bytes; reference default 16 MiB (src/main.c:62) */
     int      filt;          /* -F */
     int      prec;          /* -p */
-    int      flexible;      /* -f (ROLZ only) */
+    int      flexible;      /* -f (ROLZ, LZ77) */
+    uint32_t match_limit;   /* -m (LZ77 only; 0 = the default 40) */
 } cro_config;
 int cro_compress(const cro_config* cfg, const uint8_t* in, size_t n, cro_buf* out);
 int cro_decompress(int variant, const uint8_t* in, size_t n, cro_buf* out);

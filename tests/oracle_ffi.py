@@ -14,7 +14,7 @@ class Buf(ctypes.Structure):
 
 class Cfg(ctypes.Structure):
     _fields_ = [("variant", ctypes.c_int), ("block_size", ctypes.c_uint32), ("filt", ctypes.c_int),
-                ("prec", ctypes.c_int), ("flexible", ctypes.c_int)]
+                ("prec", ctypes.c_int), ("flexible", ctypes.c_int), ("match_limit", ctypes.c_uint32)]
 
 
 class Token(ctypes.Structure):
@@ -60,9 +60,9 @@ def _take(b):
     return r
 
 
-def compress(data, variant=0, block_size=16 << 20, filt=0, prec=0, flexible=0):
+def compress(data, variant=0, block_size=16 << 20, filt=0, prec=0, flexible=0, match_limit=0):
     b = Buf()
-    cfg = Cfg(variant, block_size, filt, prec, flexible)
+    cfg = Cfg(variant, block_size, filt, prec, flexible, match_limit)
     lib().cro_compress(ctypes.byref(cfg), data, ctypes.c_size_t(len(data)), ctypes.byref(b))
     return _take(b)
 

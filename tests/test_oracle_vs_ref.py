@@ -9,12 +9,12 @@ import os
 import pytest
 
 import oracle_ffi as O
-from golden_inputs import INPUTS, parse_flags
+from golden_inputs import INPUTS, parse_flags, parse_match_limit
 from comprox_b200 import synth
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 KAT = json.load(open(os.path.join(HERE, "golden", "kat.json")))
-VARIANT = {"comprolz": 0, "comprop": 1}
+VARIANT = {"comprolz": 0, "comprop": 1, "comprox": 2}
 _cache = {}
 
 
@@ -30,14 +30,14 @@ def test_oracle_matches_golden(key):
     data = _input(name)
     assert hashlib.sha256(data).hexdigest() == KAT[key]["input_sha256"], "generator drifted: regenerate tests/golden/kat.json"
     bs, filt, prec, flex = parse_flags(flags.split())
-    c = O.compress(data, VARIANT[binary], bs, filt, prec, flex)
+    c = O.compress(data, VARIANT[binary], bs, filt, prec, flex, parse_match_limit(flags.split()))
     assert len(c) == KAT[key]["container_bytes"]
     assert hashlib.sha256(c).hexdigest() == KAT[key]["container_sha256"]
     assert O.decompress(c, VARIANT[binary]) == data
 
 
 @pytest.mark.skipif(O.ref_binary("comprolz") is None, reason="oracle/_ref not built")
-@pytest.mark.parametrize("binary", ["comprolz", "comprop"])
+@pytest.mark.parametrize("binary", ["comprolz", "comprop", "comprox"])
 def test_oracle_matches_reference_cli_fresh_input(binary):
     """An input that is NOT in the golden set, straight against the reference binary."""
     data = synth.markov_text((1 << 20) + 333, seed=1234) + synth.x86_corpus(1 << 20, seed=5, elf_bytes=0, pe_min=1 << 19, pe_max=1 << 20)

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcrgpu.so")
 
-ROLZ, LZP = 0, 1
+ROLZ, LZP, LZ77 = 0, 1, 2
 OWN_STREAM = 1   # pass as `stream`: private stream per handle (several handles then overlap on one GPU)
 
 _lib = None

@@ -17,7 +17,7 @@ struct CrConfig {
     uint32_t block_size;     // bytes, reference default 16 MiB (src/main.c:62)
     int filt;                // -F
     int prec;                // -p
-    int flexible;            // -f (ROLZ) -- not implemented on the GPU yet
+    int flexible;            // -f (ROLZ, LZ77)
     uint64_t window_bytes;   // raw bytes per window (0 = default)
 };
 
@@ -282,7 +282,9 @@ inline int Compressor::dict_encode_window(const uint8_t* d_rawwin, const std::ve
     return CRGPU_OK;
 }
 
-static inline const char* cr_magic(int variant) { return variant == CR_ROLZ ? "\x1f\x9d\x01\x01::0.11.0-comprolz" : "\x1f\x9d\x01\x01::0.11.0-comprop"; }
+static inline const char* cr_magic(int variant) {          // src/rolzmain/main.c:35, src/ropmain/main.c:35, src/roxmain/main.c:35
+    return variant == CR_ROLZ ? "\x1f\x9d\x01\x01::0.11.0-comprolz" : variant == CR_LZP ? "\x1f\x9d\x01\x01::0.11.0-comprop" : "\x1f\x9d\x01\x01::0.11.0-comprox";
+}
 static inline uint64_t cr_compress_bound(uint64_t n, uint32_t block_size) {
     uint64_t nblocks = n / (block_size ? block_size : 1) + 2;
     return 64 + (1u << 20) + n + nblocks * 64;
@@ -290,7 +292,7 @@ static inline uint64_t cr_compress_bound(uint64_t n, uint32_t block_size) {
 
 inline int Compressor::compress(const CrConfig& cfg, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_n) {
     if (cfg.block_size == 0 || (n && !in) || !out || !out_n) return CRGPU_ERR_ARG;
-    if (cfg.flexible && chain->variant != CR_ROLZ) return CRGPU_ERR_ARG;     // comprop has no -f (src/ropmain/main.c)
+    if (cfg.flexible && chain->variant == CR_LZP) return CRGPU_ERR_ARG;      // comprop has no -f (src/ropmain/main.c)
     stream = chain->stream;
     StageTimer& tm = chain->timer;
     const size_t mlen = strlen(cr_magic(chain->variant));

@@ -12,11 +12,12 @@
 #include "cr_chain.cuh"
 #include "cr_rolz.cuh"
 #include "cr_lzp.cuh"
+#include "cr_lz77.cuh"
 #include "cr_ppm.cuh"
 #include "cr_rc.cuh"
 #include "cr_warp.cuh"
 
-enum { CR_ROLZ = 0, CR_LZP = 1 };
+enum { CR_ROLZ = 0, CR_LZP = 1, CR_LZ77 = 2 };
 
 struct BlockIO {
     uint64_t off;        // in: offset of the dictionary-coded block in the window buffer
@@ -51,6 +52,11 @@ struct LzChain {
     DevBuf b_o1info, b_o1ord, b_o1incl, b_bounds, b_o3hot, b_cinm, b_cins, b_segstart, b_segkey, b_rank, b_flexlen;
     DevBuf b_qm, b_shm, b_bm, b_qs, b_shs, b_bs, b_stot, b_dsum, b_lsm, b_lss, b_rsm, b_rss, b_fb;
     DevBuf b_dense, b_denseside, b_streams, b_rcres, b_rcout, b_copy, b_hdr;
+    // LZ77 (cr_lz77.cuh): per-position candidates, guesses and token distances; per-chunk `last` propagation; per-model symbol lists
+    DevBuf x_npos, x_nlen, x_sdist, x_slen, x_G, x_tdist, x_h16, x_rank, x_mpos0, x_mlen0, x_clast, x_ckey, x_cmax, x_lastin, x_mism, x_msym, x_mpos;
+    uint32_t match_limit = 40;     // -m (src/roxmain/cr-matcher.c:38)
+    uint32_t x_max_iter = 48;      // fixed-point passes before the serial parse takes over (0 = always serial; tests)
+    uint32_t last_x_iters = 0;
     // ---- sizes of the last window (for the debug/trace fetch used by the tests)
     uint32_t last_nev = 0, last_nside = 0, last_nesc = 0, last_nent = 0;
     size_t last_dtotal = 0;
@@ -63,7 +69,7 @@ struct LzChain {
     int init(int variant_, cudaStream_t s) {
         variant = variant_; stream = s; prims.stream = s;
         CR_TRY(s_o3b.reserve(PPM_O3_SLOTS)); CR_TRY(s_o3c.reserve(PPM_O3_SLOTS));
-        CR_TRY(s_o2.reserve((size_t)65536 * PPM_O2_STRIDE)); CR_TRY(s_o1.reserve(65536)); CR_TRY(s_m0.reserve(2 * 256 * 2));
+        CR_TRY(s_o2.reserve((size_t)65536 * PPM_O2_STRIDE)); CR_TRY(s_o1.reserve(65536)); CR_TRY(s_m0.reserve(X_NMODEL * 256 * 2));
         st.o3_byte = s_o3b.as<uint8_t>(); st.o3_conf = s_o3c.as<uint8_t>(); st.o2 = s_o2.as<uint8_t>();
         st.o1 = s_o1.as<uint8_t>(); st.m0 = s_m0.as<uint16_t>();
 #ifndef CRGPU_SIM
@@ -80,7 +86,8 @@ struct LzChain {
         DevBuf* all[] = { &s_o3b, &s_o3c, &s_o2, &s_o1, &s_m0, &b_blocks, &b_segoff, &b_seglen, &b_hist, &b_esc1, &b_first, &b_ctxout,
             &b_k0, &b_k1, &b_v0, &b_v1, &b_ks0, &b_M, &b_S, &b_span, &b_tidx, &b_segs, &b_xt, &b_entry, &b_cnt, &b_scan, &b_chainwork,
             &b_evctx, &b_evsym, &b_tokend, &b_pred, &b_T1, &b_T2, &b_TS, &b_side, &b_escrec, &b_esccount, &b_k64a, &b_k64b, &b_ord,
-            &b_flag, &b_escord, &b_lensym, &b_lenpos, &b_idxsym, &b_idxpos, &b_hits, &b_o1info, &b_o1ord, &b_o1incl, &b_bounds, &b_o3hot, &b_cinm, &b_cins, &b_segstart, &b_segkey, &b_rank, &b_flexlen, &b_qm, &b_shm, &b_bm, &b_qs, &b_shs, &b_bs, &b_stot, &b_dsum, &b_lsm, &b_lss, &b_rsm, &b_rss, &b_fb, &b_dense, &b_denseside, &b_streams, &b_rcres, &b_rcout, &b_copy, &b_hdr };
+            &b_flag, &b_escord, &b_lensym, &b_lenpos, &b_idxsym, &b_idxpos, &b_hits, &b_o1info, &b_o1ord, &b_o1incl, &b_bounds, &b_o3hot, &b_cinm, &b_cins, &b_segstart, &b_segkey, &b_rank, &b_flexlen, &b_qm, &b_shm, &b_bm, &b_qs, &b_shs, &b_bs, &b_stot, &b_dsum, &b_lsm, &b_lss, &b_rsm, &b_rss, &b_fb, &b_dense, &b_denseside, &b_streams, &b_rcres, &b_rcout, &b_copy, &b_hdr,
+            &x_npos, &x_nlen, &x_sdist, &x_slen, &x_G, &x_tdist, &x_h16, &x_rank, &x_mpos0, &x_mlen0, &x_clast, &x_ckey, &x_cmax, &x_lastin, &x_mism, &x_msym, &x_mpos };
         for (DevBuf* b : all) b->release();
         prims.release();
 #ifndef CRGPU_SIM
@@ -93,6 +100,7 @@ struct LzChain {
         CR_CUDA(cudaMemsetAsync(st.o3_byte, 0, PPM_O3_SLOTS, stream));
         CR_CUDA(cudaMemsetAsync(st.o3_conf, 0, PPM_O3_SLOTS, stream));
         CR_LAUNCH(k_ppm_reset, dim3(65536 / 256), dim3(256), stream, st);
+        if (variant == CR_LZ77) CR_LAUNCH(k_x_reset_models, dim3(1), dim3(256), stream, st.m0);
         chain_ctx = 0;
         return CRGPU_OK;
     }
@@ -141,7 +149,7 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
     const uint32_t nb = (uint32_t)blk.size();
     if (nb == 0) { out_total = 0; return CRGPU_OK; }
     if (variant == CR_ROLZ && nb > RZ_MAX_BLOCKS) return CRGPU_ERR_ARG;            // callers split (sort key layout, cr_rolz.cuh)
-    const uint32_t hdr_size = variant == CR_ROLZ ? 16 : 20;
+    const uint32_t hdr_size = variant == CR_ROLZ ? 16 : variant == CR_LZP ? 20 : 32;
     const uint32_t prefix = prefix_mode == 0 ? 4 : prefix_mode == 1 ? 6 : 0;
 
     timer.begin(stream);
@@ -157,7 +165,8 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
         hb[b].ctx4 = blk[b].size >= 4194304;
         uint32_t first_entry = variant == CR_ROLZ ? 16 : LZP_FIRST;
         if (variant == CR_LZP && blk[b].size < 16) first_entry = blk[b].size;      // stored without coding (src/ropmain/cr-coder.c:140)
-        nent += blk[b].size > first_entry ? blk[b].size - first_entry : 0;
+        if (variant == CR_LZ77) nent += x_entries(blk[b].size);
+        else nent += blk[b].size > first_entry ? blk[b].size - first_entry : 0;
         segoff[b] = blk[b].off; seglen[b] = blk[b].size;
         if (blk[b].size > maxsize) maxsize = blk[b].size;
         if (blk[b].off + blk[b].size > dtotal) dtotal = blk[b].off + blk[b].size;
@@ -193,6 +202,34 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
             CR_LAUNCH(k_rolz_match_short, dim3(cr_div_up(nent, 128)), dim3(128), stream, dD, d_blocks, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nent, b_M.as<uint16_t>(), b_S.as<uint16_t>());
         }
         if (maxsize) CR_LAUNCH(k_rolz_tokens, dim3(cr_div_up(maxsize, 256), nb), dim3(256), stream, d_blocks, b_M.as<uint16_t>(), b_S.as<uint16_t>(), nent, b_span.as<uint8_t>(), b_tidx.as<uint8_t>(), flexible ? b_flexlen.as<uint8_t>() : (const uint8_t*)nullptr);
+    } else if (variant == CR_LZ77) {
+        CR_LAUNCH(k_x_finish_blocks, dim3(1), dim3(1), stream, dD, d_blocks, nb, b_esc1.as<uint8_t>(), chain_ctx, b_ctxout.as<uint32_t>());
+        CR_TRY(x_npos.reserve(dtotal * 4 + 64)); CR_TRY(x_nlen.reserve(dtotal + 64)); CR_TRY(x_sdist.reserve(dtotal + 64)); CR_TRY(x_slen.reserve(dtotal + 64));
+        CR_TRY(x_h16.reserve(dtotal * 2 + 64)); CR_TRY(x_G.reserve(dtotal * 4 + 64)); CR_TRY(x_tdist.reserve(dtotal * 4 + 64));
+        if (maxsize) {
+            const dim3 gp(cr_div_up(maxsize, 256), nb), tp(256);
+            uint32_t maxkey = 0;
+            for (uint32_t b = 0; b < nb; b++) { const uint32_t k = 20u * x_bucket2(blk[b].size); if (k > maxkey) maxkey = k; }
+            const int kbits = cr_bits_for(maxkey);
+            if (kbits + bbits > 32) return CRGPU_ERR_UNSUPPORTED;
+            CR_TRY(b_k0.reserve((size_t)nent * 4 + 16)); CR_TRY(b_k1.reserve((size_t)nent * 4 + 16));
+            CR_TRY(b_v0.reserve((size_t)nent * 4 + 16)); CR_TRY(b_v1.reserve((size_t)nent * 4 + 16)); CR_TRY(x_rank.reserve((size_t)nent * 4 + 16));
+            if (nent) {
+                CR_LAUNCH(k_x_keys, gp, tp, stream, dD, d_blocks, kbits, b_k0.as<uint32_t>(), b_v0.as<uint32_t>());
+                CR_TRY(cr_sort_pairs<uint32_t>(prims, b_k0.as<uint32_t>(), b_k1.as<uint32_t>(), b_v0.as<uint32_t>(), b_v1.as<uint32_t>(), nent, 0, kbits + bbits));
+                CR_LAUNCH(k_x_ranks, dim3(cr_div_up(nent, 256)), dim3(256), stream, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nent, d_blocks, kbits, x_rank.as<uint32_t>());
+            }
+            if (flexible) {
+                CR_TRY(x_mpos0.reserve(dtotal * 4 + 64)); CR_TRY(x_mlen0.reserve(dtotal + 64));
+                CR_LAUNCH(k_x_match0, gp, tp, stream, dD, d_blocks, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), x_rank.as<uint32_t>(), match_limit, x_mpos0.as<uint32_t>(), x_mlen0.as<uint8_t>());
+                CR_LAUNCH(k_x_flex, gp, tp, stream, d_blocks, x_mpos0.as<uint32_t>(), x_mlen0.as<uint8_t>(), x_npos.as<uint32_t>(), x_nlen.as<uint8_t>());
+            } else {
+                CR_LAUNCH(k_x_match, gp, tp, stream, dD, d_blocks, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), x_rank.as<uint32_t>(), match_limit, x_npos.as<uint32_t>(), x_nlen.as<uint8_t>());
+            }
+            CR_LAUNCH(k_x_short_hash, gp, tp, stream, dD, d_blocks, x_h16.as<uint16_t>());
+            CR_LAUNCH(k_x_short, gp, tp, stream, dD, d_blocks, x_h16.as<uint16_t>(), x_sdist.as<uint8_t>(), x_slen.as<uint8_t>());
+            CR_CUDA(cudaMemsetAsync(x_G.p, 0, dtotal * 4, stream));
+        }
     } else {
         CR_LAUNCH(k_lzp_finish_blocks, dim3(cr_div_up(nb, 64)), dim3(64), stream, d_blocks, nb, b_esc1.as<uint8_t>());
         CR_TRY(b_k0.reserve((size_t)nent * 4 + 16)); CR_TRY(b_k1.reserve((size_t)nent * 4 + 16));
@@ -212,17 +249,59 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
     std::vector<ChainSeg> segs(nb);
     for (uint32_t b = 0; b < nb; b++) {
         segs[b].off = blk[b].off; segs[b].len = blk[b].size;
-        segs[b].start = variant == CR_ROLZ ? 1 : (blk[b].size < 16 ? blk[b].size : LZP_FIRST);
+        segs[b].start = variant == CR_ROLZ ? 1 : variant == CR_LZ77 ? 0 : (blk[b].size < 16 ? blk[b].size : LZP_FIRST);
     }
     for (uint32_t b = 0; b < nb; b++) if (segs[b].start > 255) { segs[b].len = 0; segs[b].start = 0; }   // tiny stored LZP block: nothing to walk
     const uint32_t nchunk = cr_chain_layout(segs.data(), nb);
     CR_TRY(upload(b_segs, segs));
     CR_TRY(b_xt.reserve((size_t)nchunk * 256 + 16)); CR_TRY(b_entry.reserve(nchunk + 16));
-    CR_TRY(b_cnt.reserve((size_t)(nchunk + 1) * 4 * 3 + 16)); CR_TRY(b_scan.reserve((size_t)(nchunk + 1) * 4 * 3 + 16));
+    const uint32_t ncount = variant == CR_LZ77 ? X_NCOUNT : 3;
+    CR_TRY(b_cnt.reserve((size_t)(nchunk + 1) * 4 * ncount + 16)); CR_TRY(b_scan.reserve((size_t)(nchunk + 1) * 4 * ncount + 16));
     const ChainSeg* d_segs = b_segs.as<ChainSeg>();
     uint32_t* cnt = b_cnt.as<uint32_t>(); uint32_t* scan = b_scan.as<uint32_t>();
-    CR_CUDA(cudaMemsetAsync(cnt, 0, (size_t)(nchunk + 1) * 4 * 3, stream));
-    if (nchunk) {
+    CR_CUDA(cudaMemsetAsync(cnt, 0, (size_t)(nchunk + 1) * 4 * ncount, stream));
+    if (nchunk && variant == CR_LZ77) {
+        // fixed point over m_last_match (cr_lz77.cuh header)
+        const dim3 gp(cr_div_up(maxsize, 256), nb), tp(256), gc(cr_div_up(nchunk, 64)), tc(64);
+        const XTables XT = { x_npos.as<uint32_t>(), x_nlen.as<uint8_t>(), x_sdist.as<uint8_t>(), x_slen.as<uint8_t>() };
+        CR_TRY(x_clast.reserve((size_t)nchunk * 4 + 16)); CR_TRY(x_ckey.reserve((size_t)nchunk * 12 + 16)); CR_TRY(x_cmax.reserve((size_t)nchunk * 4 + 16));
+        CR_TRY(x_lastin.reserve((size_t)nchunk * 4 + 16)); CR_TRY(x_mism.reserve(16));
+        auto propagate = [&]() -> int {
+            CR_LAUNCH(k_chain_exits, gc, tc, stream, b_span.as<uint8_t>(), d_segs, nb, nchunk, b_xt.as<uint8_t>());
+            CR_TRY(cr_chain_run_entries(*this, b_chainwork, segs, d_segs, nchunk, b_xt.as<uint8_t>(), b_entry.as<uint8_t>()));
+            XLastOfChunk fa = { d_blocks, x_tdist.as<uint32_t>(), x_clast.as<uint32_t>() };
+            CR_LAUNCH(k_chain_walk<XLastOfChunk>, gc, tc, stream, b_span.as<uint8_t>(), d_segs, nb, nchunk, b_entry.as<uint8_t>(), fa);
+            CR_LAUNCH(k_x_chunk_keys, dim3(cr_div_up(nchunk, 256)), dim3(256), stream, x_clast.as<uint32_t>(), nchunk, x_ckey.as<uint32_t>());
+            CR_TRY(cr_inclusive_max(prims, x_ckey.as<uint32_t>(), x_cmax.as<uint32_t>(), nchunk));
+            CR_LAUNCH(k_x_chunk_in, dim3(cr_div_up(nchunk, 256)), dim3(256), stream, x_clast.as<uint32_t>(), x_cmax.as<uint32_t>(), d_segs, nb, nchunk, x_lastin.as<uint32_t>());
+            return CRGPU_OK;
+        };
+        bool converged = false;
+        uint32_t it = 0;
+        for (; it < x_max_iter; it++) {
+            CR_LAUNCH(k_x_decide, gp, tp, stream, dD, d_blocks, XT, x_G.as<uint32_t>(), it == 0 ? 1 : 0, b_span.as<uint8_t>(), x_tdist.as<uint32_t>());
+            CR_TRY(propagate());
+            CR_CUDA(cudaMemsetAsync(x_mism.p, 0, 4, stream));
+            XCheck fb = { d_blocks, x_tdist.as<uint32_t>(), x_npos.as<uint32_t>(), x_lastin.as<uint32_t>(), x_G.as<uint32_t>(), x_mism.as<uint32_t>() };
+            CR_LAUNCH(k_chain_walk<XCheck>, gc, tc, stream, b_span.as<uint8_t>(), d_segs, nb, nchunk, b_entry.as<uint8_t>(), fb);
+            std::vector<uint32_t> hm;
+            CR_TRY(download(hm, x_mism.p, 1));
+            if (hm[0] == 0) { converged = true; it++; break; }
+        }
+        last_x_iters = it;
+        timer.count("#x_iters", it);
+        if (!converged) {
+            CR_LAUNCH(k_x_parse_serial, dim3(cr_div_up(nb, 32)), dim3(32), stream, dD, d_blocks, nb, XT, b_span.as<uint8_t>(), x_tdist.as<uint32_t>());
+            CR_TRY(propagate());
+        }
+        // the coder's own last_match on entry to every chunk (reuses the guess / key buffers of the iteration)
+        CR_TRY(x_ckey.reserve((size_t)nchunk * 12 + 16));
+        XCoderSum fs = { d_blocks, x_tdist.as<uint32_t>(), x_ckey.as<uint32_t>() };
+        CR_LAUNCH(k_chain_walk<XCoderSum>, gc, tc, stream, b_span.as<uint8_t>(), d_segs, nb, nchunk, b_entry.as<uint8_t>(), fs);
+        CR_LAUNCH(k_x_coder_in, dim3(cr_div_up(nb, 32)), dim3(32), stream, x_ckey.as<uint32_t>(), d_segs, nb, x_lastin.as<uint32_t>());
+        XCount fc = { dD, d_blocks, x_tdist.as<uint32_t>(), x_lastin.as<uint32_t>(), cnt, nchunk + 1 };
+        CR_LAUNCH(k_chain_walk<XCount>, gc, tc, stream, b_span.as<uint8_t>(), d_segs, nb, nchunk, b_entry.as<uint8_t>(), fc);
+    } else if (nchunk) {
         CR_LAUNCH(k_chain_exits, dim3(cr_div_up(nchunk, 64)), dim3(64), stream, b_span.as<uint8_t>(), d_segs, nb, nchunk, b_xt.as<uint8_t>());
         CR_TRY(cr_chain_run_entries(*this, b_chainwork, segs, d_segs, nchunk, b_xt.as<uint8_t>(), b_entry.as<uint8_t>()));
         if (variant == CR_ROLZ) {
@@ -234,21 +313,25 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
         }
     }
     timer.mark("chain_count");
-    for (int k = 0; k < 3; k++) CR_TRY(cr_exclusive_sum(prims, cnt + k * (nchunk + 1), scan + k * (nchunk + 1), nchunk + 1));
+    for (uint32_t k = 0; k < ncount; k++) CR_TRY(cr_exclusive_sum(prims, cnt + (size_t)k * (nchunk + 1), scan + (size_t)k * (nchunk + 1), nchunk + 1));
     std::vector<uint32_t> hscan; std::vector<uint8_t> hfirst, hesc;
-    CR_TRY(download(hscan, scan, (size_t)(nchunk + 1) * 3));
+    CR_TRY(download(hscan, scan, (size_t)(nchunk + 1) * ncount));
     CR_TRY(download(hfirst, b_first.p, (size_t)nb * 16));
     CR_TRY(download(hesc, b_esc1.p, nb));
     const uint32_t* sc_ev = hscan.data(); const uint32_t* sc_a = sc_ev + (nchunk + 1); const uint32_t* sc_b = sc_a + (nchunk + 1);
     // ROLZ: a = match tokens, b = escape literals -> side symbols 2a+b.  LZP: a = tokens closing... unused.
     const uint32_t nev = sc_ev[nchunk];
-    const uint32_t nside = variant == CR_ROLZ ? 2 * sc_a[nchunk] + sc_b[nchunk] : 0;
+    // LZ77: counters 1 = len symbols, 2 = spos symbols, 3 = pos tokens, 4 = pos symbols, 5.. = symbols per pos model
+    auto xsc = [&](uint32_t k, uint32_t c) { return hscan[(size_t)k * (nchunk + 1) + c]; };
+    const uint32_t x_nlen_sym = variant == CR_LZ77 ? xsc(1, nchunk) : 0, x_nspos = variant == CR_LZ77 ? xsc(2, nchunk) : 0, x_npossym = variant == CR_LZ77 ? xsc(4, nchunk) : 0;
+    const uint32_t nside = variant == CR_ROLZ ? 2 * sc_a[nchunk] + sc_b[nchunk] : variant == CR_LZ77 ? x_nlen_sym + x_nspos + x_npossym : 0;
     last_nev = nev; last_nside = nside;
 
     // ---- events
     CR_TRY(b_evctx.reserve((size_t)nev * 4 + 16)); CR_TRY(b_evsym.reserve(nev + 16)); CR_TRY(b_tokend.reserve(nev + 16)); CR_TRY(b_pred.reserve(nev + 16));
     CR_TRY(b_T1.reserve((size_t)nev * 8 + 16)); CR_TRY(b_side.reserve((size_t)nside * 2 + 16)); CR_TRY(b_TS.reserve((size_t)nside * 8 + 16));
     const uint32_t n_idxsym = variant == CR_ROLZ ? sc_a[nchunk] : 0, n_lensym = variant == CR_ROLZ ? sc_a[nchunk] + sc_b[nchunk] : 0;
+    SideJobs xjobs; memset(&xjobs, 0, sizeof xjobs);
     CR_TRY(b_lensym.reserve(n_lensym + 16)); CR_TRY(b_lenpos.reserve((size_t)n_lensym * 4 + 16));
     CR_TRY(b_idxsym.reserve(n_idxsym + 16)); CR_TRY(b_idxpos.reserve((size_t)n_idxsym * 4 + 16));
     if (nchunk) {
@@ -256,6 +339,23 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
             RolzEmit f = { dD, d_blocks, b_tidx.as<uint8_t>(), scan, scan + (nchunk + 1), scan + 2 * (nchunk + 1), b_evctx.as<uint32_t>(), b_evsym.as<uint8_t>(), b_side.as<uint16_t>(),
                            b_lensym.as<uint8_t>(), b_lenpos.as<uint32_t>(), b_idxsym.as<uint8_t>(), b_idxpos.as<uint32_t>() };
             CR_LAUNCH(k_chain_walk<RolzEmit>, dim3(cr_div_up(nchunk, 64)), dim3(64), stream, b_span.as<uint8_t>(), d_segs, nb, nchunk, b_entry.as<uint8_t>(), f);
+        } else if (variant == CR_LZ77) {
+            // per-model symbol lists: [len | spos | pos0..pos5], each (symbol u8, index in the side array u32)
+            uint32_t mcount[X_NMODEL] = { x_nlen_sym, x_nspos, 0, 0, 0, 0, 0, 0 };
+            for (int k = 0; k < 6; k++) mcount[2 + k] = xsc(5 + k, nchunk);
+            size_t mtotal = 0; size_t moff[X_NMODEL];
+            for (int k = 0; k < X_NMODEL; k++) { moff[k] = mtotal; mtotal += mcount[k]; }
+            CR_TRY(x_msym.reserve(mtotal + 64)); CR_TRY(x_mpos.reserve(mtotal * 4 + 64));
+            XEmit f;
+            f.D = dD; f.blocks = d_blocks; f.tdist = x_tdist.as<uint32_t>(); f.last_in = x_lastin.as<uint32_t>(); f.scan = scan; f.stride = nchunk + 1;
+            f.base_pos = x_nspos; f.base_len = x_nspos + x_npossym;
+            f.ev_ctx = b_evctx.as<uint32_t>(); f.ev_sym = b_evsym.as<uint8_t>();
+            for (int k = 0; k < X_NMODEL; k++) {
+                f.msym[k] = x_msym.as<uint8_t>() + moff[k]; f.mpos[k] = x_mpos.as<uint32_t>() + moff[k];
+                xjobs.sym[k] = f.msym[k]; xjobs.pos[k] = f.mpos[k]; xjobs.n[k] = mcount[k]; xjobs.inc[k] = x_inc(k); xjobs.state[k] = st.m0 + k * 256;
+            }
+            xjobs.nmodel = X_NMODEL;
+            CR_LAUNCH(k_chain_walk<XEmit>, dim3(cr_div_up(nchunk, 64)), dim3(64), stream, b_span.as<uint8_t>(), d_segs, nb, nchunk, b_entry.as<uint8_t>(), f);
         } else {
             CR_TRY(b_ord.reserve((size_t)(nchunk + 1) * 4 + 16));
             CR_LAUNCH(k_lzp_ctx_in, dim3(cr_div_up(nchunk + 1, 128)), dim3(128), stream, cnt + (nchunk + 1), cnt + 2 * (nchunk + 1), nchunk, chain_ctx, b_ord.as<uint32_t>());
@@ -276,7 +376,8 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
         CR_TRY(b_denseside.reserve((size_t)nside * sizeof(Tri) + 16));
         CR_CUDA(cudaEventRecord(ev_side_go, stream));
         CR_CUDA(cudaStreamWaitEvent(side_stream, ev_side_go, 0));
-        CR_LAUNCH(k_side_epochs, dim3(2), dim3(SE_THREADS), side_stream, b_lensym.as<uint8_t>(), b_lenpos.as<uint32_t>(), n_lensym, b_idxsym.as<uint8_t>(), b_idxpos.as<uint32_t>(), n_idxsym, st, b_TS.as<uint64_t>());
+        if (variant == CR_LZ77) CR_LAUNCH(k_side_epochs_jobs, dim3(X_NMODEL), dim3(SE_THREADS), side_stream, xjobs, b_TS.as<uint64_t>());
+        else CR_LAUNCH(k_side_epochs, dim3(2), dim3(SE_THREADS), side_stream, b_lensym.as<uint8_t>(), b_lenpos.as<uint32_t>(), n_lensym, b_idxsym.as<uint8_t>(), b_idxpos.as<uint32_t>(), n_idxsym, st, b_TS.as<uint64_t>());
         CR_LAUNCH(k_expand_side, dim3(cr_div_up(nside, 256)), dim3(256), side_stream, b_TS.as<uint64_t>(), nside, b_denseside.as<Tri>());
         CR_CUDA(cudaEventRecord(ev_side_done, side_stream));
         side_async = true;
@@ -367,7 +468,9 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
     timer.mark("o1");
     last_nesc = nesc;
     timer.count("#events", nev); timer.count("#triples", (double)nev + nesc + nside); timer.count("#escapes", nesc); timer.count("#side_symbols", nside);
-    if (nside && !side_async) {
+    if (nside && !side_async && variant == CR_LZ77) {
+        CR_LAUNCH(k_side_models_jobs, dim3(1), dim3(X_NMODEL), stream, xjobs, b_TS.as<uint64_t>());
+    } else if (nside && !side_async) {
 #ifndef CRGPU_SIM
         if (!scalar_models) CR_LAUNCH(k_side_epochs, dim3(2), dim3(SE_THREADS), stream, b_lensym.as<uint8_t>(), b_lenpos.as<uint32_t>(), n_lensym, b_idxsym.as<uint8_t>(), b_idxpos.as<uint32_t>(), n_idxsym, st, b_TS.as<uint64_t>());
         else
@@ -390,7 +493,8 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
 
     timer.mark("expand");
     // ---- range coding: one serial coder per (block, stream)
-    const uint32_t spb = variant == CR_ROLZ ? 2 : 1;
+    const uint32_t spb = variant == CR_ROLZ ? 2 : variant == CR_LZ77 ? 4 : 1;
+    std::vector<uint32_t> x_hdr_counts((size_t)nb * 3, 0);          // LZ77: num_spos, num_pos (tokens), num_len per block
     std::vector<RcStream> streams((size_t)nb * spb);
     std::vector<uint32_t> num_idx(nb, 0);
     size_t rc_total = 0;
@@ -407,6 +511,17 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
             s.ev_begin = 2 * sc_a[c0] + sc_b[c0]; s.ev_end = 2 * sc_a[c1] + sc_b[c1]; s.is_main = 0; s.limit = 0xFFFFFFFFu;
             s.out_off = rc_total; s.out_cap = 3 * (s.ev_end - s.ev_begin) + 16; rc_total += s.out_cap;
             num_idx[b] = (sc_a[c1] - sc_a[c0]) + (sc_b[c1] - sc_b[c0]);
+        }
+        if (variant == CR_LZ77) {                                    // side streams in payload order: spos, pos, len (cr-coder.c:283-294)
+            const uint32_t lo[3] = { xsc(2, c0), x_nspos + xsc(4, c0), x_nspos + x_npossym + xsc(1, c0) };
+            const uint32_t hi[3] = { xsc(2, c1), x_nspos + xsc(4, c1), x_nspos + x_npossym + xsc(1, c1) };
+            for (int k = 0; k < 3; k++) {
+                RcStream& s = streams[(size_t)b * spb + 1 + k];
+                memset(&s, 0, sizeof s);
+                s.ev_begin = lo[k]; s.ev_end = hi[k]; s.is_main = 0; s.limit = 0xFFFFFFFFu;
+                s.out_off = rc_total; s.out_cap = 3 * (hi[k] - lo[k]) + 16; rc_total += s.out_cap;
+            }
+            x_hdr_counts[(size_t)b * 3] = xsc(2, c1) - xsc(2, c0); x_hdr_counts[(size_t)b * 3 + 1] = xsc(3, c1) - xsc(3, c0); x_hdr_counts[(size_t)b * 3 + 2] = xsc(1, c1) - xsc(1, c0);
         }
     }
     CR_TRY(upload(b_streams, streams));
@@ -519,6 +634,15 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
             memcpy(hp + 4, v, 12);
             CopyDesc c0 = { m.out_off, pos + prefix + 16, rm.nbytes, 0 }; copies.push_back(c0);
             CopyDesc c1 = { s.out_off, pos + prefix + 16 + rm.nbytes, rs.nbytes, 0 }; copies.push_back(c1);
+        } else if (variant == CR_LZ77) {                             // block_header, src/roxmain/cr-coder.c:68-80,276-294
+            const uint32_t nby[4] = { rm.nbytes, res[(size_t)b * spb + 1].nbytes, res[(size_t)b * spb + 2].nbytes, res[(size_t)b * spb + 3].nbytes };
+            payload = 32 + nby[0] + nby[1] + nby[2] + nby[3];
+            hp[0] = 1; hp[1] = (uint8_t)x_match_min(blk[b].size); hp[2] = hesc[b];
+            uint32_t v[7] = { blk[b].size, x_hdr_counts[(size_t)b * 3], x_hdr_counts[(size_t)b * 3 + 1], x_hdr_counts[(size_t)b * 3 + 2],
+                              32 + nby[0], 32 + nby[0] + nby[1], 32 + nby[0] + nby[1] + nby[2] };
+            memcpy(hp + 4, v, 28);
+            size_t at = pos + prefix + 32;
+            for (int k = 0; k < 4; k++) { CopyDesc c = { streams[(size_t)b * spb + k].out_off, at, nby[k], 0 }; copies.push_back(c); at += nby[k]; }
         } else {
             payload = 20 + rm.nbytes;
             hp[0] = 1; memcpy(hp + 4, &blk[b].size, 4); hp[8] = hesc[b]; memcpy(hp + 9, &hfirst[b * 16], 9);

@@ -117,7 +117,7 @@ __global__ void k_copy_segments(const CopyDesc* __restrict__ descs, const uint8_
     const uint8_t* src = (d.src_buf ? buf1 : buf0) + d.src;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < d.len; i += gridDim.x * blockDim.x) dst[d.dst + i] = src[i];
 }
-struct HeaderDesc { uint64_t dst; uint32_t len; uint8_t bytes[36]; };
+struct HeaderDesc { uint64_t dst; uint32_t len; uint8_t bytes[44]; };   // 6-byte block prefix + the largest inner header (32, LZ77)
 __global__ void k_write_headers(const HeaderDesc* __restrict__ h, uint32_t n, uint8_t* __restrict__ dst) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;

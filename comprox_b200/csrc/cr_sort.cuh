@@ -60,6 +60,55 @@ static int cr_scan_rec(cudaStream_t stream, const uint32_t* in, uint32_t* out, s
 }
 #endif
 
+#ifndef CRGPU_SIM
+// inclusive prefix MAXIMUM, same three-level shape
+__global__ void __launch_bounds__(SC_BLOCK) k_maxscan_block(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, size_t n, uint32_t* __restrict__ tops) {
+    __shared__ uint32_t wmax[32];
+    const size_t i = (size_t)blockIdx.x * SC_BLOCK + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t v = i < n ? in[i] : 0u;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, d); if (lane >= (uint32_t)d && t > v) v = t; }
+    if (lane == 31) wmax[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t s = wmax[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, s, d); if (lane >= (uint32_t)d && t > s) s = t; }
+        wmax[lane] = s;
+        if (lane == 31 && tops) tops[blockIdx.x] = s;
+    }
+    __syncthreads();
+    if (w > 0 && wmax[w - 1] > v) v = wmax[w - 1];
+    if (i < n) out[i] = v;
+}
+__global__ void k_maxscan_add(uint32_t* __restrict__ out, size_t n, const uint32_t* __restrict__ tops) {
+    const size_t i = (size_t)blockIdx.x * SC_BLOCK + threadIdx.x;
+    if (i < n && blockIdx.x > 0) { const uint32_t t = tops[blockIdx.x - 1]; if (t > out[i]) out[i] = t; }
+}
+static int cr_maxscan_rec(cudaStream_t stream, const uint32_t* in, uint32_t* out, size_t n, uint32_t* scratch) {
+    const unsigned nblk = cr_div_up(n, SC_BLOCK);
+    if (nblk <= 1) { CR_LAUNCH(k_maxscan_block, dim3(1), dim3(SC_BLOCK), stream, in, out, n, (uint32_t*)nullptr); return CRGPU_OK; }
+    uint32_t* tops = scratch;
+    CR_LAUNCH(k_maxscan_block, dim3(nblk), dim3(SC_BLOCK), stream, in, out, n, tops);
+    CR_TRY(cr_maxscan_rec(stream, tops, tops, nblk, scratch + ((nblk + 31) & ~31u)));
+    CR_LAUNCH(k_maxscan_add, dim3(nblk), dim3(SC_BLOCK), stream, out, n, tops);
+    return CRGPU_OK;
+}
+#endif
+static int cr_inclusive_max(Prims& P, const uint32_t* in, uint32_t* out, size_t n) {
+    if (n == 0) return CRGPU_OK;
+#ifdef CRGPU_SIM
+    uint32_t acc = 0;
+    for (size_t i = 0; i < n; i++) { if (in[i] > acc) acc = in[i]; out[i] = acc; }
+    (void)P;
+    return CRGPU_OK;
+#else
+    CR_TRY(P.temp2.reserve((n / SC_BLOCK + 64) * 8 + 4096));
+    return cr_maxscan_rec(P.stream, in, out, n, P.temp2.as<uint32_t>());
+#endif
+}
+
 static int cr_exclusive_sum(Prims& P, const uint32_t* in, uint32_t* out, size_t n) {
     if (n == 0) return CRGPU_OK;
 #ifdef CRGPU_SIM

@@ -15,6 +15,7 @@
 #include "cr_ppm.cuh"
 #include "cr_rc.cuh"
 #include "cr_decode.cuh"
+#include "cr_lz77.cuh"
 
 #define FULLMASK 0xFFFFFFFFu
 
@@ -780,6 +781,89 @@ __global__ void __launch_bounds__(SE_THREADS) k_side_epochs(const uint8_t* __res
     }
     if (tid < 256) state[tid] = (uint16_t)cnt[tid];
 }
+
+// The same with one CTA per job: any number of models, each with its own increment (comprox's LZ77 front-end uses
+// 30 for lengths, 1 for short distances and 1, 4, 16, 64, 256, 1024 for the skewed position models; cr_lz77.cuh).
+__global__ void __launch_bounds__(SE_THREADS) k_side_epochs_jobs(SideJobs J, uint64_t* __restrict__ TS) {
+    const uint32_t m = blockIdx.x;                       // model
+    const uint8_t* sym = J.sym[m];
+    const uint32_t* pos = J.pos[m];
+    const uint32_t n = J.n[m];
+    const uint32_t inc_m = J.inc[m];
+    uint16_t* state = J.state[m];
+    __shared__ uint32_t cnt[256];                         // counts at the start of the current step
+    __shared__ uint32_t cumt[256];                        // exclusive prefix of cnt
+    __shared__ uint32_t s_total;
+    __shared__ __align__(4) uint16_t hist[32][256];       // per-warp histogram of the step -> exclusive prefix over warps
+    __shared__ uint16_t below[32][256];                   // per warp: exclusive prefix over symbols of its hist row
+    __shared__ uint16_t steptot[256];                     // occurrences of each symbol in the step
+    const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid < 256) cnt[tid] = state[tid];
+    __syncthreads();
+    uint32_t done = 0;
+    for (;;) {
+        // cumt / total from cnt: warp 0, 8 symbols per lane
+        if (w == 0) {
+            uint32_t v[8], sum = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { v[k] = cnt[lane * 8 + k]; sum += v[k]; }
+            uint32_t inc = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(FULLMASK, inc, d); if (lane >= d) inc += t; }
+            uint32_t run = inc - sum;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { cumt[lane * 8 + k] = run; run += v[k]; }
+            if (lane == 31) s_total = inc;
+        }
+        for (uint32_t i = tid; i < 32 * 128; i += SE_THREADS) ((uint32_t*)&hist[0][0])[i] = 0;
+        __syncthreads();
+        if (done >= n) break;
+        const uint32_t total = s_total;
+        // symbols up to and including the one whose update pushes the total past 32000 (cr-model.c:65)
+        const uint32_t to_rescale = (32000 - (total > 32000 ? 32000 : total)) / inc_m + 1;
+        uint32_t step = n - done; if (step > SE_THREADS) step = SE_THREADS; if (step > to_rescale) step = to_rescale;
+        const bool active = tid < step;
+        const uint32_t s = active ? sym[done + tid] : 0xFFFFu;
+        if (active) atomicAdd((uint32_t*)&hist[w][0] + (s >> 1), (s & 1u) ? 0x10000u : 1u);
+        __syncthreads();
+        if (tid < 256) {                                   // exclusive prefix over warps, one symbol per thread
+            uint32_t run = 0;
+            for (int k = 0; k < 32; k++) { uint32_t h = hist[k][tid]; hist[k][tid] = (uint16_t)run; run += h; }
+            steptot[tid] = (uint16_t)run;
+        }
+        __syncthreads();
+        {                                                  // exclusive prefix over symbols, one row per warp
+            uint32_t v[8], sum = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { v[k] = hist[w][lane * 8 + k]; sum += v[k]; }
+            uint32_t inc = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(FULLMASK, inc, d); if (lane >= d) inc += t; }
+            uint32_t run = inc - sum;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { below[w][lane * 8 + k] = (uint16_t)run; run += v[k]; }
+        }
+        __syncwarp();
+        uint32_t lt = 0, eq = 0;                           // earlier lanes of this warp with a smaller / the same symbol
+#pragma unroll 8
+        for (uint32_t j = 0; j < 32; j++) { const uint32_t sj = __shfl_sync(FULLMASK, s, j); if (j < lane) { lt += sj < s; eq += sj == s; } }
+        if (active) {
+            const uint32_t cum = cumt[s] + inc_m * ((uint32_t)below[w][s] + lt);
+            const uint32_t frq = cnt[s] + inc_m * ((uint32_t)hist[w][s] + eq);
+            TS[pos[done + tid]] = ppm_pack(cum, frq, total + inc_m * tid, 0);
+        }
+        __syncthreads();
+        if (tid < 256) {
+            uint32_t c = cnt[tid] + inc_m * steptot[tid];
+            if (step == to_rescale) c = (c + 1) >> 1;      // halve, rounding up (cr-model.c:66-73)
+            cnt[tid] = c;
+        }
+        done += step;
+        __syncthreads();
+    }
+    if (tid < 256) state[tid] = (uint16_t)cnt[tid];
+}
+
 
 // ------------------------------------------------------------------ range coder, one warp per stream
 // All lanes stage triples through shared memory one batch ahead; lane 0 runs the serial recurrence.

@@ -7,6 +7,7 @@
 // parallel over contexts; only the range coders are serial, one per (block, stream).
 #pragma once
 #include <vector>
+#include <algorithm>
 #include "cr_common.cuh"
 #include "cr_prims.cuh"
 #include "cr_chain.cuh"
@@ -575,6 +576,17 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
             if (L.length > streams[i].out_cap) return CRGPU_ERR_ARG;
             if (streams[i].is_main) { lsm.push_back(L); rsm.push_back(streams[i]); } else { lss.push_back(L); rss.push_back(streams[i]); }
             res[i].nbytes = L.length; res[i].aborted = 0;
+        }
+        // k_low_scatter finds the stream of a triple by binary search over tri_begin: keep the side list ordered (LZ77 lays its
+        // three side streams per block out by kind, not by block)
+        if (lss.size() > 1) {
+            std::vector<size_t> order(lss.size());
+            for (size_t k = 0; k < order.size(); k++) order[k] = k;
+            std::sort(order.begin(), order.end(), [&](size_t a, size_t b) {      // empty streams first among equal starts: the search takes the last one
+                return lss[a].tri_begin != lss[b].tri_begin ? lss[a].tri_begin < lss[b].tri_begin : lss[a].tri_end < lss[b].tri_end; });
+            std::vector<LowStream> l2(lss.size()); std::vector<RcStream> r2(rss.size());
+            for (size_t k = 0; k < order.size(); k++) { l2[k] = lss[order[k]]; r2[k] = rss[order[k]]; }
+            lss.swap(l2); rss.swap(r2);
         }
         CR_TRY(b_dsum.reserve(dsum_total * 4 + 16));
         CR_CUDA(cudaMemsetAsync(b_dsum.p, 0, dsum_total * 4, stream));

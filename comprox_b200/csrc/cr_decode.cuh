@@ -101,15 +101,15 @@ CR_D uint32_t dec_ppm(PpmState& st, uint32_t ctx, RcDec& rc) {
     return d;
 }
 // M_my_dec_ with increment 4 (cr-model.h:66-74, cr-model.c:55-77,98-115)
-CR_D uint32_t dec_m0(uint16_t* f, RcDec& rc) {
+CR_D uint32_t dec_m0(uint16_t* f, RcDec& rc, uint32_t inc = 4) {
     uint32_t total = 0;
     for (int i = 0; i < 256; i++) total += f[i];
     const uint32_t tgt = rc.target(total);
     uint32_t acc = 0, s = 0;
     while (s < 255 && acc + f[s] <= tgt) acc += f[s++];
     rc.consume(acc, f[s]);
-    f[s] += 4;
-    if (total + 4 > 32000) for (int i = 0; i < 256; i++) f[i] = (uint16_t)((f[i] + 1) / 2);
+    f[s] = (uint16_t)(f[s] + inc);
+    if (total + inc > 32000) for (int i = 0; i < 256; i++) f[i] = (uint16_t)((f[i] + 1) / 2);
     return s;
 }
 
@@ -154,6 +154,15 @@ struct LzpDec {
     }
 };
 
+// distance of a long LZ77 match: lzdecode_pos_thread, src/roxmain/cr-coder.c:350-373.  next(j) decodes one symbol with pos_models[j].
+template <class F> CR_D uint32_t x_decode_distance(F next) {
+    uint32_t j = 0, v = 0, sym = 0;
+    while (j < 2 && (sym = next(j)) >= 128) { v += (sym - 128) * (1u << (7 * j)); j++; }
+    if (j < 2) return (v + sym * (1u << (7 * j))) / 8;
+    while (j < 5 && (sym = next(j)) >= 64) { v += (sym - 64) * (1u << (6 * j + 2)); j++; }
+    return (v + sym * (1u << (6 * j + 2))) / 8;
+}
+
 // One thread decodes all lz-coded blocks of one container in order.  ctx_io carries the PPM context in and out.
 __global__ void k_lzdecode_serial(int variant, const uint8_t* __restrict__ cont, const DecBlock* __restrict__ blocks, uint32_t nb,
                                   PpmState st, DecTables tabs, uint32_t* __restrict__ ctx_io, uint8_t* __restrict__ D) {
@@ -185,6 +194,29 @@ __global__ void k_lzdecode_serial(int variant, const uint8_t* __restrict__ cont,
                     }
                 } else out[n++] = (uint8_t)s;
                 for (; len; len--) { const uint32_t p = n - len; m.insert(out, p); ctx = ctx << 8 | out[p]; }
+            }
+        } else if (variant == 2) {                                             // src/roxmain/cr-coder.c:388-526
+            const uint32_t mm = in[1], esc = in[2];
+            RcDec rc, rs, rp, rl; rc.init(in + 32); rs.init(in + cr_ld32(in + 20)); rp.init(in + cr_ld32(in + 24)); rl.init(in + cr_ld32(in + 28));
+            uint32_t n = 0, last = 0;
+            while (n < orig) {
+                uint32_t len = 1;
+                const uint32_t s = dec_ppm(st, ctx, rc);
+                if (s != esc) out[n++] = (uint8_t)s;
+                else {
+                    const uint32_t l = dec_m0(st.m0, rl, 30);
+                    if (l == 0) out[n++] = (uint8_t)esc;
+                    else {
+                        uint32_t dist;
+                        if (l < mm) dist = dec_m0(st.m0 + 256, rs, 1);
+                        else dist = x_decode_distance([&](uint32_t j) { return dec_m0(st.m0 + (2 + j) * 256, rp, 1u << (2 * j)); });
+                        if (dist == 0) dist = last;
+                        last = dist; len = l;
+                        const uint32_t q = n - dist;
+                        for (uint32_t i = 0; i < len; i++) { out[n] = out[q + i]; n++; }
+                    }
+                }
+                for (; len; len--) ctx = ctx << 8 | out[n - len];
             }
         } else {                                                               // src/ropmain/cr-coder.c:231-292
             const uint32_t esc = in[8];

@@ -17,6 +17,7 @@ struct Decompressor {
         filt.release();
     }
     int tables(DecTables& T) {
+        if (chain->variant == CR_LZ77) { memset(&T, 0, sizeof T); return CRGPU_OK; }     // LZ77 copies by distance: no matcher state
         if (chain->variant == CR_ROLZ) {
             const bool fresh = t_meta.p == nullptr;
             CR_TRY(t_meta.reserve((size_t)RZ_BUCKETS * 4)); CR_TRY(t_items.reserve((size_t)RZ_BUCKETS * 64 * 4)); CR_TRY(t_short.reserve(256 * 16 * 4));
@@ -93,7 +94,7 @@ struct Decompressor {
 // payload -> DecBlock: sizes come from the inner headers (src/rolzmain/cr-coder.c:63-71, src/ropmain/cr-coder.c:60-66)
 inline int Decompressor::describe(uint64_t off, uint32_t size, int prec, uint64_t d_off, DecBlock& b) {
     const int variant = chain->variant;
-    const uint32_t hdr = variant == CR_ROLZ ? 16 : 20;
+    const uint32_t hdr = variant == CR_ROLZ ? 16 : variant == CR_LZP ? 20 : 32;
     memset(&b, 0, sizeof b);
     b.in_off = off; b.in_size = size; b.d_off = d_off;
     if (prec) { b.coded = 0; b.d_size = size; return CRGPU_OK; }

@@ -1219,6 +1219,31 @@ CR_D uint32_t wdec_m0(uint32_t (&f)[4], uint32_t& total, WRc& rc, uint32_t lane)
     if (total > 32000) { for (int q = 0; q < 4; q++) f[q] = ((f[q] + 0x00010001u) >> 1) & 0x7fff7fffu; total = __reduce_add_sync(FULLMASK, side_part(f, 8)); }
     return L * 8 + k;
 }
+// order-0 model in memory (8 x u16 per lane, L1 resident): M_my_dec_ with an arbitrary increment (the LZ77 front-end has eight models)
+CR_D uint32_t wdec_m0g(uint16_t* __restrict__ fg, WRc& rc, uint32_t inc, uint32_t lane) {
+    uint4 v = ((const uint4*)fg)[lane];
+    uint32_t f[4] = { v.x, v.y, v.z, v.w };
+    const uint32_t ls = side_part(f, 8);
+    const uint32_t incl = wscan_incl(ls, lane);
+    const uint32_t total = __shfl_sync(FULLMASK, incl, 31);
+    const uint32_t tgt = rc.target(total);
+    const uint32_t hm = __ballot_sync(FULLMASK, incl > tgt);
+    const uint32_t L = hm ? __ffs(hm) - 1 : 31;
+    uint32_t acc = __shfl_sync(FULLMASK, incl - ls, L);
+    uint32_t g[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) g[q] = __shfl_sync(FULLMASK, f[q], L);
+    uint32_t k = 0, fr = 0;
+    for (; k < 8; k++) { fr = (g[k >> 1] >> (16 * (k & 1))) & 0xffff; if (acc + fr > tgt) break; acc += fr; }
+    if (k == 8) k = 7;
+    rc.consume(acc, fr);
+    if (lane == L) f[k >> 1] += inc << (16 * (k & 1));
+    const bool halve = total + inc > 32000;
+    if (halve) for (int q = 0; q < 4; q++) f[q] = ((f[q] + 0x00010001u) >> 1) & 0x7fff7fffu;
+    if (halve || lane == L) ((uint4*)fg)[lane] = make_uint4(f[0], f[1], f[2], f[3]);
+    __syncwarp();
+    return L * 8 + k;
+}
 // copy `len` bytes from out[q..] to out[n..] with the byte-serial semantics of the reference's copy loop
 CR_D void wcopy_match(uint8_t* out, uint32_t n, uint32_t q, uint32_t len, uint32_t lane) {
     const uint32_t dist = n - q;
@@ -1290,6 +1315,32 @@ __device__ __forceinline__ void lzdecode_warp_body(int variant, const uint8_t* _
                     ctx = ctx << 8 | byte;
                 }
             }
+        } else if (variant == 2) {                                             // LZ77, src/roxmain/cr-coder.c:388-526
+            const uint32_t mm = in[1], esc = in[2];
+            WRc rc, rs, rp, rl; rc.init(in + 32); rs.init(in + cr_ld32(in + 20)); rp.init(in + cr_ld32(in + 24)); rl.init(in + cr_ld32(in + 28));
+            // the two ROLZ models cached in registers above alias slots 0 and 1: write them through memory instead
+            uint32_t n = 0, last = 0;
+            while (n < orig) {
+                uint32_t len = 1;
+                const uint32_t s = wdec_ppm(st, ctx, rc, lane);
+                if (s != esc) { if (lane == 0) out[n] = (uint8_t)s; n++; ctx = ctx << 8 | s; }
+                else {
+                    const uint32_t l = wdec_m0g(st.m0, rl, 30, lane);
+                    if (l == 0) { if (lane == 0) out[n] = (uint8_t)esc; n++; ctx = ctx << 8 | esc; }
+                    else {
+                        uint32_t dist;
+                        if (l < mm) dist = wdec_m0g(st.m0 + 256, rs, 1, lane);
+                        else dist = x_decode_distance([&](uint32_t j) { return wdec_m0g(st.m0 + (2 + j) * 256, rp, 1u << (2 * j), lane); });
+                        if (dist == 0) dist = last;
+                        last = dist; len = l;
+                        wcopy_match(out, n, n - dist, len, lane);
+                        n += len;
+                        __syncwarp();
+                        for (uint32_t i = len < 4 ? len : 4; i; i--) ctx = ctx << 8 | out[n - i];
+                    }
+                }
+                __syncwarp();
+            }
         } else {
             const uint32_t esc = in[8];
             if (lane < 9) out[lane] = in[9 + lane];
@@ -1331,8 +1382,10 @@ __device__ __forceinline__ void lzdecode_warp_body(int variant, const uint8_t* _
             }
         }
     }
-    ((uint4*)(st.m0))[lane] = make_uint4(fa[0], fa[1], fa[2], fa[3]);
-    ((uint4*)(st.m0 + 256))[lane] = make_uint4(fb[0], fb[1], fb[2], fb[3]);
+    if (variant != 2) {
+        ((uint4*)(st.m0))[lane] = make_uint4(fa[0], fa[1], fa[2], fa[3]);
+        ((uint4*)(st.m0 + 256))[lane] = make_uint4(fb[0], fb[1], fb[2], fb[3]);
+    }
     if (lane == 0) *ctx_io = ctx;
 }
 __global__ void __launch_bounds__(32) k_lzdecode_warp(int variant, const uint8_t* __restrict__ cont, const DecBlock* __restrict__ blocks, uint32_t nb,

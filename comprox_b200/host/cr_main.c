@@ -20,10 +20,11 @@
 #ifndef CR_VARIANT
 #define CR_VARIANT 0
 #endif
-static const char* NAME = CR_VARIANT == 0 ? "comprolz" : "comprop";
+static const char* NAME = CR_VARIANT == 0 ? "comprolz" : CR_VARIANT == 1 ? "comprop" : "comprox";
 
 static uint32_t cr_split_size = 16 * 1048576;    /* src/main.c:62 */
 static int cr_filt_enable = 0, cr_prec_enable = 0, flexible_parsing = 0, quiet = 0;
+static int match_limit = 0;                      /* comprox -m (src/roxmain/main.c:94-98); 0 = default 40 */
 
 static void usage(void) {
     fprintf(stderr,
@@ -34,8 +35,9 @@ static void usage(void) {
             "   -b  set block size(MB), default = 16.\n"
             "   -p  work as a precompressor.\n"
             "   -F  use PE/ELF/BMP filter.\n"
-            "%s"
-            "   -q  quiet mode.\n", NAME, NAME, CR_VARIANT == 0 ? "   -f  use flexible parsing.\n" : "");
+            "%s%s"
+            "   -q  quiet mode.\n", NAME, NAME, CR_VARIANT != 1 ? "   -f  use flexible parsing.\n" : "",
+            CR_VARIANT == 2 ? "   -m  set maximum searching depth for LZ77 matching, default = 40.\n" : "");
 }
 
 /* src/rolzmain/main.c:67-112 */
@@ -46,7 +48,8 @@ static int process_arguments(int argc, char** argv) {
             case 'p': if (argv[1][2]) goto bad; cr_prec_enable = 1; break;
             case 'F': if (argv[1][2]) goto bad; cr_filt_enable = 1; break;
             case 'q': if (argv[1][2]) goto bad; quiet = 1; break;
-            case 'f': if (CR_VARIANT != 0 || argv[1][2]) goto bad; flexible_parsing = 1; break;
+            case 'f': if (CR_VARIANT == 1 || argv[1][2]) goto bad; flexible_parsing = 1; break;
+            case 'm': if (CR_VARIANT != 2 || (match_limit = atoi(argv[1] + 2)) <= 0) goto bad; break;
             default:
             bad:
                 fprintf(stderr, "invalid switch '%s'.\n", argv[1]);
@@ -96,6 +99,7 @@ int main(int argc, char** argv) {
     int (*p_decompress)(crgpu_handle*, const uint8_t*, uint64_t, uint8_t*, uint64_t, uint64_t*) = dlsym(lib, "crgpu_decompress");
     uint64_t (*p_bound)(uint64_t, uint32_t) = dlsym(lib, "crgpu_compress_bound");
     const char* (*p_err)(int) = dlsym(lib, "crgpu_strerror");
+    int (*p_option)(crgpu_handle*, const char*, int64_t) = dlsym(lib, "crgpu_set_option");
     void (*p_destroy)(crgpu_handle*) = dlsym(lib, "crgpu_destroy");
 
     uint64_t n = 0, out_n = 0;
@@ -105,6 +109,7 @@ int main(int argc, char** argv) {
     crgpu_handle* h = NULL;
     int rc = p_create(&h, CR_VARIANT, getenv("CRGPU_DEVICE") ? atoi(getenv("CRGPU_DEVICE")) : 0, NULL);
     if (rc) { fprintf(stderr, "%s: %s\n", NAME, p_err(rc)); return -1; }
+    if (match_limit && (rc = p_option(h, "match_limit", match_limit)) != 0) { fprintf(stderr, "%s: %s\n", NAME, p_err(rc)); return -1; }
     crgpu_config cfg = { cr_split_size, cr_filt_enable, cr_prec_enable, flexible_parsing, 0 };
     uint64_t cap = decode ? 64 : p_bound(n, cr_split_size);
     uint8_t* out = malloc(cap);

@@ -30,7 +30,7 @@ extern "C" {
 
 #define CRGPU_ROLZ 0   /* comprolz: src/rolzmain */
 #define CRGPU_LZP  1   /* comprop : src/ropmain  */
-#define CRGPU_LZ77 2   /* comprox : src/roxmain (compression; containers of this variant are decoded by the reference CLI) */
+#define CRGPU_LZ77 2   /* comprox : src/roxmain  */
 
 typedef struct crgpu_handle crgpu_handle;
 

@@ -7,7 +7,7 @@ from comprox_b200 import api, synth
 
 pytestmark = pytest.mark.gpu
 MiB = 1 << 20
-BIN = {api.ROLZ: "comprolz", api.LZP: "comprop"}
+BIN = {api.ROLZ: "comprolz", api.LZP: "comprop", api.LZ77: "comprox"}
 
 
 def _sources(variant, data, bs, flags, filt):
@@ -17,7 +17,7 @@ def _sources(variant, data, bs, flags, filt):
         yield "reference", ref
 
 
-@pytest.mark.parametrize("variant", [api.ROLZ, api.LZP])
+@pytest.mark.parametrize("variant", [api.ROLZ, api.LZP, api.LZ77])
 def test_gpu_decompress_text(gpulib, variant):
     data = synth.markov_text(3 * MiB + 4321, seed=42)
     for who, container in _sources(variant, data, MiB, [], 0):
@@ -25,7 +25,7 @@ def test_gpu_decompress_text(gpulib, variant):
             assert h.decompress(container, len(data) + 64) == data, who
 
 
-@pytest.mark.parametrize("variant", [api.ROLZ, api.LZP])
+@pytest.mark.parametrize("variant", [api.ROLZ, api.LZP, api.LZ77])
 @pytest.mark.parametrize("data", [b"", b"A", bytes(MiB), (b"The quick brown fox jumps over the lazy dog. " * 30000)[:1300000]],
                          ids=["empty", "A", "zeros", "fox"])
 def test_gpu_decompress_known_answers(gpulib, variant, data):
@@ -48,7 +48,7 @@ def test_gpu_decompress_filtered_bmp(gpulib):
             assert h.decompress(container, len(data) + 64) == data, who
 
 
-@pytest.mark.parametrize("variant", [api.ROLZ, api.LZP])
+@pytest.mark.parametrize("variant", [api.ROLZ, api.LZP, api.LZ77])
 def test_gpu_roundtrip_own_container(gpulib, variant):
     data = synth.markov_text(2 * MiB, seed=5) + synth.x86_corpus(MiB, elf_bytes=0, pe_min=MiB // 2, pe_max=MiB)
     with api.Handle(variant, lib=gpulib) as h:
@@ -57,7 +57,7 @@ def test_gpu_roundtrip_own_container(gpulib, variant):
         assert h.decompress(container, len(data) + 64) == data
 
 
-@pytest.mark.parametrize("variant", [api.ROLZ, api.LZP])
+@pytest.mark.parametrize("variant", [api.ROLZ, api.LZP, api.LZ77])
 def test_gpu_decompress_scalar_kernel(gpulib, variant):
     """The single-thread decoder (the one the CPU simulation checks) agrees with the warp decoder on the GPU."""
     data = synth.markov_text(300000, seed=8)
@@ -67,7 +67,7 @@ def test_gpu_decompress_scalar_kernel(gpulib, variant):
         assert h.decompress(container, len(data) + 64) == data
 
 
-@pytest.mark.parametrize("variant", [api.ROLZ, api.LZP])
+@pytest.mark.parametrize("variant", [api.ROLZ, api.LZP, api.LZ77])
 def test_gpu_decompress_batch(gpulib, variant):
     """Many containers in flight: one launch decodes all of them (one warp each); ragged, empty, filtered and -p members."""
     inputs = [

@@ -20,7 +20,7 @@ def _cases():
     }
 
 
-@pytest.mark.parametrize("variant", [api.ROLZ, api.LZP])
+@pytest.mark.parametrize("variant", [api.ROLZ, api.LZP, api.LZ77])
 @pytest.mark.parametrize("name", sorted(_cases().keys()))
 def test_sim_decompress_oracle_container(simlib, variant, name):
     data, bs, filt, prec = _cases()[name]

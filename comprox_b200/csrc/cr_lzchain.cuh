@@ -550,13 +550,17 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
             timer.mark("expand");
             if (rc_variant == 2) CR_LAUNCH(k_range_chain<2>, gchain, dim3(128), stream, b_cinm.as<uint4>(), b_cins.as<uint4>(), b_escord.as<uint32_t>(),
                       b_streams.as<RcStream>(), nstr, b_qm.as<uint32_t>(), b_shm.as<uint32_t>(), b_qs.as<uint32_t>(), b_shs.as<uint32_t>());
+            else if (rc_variant == 6) CR_LAUNCH(k_range_chain<6>, gchain, dim3(128), stream, b_cinm.as<uint4>(), b_cins.as<uint4>(), b_escord.as<uint32_t>(),
+                      b_streams.as<RcStream>(), nstr, b_qm.as<uint32_t>(), b_shm.as<uint32_t>(), b_qs.as<uint32_t>(), b_shs.as<uint32_t>());
+            else if (rc_variant == 5) CR_LAUNCH(k_range_chain<5>, gchain, dim3(128), stream, b_cinm.as<uint4>(), b_cins.as<uint4>(), b_escord.as<uint32_t>(),
+                      b_streams.as<RcStream>(), nstr, b_qm.as<uint32_t>(), b_shm.as<uint32_t>(), b_qs.as<uint32_t>(), b_shs.as<uint32_t>());
             else if (rc_variant == 4) CR_LAUNCH(k_range_chain<4>, gchain, dim3(128), stream, b_cinm.as<uint4>(), b_cins.as<uint4>(), b_escord.as<uint32_t>(),
                       b_streams.as<RcStream>(), nstr, b_qm.as<uint32_t>(), b_shm.as<uint32_t>(), b_qs.as<uint32_t>(), b_shs.as<uint32_t>());
             else CR_LAUNCH(k_range_chain<3>, gchain, dim3(128), stream, b_cinm.as<uint4>(), b_cins.as<uint4>(), b_escord.as<uint32_t>(),
                       b_streams.as<RcStream>(), nstr, b_qm.as<uint32_t>(), b_shm.as<uint32_t>(), b_qs.as<uint32_t>(), b_shs.as<uint32_t>());
         }
         timer.mark("range_chain");
-        if (rc_variant == 4) {
+        if (rc_variant >= 4) {
             if (ntm) CR_LAUNCH(k_msb_to_shifts, dim3(cr_div_up(ntm, 256)), dim3(256), stream, b_shm.as<uint32_t>(), (uint64_t)ntm);
             if (nts) CR_LAUNCH(k_msb_to_shifts, dim3(cr_div_up(nts, 256)), dim3(256), stream, b_shs.as<uint32_t>(), (uint64_t)nts);
         }

@@ -941,11 +941,38 @@ __global__ void k_chain_inputs(const Tri* __restrict__ dense, uint64_t n, uint4*
 // VARIANT 4: as 2, but the range is never normalised explicitly: with r = q*frq (un-normalised) and k = leading zero
 //            bytes of r, the next quotient is ((r << 8k) * M) >> 63 == (r * M) >> (63 - 8k), so the multiply runs
 //            beside the leading-zero count instead of behind it (the count was ~1/4 of the dependent chain).
+// VARIANTS 5, 6: one symbol of the chain without a leading-zero count (FLO is a ~25-cycle variable-latency op and sat on the
+// chain).  range is the un-normalised product q * frq of the previous symbol; amt = 31 - 8 * (its leading zero bytes) comes from
+// three independent compares that run beside the two multiplies.
+//   5: amt = (range < 2^16) ? (range < 2^8 ? 7 : 15) : (range < 2^24 ? 23 : 31), then one shift
+//   6: only the common case (0 or 1 leading zero bytes: one compare + one select) feeds the shift on the chain; 2 or 3 leading
+//      zero bytes (~1 % of the symbols) override the quotient with a predicated second shift.
+template <int VARIANT>
+CR_D void rc_step_cmp(uint32_t& range, const uint4 t, uint32_t& q, uint32_t& amt) {
+    const uint32_t ahi = __umulhi(range, t.y);                                   // t = {frq, M_lo, M_hi, sum}, M = floor(2^63 / sum) + 1
+    const unsigned long long S2 = (unsigned long long)range * t.z + ahi;         // (range * M) >> 32
+    if (VARIANT == 5) {
+        const uint32_t a01 = range < (1u << 24) ? 23u : 31u, a23 = range < (1u << 8) ? 7u : 15u;
+        asm("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %1, 65536;\n\tselp.u32 %0, %2, %3, p;\n\t}" : "=r"(amt) : "r"(range), "r"(a23), "r"(a01));
+        q = (uint32_t)(S2 >> amt);
+    } else {
+        const uint32_t lo = (uint32_t)S2, hi = (uint32_t)(S2 >> 32);
+        asm("{\n\t.reg .pred p24, p16, p8;\n\t.reg .u32 b;\n\t"
+            "setp.lt.u32 p24, %2, 16777216;\n\tsetp.lt.u32 p16, %2, 65536;\n\tsetp.lt.u32 p8, %2, 256;\n\t"
+            "selp.u32 %1, 23, 31, p24;\n\tselp.u32 b, 7, 15, p8;\n\t"
+            "shf.r.clamp.b32 %0, %3, %4, %1;\n\t"
+            "@p16 shf.r.clamp.b32 %0, %3, %4, b;\n\t"
+            "@p16 mov.u32 %1, b;\n\t}"
+            : "=&r"(q), "=&r"(amt) : "r"(range), "r"(lo), "r"(hi));
+    }
+    range = q * t.x;                                                             // range *= frq, left un-normalised (cr-rangecoder.c:64)
+}
+
 template <int VARIANT>
 __global__ void __launch_bounds__(128) k_range_chain(const uint4* __restrict__ in_main, const uint4* __restrict__ in_side, const uint32_t* __restrict__ escord,
                                                       const RcStream* __restrict__ streams, uint32_t nstreams,
                                                       uint32_t* __restrict__ q_main, uint32_t* __restrict__ sh_main, uint32_t* __restrict__ q_side, uint32_t* __restrict__ sh_side) {
-    __shared__ uint4 stage[4][RC_BATCH + 1];          // +1: the look-ahead read of the last symbol needs no clamp
+    __shared__ uint4 stage[4][RC_BATCH + 8];          // slack: the look-ahead reads past the last symbol need no clamp
     __shared__ uint32_t oq[4][RC_BATCH], os[4][RC_BATCH + 1];   // VARIANT 4: os[j] = top-bit index BEFORE symbol j (stored late, off the chain)
     const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -972,7 +999,7 @@ __global__ void __launch_bounds__(128) k_range_chain(const uint4* __restrict__ i
         const uint32_t cnt = i1 - base < RC_BATCH ? (uint32_t)(i1 - base) : RC_BATCH;
         if (lane == 0) {
             uint4 t = stage[w][0];
-            for (uint32_t j = 0; j < cnt; j++) {
+            for (uint32_t j = 0; j < cnt && VARIANT < 5; j++) {
                 const uint4 tn = stage[w][j + 1];
                 uint32_t q, sh;
                 if (VARIANT == 1) {
@@ -1013,17 +1040,44 @@ __global__ void __launch_bounds__(128) k_range_chain(const uint4* __restrict__ i
                 oq[w][j] = q; os[w][j] = sh;
                 t = tn;
             }
+            if (VARIANT >= 5) {
+                // a symbol takes less than one LDS latency here: full batches keep 8 symbols in registers and refill each slot
+                // 8 symbols ahead of its use
+                if (cnt == RC_BATCH) {
+                    uint4 p[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) p[u] = stage[w][u];
+#pragma unroll 1
+                    for (uint32_t j0 = 0; j0 < RC_BATCH; j0 += 8) {
+#pragma unroll
+                        for (int u = 0; u < 8; u++) {
+                            const uint4 t8 = p[u];
+                            p[u] = stage[w][j0 + u + 8];
+                            uint32_t q, amt;
+                            rc_step_cmp<VARIANT>(range, t8, q, amt);
+                            os[w][j0 + u] = amt; oq[w][j0 + u] = q;
+                        }
+                    }
+                } else {
+                    for (uint32_t j = 0; j < cnt; j++) {
+                        uint32_t q, amt;
+                        rc_step_cmp<VARIANT>(range, stage[w][j], q, amt);
+                        os[w][j] = amt; oq[w][j] = q;
+                    }
+                }
+            }
             if (VARIANT == 4) os[w][cnt] = msb;
+            if (VARIANT >= 5) os[w][cnt] = 31u - (__clz(range) & 24u);
         }
         __syncwarp();
-        const uint32_t so_off = VARIANT == 4 ? 1u : 0u;                    // VARIANT 4 keeps the value after symbol j in slot j+1
+        const uint32_t so_off = VARIANT >= 4 ? 1u : 0u;                    // VARIANT 4 keeps the value after symbol j in slot j+1
         if (lane < cnt) { qo[base + lane] = oq[w][lane]; so[base + lane] = os[w][lane + so_off]; }
         if (lane + 32 < cnt) { qo[base + lane + 32] = oq[w][lane + 32]; so[base + lane + 32] = os[w][lane + 32 + so_off]; }
         __syncwarp();
     }
 }
 
-// VARIANT 4 stores the top-bit index of the un-normalised range; the renormalisation shift count is 3 - (msb >> 3)
+// VARIANTS 4, 5 store the top-bit index of the un-normalised range (5: rounded up to 8k+7); shift count = 3 - (msb >> 3)
 __global__ void k_msb_to_shifts(uint32_t* __restrict__ sh, uint64_t n) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) sh[i] = 3u - (sh[i] >> 3);

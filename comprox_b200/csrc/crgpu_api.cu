@@ -186,7 +186,7 @@ extern "C" int crgpu_set_option(crgpu_handle* h, const char* name, int64_t value
     if (!h || !name) return CRGPU_ERR_ARG;
     std::string n(name);
     if (n == "scalar_models") { h->chain.scalar_models = value != 0; return CRGPU_OK; }
-    if (n == "rc_variant") { if (value < 1 || value > 4) return CRGPU_ERR_ARG; h->chain.rc_variant = (int)value; return CRGPU_OK; }
+    if (n == "rc_variant") { if (value < 1 || value > 6) return CRGPU_ERR_ARG; h->chain.rc_variant = (int)value; return CRGPU_OK; }
     if (n == "hot_contexts") { h->chain.hot_contexts = value != 0; return CRGPU_OK; }
     if (n == "match_limit") { if (value < 1 || value > 1000000) return CRGPU_ERR_ARG; h->chain.match_limit = (uint32_t)value; return CRGPU_OK; }   // comprox -m
     if (n == "lz77_max_iter") { if (value < 0) return CRGPU_ERR_ARG; h->chain.x_max_iter = (uint32_t)value; return CRGPU_OK; }

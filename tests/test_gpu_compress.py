@@ -87,3 +87,17 @@ def test_gpu_dicpick_vocabulary_overflow(gpulib):
     with api.Handle(api.LZP, lib=gpulib) as h:
         assert h.dicpick(data) == O.dicpick(data)
         assert h.compress(data, 16 * MiB) == O.compress(data, api.LZP, 16 * MiB)
+
+
+@pytest.mark.parametrize("rcv", [1, 2, 3, 4, 5, 6])
+def test_gpu_range_chain_variants_identical(gpulib, rcv):
+    """Every formulation of the serial range chain (k_range_chain<1..6>, cr_warp.cuh) yields the oracle's bytes: skewed
+    inputs make 2- and 3-byte renormalisations (the rare path of variants 5/6) frequent."""
+    import numpy as np
+    rng = np.random.default_rng(7)
+    skew = rng.choice(np.arange(256, dtype=np.uint8), size=3 * MiB, p=np.r_[0.97, np.full(255, 0.03 / 255)]).tobytes()
+    for variant, data in ((api.ROLZ, synth.markov_text(3 * MiB, seed=5)), (api.LZP, skew), (api.ROLZ, skew[:MiB] + synth.markov_text(MiB, seed=6))):
+        with api.Handle(variant, lib=gpulib) as h:
+            h.set_option("rc_variant", rcv)
+            got = h.compress(data, MiB)
+        assert got == O.compress(data, variant, MiB), "rc_variant %d differs from the oracle" % rcv

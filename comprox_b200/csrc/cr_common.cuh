@@ -29,6 +29,8 @@ extern thread_local crsim_dim3 threadIdx, blockIdx, blockDim, gridDim;
 #define __launch_bounds__(...)
 typedef void* cudaStream_t;
 typedef int cudaError_t;
+struct alignas(16) uint4 { uint32_t x, y, z, w; };
+static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { uint4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 #define cudaSuccess 0
 template <class T> static inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
 template <class T> static inline T atomicMin(T* p, T v) { T o = *p; if (v < o) *p = v; return o; }

@@ -20,12 +20,29 @@
 #include "cr_rc.cuh"      // CopyDesc / k_copy_segments
 
 // ------------------------------------------------------------------ candidate scan
-__global__ void k_filter_scan(const uint8_t* __restrict__ d, uint64_t n, uint32_t* __restrict__ list, uint32_t cap, uint32_t* __restrict__ count) {
-    uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p + 1 >= n) return;
-    const uint32_t a = d[p], b = d[p + 1];
-    bool hit = (a == 'M' && b == 'Z') || (a == 'B' && b == 'M') || (a == 0x7F && b == 'E' && p + 3 < n && d[p + 2] == 'L' && d[p + 3] == 'F');
-    if (hit) { uint32_t i = atomicAdd(count, 1u); if (i < cap) list[i] = (uint32_t)p; }
+// One thread tests the 16 positions of one aligned 16-byte chunk: a SWAR zero-byte test rejects chunks that hold none of the
+// three first bytes ('M', 'B', 0x7F); only the others look at their positions one by one.  d must be 16-byte aligned and
+// readable for 4 bytes past the chunk that holds position n - 1 (the window buffers carry 128 bytes of slack).
+CR_D uint32_t fs_has(uint32_t w, uint32_t b) { const uint32_t x = w ^ (b * 0x01010101u); return (x - 0x01010101u) & ~x & 0x80808080u; }
+// Positions skip .. n - 1 of d are tested and reported relative to skip (skip < 16 aligns a window that does not start on a 16-byte boundary).
+__global__ void k_filter_scan(const uint8_t* __restrict__ d, uint32_t skip, uint64_t n, uint32_t* __restrict__ list, uint32_t cap, uint32_t* __restrict__ count) {
+    const uint64_t p0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (p0 + 1 >= n) return;
+    const uint4 v = *(const uint4*)(d + p0);
+    const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+    uint32_t any = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) any |= fs_has(w[k], 'M') | fs_has(w[k], 'B') | fs_has(w[k], 0x7F);
+    if (!any) return;
+    const uint32_t nx = *(const uint32_t*)(d + p0 + 16);
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const uint64_t p = p0 + k;
+        auto B = [&](int r) -> uint32_t { return r < 16 ? (w[r >> 2] >> ((r & 3) * 8)) & 255u : (nx >> ((r - 16) * 8)) & 255u; };
+        const uint32_t a = B(k), b = B(k + 1);
+        const bool hit = p >= skip && p + 1 < n && ((a == 'M' && b == 'Z') || (a == 'B' && b == 'M') || (a == 0x7F && b == 'E' && p + 3 < n && B(k + 2) == 'L' && B(k + 3) == 'F'));
+        if (hit) { uint32_t i = atomicAdd(count, 1u); if (i < cap) list[i] = (uint32_t)(p - skip); }
+    }
 }
 
 // ------------------------------------------------------------------ E8/E9
@@ -74,24 +91,64 @@ struct BmpOp {
     uint64_t src_off;    // offset of the tile's untouched copy
     uint32_t rows, width, row_size, bytes;   // bytes per pixel (3 or 4)
 };
-// colour-decorrelated value of byte xb of row y (src/filter_bmp.c:63-73)
-CR_D uint32_t bmp_c(const uint8_t* src, const BmpOp& o, uint32_t y, uint32_t xb) {
-    const uint32_t ch = xb % o.bytes;
-    const uint8_t* row = src + o.src_off + (uint64_t)y * o.row_size;
-    uint32_t v = row[xb];
-    if (ch == 0 || ch == 2) v -= row[xb - ch + 1];
-    return v;
+// Forward transform, 16 output bytes per thread (one aligned 16-byte chunk of the window).  The untouched copy of the tile sits
+// in `snap` at an address congruent to the window address mod 16 (k_copy_chunks), so the chunk, its two neighbours and the
+// 28-byte window one row up are aligned vector / word loads.  Per byte (row y, byte xb of the row, channel ch = xb % BPP):
+//   c(y, xb)  = b - g for ch 0 and 2, b otherwise                                  colour       src/filter_bmp.c:63-73
+//   h(y, xb)  = c(y, xb) - c(y, xb - BPP)          for xb >= BPP                   left delta   :75-88
+//   out       = h(y, xb) - h(y - 1, xb)            for y > 0                       up delta     :89-102
+// Bytes of the row padding keep their value.  Chunks that straddle the ends of the tile write their own bytes one by one
+// (the neighbouring bytes may belong to another tile whose thread writes them).
+__global__ void k_copy_chunks(const CopyDesc* __restrict__ descs, const uint8_t* __restrict__ src, uint8_t* __restrict__ dst) {
+    const CopyDesc c = descs[blockIdx.y];                                     // c.dst == c.src (mod 16)
+    const uint64_t a0 = c.src & ~15ull, n = ((c.src + c.len + 15) & ~15ull) - a0 >> 4;
+    const uint4* s = (const uint4*)(src + a0);
+    uint4* t = (uint4*)(dst + (c.dst - (c.src - a0)));
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) t[i] = s[i];
 }
-__global__ void k_bmp_rows(const uint8_t* __restrict__ src, uint8_t* __restrict__ d, const BmpOp* __restrict__ ops) {
+template <int BPP>
+CR_D void bmp_chunk(const uint8_t* __restrict__ snap, uint8_t* __restrict__ d, const BmpOp& o, const uint64_t chunk) {
+    const int64_t total = (int64_t)o.rows * o.row_size;
+    const uint64_t A = (o.off & ~15ull) + 16 * chunk;                         // window address of the chunk
+    const int64_t idx0 = (int64_t)A - (int64_t)o.off;                         // tile index of its byte 0 (negative only in the first chunk)
+    if (idx0 >= total) return;
+    const uint8_t* sp = snap + (int64_t)o.src_off + idx0;                     // 16-byte aligned by construction
+    uint32_t cur[12], up[7];                                                  // tile bytes idx0 - 16 .. idx0 + 31;  idx0 - row_size - 8 .. + 19
+    { const uint4 a = *(const uint4*)(sp - 16), b = *(const uint4*)sp, c = *(const uint4*)(sp + 16);
+      cur[0] = a.x; cur[1] = a.y; cur[2] = a.z; cur[3] = a.w; cur[4] = b.x; cur[5] = b.y; cur[6] = b.z; cur[7] = b.w; cur[8] = c.x; cur[9] = c.y; cur[10] = c.z; cur[11] = c.w; }
+    const bool has_up = idx0 + 15 >= (int64_t)o.row_size;
+#pragma unroll
+    for (int k = 0; k < 7; k++) up[k] = has_up ? ((const uint32_t*)(sp - o.row_size - 8))[k] : 0u;
+    auto CB = [&](int r) -> uint32_t { return (cur[(r + 16) >> 2] >> (((r + 16) & 3) * 8)) & 255u; };
+    auto UB = [&](int r) -> uint32_t { return (up[(r + 8) >> 2] >> (((r + 8) & 3) * 8)) & 255u; };
+    const uint32_t wb = o.width * BPP;
+    const int64_t first = idx0 < 0 ? 0 : idx0;
+    uint32_t y = (uint32_t)(first / o.row_size), xb = (uint32_t)(first % o.row_size), ch = xb % BPP;
+    uint32_t out[4] = { cur[4], cur[5], cur[6], cur[7] };
+    const bool interior = idx0 >= 0 && idx0 + 16 <= total;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const int64_t idx = idx0 + k;
+        if (idx < 0 || idx >= total) continue;
+        if (xb < wb) {
+            auto C = [&](int r) -> uint32_t { return ch == 0 ? CB(r) - CB(r + 1) : ch == 2 ? CB(r) - CB(r - 1) : CB(r); };
+            auto U = [&](int r) -> uint32_t { return ch == 0 ? UB(r) - UB(r + 1) : ch == 2 ? UB(r) - UB(r - 1) : UB(r); };
+            uint32_t v = C(k);
+            if (xb >= BPP) v -= C(k - BPP);
+            if (y > 0) { v -= U(k); if (xb >= BPP) v += U(k - BPP); }
+            v &= 255u;
+            if (interior) out[k >> 2] = (out[k >> 2] & ~(255u << ((k & 3) * 8))) | v << ((k & 3) * 8);
+            else d[A + k] = (uint8_t)v;
+        }
+        if (++xb == o.row_size) { xb = 0; ch = 0; y++; } else if (++ch == BPP) ch = 0;
+    }
+    if (interior) *(uint4*)(d + A) = make_uint4(out[0], out[1], out[2], out[3]);
+}
+__global__ void k_bmp_rows(const uint8_t* __restrict__ snap, uint8_t* __restrict__ d, const BmpOp* __restrict__ ops) {
     const BmpOp o = ops[blockIdx.y];
-    const uint32_t wb = o.width * o.bytes;
-    const uint64_t total = (uint64_t)o.rows * wb;
-    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t y = (uint32_t)(t / wb), xb = (uint32_t)(t % wb);
-        uint32_t v = bmp_c(src, o, y, xb);
-        if (xb >= o.bytes) v -= bmp_c(src, o, y, xb - o.bytes);                                       // left delta  (:75-88)
-        if (y > 0) { v -= bmp_c(src, o, y - 1, xb); if (xb >= o.bytes) v += bmp_c(src, o, y - 1, xb - o.bytes); }   // up delta (:89-102)
-        d[o.off + (uint64_t)y * o.row_size + xb] = (uint8_t)v;
+    const uint64_t nchunk = ((o.off & 15) + (uint64_t)o.rows * o.row_size + 15) >> 4;
+    for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nchunk; c += (uint64_t)gridDim.x * blockDim.x) {
+        if (o.bytes == 3) bmp_chunk<3>(snap, d, o, c); else bmp_chunk<4>(snap, d, o, c);
     }
 }
 
@@ -212,10 +269,15 @@ struct FilterHost {
                 uint32_t n = run(lastproc, v, boff + pos);
                 if ((int)n == 0) lastproc = 0; else { filt = 1; pos += n; continue; }
             }
-            while (ci < cand.size() && cand[ci] < boff + pos) ci++;
-            if (ci >= cand.size() || cand[ci] >= boff + len) break;
-            pos = (uint32_t)(cand[ci] - boff);
-            v.p = h_block + pos; v.len = len - pos;
+            // A sub-filter whose sticky flag is set (an image in progress) needs no magic to fire: after bmp_transform has
+            // returned 0 for a broken row, the loop over all sub-filters calls it again at the SAME position and it skips
+            // the row (src/filter_bmp.c:188-203, src/cr-filter.c:60-68).  Only with all flags clear may we jump to the next magic.
+            if (!(pe.flag || elf.flag || bmp.flag)) {
+                while (ci < cand.size() && cand[ci] < boff + pos) ci++;
+                if (ci >= cand.size() || cand[ci] >= boff + len) break;
+                pos = (uint32_t)(cand[ci] - boff);
+                v.p = h_block + pos; v.len = len - pos;
+            }
             bool fired = false;
             for (int k = 1; k <= 3 && !fired; k++) {
                 uint32_t n = run(k, v, boff + pos);
@@ -233,6 +295,7 @@ struct FilterHost {
         uint64_t wlen = 0;
         for (size_t b = 0; b < roff.size(); b++) if (roff[b] + rsize[b] > wlen) wlen = roff[b] + rsize[b];
         (void)nwin_total;
+        const uint32_t mis = (uint32_t)((uintptr_t)d_win & 15);          // the vector kernels address the window from the 16-byte boundary below it
         // ---- candidates
         std::vector<uint32_t> cand;
         if (wlen >= 2) {
@@ -240,7 +303,7 @@ struct FilterHost {
             for (;;) {
                 CR_TRY(b_list.reserve((size_t)cap * 4)); CR_TRY(b_count.reserve(16));
                 CR_CUDA(cudaMemsetAsync(b_count.p, 0, 4, stream));
-                CR_LAUNCH(k_filter_scan, dim3(cr_div_up(wlen, 256)), dim3(256), stream, d_win, wlen, b_list.as<uint32_t>(), cap, b_count.as<uint32_t>());
+                CR_LAUNCH(k_filter_scan, dim3(cr_div_up(cr_div_up(wlen + mis, 16), 256)), dim3(256), stream, d_win - mis, mis, wlen + mis, b_list.as<uint32_t>(), cap, b_count.as<uint32_t>());
                 std::vector<uint32_t> cnt;
                 CR_TRY(C.download(cnt, b_count.p, 1));
                 if (cnt[0] <= cap) { CR_TRY(C.download(cand, b_list.p, cnt[0])); break; }
@@ -278,17 +341,22 @@ struct FilterHost {
             CR_LAUNCH(k_bmp_dec_cols, dim3(cr_div_up(maxwb, 128), (unsigned)bmpops.size()), dim3(128), stream, d_win, b_bmp.as<BmpOp>());
             CR_LAUNCH(k_bmp_dec_colour, dim3(296, (unsigned)bmpops.size()), dim3(256), stream, d_win, b_bmp.as<BmpOp>());
         } else if (!bmpops.empty()) {
+            // snapshots: 32 bytes of slack on both sides (the kernel reads the neighbouring chunks and 8 bytes in front of the
+            // row above), each placed congruent to its window address mod 16
             std::vector<CopyDesc> copies(bmpops.size());
-            uint64_t to = 0;
+            uint64_t to = 0, maxchunk = 0;
             for (size_t i = 0; i < bmpops.size(); i++) {
-                uint64_t bytes = (uint64_t)bmpops[i].rows * bmpops[i].row_size;
-                bmpops[i].src_off = to;
-                CopyDesc c = { bmpops[i].off, to, (uint32_t)bytes, 0 }; copies[i] = c;
-                to += (bytes + 15) & ~15ull;
+                bmpops[i].off += mis;                                                       // relative to d_win - mis from here on
+                const uint64_t bytes = (uint64_t)bmpops[i].rows * bmpops[i].row_size, mo = bmpops[i].off & 15;
+                bmpops[i].src_off = to + 32 + mo;
+                CopyDesc c = { bmpops[i].off, bmpops[i].src_off, (uint32_t)bytes, 0 }; copies[i] = c;
+                to += 32 + ((mo + bytes + 15) & ~15ull) + 32;
+                maxchunk = std::max<uint64_t>(maxchunk, (mo + bytes + 15) >> 4);
             }
             CR_TRY(b_tmp.reserve(to + 16)); CR_TRY(C.upload(b_copy, copies)); CR_TRY(C.upload(b_bmp, bmpops));
-            CR_LAUNCH(k_copy_segments, dim3(128, (unsigned)copies.size()), dim3(256), stream, b_copy.as<CopyDesc>(), d_win, d_win, b_tmp.as<uint8_t>());
-            CR_LAUNCH(k_bmp_rows, dim3(296, (unsigned)bmpops.size()), dim3(256), stream, b_tmp.as<uint8_t>(), d_win, b_bmp.as<BmpOp>());
+            const unsigned gx = (unsigned)std::min<uint64_t>(cr_div_up(maxchunk, 256), 148 * 8);
+            CR_LAUNCH(k_copy_chunks, dim3(gx, (unsigned)copies.size()), dim3(256), stream, b_copy.as<CopyDesc>(), d_win - mis, b_tmp.as<uint8_t>());
+            CR_LAUNCH(k_bmp_rows, dim3(gx, (unsigned)bmpops.size()), dim3(256), stream, b_tmp.as<uint8_t>(), d_win - mis, b_bmp.as<BmpOp>());
         }
         return CRGPU_OK;
     }

@@ -235,10 +235,10 @@ def main():
     triples = prof.get("#triples", 0.0) / steps
     rc_bytes = 12.0 * triples + container_bytes
     achieved = rc_bytes / (rc_ms / 1e3) / 1e9 if rc_ms > 0 else 0.0
-    # DRAM traffic of the same kernel from the committed `ncu --set full` capture (profiles/round1_ncu_range_chain_v4.txt:
-    # 173.83 MB read + 55.28 MB written by one launch over 10.62 M triples = 21.6 B per triple: the 16-B padded triple in,
-    # 4 B range/shift record + coded bytes out), scaled to the triples of this launch.
-    NCU_TRAFFIC_PER_TRIPLE = (173.829888e6 + 55.276032e6) / 10.62e6
+    # DRAM traffic of the same kernel from the committed `ncu --set full` capture (profiles/round1b_ncu_range_chain_v4.txt:
+    # 174.08 MB read + 55.39 MB written by one launch over 10.81 M triples = 21.2 B per triple: the 16-B padded triple in,
+    # 4 B quotient + 4 B shift record out, minus what stays in L2), scaled to the triples of this launch.
+    NCU_TRAFFIC_PER_TRIPLE = (174.081536e6 + 55.391488e6) / 10.809709e6
     traffic = NCU_TRAFFIC_PER_TRIPLE * triples if triples else None
     pipe_gbs = (n + container_bytes) / (ms_res / steps / 1e3) / 1e9
     line = {
@@ -249,7 +249,7 @@ def main():
         "gpu_launches": int(launches), "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "k_range_chain", "achieved": round(achieved, 3), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                      "frac": round(achieved / peak, 6), "traffic": None if traffic is None else int(traffic),
-                     "traffic_source": "ncu --set full capture of this kernel (profiles/round1_ncu_range_chain_v4.txt), bytes per triple x triples of this launch",
+                     "traffic_source": "ncu --set full capture of this kernel (profiles/round1b_ncu_range_chain_v4.txt), bytes per triple x triples of this launch",
                      "algorithmic_bytes": int(rc_bytes), "launch_ms": round(rc_ms, 2),
                      "note": "serial recurrence per (block, stream): latency bound by construction, see DESIGN.md section 5"},
         "pipeline_roofline": {"achieved_gbs": round(pipe_gbs, 3), "frac": round(pipe_gbs / peak, 6), "algorithmic_bytes": "raw + container (SURVEY.md 8d)"},

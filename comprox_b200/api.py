@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import time
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcrgpu.so")
@@ -116,8 +117,11 @@ class Handle:
         cap = self.L.crgpu_compress_bound(ctypes.c_uint64(len(data)), ctypes.c_uint32(block_size))
         out = ctypes.create_string_buffer(cap)
         n = ctypes.c_uint64()
-        _check(self.L, self.L.crgpu_compress(self.h, ctypes.byref(cfg), data, ctypes.c_uint64(len(data)), out, ctypes.c_uint64(cap), ctypes.byref(n)))
-        return out.raw[:n.value]
+        t0 = time.perf_counter()
+        rc = self.L.crgpu_compress(self.h, ctypes.byref(cfg), data, ctypes.c_uint64(len(data)), out, ctypes.c_uint64(cap), ctypes.byref(n))
+        self.last_call_s = time.perf_counter() - t0          # the C ABI call alone (pageable host buffers), without the Python copies
+        _check(self.L, rc)
+        return ctypes.string_at(out, n.value)
 
     def dicpick(self, data: bytes) -> bytes:
         """dicpick(): the dictionary text (with the final NUL) built from the whole input."""
@@ -131,8 +135,11 @@ class Handle:
         """The bytes `comprolz/comprop d` would write for this container."""
         out = ctypes.create_string_buffer(max(out_cap, 1))
         n = ctypes.c_uint64()
-        _check(self.L, self.L.crgpu_decompress(self.h, container, ctypes.c_uint64(len(container)), out, ctypes.c_uint64(out_cap), ctypes.byref(n)))
-        return out.raw[:n.value]
+        t0 = time.perf_counter()
+        rc = self.L.crgpu_decompress(self.h, container, ctypes.c_uint64(len(container)), out, ctypes.c_uint64(out_cap), ctypes.byref(n))
+        self.last_call_s = time.perf_counter() - t0
+        _check(self.L, rc)
+        return ctypes.string_at(out, n.value)
 
     def set_option(self, name, value):
         _check(self.L, self.L.crgpu_set_option(self.h, name.encode(), ctypes.c_int64(int(value))))

@@ -40,6 +40,7 @@ template <class T> static inline T atomicCAS(T* p, T c, T v) { T o = *p; if (o =
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
 static inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __ffs(int v) { return __builtin_ffs(v); }
 #define CR_LAUNCH(kernel, grid, block, stream, ...)                                            \
     do {                                                                                       \
         crsim_dim3 g_ = (grid), b_ = (block);                                                  \

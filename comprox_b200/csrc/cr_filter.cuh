@@ -34,14 +34,19 @@ __global__ void k_filter_scan(const uint8_t* __restrict__ d, uint32_t skip, uint
 #pragma unroll
     for (int k = 0; k < 4; k++) any |= fs_has(w[k], 'M') | fs_has(w[k], 'B') | fs_has(w[k], 0x7F);
     if (!any) return;
-    const uint32_t nx = *(const uint32_t*)(d + p0 + 16);
+    const uint32_t w5[5] = { v.x, v.y, v.z, v.w, *(const uint32_t*)(d + p0 + 16) };
 #pragma unroll
-    for (int k = 0; k < 16; k++) {
-        const uint64_t p = p0 + k;
-        auto B = [&](int r) -> uint32_t { return r < 16 ? (w[r >> 2] >> ((r & 3) * 8)) & 255u : (nx >> ((r - 16) * 8)) & 255u; };
-        const uint32_t a = B(k), b = B(k + 1);
-        const bool hit = p >= skip && p + 1 < n && ((a == 'M' && b == 'Z') || (a == 'B' && b == 'M') || (a == 0x7F && b == 'E' && p + 3 < n && B(k + 2) == 'L' && B(k + 3) == 'F'));
-        if (hit) { uint32_t i = atomicAdd(count, 1u); if (i < cap) list[i] = (uint32_t)(p - skip); }
+    for (int k = 0; k < 4; k++) {
+        uint32_t m = fs_has(w[k], 'M') | fs_has(w[k], 'B') | fs_has(w[k], 0x7F);          // bit 7 of every candidate byte (may over-report, never under)
+        while (m) {
+            const uint32_t b = (uint32_t)(__ffs((int)m) - 1) >> 3;                        // byte within the word
+            m &= m - 1;
+            const uint32_t q = (uint32_t)((((unsigned long long)w5[k + 1] << 32) | w5[k]) >> (8 * b));   // the four bytes at the position
+            const uint64_t p = p0 + 4 * k + b;
+            const uint32_t a = q & 255u, c = (q >> 8) & 255u;
+            const bool hit = p >= skip && p + 1 < n && ((a == 'M' && c == 'Z') || (a == 'B' && c == 'M') || (p + 3 < n && q == 0x464C457Fu));
+            if (hit) { uint32_t i = atomicAdd(count, 1u); if (i < cap) list[i] = (uint32_t)(p - skip); }
+        }
     }
 }
 
@@ -106,6 +111,16 @@ __global__ void k_copy_chunks(const CopyDesc* __restrict__ descs, const uint8_t*
     uint4* t = (uint4*)(dst + (c.dst - (c.src - a0)));
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) t[i] = s[i];
 }
+CR_D uint32_t cr_funnel_r(uint32_t lo, uint32_t hi, uint32_t bits) { return (uint32_t)((((unsigned long long)hi << 32) | lo) >> bits); }
+// byte-wise a - b (mod 256) on four packed bytes
+CR_D uint32_t bmp_sub4(uint32_t a, uint32_t b) { return ((a | 0x80808080u) - (b & 0x7f7f7f7fu)) ^ ((a ^ ~b) & 0x80808080u); }
+// 0xFF in every byte b of a word whose channel (phase + b) mod BPP equals `want`
+template <int BPP> CR_D uint32_t bmp_chmask(uint32_t phase, uint32_t want) {
+    uint32_t m = 0;
+#pragma unroll
+    for (uint32_t b = 0; b < 4; b++) if ((phase + b) % BPP == want) m |= 255u << (8 * b);
+    return m;
+}
 template <int BPP>
 CR_D void bmp_chunk(const uint8_t* __restrict__ snap, uint8_t* __restrict__ d, const BmpOp& o, const uint64_t chunk) {
     const int64_t total = (int64_t)o.rows * o.row_size;
@@ -126,6 +141,29 @@ CR_D void bmp_chunk(const uint8_t* __restrict__ snap, uint8_t* __restrict__ d, c
     uint32_t y = (uint32_t)(first / o.row_size), xb = (uint32_t)(first % o.row_size), ch = xb % BPP;
     uint32_t out[4] = { cur[4], cur[5], cur[6], cur[7] };
     const bool interior = idx0 >= 0 && idx0 + 16 <= total;
+    if (interior && xb >= 8 && xb + 16 <= wb) {
+        // All 16 bytes are pixel bytes of one row with their left neighbours in the same row: four bytes per operation.
+        // Word i covers bytes 4i .. 4i+3 of the chunk; the channel of byte b of word i is (ch + 4i + b) mod BPP.
+        uint32_t C[5], UC[5];                                                   // colour-decorrelated words -1 .. 3, this row and the row above
+#pragma unroll
+        for (int i = -1; i < 4; i++) {
+            const uint32_t ph = (ch + (uint32_t)(4 * i + 4 * BPP)) % BPP;
+            const uint32_t m0 = bmp_chmask<BPP>(ph, 0), m2 = bmp_chmask<BPP>(ph, 2);
+            const uint32_t o = cur[i + 4], op = cr_funnel_r(cur[i + 4], cur[i + 5], 8), om = cr_funnel_r(cur[i + 3], cur[i + 4], 24);
+            C[i + 1] = bmp_sub4(o, (op & m0) | (om & m2));
+            const uint32_t u = up[i + 2], upl = cr_funnel_r(up[i + 2], up[i + 3], 8), umi = cr_funnel_r(up[i + 1], up[i + 2], 24);
+            UC[i + 1] = bmp_sub4(u, (upl & m0) | (umi & m2));
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t cl = BPP == 4 ? C[i] : cr_funnel_r(C[i], C[i + 1], 8);        // the same channel one pixel to the left
+            const uint32_t ul = BPP == 4 ? UC[i] : cr_funnel_r(UC[i], UC[i + 1], 8);
+            const uint32_t h = bmp_sub4(C[i + 1], cl);
+            out[i] = y > 0 ? bmp_sub4(h, bmp_sub4(UC[i + 1], ul)) : h;
+        }
+        *(uint4*)(d + A) = make_uint4(out[0], out[1], out[2], out[3]);
+        return;
+    }
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         const int64_t idx = idx0 + k;

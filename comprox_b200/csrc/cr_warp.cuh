@@ -1329,6 +1329,11 @@ __device__ __forceinline__ void lzdecode_warp_body(int variant, const uint8_t* _
             if (lane == 0) out[0] = in[0];
             hist = in[0]; n = 1;
             __syncwarp();
+            // The order-1 lists (16 most recent positions per previous byte) are rings here: lane l keeps the 4-bit heads of
+            // bytes 8l..8l+7 in one register, an update is one store instead of a 16-entry shift.  The bucket word the next
+            // update needs is loaded by lane 0 as soon as the bucket is known (one symbol ahead of its use).
+            uint32_t sheads = 0;
+            uint32_t m_pref = lane == 0 ? T.rz_meta[0] : 0u;
             while (n < orig) {
                 uint32_t len = 1;
                 const uint32_t s = wdec_ppm(st, ctx, rc, lane);
@@ -1339,7 +1344,10 @@ __device__ __forceinline__ void lzdecode_warp_body(int variant, const uint8_t* _
                         const uint32_t idx = wdec_m0(fb, totb, side, lane);
                         uint32_t q;
                         if (idx < 64) { const uint32_t m = T.rz_meta[bucket]; q = T.rz_items[(size_t)bucket * 64 + (((m & 255) + 64 - idx) & 63)]; }
-                        else q = T.rz_short[sbucket * 16 + idx - 64];
+                        else {
+                            const uint32_t hd = (__shfl_sync(FULLMASK, sheads, sbucket >> 3) >> (4 * (sbucket & 7))) & 15u;
+                            q = T.rz_short[sbucket * 16 + ((hd + 64 + 16 - idx) & 15)];              // idx - 64 steps back from the newest
+                        }
                         len = l;
                         wcopy_match(out, n, q, len, lane);
                         n += len;
@@ -1350,24 +1358,27 @@ __device__ __forceinline__ void lzdecode_warp_body(int variant, const uint8_t* _
                     const uint32_t byte = len == 1 ? (s == esc ? esc : s) : out[p];
                     hist = hist << 8 | byte;
                     if (p >= 16) {
-                        uint32_t m = T.rz_meta[bucket];
-                        if ((m >> 16) != B.epoch) m = B.epoch << 16;
-                        const uint32_t head = ((m & 255) + 1) & 63;
-                        uint32_t count = ((m >> 8) & 255) + 1; if (count > 64) count = 64;
-                        if (lane == 0) { T.rz_items[(size_t)bucket * 64 + head] = p; T.rz_meta[bucket] = B.epoch << 16 | count << 8 | head; }
                         uint32_t h = (hist & 255) * 1313131u + (hist >> 8 & 255) * 13131u + (hist >> 16 & 255) * 131u;
                         if (ctx4) h += hist >> 24;
-                        bucket = h & (RZ_BUCKETS - 1);
-                        uint32_t* srow = T.rz_short + sbucket * 16;
-                        const uint32_t v = lane < 16 ? srow[lane] : 0;
-                        __syncwarp();
-                        if (lane < 15) srow[lane + 1] = v;
-                        if (lane == 0) srow[0] = p;
+                        const uint32_t nbucket = h & (RZ_BUCKETS - 1);
+                        if (lane == 0) {
+                            uint32_t m = m_pref;
+                            if ((m >> 16) != B.epoch) m = B.epoch << 16;
+                            const uint32_t head = ((m & 255) + 1) & 63;
+                            uint32_t count = ((m >> 8) & 255) + 1; if (count > 64) count = 64;
+                            T.rz_items[(size_t)bucket * 64 + head] = p; T.rz_meta[bucket] = B.epoch << 16 | count << 8 | head;
+                            m_pref = T.rz_meta[nbucket];                        // behind the store above in program order: never stale
+                        }
+                        bucket = nbucket;
+                        const uint32_t sh4 = 4 * (sbucket & 7);
+                        const uint32_t nh = (((__shfl_sync(FULLMASK, sheads, sbucket >> 3) >> sh4) & 15u) + 1u) & 15u;
+                        if (lane == (sbucket >> 3)) sheads = (sheads & ~(15u << sh4)) | nh << sh4;
+                        if (lane == 0) T.rz_short[sbucket * 16 + nh] = p;
                         sbucket = byte;
-                        __syncwarp();
                     }
                     ctx = ctx << 8 | byte;
                 }
+                __syncwarp();
             }
         } else if (variant == 2) {                                             // LZ77, src/roxmain/cr-coder.c:388-526
             const uint32_t mm = in[1], esc = in[2];

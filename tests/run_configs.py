@@ -41,7 +41,7 @@ for name in a.names:
         h.compress(data if a.full_warmup else data[:4 * MiB], 16 * MiB, filt=c["filt"])   # warm-up (allocations, module load)
         h.profile(True)
         t0 = time.time(); out = h.compress(data, 16 * MiB, filt=c["filt"], window_bytes=a.window_mb * MiB); dt = time.time() - t0
-        rec.update(gpu_s=round(dt, 3), gpu_mibs=round(len(data) / MiB / dt, 1), container=len(out), sha=hashlib.sha256(out).hexdigest()[:16],
+        rec.update(gpu_s=round(dt, 3), gpu_mibs=round(len(data) / MiB / dt, 1), abi_s=round(h.last_call_s, 3), abi_mibs=round(len(data) / MiB / h.last_call_s, 1), container=len(out), sha=hashlib.sha256(out).hexdigest()[:16],
                    stages_ms={k: round(v, 1) for k, v in h.profile_report().items()})
         if a.window_check_mb:
             out2 = h.compress(data, 16 * MiB, filt=c["filt"], window_bytes=a.window_check_mb * MiB)

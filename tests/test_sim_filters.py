@@ -23,7 +23,7 @@ def _bmp32(rng, w, h):
 def _corpus():
     rng = np.random.default_rng(5)
     parts = [synth.bmp_corpus(700000, seed=3, wmin=5, wmax=40, hmin=4, hmax=60),         # rows shorter than a 16-byte chunk
-             _bmp32(rng, 37, 50), b"xyz", _bmp32(rng, 4, 4), b"BM", b"MZ", b"\x7fELF",
+             _bmp32(rng, 37, 50), b"xyz", _bmp32(rng, 4, 4), _bmp32(rng, 301, 40), b"q", _bmp32(rng, 130, 33), b"qq", _bmp32(rng, 63, 21), b"BM", b"MZ", b"\x7fELF",
              synth.bmp_corpus(900000, seed=4, wmin=301, wmax=700, hmin=40, hmax=200)]
     return b"".join(parts)
 

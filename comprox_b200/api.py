@@ -62,6 +62,24 @@ def decompress_batch(handles, containers, out_caps):
     return [outs[i].raw[:lens[i]] for i in range(k)]
 
 
+def lcp_encode(text: bytes, lib=None) -> bytes:
+    """dic_lcp_encode(): front coding of the NUL-terminated dictionary text (host side)."""
+    L = lib or load()
+    out = ctypes.create_string_buffer(len(text) + 64)
+    n = ctypes.c_uint64()
+    _check(L, L.crgpu_dic_lcp_encode(bytes(text), ctypes.c_uint64(len(text)), out, ctypes.c_uint64(len(text) + 64), ctypes.byref(n)))
+    return out.raw[:n.value]
+
+
+def lcp_decode(data: bytes, lib=None, cap: int = 25000 * 24 + 64) -> bytes:
+    """dic_lcp_decode(): the dictionary text with its final NUL."""
+    L = lib or load()
+    out = ctypes.create_string_buffer(cap)
+    n = ctypes.c_uint64()
+    _check(L, L.crgpu_dic_lcp_decode(bytes(data), ctypes.c_uint64(len(data)), out, ctypes.c_uint64(cap), ctypes.byref(n)))
+    return out.raw[:n.value]
+
+
 class Config(ctypes.Structure):
     _fields_ = [("block_size", ctypes.c_uint32), ("filt", ctypes.c_int32), ("prec", ctypes.c_int32), ("flexible", ctypes.c_int32),
                 ("window_bytes", ctypes.c_uint64)]
@@ -130,6 +148,40 @@ class Handle:
         n = ctypes.c_uint64()
         _check(self.L, self.L.crgpu_dicpick(self.h, data, ctypes.c_uint64(len(data)), out, ctypes.c_uint64(cap), ctypes.byref(n)))
         return out.raw[:n.value]
+
+    # ---- stage-level entry points (one block per call; argument meaning of the reference's cr-* functions)
+    def filter_inplace(self, data: bytes, en_de: int = 0):
+        """filter_inplace(): returns (fired, transformed bytes); filter state carries over between calls."""
+        buf = ctypes.create_string_buffer(bytes(data), max(len(data), 1))
+        rc = self.L.crgpu_filter_inplace(self.h, buf, ctypes.c_uint32(len(data)), int(en_de))
+        if rc < 0:
+            _check(self.L, rc)
+        return rc, buf.raw[:len(data)]
+
+    def dictionary_load(self, text: bytes, init_trie: int = 1) -> int:
+        rc = self.L.crgpu_dictionary_load(self.h, ctypes.c_char_p(text), int(init_trie))
+        if rc < 0:
+            _check(self.L, rc)
+        return rc
+
+    def _block_call(self, fn, data, cap):
+        out = ctypes.create_string_buffer(max(cap, 1))
+        n = ctypes.c_uint32()
+        _check(self.L, fn(self.h, bytes(data), ctypes.c_uint32(len(data)), out, ctypes.c_uint64(cap), ctypes.byref(n)))
+        return out.raw[:n.value]
+
+    def dictionary_encode(self, data: bytes) -> bytes:
+        return self._block_call(self.L.crgpu_dictionary_encode, data, len(data) + 1)
+
+    def dictionary_decode(self, data: bytes, out_cap: int) -> bytes:
+        return self._block_call(self.L.crgpu_dictionary_decode, data, out_cap)
+
+    def lzdecode(self, payload: bytes) -> bytes:
+        self.L.crgpu_lzdecode_size.restype = ctypes.c_int64
+        size = self.L.crgpu_lzdecode_size(self.variant, bytes(payload), ctypes.c_uint32(len(payload)))
+        if size < 0:
+            _check(self.L, int(size))
+        return self._block_call(self.L.crgpu_lzdecode, payload, int(size))
 
     def decompress(self, container: bytes, out_cap: int) -> bytes:
         """The bytes `comprolz/comprop d` would write for this container."""

@@ -80,6 +80,10 @@ struct Decompressor {
     int begin(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_n);   // -> job = dictionary payload
     int middle();                                                                                  // -> job = data blocks (nb may be 0)
     int finish_layout();                                                                           // -> ddjob = the sub-chunks to expand
+    int layout();
+    int load_words(const char* text);
+    int lzdecode_block(const uint8_t* in, uint32_t n, uint8_t* out, uint64_t out_cap, uint32_t* out_n);          // stage shims (crgpu_lzdecode,
+    int dict_decode_block(const uint8_t* in, uint32_t n, uint8_t* out, uint64_t out_cap, uint32_t* out_n);       //  crgpu_dictionary_decode)
     int dd_launch();
     int finish_output();                                                                           // inverse filters, copy out
     DdJob ddjob; uint32_t dd_nsub = 0; std::vector<DdBlock> c_ddb; uint64_t c_raw_total = 0;
@@ -138,17 +142,23 @@ inline int Decompressor::begin(const uint8_t* in, uint64_t n, uint8_t* out, uint
     return lz_prepare(c_dblk);
 }
 
+// dictionary_load(dicstr, 0) (src/cr-diccode.c:76-104): the word table the expansion kernel indexes
+inline int Decompressor::load_words(const char* text) {
+    const std::vector<std::string> entries = hd_entries(text);
+    std::vector<char> words(entries.size() * 24 + 24, 0); std::vector<uint8_t> lens(entries.size() + 1, 0);
+    for (size_t i = 0; i < entries.size(); i++) { lens[i] = (uint8_t)entries[i].size(); memcpy(&words[i * 24], entries[i].data(), entries[i].size() < 24 ? entries[i].size() : 24); }
+    CR_TRY(chain->upload(d_words, words)); CR_TRY(chain->upload(d_lens, lens));
+    c_dic = DdDict{ d_words.as<char>(), d_lens.as<uint8_t>(), (int32_t)entries.size(), HD_LEVEL1((int)entries.size()) };
+    return CRGPU_OK;
+}
+
 inline int Decompressor::middle() {
     CR_TRY(lz_finish());
     std::vector<uint8_t> lcp;
     CR_TRY(chain->download(lcp, d_D.p, c_dblk[0].d_size));
     CR_TRY(chain->reset_models());
     const std::string text = hd_lcp_decode(lcp.data(), lcp.size());
-    const std::vector<std::string> entries = hd_entries(text.c_str());
-    std::vector<char> words(entries.size() * 24 + 24, 0); std::vector<uint8_t> lens(entries.size() + 1, 0);
-    for (size_t i = 0; i < entries.size(); i++) { lens[i] = (uint8_t)entries[i].size(); memcpy(&words[i * 24], entries[i].data(), entries[i].size() < 24 ? entries[i].size() : 24); }
-    CR_TRY(chain->upload(d_words, words)); CR_TRY(chain->upload(d_lens, lens));
-    c_dic = DdDict{ d_words.as<char>(), d_lens.as<uint8_t>(), (int32_t)entries.size(), HD_LEVEL1((int)entries.size()) };
+    CR_TRY(load_words(text.c_str()));
     // ---- data blocks (src/main.c:263-292)
     job.nb = 0;
     if (!c_blk.empty()) CR_TRY(lz_prepare(c_blk));
@@ -156,12 +166,15 @@ inline int Decompressor::middle() {
 }
 
 inline int Decompressor::finish_layout() {
+    if (!c_blk.empty()) CR_TRY(lz_finish());
+    return layout();
+}
+
+// dictionary_decode of the blocks described by c_blk (their dictionary-coded bytes sit in d_D): pair framing -> sub-chunks
+inline int Decompressor::layout() {
     std::vector<DecBlock>& blk = c_blk;
-    uint8_t* out = c_out;
-    if (!blk.empty()) CR_TRY(lz_finish());
     // ---- dictionary_decode
     const DdDict dic = c_dic;
-    const std::vector<uint8_t>& filt_flags = c_filt;
     const uint64_t out_cap = c_out_cap;
     const uint32_t nb = (uint32_t)blk.size();
     std::vector<DdBlock> ddb(nb);
@@ -218,5 +231,39 @@ inline int Decompressor::finish_output() {
     CR_CUDA(cudaMemcpyAsync(out, d_out.p, raw_total, cudaMemcpyDeviceToHost, stream));
     CR_CUDA(cudaStreamSynchronize(stream));
     *c_out_n = raw_total;
+    return CRGPU_OK;
+}
+
+// ------------------------------------------------------------------ stage-level forms (one block per call, like the reference)
+// lzdecode(ib, ob) (src/rolzmain/cr-coder.c:287-379, src/ropmain/cr-coder.c:231-292, src/roxmain/cr-coder.c:321-526): models and
+// the PPM context carry over from the previous call of this handle until reset_models().
+inline int Decompressor::lzdecode_block(const uint8_t* in, uint32_t n, uint8_t* out, uint64_t out_cap, uint32_t* out_n) {
+    stream = chain->stream;
+    c_in = in; c_n = n;
+    CR_TRY(d_cont.reserve((size_t)n + 64));
+    if (n) CR_CUDA(cudaMemcpyAsync(d_cont.p, in, n, cudaMemcpyHostToDevice, stream));
+    std::vector<DecBlock> blk(1);
+    CR_TRY(describe(0, n, 0, 0, blk[0]));
+    if (blk[0].d_size > out_cap) return CRGPU_ERR_ARG;
+    CR_TRY(d_D.reserve((size_t)blk[0].d_size + 64));
+    CR_TRY(lz_prepare(blk)); CR_TRY(lz_launch()); CR_TRY(lz_finish());
+    if (blk[0].d_size) CR_CUDA(cudaMemcpyAsync(out, d_D.p, blk[0].d_size, cudaMemcpyDeviceToHost, stream));
+    CR_CUDA(cudaStreamSynchronize(stream));
+    *out_n = blk[0].d_size;
+    return CRGPU_OK;
+}
+
+// dictionary_decode(ib, ob, NULL) (src/cr-diccode.c:223-283) of one block; needs load_words() first.
+inline int Decompressor::dict_decode_block(const uint8_t* in, uint32_t n, uint8_t* out, uint64_t out_cap, uint32_t* out_n) {
+    stream = chain->stream;
+    if (n == 0 || !d_words.p) return CRGPU_ERR_ARG;          // the reference reads ib->m_data[size - 1]: an empty block is not a valid input
+    CR_TRY(d_D.reserve((size_t)n + 64));
+    CR_CUDA(cudaMemcpyAsync(d_D.p, in, n, cudaMemcpyHostToDevice, stream));
+    c_blk.assign(1, DecBlock()); memset(&c_blk[0], 0, sizeof(DecBlock)); c_blk[0].d_size = n;
+    c_filt.assign(1, 0);
+    uint64_t raw_n = 0;
+    c_out = out; c_out_cap = out_cap; c_out_n = &raw_n;
+    CR_TRY(layout()); CR_TRY(dd_launch()); CR_TRY(finish_output());
+    *out_n = (uint32_t)raw_n;
     return CRGPU_OK;
 }

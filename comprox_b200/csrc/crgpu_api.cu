@@ -19,6 +19,7 @@ struct crgpu_handle {
     DevBuf d_in, d_out;
     Compressor comp;
     Decompressor decomp;
+    FilterHost stage_filt;          // continuation state of crgpu_filter_inplace (the reference's function-local statics)
     bool owns_stream = false;
 };
 
@@ -70,7 +71,7 @@ extern "C" void crgpu_destroy(crgpu_handle* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
 #endif
-    h->chain.release(); h->d_in.release(); h->d_out.release(); h->comp.release(); h->decomp.release();
+    h->chain.release(); h->d_in.release(); h->d_out.release(); h->comp.release(); h->decomp.release(); h->stage_filt.release();
 #ifndef CRGPU_SIM
     if (h->owns_stream) cudaStreamDestroy(h->stream);
 #endif
@@ -189,6 +190,7 @@ extern "C" int crgpu_set_option(crgpu_handle* h, const char* name, int64_t value
     if (n == "rc_variant") { if (value < 1 || value > 6) return CRGPU_ERR_ARG; h->chain.rc_variant = (int)value; return CRGPU_OK; }
     if (n == "hot_contexts") { h->chain.hot_contexts = value != 0; return CRGPU_OK; }
     if (n == "match_limit") { if (value < 1 || value > 1000000) return CRGPU_ERR_ARG; h->chain.match_limit = (uint32_t)value; return CRGPU_OK; }   // comprox -m
+    if (n == "flexible") { h->chain.flexible = value != 0; return CRGPU_OK; }                    // -f: the reference's global flexible_parsing
     if (n == "lz77_max_iter") { if (value < 0) return CRGPU_ERR_ARG; h->chain.x_max_iter = (uint32_t)value; return CRGPU_OK; }
     return CRGPU_ERR_ARG;
 }
@@ -294,4 +296,102 @@ extern "C" int crgpu_dicpick(crgpu_handle* h, const uint8_t* in, uint64_t n, uin
     memcpy(out, text.data(), text.size());
     *out_n = text.size();
     return CRGPU_OK;
+}
+
+// ------------------------------------------------------------------ stage-level entry points: one block per call, with the
+// argument meaning of the reference's cr-* functions.  host/cr_shim.c wraps them into the reference's
+// own signatures so that the UNMODIFIED src/main.c links against this library.
+#ifndef CRGPU_SIM
+#define CR_SET_DEVICE(h) CR_CUDA(cudaSetDevice((h)->device))
+#else
+#define CR_SET_DEVICE(h) do { } while (0)
+#endif
+
+// filter_inplace(buf, len, en_de) -- src/cr-filter.c:33-73
+extern "C" int crgpu_filter_inplace(crgpu_handle* h, uint8_t* buf, uint32_t len, int en_de) {
+    if (!h || (len && !buf) || (en_de != 0 && en_de != 1)) return CRGPU_ERR_ARG;
+    if (len == 0) return 0;
+    CR_SET_DEVICE(h);
+    cudaStream_t stream = h->chain.stream;
+    CR_TRY(h->d_in.reserve((size_t)len + 256));
+    CR_CUDA(cudaMemcpyAsync(h->d_in.p, buf, len, cudaMemcpyHostToDevice, stream));
+    CR_CUDA(cudaMemsetAsync(h->d_in.as<uint8_t>() + len, 0, 128, stream));
+    std::vector<uint64_t> roff(1, 0); std::vector<uint32_t> rsize(1, len); std::vector<uint8_t> flags(1, 0);
+    int fired = 0;
+    CR_TRY(h->stage_filt.run_window(h->chain, buf, h->d_in.as<uint8_t>(), len, roff, rsize, flags, fired, en_de));
+    if (flags[0]) CR_CUDA(cudaMemcpyAsync(buf, h->d_in.p, len, cudaMemcpyDeviceToHost, stream));
+    CR_CUDA(cudaStreamSynchronize(stream));
+    return flags[0] ? 1 : 0;
+}
+
+// dic_lcp_encode / dic_lcp_decode -- src/cr-dicpick.c:261-346.  Host only: the dictionary text is at most a few hundred KB.
+extern "C" int crgpu_dic_lcp_encode(const uint8_t* text, uint64_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_n) {
+    if (!text || !out || !out_n || n == 0 || text[n - 1] != 0) return CRGPU_ERR_ARG;        // NUL-terminated, as dicpick leaves it
+    const std::vector<uint8_t> enc = hd_lcp_encode(std::string((const char*)text, n - 1));
+    if (enc.size() > out_cap) return CRGPU_ERR_ARG;
+    memcpy(out, enc.data(), enc.size());
+    *out_n = enc.size();
+    return CRGPU_OK;
+}
+extern "C" int crgpu_dic_lcp_decode(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_n) {
+    if ((n && !in) || !out || !out_n) return CRGPU_ERR_ARG;
+    const std::string text = hd_lcp_decode(in, n);
+    if (text.size() + 1 > out_cap) return CRGPU_ERR_ARG;
+    memcpy(out, text.c_str(), text.size() + 1);
+    *out_n = text.size() + 1;
+    return CRGPU_OK;
+}
+
+// dictionary_load(dicstr, init_trie) -- src/cr-diccode.c:76-120.  Returns the number of dictionary entries (>= 0) or an error.
+extern "C" int crgpu_dictionary_load(crgpu_handle* h, const char* dicstr, int init_trie) {
+    if (!h || !dicstr) return CRGPU_ERR_ARG;
+    CR_SET_DEVICE(h);
+    h->comp.chain = &h->chain; h->comp.stream = h->chain.stream;
+    h->decomp.chain = &h->chain; h->decomp.stream = h->chain.stream;
+    if (init_trie) CR_TRY(h->comp.load_dictionary(std::string(dicstr)));
+    CR_TRY(h->decomp.load_words(dicstr));
+    return h->decomp.c_dic.nentries;
+}
+
+// dictionary_encode(ib, ob) -- src/cr-diccode.c:142-221
+extern "C" int crgpu_dictionary_encode(crgpu_handle* h, const uint8_t* in, uint32_t n, uint8_t* out, uint64_t out_cap, uint32_t* out_n) {
+    if (!h || (n && !in) || !out || !out_n) return CRGPU_ERR_ARG;
+    if (!h->comp.d_trie_key.p) return CRGPU_ERR_ARG;                                         // crgpu_dictionary_load(.., 1) first
+    CR_SET_DEVICE(h);
+    h->comp.chain = &h->chain; h->comp.stream = h->chain.stream;
+    CR_TRY(h->comp.stage(in, n));
+    h->comp.staged_ptr = nullptr;
+    std::vector<uint64_t> roff(1, 0); std::vector<uint32_t> rsize(1, n); std::vector<BlockIO> blk; size_t dtotal = 0;
+    CR_TRY(h->comp.dict_encode_window(h->comp.d_raw.as<uint8_t>(), roff, rsize, blk, dtotal));
+    if (blk[0].size > out_cap) return CRGPU_ERR_ARG;
+    CR_CUDA(cudaMemcpyAsync(out, h->comp.d_D.as<uint8_t>() + blk[0].off, blk[0].size, cudaMemcpyDeviceToHost, h->chain.stream));
+    CR_CUDA(cudaStreamSynchronize(h->chain.stream));
+    *out_n = blk[0].size;
+    return CRGPU_OK;
+}
+
+// dictionary_decode(ib, ob, NULL) -- src/cr-diccode.c:223-283
+extern "C" int crgpu_dictionary_decode(crgpu_handle* h, const uint8_t* in, uint32_t n, uint8_t* out, uint64_t out_cap, uint32_t* out_n) {
+    if (!h || !in || !out_n || (out_cap && !out)) return CRGPU_ERR_ARG;
+    CR_SET_DEVICE(h);
+    h->decomp.chain = &h->chain;
+    return h->decomp.dict_decode_block(in, n, out, out_cap, out_n);
+}
+
+// lzdecode(ib, ob, print) -- src/main.c:59
+extern "C" int crgpu_lzdecode(crgpu_handle* h, const uint8_t* in, uint32_t n, uint8_t* out, uint64_t out_cap, uint32_t* out_n) {
+    if (!h || !in || !out_n || (out_cap && !out)) return CRGPU_ERR_ARG;
+    CR_SET_DEVICE(h);
+    h->decomp.chain = &h->chain;
+    return h->decomp.lzdecode_block(in, n, out, out_cap, out_n);
+}
+
+// size of the block an lzencode payload decodes to (the inner headers, src/rolzmain/cr-coder.c:63-71 etc.), so callers can size `out`
+extern "C" int64_t crgpu_lzdecode_size(int variant, const uint8_t* in, uint32_t n) {
+    const uint32_t hdr = variant == CRGPU_ROLZ ? 16 : variant == CRGPU_LZP ? 20 : variant == CRGPU_LZ77 ? 32 : 0;
+    if (!hdr || !in || n < hdr) return CRGPU_ERR_ARG;
+    const int compressed = variant == CRGPU_ROLZ ? in[1] : in[0];
+    if (!compressed) return (int64_t)n - hdr;
+    uint32_t sz; memcpy(&sz, in + 4, 4);
+    return sz;
 }

@@ -93,6 +93,43 @@ int crgpu_decompress(crgpu_handle* h, const uint8_t* in, uint64_t n, uint8_t* ou
 int crgpu_decompress_batch(crgpu_handle* const* hs, uint32_t count, const uint8_t* const* ins, const uint64_t* in_lens,
                            uint8_t* const* outs, const uint64_t* out_caps, uint64_t* out_lens);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Stage-level entry points: ONE block per call, argument meaning of the reference's cr-* functions.
+ * The handle carries what the reference keeps in statics between calls (filter continuation state, dictionary trie and
+ * word table, adaptive models + PPM context).  comprox_b200/host/cr_shim.c wraps them into the reference's own
+ * signatures (data_block_t, void returns), so that the UNMODIFIED src/main.c links against this library.  The
+ * whole-container calls above are the fast path: per-block calls are exact but expose one block of parallelism.
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* filter_inplace(buf, len, en_de)  -- src/cr-filter.h:38, src/cr-filter.c:33-73.  In place on HOST memory;
+ * en_de: 0 = FILTER_ENC, 1 = FILTER_DEC.  Returns 1 if a filter fired (-> block header m_filt), 0 if not, < 0 on error.
+ * An image may straddle calls, exactly as it straddles blocks in the reference. */
+int crgpu_filter_inplace(crgpu_handle* h, uint8_t* buf, uint32_t len, int en_de);
+
+/* dic_lcp_encode / dic_lcp_decode  -- src/cr-dicpick.h:41-42, src/cr-dicpick.c:261-346.  Front coding of the dictionary
+ * text; host-side (the text is a few hundred KB at most), no handle needed.  `text` includes its final NUL, as dicpick
+ * leaves it; the decoder returns the text with the NUL. */
+int crgpu_dic_lcp_encode(const uint8_t* text, uint64_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_n);
+int crgpu_dic_lcp_decode(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_n);
+
+/* dictionary_load(dicstr, init_trie)  -- src/cr-diccode.h:44, src/cr-diccode.c:76-120.  init_trie = 1 before encoding
+ * (builds and uploads the trie), 0 before decoding.  Returns the number of dictionary words, or < 0. */
+int crgpu_dictionary_load(crgpu_handle* h, const char* dicstr, int init_trie);
+
+/* dictionary_encode(ib, ob)  -- src/cr-diccode.h:46, src/cr-diccode.c:142-221,285-362: escape selection, 1 000 000-byte
+ * sub-chunk pairs, framing, "raw + 0" when not smaller.  out_cap >= n + 1. */
+int crgpu_dictionary_encode(crgpu_handle* h, const uint8_t* in, uint32_t n, uint8_t* out, uint64_t out_cap, uint32_t* out_n);
+
+/* dictionary_decode(ib, ob, NULL)  -- src/cr-diccode.h:48, src/cr-diccode.c:223-283,364-425.  Returns CRGPU_ERR_ARG if
+ * out_cap is too small (the decoded size is only known after the framing has been walked). */
+int crgpu_dictionary_decode(crgpu_handle* h, const uint8_t* in, uint32_t n, uint8_t* out, uint64_t out_cap, uint32_t* out_n);
+
+/* lzdecode(ib, ob, print)  -- src/main.c:59, src/rolzmain/cr-coder.c:287-379, src/ropmain/cr-coder.c:231-292,
+ * src/roxmain/cr-coder.c:321-526.  One payload per call; models carry over from call to call until
+ * crgpu_reset_models().  crgpu_lzdecode_size() reads the decoded size from the payload's inner header. */
+int crgpu_lzdecode(crgpu_handle* h, const uint8_t* in, uint32_t n, uint8_t* out, uint64_t out_cap, uint32_t* out_n);
+int64_t crgpu_lzdecode_size(int variant, const uint8_t* in, uint32_t n);
+
 /* Copies `in` to HBM ahead of time.  A following crgpu_compress(h, cfg, in, n, ...) with the same pointer and
  * length (and no -F, which rewrites the staged bytes in place) then skips its host-to-device copy; used by
  * bench.py to time the device-resident path separately from the end-to-end path. */
@@ -114,7 +151,9 @@ int crgpu_debug_sort(crgpu_handle* h, const void* keys, const uint32_t* vals, ui
                      void* keys_out, uint32_t* vals_out);
 
 /* Tuning / test switches.  "scalar_models" = 1 runs the scalar model and coder kernels (the ones the CPU
- * kernel-logic simulation checks) instead of the warp-cooperative ones; results are identical. */
+ * kernel-logic simulation checks) instead of the warp-cooperative ones; results are identical.
+ * "flexible" = the reference's global flexible_parsing (-f) for crgpu_lzencode (crgpu_compress takes it from its
+ * config); "match_limit" = comprox -m. */
 int crgpu_set_option(crgpu_handle* h, const char* name, int64_t value);
 
 /* Stage timing (CUDA events on the handle's stream, accumulated over calls until reset).

@@ -128,6 +128,16 @@ class Oracle:
         self.L.cro_dictionary_encode(self.c, data, ctypes.c_uint32(len(data)), ctypes.byref(b))
         return _take(b)
 
+    def dictionary_decode(self, data):
+        b = Buf()
+        self.L.cro_dictionary_decode(self.c, data, ctypes.c_uint32(len(data)), ctypes.byref(b))
+        return _take(b)
+
+    def lzdecode(self, data):
+        b = Buf()
+        self.L.cro_lzdecode(self.c, data, ctypes.c_uint32(len(data)), ctypes.byref(b))
+        return _take(b)
+
     def lzencode(self, data):
         b = Buf()
         self.L.cro_lzencode(self.c, data, ctypes.c_uint32(len(data)), ctypes.byref(b))

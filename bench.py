@@ -26,6 +26,8 @@ MiB = 1 << 20
 WORKLOAD_BYTES = 100 * MiB
 BLOCK = 16 * MiB
 REF_SAMPLE = 32 * MiB          # bounded sample for the CPU arms (2 blocks; models still chain across them)
+SHARD_SAMPLE = 16 * MiB        # container size of the supplementary shard-mode legs (many independent containers side by side)
+SHARD_HANDLES = 8
 
 
 def peaks():
@@ -118,6 +120,39 @@ def time_reference(data, steps, warmup):
     return sec, cores, ("reference" if exe else "port")
 
 
+def time_reference_shards(data, nproc):
+    """Shard mode of the reference: `nproc` unmodified reference CLI processes side by side, one independent
+    container each (the same sample), wall time around all of them.  Returns aggregate MiB/s or None without the binary."""
+    exe = reference_binary()
+    if not exe or nproc < 2:
+        return None
+    tmp = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+    src = os.path.join(tmp, "crbench_%d.sin" % os.getpid())
+    with open(src, "wb") as f:
+        f.write(data)
+    outs = ["%s.%d.out" % (src, i) for i in range(nproc)]
+    try:
+        t0 = time.perf_counter()
+        ps = [subprocess.Popen([exe, "-q", "e", src, o]) for o in outs]
+        ok = all(p.wait() == 0 for p in ps)
+        dt = time.perf_counter() - t0
+    finally:
+        for p in [src] + outs:
+            if os.path.exists(p):
+                os.unlink(p)
+    return nproc * len(data) / MiB / dt if ok else None
+
+
+def shard_procs():
+    """How many reference processes the shard-mode leg runs: every host core, bounded by memory (~0.4 GB per process) and by 64."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        pass
+    return max(1, min(n, 64))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -126,6 +161,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--bytes", type=int, default=WORKLOAD_BYTES, help="workload size (default: the 100 MiB the metric is quoted on)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-shard-leg", action="store_true", help="skip the supplementary shard-mode legs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -144,11 +180,21 @@ def main():
         sec, cores, kind = time_reference(data, max(steps, 1), min(warmup, 1))
         v = len(data) / MiB / sec
         sample = "first %d MiB of the workload (2 blocks), unmodified reference CLI, files in /dev/shm" % (len(data) // MiB)
-        print(json.dumps({"impl": "reference", "metric": "compress_throughput", "value": round(v, 3), "unit": "MiB/s", "n_gpus": args.gpus,
-                          "steps": steps, "warmup": warmup, "ms_per_step": round(sec * 1e3, 1), "higher_is_better": True, "scaling": "weak",
-                          "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
-                          "cpu_baseline": {"value": round(v, 3), "unit": "MiB/s", "cores": cores, "kind": kind, "sample": sample},
-                          "e2e": {"value": round(v, 3), "unit": "MiB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        line = {"impl": "reference", "metric": "compress_throughput", "value": round(v, 3), "unit": "MiB/s", "n_gpus": args.gpus,
+                "steps": steps, "warmup": warmup, "ms_per_step": round(sec * 1e3, 1), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": round(v, 3), "unit": "MiB/s", "cores": cores, "kind": kind, "sample": sample,
+                                 "note": "one container = one serial model chain: the reference's threads are intra-block helpers (SURVEY.md F1), "
+                                         "so this workload cannot use more host cores than this"},
+                "e2e": {"value": round(v, 3), "unit": "MiB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        if not args.no_shard_leg:
+            # supplementary: what ALL host cores give when the job is many independent containers (not this line's workload)
+            P = shard_procs()
+            sv = time_reference_shards(data[:SHARD_SAMPLE], P)
+            if sv is not None:
+                line["shard_mode"] = {"value": round(sv, 2), "unit": "MiB/s", "processes": P, "host_cores": os.cpu_count(),
+                                      "sample": "%d independent containers of %d MiB, one unmodified reference CLI process each, side by side" % (P, SHARD_SAMPLE // MiB)}
+        print(json.dumps(line))
         return
 
     # ------------------------------------------------------------------ our arm (GPU)
@@ -286,6 +332,39 @@ def main():
                                     "roundtrip_ok": backs == parts}
     except Exception as e:
         line["decompress_batch"] = {"error": str(e)}
+    # supplementary: shard mode on ONE GPU -- independent containers compressed side by side by several handles with
+    # private streams, one host thread each; the serial range chains of different containers overlap on different SMs.  Wall clock
+    # around the C ABI calls (host buffers in and out), not part of `value`.
+    if not args.no_shard_leg:
+        try:
+            K, per, rounds = SHARD_HANDLES, SHARD_SAMPLE, 4
+            shards = [raw[k * 4096:k * 4096 + per] for k in range(K * rounds)]
+            hs = [api.Handle(api.ROLZ, device=local_rank, stream=api.OWN_STREAM) for _ in range(K)]
+            outs = [None] * len(shards)
+
+            def work(j):
+                for i in range(j, len(shards), K):
+                    outs[i] = hs[j].compress(shards[i], BLOCK)
+
+            def run_all():
+                th = [threading.Thread(target=work, args=(j,)) for j in range(K)]
+                t0 = time.perf_counter()
+                [t.start() for t in th]; [t.join() for t in th]
+                torch.cuda.synchronize()
+                return time.perf_counter() - t0
+            try:
+                run_all()                                   # allocations, first touch
+                dt = run_all()
+            finally:
+                for hh in hs:
+                    hh.close()
+            with api.Handle(api.ROLZ, device=local_rank, stream=stream.cuda_stream) as h1:
+                same = all(outs[i] == h1.compress(shards[i], BLOCK) for i in (0, len(shards) - 1))
+            line["shard_mode"] = {"value": round(len(shards) * per / MiB / dt, 1), "unit": "MiB/s", "handles": K, "containers": len(shards),
+                                  "sample": "%d independent containers of %d MiB, %d handles with private streams, host buffers, wall clock" % (len(shards), per // MiB, K),
+                                  "identical_to_single_handle": same}
+        except Exception as e:
+            line["shard_mode"] = {"error": str(e)}
     if not args.no_cpu_baseline and world == 1:
         sample = raw[:REF_SAMPLE]
         sec, cores, kind = time_reference(sample, 1, 0)

@@ -53,3 +53,18 @@ def test_product_library_does_not_link_the_oracle(lib):
     d = os.path.join(ROOT, "comprox_b200", "csrc")
     src = "".join(open(os.path.join(d, f)).read() for f in os.listdir(d) if os.path.isfile(os.path.join(d, f)))
     assert "cr_oracle" not in src and "liboracle" not in src
+
+
+@pytest.mark.parametrize("variant,extra", [("rolz", ["flexible_parsing"]), ("rop", []), ("rox", ["flexible_parsing", "match_limit"])])
+def test_shim_archives_define_the_reference_symbols(variant, extra):
+    """bin/libcrshim_*.a (comprox_b200/host/cr_shim.c) must define exactly what the reference's src/main.c and src/<variant>/main.c link
+    against (/root/reference/src/main.c:33-59, src/cr-datablock.h:43-46)."""
+    subprocess.run(["make", "-C", os.path.join(ROOT, "comprox_b200", "host")], check=True, capture_output=True)
+    out = subprocess.run(["nm", "--defined-only", os.path.join(ROOT, "bin", "libcrshim_%s.a" % variant)], capture_output=True, text=True).stdout
+    defined = {ln.split()[-1] for ln in out.splitlines() if len(ln.split()) == 3 and ln.split()[1] in "TDB"}
+    want = ["data_block_reserve", "data_block_resize", "data_block_add", "data_block_destroy", "filter_inplace", "dicpick", "dic_lcp_encode",
+            "dic_lcp_decode", "dictionary_load", "dictionary_encode", "dictionary_decode", "reset_models", "lzencode", "lzdecode", *extra]
+    for s in want:
+        assert s in defined, "libcrshim_%s.a does not define %s" % (variant, s)
+    undefined = subprocess.run(["nm", "-u", os.path.join(ROOT, "bin", "libcrshim_%s.a" % variant)], capture_output=True, text=True).stdout
+    assert "cro_" not in undefined and "cuda" not in undefined.lower()          # the shim reaches CUDA only through dlopen(libcrgpu.so)

@@ -26,7 +26,8 @@ MiB = 1 << 20
 WORKLOAD_BYTES = 100 * MiB
 BLOCK = 16 * MiB
 REF_SAMPLE = 32 * MiB          # bounded sample for the CPU arms (2 blocks; models still chain across them)
-SHARD_SAMPLE = 16 * MiB        # container size of the supplementary shard-mode legs (many independent containers side by side)
+SHARD_SAMPLE = 16 * MiB        # container size of the reference's supplementary shard-mode leg (one process per host core)
+SHARD_BYTES = 64 * MiB         # container size of our shard-mode leg (profiles/round1_shards_one_gpu.jsonl uses the same)
 SHARD_HANDLES = 8
 
 
@@ -334,20 +335,30 @@ def main():
         line["decompress_batch"] = {"error": str(e)}
     # supplementary: shard mode on ONE GPU -- independent containers compressed side by side by several handles with
     # private streams, one host thread each; the serial range chains of different containers overlap on different SMs.  Wall clock
-    # around the C ABI calls (host buffers in and out), not part of `value`.
+    # around the C ABI calls (pinned host buffers in and out, copies inside), not part of `value`.
     if not args.no_shard_leg:
         try:
-            K, per, rounds = SHARD_HANDLES, SHARD_SAMPLE, 4
-            shards = [raw[k * 4096:k * 4096 + per] for k in range(K * rounds)]
+            K, per, rounds = SHARD_HANDLES, SHARD_BYTES, 2
             hs = [api.Handle(api.ROLZ, device=local_rank, stream=api.OWN_STREAM) for _ in range(K)]
-            outs = [None] * len(shards)
+            scap = int(L.crgpu_compress_bound(ctypes.c_uint64(per), ctypes.c_uint32(BLOCK)))
+            ins, outs, lens = [], [], [ctypes.c_uint64() for _ in range(K)]
+            for j in range(K):                              # distinct containers: the workload's text from different offsets
+                t = torch.empty(per, dtype=torch.uint8).pin_memory()
+                off = (j * 4099 * 1021) % (n - per)
+                t.numpy()[:] = memoryview(raw)[off:off + per]
+                ins.append(t); outs.append(torch.empty(scap, dtype=torch.uint8).pin_memory())
+            errs = []
 
             def work(j):
-                for i in range(j, len(shards), K):
-                    outs[i] = hs[j].compress(shards[i], BLOCK)
+                for _ in range(rounds):
+                    rc = L.crgpu_compress(hs[j].h, ctypes.byref(cfg), ctypes.c_void_p(ins[j].data_ptr()), ctypes.c_uint64(per),
+                                          ctypes.c_void_p(outs[j].data_ptr()), ctypes.c_uint64(scap), ctypes.byref(lens[j]))
+                    if rc != 0:
+                        errs.append(rc)
 
             def run_all():
                 th = [threading.Thread(target=work, args=(j,)) for j in range(K)]
+                torch.cuda.synchronize()
                 t0 = time.perf_counter()
                 [t.start() for t in th]; [t.join() for t in th]
                 torch.cuda.synchronize()
@@ -358,10 +369,13 @@ def main():
             finally:
                 for hh in hs:
                     hh.close()
+            if errs:
+                raise RuntimeError("crgpu_compress failed in shard mode: %s" % errs[:3])
             with api.Handle(api.ROLZ, device=local_rank, stream=stream.cuda_stream) as h1:
-                same = all(outs[i] == h1.compress(shards[i], BLOCK) for i in (0, len(shards) - 1))
-            line["shard_mode"] = {"value": round(len(shards) * per / MiB / dt, 1), "unit": "MiB/s", "handles": K, "containers": len(shards),
-                                  "sample": "%d independent containers of %d MiB, %d handles with private streams, host buffers, wall clock" % (len(shards), per // MiB, K),
+                same = all(bytes(outs[j].numpy()[:lens[j].value]) == h1.compress(bytes(ins[j].numpy()), BLOCK) for j in (0, K - 1))
+            line["shard_mode"] = {"value": round(K * rounds * per / MiB / dt, 1), "unit": "MiB/s", "handles": K, "containers": K * rounds,
+                                  "sample": "%d independent containers of %d MiB, %d handles with private streams on %d host threads, pinned host buffers, wall clock"
+                                            % (K * rounds, per // MiB, K, K),
                                   "identical_to_single_handle": same}
         except Exception as e:
             line["shard_mode"] = {"error": str(e)}

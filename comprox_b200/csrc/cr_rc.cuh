@@ -65,7 +65,7 @@ struct RcStream {
     uint32_t out_cap;
     uint32_t pad;
 };
-struct RcResult { uint32_t nbytes; uint32_t aborted; };
+struct RcResult { uint32_t nbytes; uint32_t aborted; uint32_t abort_tri; uint32_t pad; };   // abort_tri: dense index of the token-end triple the abort was taken at
 
 struct RcCoder {
     uint32_t low, range, follow, carry, cache, n, cap;
@@ -92,7 +92,7 @@ __global__ void k_range_encode(const Tri* __restrict__ dense_main, const Tri* __
     if (S.is_main) { i0 += escord[S.ev_begin]; i1 += escord[S.ev_end]; }
     RcCoder c;
     c.low = 0; c.range = 0xFFFFFFFFu; c.follow = 0; c.carry = 0; c.cache = 0; c.n = 0; c.cap = S.out_cap; c.out = outbuf + S.out_off;
-    uint32_t aborted = 0;
+    uint32_t aborted = 0, abort_tri = 0;
     for (size_t i = i0; i < i1; i++) {
         const Tri t = tri[i];
         uint32_t q = __umulhi(c.range, t.magic);
@@ -103,11 +103,12 @@ __global__ void k_range_encode(const Tri* __restrict__ dense_main, const Tri* __
         c.low = nl;
         c.range = q * (t.frq & 0x7FFFFFFFu);
         while (c.range < (1u << 24)) { c.range <<= 8; c.shift_out(); }
-        if ((t.frq & TRI_TOKEND) && c.n >= S.limit) { aborted = 1; break; }     // cr-coder.c:231-233
+        if ((t.frq & TRI_TOKEND) && c.n >= S.limit) { aborted = 1; abort_tri = (uint32_t)i; break; }     // cr-coder.c:231-233
     }
     if (!aborted) for (int k = 0; k < 5; k++) c.shift_out();                    // range_encoder_flush
     res[s].nbytes = c.n;
     res[s].aborted = aborted;
+    res[s].abort_tri = abort_tri; res[s].pad = 0;
 }
 
 // ------------------------------------------------------------------ payload assembly

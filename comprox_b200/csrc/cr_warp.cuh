@@ -880,7 +880,7 @@ __global__ void __launch_bounds__(128) k_range_encode_warp(const Tri* __restrict
     if (S.is_main) { i0 += escord[S.ev_begin]; i1 += escord[S.ev_end]; }
     RcCoder c;
     c.low = 0; c.range = 0xFFFFFFFFu; c.follow = 0; c.carry = 0; c.cache = 0; c.n = 0; c.cap = S.out_cap; c.out = outbuf + S.out_off;
-    uint32_t aborted = 0;
+    uint32_t aborted = 0, abort_tri = 0;
     uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
     if (i0 + lane < i1) r0 = tri[i0 + lane];
     if (i0 + 32 + lane < i1) r1 = tri[i0 + 32 + lane];
@@ -905,7 +905,7 @@ __global__ void __launch_bounds__(128) k_range_encode_warp(const Tri* __restrict
                 c.low = nl;
                 c.range = q * (t.y & 0x7FFFFFFFu);
                 while (c.range < (1u << 24)) { c.range <<= 8; c.shift_out(); }
-                if ((t.y & TRI_TOKEND) && c.n >= S.limit) { aborted = 1; break; }
+                if ((t.y & TRI_TOKEND) && c.n >= S.limit) { aborted = 1; abort_tri = (uint32_t)(base + j); break; }
                 t = tn;
             }
         }
@@ -916,6 +916,7 @@ __global__ void __launch_bounds__(128) k_range_encode_warp(const Tri* __restrict
         if (!aborted) for (int k = 0; k < 5; k++) c.shift_out();
         res[s].nbytes = c.n;
         res[s].aborted = aborted;
+        res[s].abort_tri = abort_tri; res[s].pad = 0;
     }
 }
 

@@ -321,7 +321,7 @@ inline int Compressor::compress(const CrConfig& cfg, const uint8_t* in, uint64_t
     std::vector<BlockIO> dblk(1);
     memset(&dblk[0], 0, sizeof(BlockIO)); dblk[0].size = (uint32_t)lcp.size();
     size_t out_pos = 0, wrote = 0;
-    CR_TRY(chain->encode_window(d_dic.as<uint8_t>(), dblk, 0, true, d_out, out_pos, wrote));
+    CR_TRY(chain->encode_blocks(d_dic.as<uint8_t>(), dblk, 0, true, d_out, out_pos, wrote));
     out_pos += wrote;
     CR_TRY(chain->reset_models());
 
@@ -355,7 +355,7 @@ inline int Compressor::compress(const CrConfig& cfg, const uint8_t* in, uint64_t
         for (size_t i = 0; i < blk.size(); i++) { blk[i].filt = filt_flags[i]; blk[i].prec = (uint8_t)cfg.prec; }
         const bool last = b1 == nblocks;
         if (!cfg.prec) {
-            CR_TRY(chain->encode_window(d_D.as<uint8_t>(), blk, 1, last, d_out, out_pos, wrote));
+            CR_TRY(chain->encode_blocks(d_D.as<uint8_t>(), blk, 1, last, d_out, out_pos, wrote));
         } else {
             // -p: the dictionary-coded block is the payload (src/main.c:191-195)
             std::vector<HeaderDesc> hdrs; std::vector<CopyDesc> copies; size_t p = out_pos;

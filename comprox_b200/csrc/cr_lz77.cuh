@@ -47,7 +47,7 @@ __global__ void k_x_finish_blocks(const uint8_t* __restrict__ D, LzBlock* __rest
     for (uint32_t b = 0; b < nb; b++) {
         blocks[b].esc = esc1[b];
         blocks[b].cin = c;
-        c = x_ctx_at(D + blocks[b].off, blocks[b].size, c);
+        c = x_ctx_at(D + blocks[b].off, blocks[b].walk, c);
     }
     *ctx_out = c;
 }

@@ -27,6 +27,8 @@ struct BlockIO {
     uint64_t out_off;    // out: offset of prefix+payload in the output buffer
     uint32_t out_size;   // out: payload size (without prefix)
     uint32_t raw;        // out: 1 = stored ("cannot compress")
+    uint32_t cut;        // in: 0, or the position at which the reference's coder loop gives up on this block (encode_blocks sets it
+                         //     for the re-run after a mid-chain "cannot compress"): only tokens before it reach models and context
 };
 
 struct LzChain {
@@ -66,6 +68,8 @@ struct LzChain {
     int rc_variant = 4;            // range-chain formulation (cr_warp.cuh: k_range_chain<1|2|3>)
     bool hot_contexts = true;      // hot o2 contexts run the rank-based CTA kernel (k_o2_pass_cta)
     bool scalar_models = false;   // GPU A/B switch: run the scalar (simulation-checked) model/coder kernels
+    bool exact_aborts = true;      // replay a mid-chain "cannot compress" exactly (encode_blocks); false = CRGPU_ERR_MIDCHAIN_ABORT
+    DevBuf b_abort;
 
     int init(int variant_, cudaStream_t s) {
         variant = variant_; stream = s; prims.stream = s;
@@ -88,7 +92,8 @@ struct LzChain {
             &b_k0, &b_k1, &b_v0, &b_v1, &b_ks0, &b_M, &b_S, &b_span, &b_tidx, &b_segs, &b_xt, &b_entry, &b_cnt, &b_scan, &b_chainwork,
             &b_evctx, &b_evsym, &b_tokend, &b_pred, &b_T1, &b_T2, &b_TS, &b_side, &b_escrec, &b_esccount, &b_k64a, &b_k64b, &b_ord,
             &b_flag, &b_escord, &b_lensym, &b_lenpos, &b_idxsym, &b_idxpos, &b_hits, &b_o1info, &b_o1ord, &b_o1incl, &b_bounds, &b_o3hot, &b_cinm, &b_cins, &b_segstart, &b_segkey, &b_rank, &b_flexlen, &b_qm, &b_shm, &b_bm, &b_qs, &b_shs, &b_bs, &b_stot, &b_dsum, &b_lsm, &b_lss, &b_rsm, &b_rss, &b_fb, &b_dense, &b_denseside, &b_streams, &b_rcres, &b_rcout, &b_copy, &b_hdr,
-            &x_npos, &x_nlen, &x_sdist, &x_slen, &x_G, &x_tdist, &x_h16, &x_rank, &x_mpos0, &x_mlen0, &x_clast, &x_ckey, &x_cmax, &x_lastin, &x_mism, &x_msym, &x_mpos };
+            &x_npos, &x_nlen, &x_sdist, &x_slen, &x_G, &x_tdist, &x_h16, &x_rank, &x_mpos0, &x_mlen0, &x_clast, &x_ckey, &x_cmax, &x_lastin, &x_mism, &x_msym, &x_mpos,
+            &snap_o3b, &snap_o3c, &snap_o2, &snap_o1, &snap_m0, &b_abort };
         for (DevBuf* b : all) b->release();
         prims.release();
 #ifndef CRGPU_SIM
@@ -123,7 +128,51 @@ struct LzChain {
     // 1: [u32 payload_len, u8 filt, u8 prec] (data block header, src/main.c:199-204); 2: none.
     // chain_ends: no further block of this chain follows (an aborted last block is then harmless).
     int encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, int prefix_mode, bool chain_ends, DevBuf& out, size_t out_base, size_t& out_total);
+
+    // ---- exact handling of a mid-chain "cannot compress" (SURVEY.md F11).  The reference's coder loop gives up on a block as soon as
+    // the main stream is as large as the block (src/rolzmain/cr-coder.c:231-233, src/ropmain/cr-coder.c:204, src/roxmain/cr-coder.c:273)
+    // and stores it raw, but the models, the side models and the PPM context keep what the tokens BEFORE that point did to them, and the
+    // following blocks are coded on top of that.  encode_window() reports such a block (CR_RETRY_CUT + retry_block/retry_cut);
+    // encode_blocks() restores the model snapshot taken before the window, re-runs the window up to and including that block with the
+    // block's token walk cut at that position (BlockIO::cut), and carries on behind it.
+    enum { CR_RETRY_CUT = 1 };
+    DevBuf snap_o3b, snap_o3c, snap_o2, snap_o1, snap_m0;
+    uint32_t snap_ctx = 0, retry_block = 0, retry_cut = 0;
+    uint32_t cut_blocks = 0;         // statistics: blocks re-run with a cut since the handle was created
+    int copy_state(bool save) {
+        DevBuf* live[] = { &s_o3b, &s_o3c, &s_o2, &s_o1, &s_m0 }; DevBuf* snap[] = { &snap_o3b, &snap_o3c, &snap_o2, &snap_o1, &snap_m0 };
+        const size_t bytes[] = { (size_t)PPM_O3_SLOTS, (size_t)PPM_O3_SLOTS, (size_t)65536 * PPM_O2_STRIDE, 65536, (size_t)X_NMODEL * 256 * 2 };
+        for (int k = 0; k < 5; k++) {
+            CR_TRY(snap[k]->reserve(bytes[k]));
+            CR_CUDA(cudaMemcpyAsync(save ? snap[k]->p : live[k]->p, save ? live[k]->p : snap[k]->p, bytes[k], cudaMemcpyDeviceToDevice, stream));
+        }
+        if (save) snap_ctx = chain_ctx; else chain_ctx = snap_ctx;
+        return CRGPU_OK;
+    }
+    int encode_blocks(const uint8_t* dD, std::vector<BlockIO>& blk, int prefix_mode, bool chain_ends, DevBuf& out, size_t out_base, size_t& out_total);
 };
+
+// Abort path only: the token whose last event is `event` ends at position t + len of block `block`.  Events per token as in the
+// Count functors: ROLZ and LZ77 one, LZP two for a match and one (two if the literal equals the escape byte) for a literal.
+struct AbortPos {
+    typedef struct { uint32_t ev; } State;
+    const uint8_t* D; const LzBlock* blocks; const uint32_t* scan_ev; int variant; uint32_t block, event; uint32_t* out;
+    CR_D State begin(uint32_t c, uint32_t) const { State s = { scan_ev[c] }; return s; }
+    CR_D void visit(State& s, uint32_t b, uint32_t t, uint32_t len) const {
+        uint32_t n = 1;
+        if (variant == CR_LZP) { const LzBlock B = blocks[b]; n = len > 1 ? 2 : 1 + (D[B.off + t] == B.esc); }
+        if (b == block && event >= s.ev && event < s.ev + n) *out = t + len;
+        s.ev += n;
+    }
+    CR_D void end(State&, uint32_t, uint32_t) const {}
+};
+// the event a dense main-stream triple belongs to: the largest e in [ev_begin, ev_end) with e + escord[e] <= dense_idx
+__global__ void k_abort_event(const uint32_t* __restrict__ escord, uint32_t ev_begin, uint32_t ev_end, uint32_t dense_idx, uint32_t* __restrict__ out) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    uint32_t lo = ev_begin, hi = ev_end;
+    while (hi - lo > 1) { const uint32_t mid = lo + (hi - lo) / 2; if (mid + escord[mid] <= dense_idx) lo = mid; else hi = mid; }
+    out[0] = lo; out[1] = 0;
+}
 
 __global__ void k_first_bytes(const uint8_t* __restrict__ D, const LzBlock* __restrict__ blocks, uint32_t nb, uint8_t* __restrict__ first) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -139,7 +188,7 @@ __global__ void k_rolz_finish_blocks(const uint8_t* __restrict__ D, LzBlock* __r
     for (uint32_t b = 0; b < nb; b++) {
         blocks[b].esc = esc1[b];
         blocks[b].cin = c;
-        c = rz_ctx_at(D + blocks[b].off, blocks[b].size, c);
+        c = rz_ctx_at(D + blocks[b].off, blocks[b].walk, c);
     }
     *ctx_out = c;
 }
@@ -163,6 +212,7 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
     for (uint32_t b = 0; b < nb; b++) {
         memset(&hb[b], 0, sizeof(LzBlock));
         hb[b].off = blk[b].off; hb[b].size = blk[b].size; hb[b].eoff = nent;
+        hb[b].walk = blk[b].cut ? blk[b].cut : blk[b].size;
         hb[b].ctx4 = blk[b].size >= 4194304;
         uint32_t first_entry = variant == CR_ROLZ ? 16 : LZP_FIRST;
         if (variant == CR_LZP && blk[b].size < 16) first_entry = blk[b].size;      // stored without coding (src/ropmain/cr-coder.c:140)
@@ -249,7 +299,7 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
     // ---- resolve the parse (cr_chain.cuh)
     std::vector<ChainSeg> segs(nb);
     for (uint32_t b = 0; b < nb; b++) {
-        segs[b].off = blk[b].off; segs[b].len = blk[b].size;
+        segs[b].off = blk[b].off; segs[b].len = hb[b].walk;
         segs[b].start = variant == CR_ROLZ ? 1 : variant == CR_LZ77 ? 0 : (blk[b].size < 16 ? blk[b].size : LZP_FIRST);
     }
     for (uint32_t b = 0; b < nb; b++) if (segs[b].start > 255) { segs[b].len = 0; segs[b].start = 0; }   // tiny stored LZP block: nothing to walk
@@ -627,13 +677,29 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
     // ---- payload layout + headers (src/rolzmain/cr-coder.c:241-262, src/ropmain/cr-coder.c:212-228)
     std::vector<CopyDesc> copies; std::vector<HeaderDesc> hdrs(nb);
     size_t pos = out_base;
+    // a block the coder gave up on while more blocks of the chain follow: report where, for the exact re-run (encode_blocks)
     for (uint32_t b = 0; b < nb; b++) {
         const RcStream& m = streams[(size_t)b * spb]; const RcResult& rm = res[(size_t)b * spb];
-        const bool stored = rm.aborted || (variant == CR_LZP && blk[b].size < 16);
-        if (rm.aborted && !(chain_ends && b == nb - 1)) {
+        if (!rm.aborted || blk[b].cut || (chain_ends && b == nb - 1)) continue;
+        if (!exact_aborts) {
             fprintf(stderr, "crgpu: block %u of %u hit 'cannot compress' in the middle of a model chain (SURVEY.md F11)\n", b, nb);
             return CRGPU_ERR_MIDCHAIN_ABORT;
         }
+        std::vector<uint32_t> got;
+        CR_TRY(b_abort.reserve(16));
+        CR_LAUNCH(k_abort_event, dim3(1), dim3(1), stream, b_escord.as<uint32_t>(), m.ev_begin, m.ev_end, rm.abort_tri, b_abort.as<uint32_t>());
+        CR_TRY(download(got, b_abort.p, 1));
+        AbortPos f = { dD, d_blocks, scan, variant, b, got[0], b_abort.as<uint32_t>() + 1 };
+        CR_LAUNCH(k_chain_walk<AbortPos>, dim3(cr_div_up(nchunk, 64)), dim3(64), stream, b_span.as<uint8_t>(), d_segs, nb, nchunk, b_entry.as<uint8_t>(), f);
+        CR_TRY(download(got, b_abort.p, 2));
+        if (got[1] == 0 || got[1] > blk[b].size) { fprintf(stderr, "crgpu: internal error: no abort position for block %u (event %u)\n", b, got[0]); return CRGPU_ERR_MIDCHAIN_ABORT; }
+        retry_block = b; retry_cut = got[1];
+        timer.finish();
+        return CR_RETRY_CUT;
+    }
+    for (uint32_t b = 0; b < nb; b++) {
+        const RcStream& m = streams[(size_t)b * spb]; const RcResult& rm = res[(size_t)b * spb];
+        const bool stored = rm.aborted || blk[b].cut || (variant == CR_LZP && blk[b].size < 16);
         HeaderDesc& h = hdrs[b];
         memset(&h, 0, sizeof h);
         uint8_t* hp = h.bytes + prefix;
@@ -683,5 +749,41 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
     timer.mark("assemble");
     CR_CUDA(cudaStreamSynchronize(stream));
     timer.finish();
+    return CRGPU_OK;
+}
+
+// encode_window with the exact replay of mid-chain "cannot compress" blocks (see the comment in LzChain).  Same contract as
+// encode_window; the blocks may end up being encoded in several consecutive sub-windows, which changes no output byte.
+inline int LzChain::encode_blocks(const uint8_t* dD, std::vector<BlockIO>& blk, int prefix_mode, bool chain_ends, DevBuf& out, size_t out_base, size_t& out_total) {
+    const size_t nb = blk.size();
+    out_total = 0;
+    if (nb == 0) return CRGPU_OK;
+    if (!exact_aborts || (nb == 1 && chain_ends)) return encode_window(dD, blk, prefix_mode, chain_ends, out, out_base, out_total);
+    size_t done = 0, take = nb;
+    while (done < nb) {
+        if (take > nb - done) take = nb - done;
+        const bool tail = done + take == nb;
+        std::vector<BlockIO> sub(blk.begin() + done, blk.begin() + done + take);
+        size_t wrote = 0;
+        CR_TRY(copy_state(true));
+        int rc = encode_window(dD, sub, prefix_mode, chain_ends && tail, out, out_base + out_total, wrote);
+        if (rc == CRGPU_OK) {
+            std::copy(sub.begin(), sub.end(), blk.begin() + done);
+            out_total += wrote; done += take;
+            take = take * 2;                                  // grow again after a window without incident
+            continue;
+        }
+        if (rc != CR_RETRY_CUT) return rc;
+        // blocks [done, done + retry_block) are fine, block done + retry_block is stored and leaves the models where its cut says
+        const uint32_t rb = retry_block;
+        CR_TRY(copy_state(false));
+        std::vector<BlockIO> head(blk.begin() + done, blk.begin() + done + rb + 1);
+        head[rb].cut = retry_cut;
+        rc = encode_window(dD, head, prefix_mode, false, out, out_base + out_total, wrote);
+        if (rc != CRGPU_OK) return rc == CR_RETRY_CUT ? CRGPU_ERR_MIDCHAIN_ABORT : rc;
+        std::copy(head.begin(), head.end(), blk.begin() + done);
+        out_total += wrote; done += rb + 1; cut_blocks++;
+        take = 1;                                             // incompressible blocks come in runs: probe one block at a time
+    }
     return CRGPU_OK;
 }

@@ -31,6 +31,8 @@ struct LzBlock {
     uint8_t  esc;       // rarest byte of the block
     uint8_t  ctx4;      // size >= 4 MiB -> 4-byte context hash (src/rolzmain/cr-coder.c:162)
     uint8_t  pad[2];
+    uint32_t walk;      // bytes the coder loop consumed: == size, or the position at which the reference gave up on the block
+    uint32_t pad2;      //   ("cannot compress", src/rolzmain/cr-coder.c:231-233): models and context only saw tokens before it
 };
 
 CR_HD uint32_t rz_hash(const uint8_t* x, int ctx4) {           // src/rolzmain/cr-matcher.c:38-42

@@ -106,7 +106,7 @@ extern "C" int crgpu_lzencode(crgpu_handle* h, const uint8_t* in, const uint32_t
             src += sizes[b];
         }
         size_t out_total = 0;
-        CR_TRY(h->chain.encode_window(h->d_in.as<uint8_t>(), blk, 2, chain_ends != 0 && b1 == nblocks, h->d_out, 0, out_total));
+        CR_TRY(h->chain.encode_blocks(h->d_in.as<uint8_t>(), blk, 2, chain_ends != 0 && b1 == nblocks, h->d_out, 0, out_total));
         if (written + out_total > out_cap) return CRGPU_ERR_ARG;
         CR_CUDA(cudaMemcpyAsync(out + written, h->d_out.p, out_total, cudaMemcpyDeviceToHost, h->stream));
         CR_CUDA(cudaStreamSynchronize(h->stream));
@@ -190,6 +190,7 @@ extern "C" int crgpu_set_option(crgpu_handle* h, const char* name, int64_t value
     if (n == "rc_variant") { if (value < 1 || value > 6) return CRGPU_ERR_ARG; h->chain.rc_variant = (int)value; return CRGPU_OK; }
     if (n == "hot_contexts") { h->chain.hot_contexts = value != 0; return CRGPU_OK; }
     if (n == "match_limit") { if (value < 1 || value > 1000000) return CRGPU_ERR_ARG; h->chain.match_limit = (uint32_t)value; return CRGPU_OK; }   // comprox -m
+    if (n == "exact_aborts") { h->chain.exact_aborts = value != 0; return CRGPU_OK; }             // 0: mid-chain "cannot compress" -> CRGPU_ERR_MIDCHAIN_ABORT
     if (n == "flexible") { h->chain.flexible = value != 0; return CRGPU_OK; }                    // -f: the reference's global flexible_parsing
     if (n == "lz77_max_iter") { if (value < 0) return CRGPU_ERR_ARG; h->chain.x_max_iter = (uint32_t)value; return CRGPU_OK; }
     return CRGPU_ERR_ARG;

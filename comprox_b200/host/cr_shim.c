@@ -78,7 +78,6 @@ static struct {
     int (*filter_inplace)(crgpu_handle*, uint8_t*, uint32_t, int);
     int (*set_option)(crgpu_handle*, const char*, int64_t);
     crgpu_handle* h;
-    int aborted;        /* the previous lzencode hit "cannot compress": harmless only if reset_models() comes next */
 } G;
 
 static void die(const char* what, int rc) {
@@ -198,17 +197,11 @@ void dictionary_decode(data_block_t* ib, data_block_t* ob, FILE* fpout_sync) {
 void reset_models(void) {
     int rc = (handle(), G.reset_models(G.h));
     if (rc) die("reset_models", rc);
-    G.aborted = 0;
 }
 
 void lzencode(data_block_t* ib, data_block_t* ob, int print_information) {
     handle();
     (void)print_information;
-    if (G.aborted) {
-        fprintf(stderr, "cr_shim: the previous block could not be compressed and more blocks of the same model chain follow; the "
-                        "reference desyncs its own decoder here (SURVEY.md F11)\n");
-        abort();
-    }
     int rc;
 #if CR_VARIANT != 1
     if ((rc = G.set_option(G.h, "flexible", flexible_parsing)) != 0) die("set_option(flexible)", rc);
@@ -218,12 +211,12 @@ void lzencode(data_block_t* ib, data_block_t* ob, int print_information) {
 #endif
     uint32_t n = 0;
     data_block_resize(ob, ib->m_size + 64);                     /* payload <= inner header + input */
-    rc = G.lzencode(G.h, ib->m_data, &ib->m_size, 1, /*chain_ends=*/1, ob->m_data, ob->m_capacity, &n);
+    /* chain_ends = 0: more blocks of this model chain may follow, so a block that hits "cannot compress"
+       (src/rolzmain/cr-coder.c:231-233) must leave the models exactly where the reference's aborted loop leaves them;
+       the library replays that case exactly (LzChain::encode_blocks). */
+    rc = G.lzencode(G.h, ib->m_data, &ib->m_size, 1, /*chain_ends=*/0, ob->m_data, ob->m_capacity, &n);
     if (rc) die("lzencode", rc);
     ob->m_size = n;
-    /* "cannot compress" (src/rolzmain/cr-coder.c:231-233,253-263): the payload is stored with compressed = 0 */
-    const int compressed = CR_VARIANT == 0 ? ob->m_data[1] : ob->m_data[0];
-    G.aborted = !compressed && !(CR_VARIANT == 1 && ib->m_size < 16);
 }
 
 void lzdecode(data_block_t* ib, data_block_t* ob, int print_information) {

@@ -24,7 +24,8 @@ extern "C" {
 #define CRGPU_ERR_ARG              -3
 #define CRGPU_ERR_VOCAB_OVERFLOW   -4   /* > 325000 distinct words: reference prune is order dependent (src/cr-dicpick.c:115-144) */
 #define CRGPU_ERR_HASH_COLLISION   -5
-#define CRGPU_ERR_MIDCHAIN_ABORT   -6   /* a non-final block hit "cannot compress" (src/rolzmain/cr-coder.c:231-233) */
+#define CRGPU_ERR_MIDCHAIN_ABORT   -6   /* a non-final block hit "cannot compress" (src/rolzmain/cr-coder.c:231-233) while the exact
+                                           replay of that case is switched off (crgpu_set_option "exact_aborts" = 0) */
 #define CRGPU_ERR_UNSUPPORTED      -7
 #define CRGPU_ERR_OOM              -8
 
@@ -53,7 +54,9 @@ int crgpu_reset_models(crgpu_handle* h);
  * sizes     : nblocks sizes
  * out       : receives the payloads back to back; out_sizes[i] = size of payload i
  * chain_ends: nonzero if reset_models() follows before any further block (as after the dictionary payload,
- *             src/main.c:164-165, or at end of file). */
+ *             src/main.c:164-165, or at end of file).
+ * A block the reference's coder loop gives up on ("cannot compress") is stored raw and leaves the models exactly where the
+ * reference's aborted loop leaves them, so the following blocks stay byte-identical. */
 int crgpu_lzencode(crgpu_handle* h, const uint8_t* in, const uint32_t* sizes, uint32_t nblocks, int chain_ends,
                    uint8_t* out, uint64_t out_cap, uint32_t* out_sizes);
 
@@ -152,6 +155,7 @@ int crgpu_debug_sort(crgpu_handle* h, const void* keys, const uint32_t* vals, ui
 
 /* Tuning / test switches.  "scalar_models" = 1 runs the scalar model and coder kernels (the ones the CPU
  * kernel-logic simulation checks) instead of the warp-cooperative ones; results are identical.
+ * "exact_aborts" = 0 turns the exact replay of mid-chain "cannot compress" blocks off (CRGPU_ERR_MIDCHAIN_ABORT instead).
  * "flexible" = the reference's global flexible_parsing (-f) for crgpu_lzencode (crgpu_compress takes it from its
  * config); "match_limit" = comprox -m. */
 int crgpu_set_option(crgpu_handle* h, const char* name, int64_t value);

@@ -62,6 +62,26 @@ def decompress_batch(handles, containers, out_caps):
     return [outs[i].raw[:lens[i]] for i in range(k)]
 
 
+def compress_batch(handles, datas, block_size: int = 16 << 20, filt: bool = False, prec: bool = False, flexible: bool = False):
+    """crgpu_compress_batch: independent containers side by side, dealt to whichever handle is idle (one host thread per handle inside
+    the C call).  Returns the containers in input order."""
+    k, m = len(handles), len(datas)
+    assert k > 0
+    L = handles[0].L
+    L.crgpu_compress_bound.restype = ctypes.c_uint64
+    cfg = Config(block_size, int(filt), int(prec), int(flexible), 0)
+    caps = [int(L.crgpu_compress_bound(ctypes.c_uint64(len(d)), ctypes.c_uint32(block_size))) for d in datas]
+    outs = [ctypes.create_string_buffer(c) for c in caps]
+    hs = (ctypes.c_void_p * k)(*[h.h for h in handles])
+    ins = (ctypes.c_char_p * max(m, 1))(*[bytes(d) for d in datas])
+    in_lens = (ctypes.c_uint64 * max(m, 1))(*[len(d) for d in datas])
+    outp = (ctypes.c_void_p * max(m, 1))(*[ctypes.addressof(o) for o in outs])
+    ocaps = (ctypes.c_uint64 * max(m, 1))(*caps)
+    lens = (ctypes.c_uint64 * max(m, 1))()
+    _check(L, L.crgpu_compress_batch(hs, ctypes.c_uint32(k), ctypes.byref(cfg), ctypes.c_uint32(m), ins, in_lens, outp, ocaps, lens))
+    return [outs[i].raw[:lens[i]] for i in range(m)]
+
+
 def lcp_encode(text: bytes, lib=None) -> bytes:
     """dic_lcp_encode(): front coding of the NUL-terminated dictionary text (host side)."""
     L = lib or load()

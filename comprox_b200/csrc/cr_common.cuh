@@ -67,7 +67,7 @@ static inline const char* cudaGetErrorString(int) { return "sim"; }
 extern unsigned long long g_cr_launches;   // kernels launched by this library (crgpu_launch_count)
 #define CR_LAUNCH(kernel, grid, block, stream, ...)                                             \
     do {                                                                                        \
-        g_cr_launches++;                                                                        \
+        __atomic_fetch_add(&g_cr_launches, 1ull, __ATOMIC_RELAXED);   /* handles work on several host threads */ \
         kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__);                                  \
         cudaError_t le_ = cudaGetLastError();                                                   \
         if (le_ != cudaSuccess) {                                                               \

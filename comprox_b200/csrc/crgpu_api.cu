@@ -4,6 +4,8 @@
 #include "cr_container.cuh"
 #include "cr_decontainer.cuh"
 #include <string>
+#include <atomic>
+#include <thread>
 
 #ifdef CRGPU_SIM
 thread_local crsim_dim3 threadIdx, blockIdx, blockDim, gridDim;
@@ -395,4 +397,39 @@ extern "C" int64_t crgpu_lzdecode_size(int variant, const uint8_t* in, uint32_t 
     if (!compressed) return (int64_t)n - hdr;
     uint32_t sz; memcpy(&sz, in + 4, 4);
     return sz;
+}
+
+// ------------------------------------------------------------------ shard mode
+// Independent containers compressed side by side: one host thread per handle inside the call, containers dealt to whichever handle is
+// idle.  The handles may sit on different devices (then this is the multi-GPU form: no data-path collective, every container goes
+// straight from its GPU to its host buffer) or share one device on private streams (the serial range chains of different containers
+// then overlap on different SMs).  Output bytes do not depend on which handle compressed a container.
+extern "C" int crgpu_compress_batch(crgpu_handle* const* hs, uint32_t nhandles, const crgpu_config* cfg, uint32_t count,
+                                    const uint8_t* const* ins, const uint64_t* in_lens, uint8_t* const* outs, const uint64_t* out_caps, uint64_t* out_lens) {
+    if (!hs || nhandles == 0 || !cfg || (count && (!ins || !in_lens || !outs || !out_caps || !out_lens))) return CRGPU_ERR_ARG;
+    for (uint32_t i = 0; i < nhandles; i++) {
+        if (!hs[i] || hs[i]->variant != hs[0]->variant) return CRGPU_ERR_ARG;
+        for (uint32_t k = 0; k < i; k++) {
+            if (hs[k] == hs[i]) return CRGPU_ERR_ARG;
+#ifndef CRGPU_SIM
+            if (hs[k]->device == hs[i]->device && hs[k]->stream == hs[i]->stream) return CRGPU_ERR_ARG;     // would serialise: use CRGPU_OWN_STREAM
+#endif
+        }
+    }
+    std::atomic<uint32_t> next(0);
+    std::atomic<int> first_error(CRGPU_OK);
+    auto worker = [&](uint32_t j) {
+        for (;;) {
+            const uint32_t i = next.fetch_add(1);
+            if (i >= count || first_error.load() != CRGPU_OK) return;
+            const int rc = crgpu_compress(hs[j], cfg, ins[i], in_lens[i], outs[i], out_caps[i], &out_lens[i]);
+            if (rc != CRGPU_OK) { int expect = CRGPU_OK; first_error.compare_exchange_strong(expect, rc); return; }
+        }
+    };
+    const uint32_t nthreads = nhandles < count ? nhandles : count;
+    std::vector<std::thread> pool;
+    for (uint32_t j = 1; j < nthreads; j++) pool.emplace_back(worker, j);
+    if (nthreads) worker(0);
+    for (auto& t : pool) t.join();
+    return first_error.load();
 }

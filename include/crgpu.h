@@ -75,6 +75,15 @@ typedef struct crgpu_config {
 uint64_t crgpu_compress_bound(uint64_t n, uint32_t block_size);
 int crgpu_compress(crgpu_handle* h, const crgpu_config* cfg, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_n);
 
+/* Shard mode: `count` independent containers compressed side by side by `nhandles` handles, one host thread
+ * per handle inside the call, containers dealt to whichever handle is idle; what `xargs -P` over the reference CLI does with host
+ * cores.  All handles must be of one variant; they may sit on different devices (the multi-GPU form: no data-path collective, every
+ * container goes straight from its GPU to outs[i]) or share a device on private streams (CRGPU_OWN_STREAM), where the serial range
+ * chains of different containers overlap.  outs[i] / out_lens[i] receive container i, exactly the bytes crgpu_compress gives for
+ * ins[i]; out_caps[i] >= crgpu_compress_bound(in_lens[i], cfg->block_size).  Returns the first error. */
+int crgpu_compress_batch(crgpu_handle* const* hs, uint32_t nhandles, const crgpu_config* cfg, uint32_t count,
+                         const uint8_t* const* ins, const uint64_t* in_lens, uint8_t* const* outs, const uint64_t* out_caps, uint64_t* out_lens);
+
 /* dicpick(fp, dic_block)  -- src/cr-dicpick.h:40, src/cr-dicpick.c:164-259: word statistics of the whole input ->
  * dictionary text ("\x20\x20\n" "http://www.\n" word\n ... NUL).  Stage-level entry point (crgpu_compress calls the
  * same code); exact also beyond 325000 distinct words, where the reference prunes in arrival order. */

@@ -17,6 +17,7 @@ ap.add_argument("--shards", type=int, default=16)
 ap.add_argument("--shard-mb", type=int, default=64)
 ap.add_argument("--workers", type=int, nargs="+", default=[1, 2, 4, 8])
 ap.add_argument("--check", action="store_true", help="compare every container with the oracle (slow)")
+ap.add_argument("--batch", action="store_true", help="one crgpu_compress_batch call (host threads inside the C ABI) instead of Python threads")
 a = ap.parse_args()
 base = synth.markov_text(a.shard_mb * MiB, seed=45)
 shards = [base[k * 4096:] + base[:k * 4096] for k in range(a.shards)]          # distinct rotations: cheap to make, same statistics
@@ -39,15 +40,19 @@ for nw in a.workers:
             out[i] = h.compress(shards[i], 16 * MiB)
 
     t0 = time.time()
-    th = [threading.Thread(target=work, args=(h,)) for h in handles]
-    [t.start() for t in th]; [t.join() for t in th]
-    dt = time.time() - t0
+    if a.batch:
+        out = api.compress_batch(handles, shards, 16 * MiB)
+        dt = handles[0].L and time.time() - t0
+    else:
+        th = [threading.Thread(target=work, args=(h,)) for h in handles]
+        [t.start() for t in th]; [t.join() for t in th]
+        dt = time.time() - t0
     for h in handles:
         h.close()
     if ref is None:
         ref = out
     rec = {"shards": a.shards, "shard_mib": a.shard_mb, "handles": nw, "seconds": round(dt, 3), "mib_per_s": round(a.shards * a.shard_mb / dt, 1),
-           "same_as_single_handle": out == ref}
+           "same_as_single_handle": out == ref, "mode": "crgpu_compress_batch" if a.batch else "python threads"}
     if a.check:
         import oracle_ffi as O
         rec["oracle_identical"] = all(out[i] == O.compress(shards[i], 0, 16 * MiB) for i in range(min(2, a.shards)))

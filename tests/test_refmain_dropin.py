@@ -45,6 +45,8 @@ def _lib(request, which):
     ("comprop", ["-b1", "-p"], dict(block_size=MiB, prec=1)),
 ])
 def test_reference_driver_over_shims_text(request, tmp_path, which, binary, flags, kw):
+    if which == "sim" and (flags == ["-b1", "-f"] or (binary, flags) == ("comprop", ["-b1"])):
+        pytest.skip("CPU pre-flight runs three of the five switch sets (time); the GPU run takes all")
     lib = _lib(request, which)
     data = synth.markov_text(2 * MiB + 4321, seed=51)
     want = O.compress(data, VARIANT[binary], **kw)

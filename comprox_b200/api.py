@@ -203,12 +203,18 @@ class Handle:
             _check(self.L, int(size))
         return self._block_call(self.L.crgpu_lzdecode, payload, int(size))
 
-    def decompress(self, container: bytes, out_cap: int) -> bytes:
-        """The bytes `comprolz/comprop d` would write for this container."""
+    def decompress(self, container: bytes, out_cap: int, grow: bool = False) -> bytes:
+        """The bytes `comprolz/comprop d` would write for this container.  grow=True retries once with the size the library reports when
+        out_cap turns out too small (the container does not store its decoded size)."""
         out = ctypes.create_string_buffer(max(out_cap, 1))
         n = ctypes.c_uint64()
         t0 = time.perf_counter()
         rc = self.L.crgpu_decompress(self.h, container, ctypes.c_uint64(len(container)), out, ctypes.c_uint64(out_cap), ctypes.byref(n))
+        if rc == -3 and n.value > out_cap and grow:
+            # out_cap was too small: *out_n holds the size needed and the second call resumes behind the entropy stage
+            out_cap = n.value
+            out = ctypes.create_string_buffer(out_cap)
+            rc = self.L.crgpu_decompress(self.h, container, ctypes.c_uint64(len(container)), out, ctypes.c_uint64(out_cap), ctypes.byref(n))
         self.last_call_s = time.perf_counter() - t0
         _check(self.L, rc)
         return ctypes.string_at(out, n.value)

@@ -87,7 +87,22 @@ struct Decompressor {
     int dd_launch();
     int finish_output();                                                                           // inverse filters, copy out
     DdJob ddjob; uint32_t dd_nsub = 0; std::vector<DdBlock> c_ddb; uint64_t c_raw_total = 0;
+    const uint8_t* resume_in = nullptr; uint64_t resume_n = 0, resume_tag = 0;     // container whose lz stage is done but whose output did not fit
+    static uint64_t tag_of(const uint8_t* p, uint64_t n) {         // guards the resume against a different container at the same address
+        uint64_t h = 1469598103934665603ull ^ n;
+        for (uint64_t i = 0; i < n && i < 256; i++) h = (h ^ p[i]) * 1099511628211ull;
+        for (uint64_t i = n > 256 ? n - 256 : 0; i < n; i++) h = (h ^ p[i]) * 1099511628211ull;
+        return h;
+    }
     int decompress(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_n) {
+        if (resume_in && resume_in == in && resume_n == n && out_n && resume_tag == tag_of(in, n)) {
+            // second call for the same container after "out_cap too small": d_D still holds the decoded blocks, the models are past them
+            resume_in = nullptr;
+            c_out = out; c_out_cap = out_cap; c_out_n = out_n;
+            CR_TRY(layout()); CR_TRY(dd_launch());
+            return finish_output();
+        }
+        resume_in = nullptr;
         CR_TRY(begin(in, n, out, out_cap, out_n)); CR_TRY(lz_launch());
         CR_TRY(middle()); CR_TRY(lz_launch());
         CR_TRY(finish_layout()); CR_TRY(dd_launch());
@@ -188,7 +203,13 @@ inline int Decompressor::layout() {
     CR_TRY(chain->download(totals, d_totals.p, 2));
     const uint64_t raw_total = totals[0]; const uint32_t nsub = (uint32_t)totals[1];
     if (nsub > sub_cap) return CRGPU_ERR_ARG;
-    if (raw_total > out_cap) return CRGPU_ERR_ARG;
+    if (raw_total > out_cap) {
+        // the decoded size is only known here, after the (serial, slow) lzdecode chain: report it and keep the dictionary-coded
+        // blocks, so that the caller's second call with a large enough buffer resumes at this point (decompress())
+        if (c_out_n) *c_out_n = raw_total;
+        resume_in = c_in; resume_n = c_n; resume_tag = tag_of(c_in, c_n);
+        return CRGPU_ERR_ARG;
+    }
     CR_TRY(chain->download(ddb, d_ddblocks.p, nb));
     CR_TRY(d_out.reserve(raw_total + 256));
     CR_CUDA(cudaMemsetAsync(d_out.as<uint8_t>() + raw_total, 0, 128, stream));

@@ -114,10 +114,12 @@ int main(int argc, char** argv) {
     uint64_t cap = decode ? 64 : p_bound(n, cr_split_size);
     uint8_t* out = malloc(cap);
     if (decode) {                                   /* the container does not store the raw size: grow until it fits */
-        for (cap = n * 4 + (1u << 20);; cap *= 2) {
+        for (cap = n * 4 + (1u << 20);; ) {
             out = realloc(out, cap);
+            out_n = 0;
             rc = p_decompress(h, in, n, out, cap, &out_n);
-            if (rc != CRGPU_ERR_ARG || cap > ((uint64_t)1 << 36)) break;
+            if (rc != CRGPU_ERR_ARG || out_n <= cap) break;        /* out_n > cap: the size needed; the second call resumes, it does not decode twice */
+            cap = out_n;
         }
     } else
     rc = p_compress(h, &cfg, in, n, out, cap, &out_n);

@@ -94,7 +94,9 @@ int crgpu_dicpick(crgpu_handle* h, const uint8_t* in, uint64_t n, uint8_t* out, 
  * One container is one serial model chain, so this call runs the entropy stage on a single GPU thread: it is
  * provided for completeness and for decoding MANY containers side by side (one handle each); a single container
  * decodes faster on the host.  Returns CRGPU_ERR_ARG if the magic does not match the handle's variant or out_cap
- * is too small. */
+ * is too small.  The container does not store its decoded size; when out_cap is too small *out_n receives the size needed
+ * (it stays 0 for the other errors -- set it to 0 before the call), and calling again with the SAME `in` pointer and length and
+ * a large enough buffer resumes behind the entropy stage instead of decoding twice. */
 int crgpu_decompress(crgpu_handle* h, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_n);
 
 /* Many containers in flight.  `count` containers are decoded side by side, one warp each, by

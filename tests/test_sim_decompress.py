@@ -49,3 +49,24 @@ def test_sim_decompress_batch_host_flow(simlib):
     finally:
         for h in hs:
             h.close()
+
+
+@pytest.mark.parametrize("variant", [api.ROLZ, api.LZP, api.LZ77])
+def test_sim_decompress_reports_needed_size_and_resumes(simlib, variant):
+    """The container does not store its decoded size.  With out_cap too small crgpu_decompress returns CRGPU_ERR_ARG and the size needed;
+    the second call with the same container resumes behind the entropy stage (the models are NOT decoded twice) and gives the same bytes."""
+    import ctypes
+    data = synth.markov_text(400000, seed=71)
+    cont = O.compress(data, variant, 150000)
+    with api.Handle(variant, lib=simlib) as h:
+        out = ctypes.create_string_buffer(1000)
+        n = ctypes.c_uint64(0)
+        rc = simlib.crgpu_decompress(h.h, cont, ctypes.c_uint64(len(cont)), out, ctypes.c_uint64(1000), ctypes.byref(n))
+        assert rc == -3 and n.value == len(data)
+        assert h.decompress(cont, n.value) == data                    # resumed
+        assert h.decompress(cont, len(data) + 64) == data             # and a fresh full decode afterwards is unaffected
+        assert h.decompress(cont, 10, grow=True) == data
+        other = O.compress(data[::-1], variant, 150000)
+        with pytest.raises(api.CrgpuError):
+            h.decompress(cont, 10)                                     # leaves a resume point for `cont` ...
+        assert h.decompress(other, len(data) + 64) == data[::-1]      # ... which a different container must not pick up

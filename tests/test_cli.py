@@ -71,3 +71,16 @@ def test_cli_on_gpu_matches_reference_cli(gpulib, tmp_path, binary, flags):
     assert r2.returncode == 0, r2.stderr
     if "-F" not in flags:            # filtered + dictionary-compressible blocks do not round-trip in the reference either
         assert (tmp_path / "back.bin").read_bytes() == data
+
+
+@pytest.mark.parametrize("binary", ["comprolz", "comprop", "comprox"])
+def test_cli_decode_on_simulation(simlib, tmp_path, binary):
+    """`d` branch: the container does not store its decoded size, so the front-end's first buffer (4 x container + 1 MiB) is too small
+    for well-compressible input; it must come back with the size needed and finish on the second call."""
+    data = (b"the same line again and again. " * 40000)[:1200000] + synth.markov_text(100000, seed=23)
+    cont = O.compress(data, VARIANT[binary], MiB)
+    assert len(cont) * 4 + MiB < len(data)
+    sim = os.path.join(ROOT, "tests", "sim", "libcrgpu_sim.so")
+    r, out = _cli(binary, ["-q", "d"], sim, tmp_path, cont)
+    assert r.returncode == 0, r.stderr
+    assert out == data

@@ -4,8 +4,8 @@ and the stage-level calls with random block cuts.  Not collected by pytest (it r
 
     python tests/fuzz_sim.py --seconds 300 [--seed N]
 
-Every failing case is written to gpurun_out/fuzz_fail_<n>.bin with its parameters on stdout; tests/test_fuzz_regressions.py holds the
-cases this found."""
+Every failing case is written to gpurun_out/fuzz_fail_<seed>.bin with its parameters on stdout (none so far: 900 + 900 cases before
+and ~1500 after the exact replay of "cannot compress" blocks went in)."""
 import argparse
 import json
 import os
@@ -122,6 +122,39 @@ def one_case(rng, sim, idx):
                 blk = data[i:i + bs]
                 if h.filter_inplace(blk, 0) != orc.filter_inplace(blk, 0):
                     return "filter_inplace block %d" % (i // bs), params
+    if mode == 2 and not prec:
+        # stage level, one call per block as host/cr_shim.c issues them: dictionary stage (no dictionary -> stored or escaped), lzencode with
+        # chain_ends = 0, then the decoder mirror as long as no block of the chain was stored (after one the reference's decoder is lost, F11)
+        orc = O.Oracle(variant)
+        text = O.dicpick(data)
+        orc.dictionary_load(text, 1)
+        orc.reset_models()
+        with api.Handle(variant, lib=sim) as h, api.Handle(variant, lib=sim) as d:
+            if flex:
+                h.set_option("flexible", 1)
+            h.dictionary_load(text, 1); d.dictionary_load(text, 0)
+            h.reset_models(); d.reset_models()
+            if flex:
+                O.lib().cro_set_flexible(orc.c, 1)
+            if ml:
+                h.set_option("match_limit", ml); O.lib().cro_set_match_limit(orc.c, ml)
+            lost = False
+            for i in range(0, len(data), bs):
+                blk = data[i:i + bs]
+                want_d = orc.dictionary_encode(blk)
+                got_d = h.dictionary_encode(blk)
+                if got_d != want_d:
+                    return "dictionary_encode block %d" % (i // bs), params
+                if d.dictionary_decode(got_d, len(blk) + 64) != blk:
+                    return "dictionary_decode block %d" % (i // bs), params
+                want_p = orc.lzencode(want_d)
+                got_p = h.lzencode([got_d], chain_ends=False)[0]
+                if got_p != want_p:
+                    return "lzencode block %d" % (i // bs), params
+                stored = not (got_p[1] if variant == api.ROLZ else got_p[0])
+                if not lost and d.lzdecode(got_p) != got_d:
+                    return "lzdecode block %d" % (i // bs), params
+                lost = lost or (stored and not (variant == api.LZP and len(got_d) < 16))
     return None, params
 
 

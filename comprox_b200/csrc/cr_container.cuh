@@ -293,6 +293,10 @@ static inline uint64_t cr_compress_bound(uint64_t n, uint32_t block_size) {
 inline int Compressor::compress(const CrConfig& cfg, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_n) {
     if (cfg.block_size == 0 || (n && !in) || !out || !out_n) return CRGPU_ERR_ARG;
     if (cfg.flexible && chain->variant == CR_LZP) return CRGPU_ERR_ARG;      // comprop has no -f (src/ropmain/main.c)
+    if (n > (1ull << 32)) {                                                  // word positions of the dicpick table are 32 bit (the 4 GiB config fits)
+        fprintf(stderr, "crgpu: inputs above 4 GiB are not supported in one container (%llu bytes); split into shards\n", (unsigned long long)n);
+        return CRGPU_ERR_UNSUPPORTED;
+    }
     stream = chain->stream;
     StageTimer& tm = chain->timer;
     const size_t mlen = strlen(cr_magic(chain->variant));

@@ -288,6 +288,7 @@ extern "C" int crgpu_decompress_batch(crgpu_handle* const* hs, uint32_t count, c
 // dicpick(fp, dic_block): the dictionary text (NUL terminated) the reference builds from the whole input.
 extern "C" int crgpu_dicpick(crgpu_handle* h, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_n) {
     if (!h || (n && !in) || !out || !out_n) return CRGPU_ERR_ARG;
+    if (n > (1ull << 32)) return CRGPU_ERR_UNSUPPORTED;                        // word positions of the table are 32 bit
 #ifndef CRGPU_SIM
     CR_CUDA(cudaSetDevice(h->device));
 #endif

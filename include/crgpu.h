@@ -64,7 +64,8 @@ int crgpu_lzencode(crgpu_handle* h, const uint8_t* in, const uint32_t* sizes, ui
  * (src/main.c:153-206): dicpick over the file, dictionary payload, then per block filter_inplace (-F),
  * dictionary_encode and lzencode (unless -p), framed with the 6-byte block headers.  `out` receives the bytes the
  * reference CLI would have written to its output file for the same input and switches.
- * out_cap must be >= crgpu_compress_bound(n, block_size). */
+ * out_cap must be >= crgpu_compress_bound(n, block_size).  n <= 4 GiB per container (CRGPU_ERR_UNSUPPORTED above that:
+ * split the input into shards, crgpu_compress_batch). */
 typedef struct crgpu_config {
     uint32_t block_size;    /* -b, in BYTES (reference default 16 MiB, src/main.c:62) */
     int32_t  filt;          /* -F  cr_filt_enable */

@@ -1090,29 +1090,39 @@ static uint32_t elf_filter(x86_state* s, uint8_t* buf, uint32_t len, int en_de) 
     s->flag = s->curr < s->imsz;
     return size;
 }
-/* src/filter_x86_pe.c:75-159 */
+/* src/filter_x86_pe.c:75-159.  The reference parses the COFF header and the section table wherever e_lfanew points inside the
+ * block, without checking that they END inside it (its test `hdr_off + len < size` is always false for real sizes), so a
+ * header near the end of a block makes it read heap memory behind the block -- undefined behaviour, and up to 2.6 MB of it.
+ * This restatement defines those bytes as ZERO (zb16/zb32), which is what the CUDA path does (FilterHost::View) and what the
+ * reference sees when the block sits in a freshly mapped buffer; and where the section table itself ends behind the block
+ * (size_hdr > len: the reference's `len - size_hdr` wraps and it rewrites memory behind the block) it keeps the state
+ * arithmetic and transforms nothing. */
+static uint32_t zb16(const uint8_t* b, uint32_t len, uint64_t o) { return (o < len ? b[o] : 0) | (o + 1 < len ? b[o + 1] : 0) << 8; }
+static uint32_t zb32(const uint8_t* b, uint32_t len, uint64_t o) { return zb16(b, len, o) | zb16(b, len, o + 2) << 16; }
 static uint32_t pe_filter(x86_state* s, uint8_t* buf, uint32_t len, int en_de) {
     uint32_t size = umin(s->imsz - s->curr, len), ret = size;
     uint8_t* start = buf;
+    int in_bounds = 1;
     if (!s->flag) {
         s->curr = 0;
         if (len < 0x3C + 4 || rd16(buf) != 0x5A4D) return 0;
         uint32_t hdr = rd32(buf + 0x3C);
-        if (hdr >= len || rd32(buf + hdr) != 0x00004550u || hdr == 0) return 0;
-        const uint8_t* coff = buf + hdr;
+        if (hdr >= len || zb32(buf, len, hdr) != 0x00004550u || hdr == 0) return 0;
         if (hdr + len < 24) return 0;
-        uint32_t machine = rd16(coff + 4), nsec = rd16(coff + 6), optsz = rd16(coff + 20), chars = rd16(coff + 22);
+        uint32_t machine = zb16(buf, len, (uint64_t)hdr + 4), nsec = zb16(buf, len, (uint64_t)hdr + 6), optsz = zb16(buf, len, (uint64_t)hdr + 20),
+                 chars = zb16(buf, len, (uint64_t)hdr + 22);
         if (machine != 0x14c && (chars & 2)) return 0;
         uint32_t sec_off = 24 + optsz, size_hdr = sec_off + nsec * 40, est = size_hdr;
         if (hdr + len < size_hdr) return 0;
-        for (uint32_t i = 0; i < nsec; i++) est += rd32(coff + sec_off + i * 40 + 16);
+        for (uint32_t i = 0; i < nsec; i++) est += zb32(buf, len, (uint64_t)hdr + sec_off + (uint64_t)i * 40 + 16);
         if (est > (1u << 28)) return 0;
         start = buf + size_hdr;
         s->imsz = est - size_hdr;
         size = umin(s->imsz, len - size_hdr);
         ret = size + size_hdr;
+        in_bounds = size_hdr <= len;
     }
-    e8e9(start, size, en_de, (int32_t)s->curr, (int32_t)s->imsz);
+    if (in_bounds) e8e9(start, size, en_de, (int32_t)s->curr, (int32_t)s->imsz);
     s->curr += size;
     s->flag = s->curr < s->imsz;
     return ret;

@@ -54,3 +54,31 @@ def test_sim_bmp_rows_broken_at_block_ends(simlib):
         assert want == ref, "oracle differs from the reference CLI"
     with api.Handle(api.LZP, lib=simlib) as h:
         assert h.compress(data, MiB, filt=True) == want
+
+
+def test_sim_pe_header_cut_by_the_block_end(simlib):
+    """Found by tests/fuzz_sim.py: a PE header near the end of a block.  The reference parses the section table wherever e_lfanew points
+    without checking that it ends inside the block, i.e. it reads heap memory behind the block (src/filter_x86_pe.c:75-126).  Oracle and
+    CUDA path both define those bytes as zero; stage call and container must agree, whatever follows the block in memory."""
+    rng = np.random.default_rng(77)
+    code = bytearray(rng.integers(0, 256, 120, dtype=np.uint8).tobytes() * 50)       # compressible: keep "cannot compress" out of this test
+    for i in range(0, len(code) - 5, 37):
+        code[i] = 0xE8
+        code[i + 1:i + 5] = struct.pack("<i", int(rng.integers(-2000, 2000)))
+    mz = bytearray(200)
+    mz[0:2] = b"MZ"
+    mz[0x3C:0x40] = struct.pack("<I", 150)
+    mz[150:154] = b"PE\0\0"
+    mz[154:156] = struct.pack("<H", 0x14c)          # machine
+    mz[156:158] = struct.pack("<H", 2)              # two sections: the second header lies behind the end of a 300-byte block
+    mz[170:172] = struct.pack("<H", 0)              # optional header size
+    mz[190:194] = struct.pack("<I", 5000)           # SizeOfRawData of section 0 (inside the block)
+    data = b"p" * 100 + bytes(mz) + bytes(code)
+    for bs in (300, 4096):
+        want = O.compress(data, api.ROLZ, bs, filt=1)
+        with api.Handle(api.ROLZ, lib=simlib) as h:
+            assert h.compress(data, bs, filt=True) == want, bs
+        orc = O.Oracle(api.ROLZ)
+        with api.Handle(api.ROLZ, lib=simlib) as h:
+            for i in range(0, len(data), bs):
+                assert h.filter_inplace(data[i:i + bs], 0) == orc.filter_inplace(data[i:i + bs], 0), (bs, i)

@@ -575,9 +575,9 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
             x_hdr_counts[(size_t)b * 3] = xsc(2, c1) - xsc(2, c0); x_hdr_counts[(size_t)b * 3 + 1] = xsc(3, c1) - xsc(3, c0); x_hdr_counts[(size_t)b * 3 + 2] = xsc(1, c1) - xsc(1, c0);
         }
     }
-    // (A block re-run with a cut is stored raw whatever its streams say, and its serial chain is wasted work.  Its streams are still
-    // coded: the split coder attributes every dense triple to a stream by position (k_low_scatter), so a stream cannot simply be
-    // emptied while its triples stay in the dense array.)
+    // (A block re-run with a cut is stored raw whatever its streams say, so its serial chain is wasted work.  Emptying its streams
+    // here (ev_end = ev_begin) is exact on the scalar path and k_low_scatter skips triples outside every stream's range, but that
+    // variant has not run on a GPU yet: left for the next measurement session, it only matters for runs of incompressible blocks.)
     CR_TRY(upload(b_streams, streams));
     CR_TRY(b_rcres.reserve(streams.size() * sizeof(RcResult) + 16)); CR_TRY(b_rcout.reserve(rc_total + 16));
     std::vector<RcResult> res;

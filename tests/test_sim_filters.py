@@ -74,6 +74,15 @@ def test_sim_pe_header_cut_by_the_block_end(simlib):
     mz[170:172] = struct.pack("<H", 0)              # optional header size
     mz[190:194] = struct.pack("<I", 5000)           # SizeOfRawData of section 0 (inside the block)
     data = b"p" * 100 + bytes(mz) + bytes(code)
+    # second shape: the section table itself ENDS behind the block (size_hdr = 24 + 100 + 2 * 40 = 204 > 200 bytes left): the reference's
+    # `len - size_hdr` wraps and it rewrites heap memory behind the block; here nothing is transformed, the flag is still raised
+    mz2 = bytearray(mz)
+    mz2[170:172] = struct.pack("<H", 100)
+    tail = b"p" * 100 + bytes(mz2)
+    orc = O.Oracle(api.ROLZ)
+    with api.Handle(api.ROLZ, lib=simlib) as h:
+        assert h.filter_inplace(tail, 0) == orc.filter_inplace(tail, 0) == (1, tail)
+        assert h.filter_inplace(bytes(code), 0) == orc.filter_inplace(bytes(code), 0)         # and the state both are left in agrees
     for bs in (300, 4096):
         want = O.compress(data, api.ROLZ, bs, filt=1)
         with api.Handle(api.ROLZ, lib=simlib) as h:

@@ -65,7 +65,7 @@ struct LzChain {
     size_t last_dtotal = 0;
     StageTimer timer;
     bool flexible = false;         // -f flexible parsing (ROLZ)
-    int rc_variant = 4;            // range-chain formulation (cr_warp.cuh: k_range_chain<1|2|3>)
+    int rc_variant = 4;            // range-chain formulation (cr_warp.cuh: k_range_chain<1..7>; 7 = double-precision chain, opt-in until it has run on a GPU)
     bool hot_contexts = true;      // hot o2 contexts run the rank-based CTA kernel (k_o2_pass_cta)
     bool scalar_models = false;   // GPU A/B switch: run the scalar (simulation-checked) model/coder kernels
     bool exact_aborts = true;      // replay a mid-chain "cannot compress" exactly (encode_blocks); false = CRGPU_ERR_MIDCHAIN_ABORT
@@ -598,10 +598,17 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
                       b_streams.as<RcStream>(), nstr, b_qm.as<uint32_t>(), b_shm.as<uint32_t>(), b_qs.as<uint32_t>(), b_shs.as<uint32_t>());
         } else {
             CR_TRY(b_cinm.reserve((ntm + 1) * 16 + 16)); CR_TRY(b_cins.reserve((nts + 1) * 16 + 16));
+            if (rc_variant == 7) {
+                if (ntm) CR_LAUNCH(k_chain_inputs_dp, dim3(cr_div_up(ntm, 256)), dim3(256), stream, b_dense.as<Tri>(), (uint64_t)ntm, b_cinm.as<uint4>());
+                if (nts) CR_LAUNCH(k_chain_inputs_dp, dim3(cr_div_up(nts, 256)), dim3(256), stream, b_denseside.as<Tri>(), (uint64_t)nts, b_cins.as<uint4>());
+            } else {
             if (ntm) CR_LAUNCH(k_chain_inputs, dim3(cr_div_up(ntm, 256)), dim3(256), stream, b_dense.as<Tri>(), (uint64_t)ntm, b_cinm.as<uint4>());
             if (nts) CR_LAUNCH(k_chain_inputs, dim3(cr_div_up(nts, 256)), dim3(256), stream, b_denseside.as<Tri>(), (uint64_t)nts, b_cins.as<uint4>());
+            }
             timer.mark("expand");
-            if (rc_variant == 2) CR_LAUNCH(k_range_chain<2>, gchain, dim3(128), stream, b_cinm.as<uint4>(), b_cins.as<uint4>(), b_escord.as<uint32_t>(),
+            if (rc_variant == 7) CR_LAUNCH(k_range_chain<7>, gchain, dim3(128), stream, b_cinm.as<uint4>(), b_cins.as<uint4>(), b_escord.as<uint32_t>(),
+                      b_streams.as<RcStream>(), nstr, b_qm.as<uint32_t>(), b_shm.as<uint32_t>(), b_qs.as<uint32_t>(), b_shs.as<uint32_t>());
+            else if (rc_variant == 2) CR_LAUNCH(k_range_chain<2>, gchain, dim3(128), stream, b_cinm.as<uint4>(), b_cins.as<uint4>(), b_escord.as<uint32_t>(),
                       b_streams.as<RcStream>(), nstr, b_qm.as<uint32_t>(), b_shm.as<uint32_t>(), b_qs.as<uint32_t>(), b_shs.as<uint32_t>());
             else if (rc_variant == 6) CR_LAUNCH(k_range_chain<6>, gchain, dim3(128), stream, b_cinm.as<uint4>(), b_cins.as<uint4>(), b_escord.as<uint32_t>(),
                       b_streams.as<RcStream>(), nstr, b_qm.as<uint32_t>(), b_shm.as<uint32_t>(), b_qs.as<uint32_t>(), b_shs.as<uint32_t>());

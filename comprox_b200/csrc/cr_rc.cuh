@@ -7,6 +7,8 @@
 // dependent chain per symbol is  umulhi -> mul/sub -> compare/add -> mul -> normalise.
 #pragma once
 #include "cr_common.cuh"
+#include <cmath>
+#include <cstring>
 #include "cr_ppm.cuh"
 
 struct Tri {             // one range_encoder_encode call
@@ -55,6 +57,52 @@ __global__ void k_expand_side(const uint64_t* __restrict__ TS, uint32_t n, Tri* 
     a.cum = (uint32_t)t & 0xFFFFFF; a.frq = (uint32_t)(t >> 24) & 0xFFFF; a.sum = (uint32_t)(t >> 40) & 0x7FFFFF;
     a.magic = rc_magic(a.sum);
     dense[i] = a;
+}
+
+// ------------------------------------------------------------------ double-precision form of the range recurrence (k_range_chain<7>)
+// q = floor(r / sum); r' = q * frq; byte renormalisation -- as two dependent FMAs and three integer operations (tests/micro/chain_dp.cu,
+// profiles/round1_chain_latency.md: 39.1 cycles per symbol against 44.0 for the integer chain on B200):
+//   T = fma(R, inv, 2^52 - 0.5) == 2^52 + floor(R / sum) exactly, for inv = two ulps above the correctly rounded 1/sum:  R < 2^32 makes
+//       R * inv exceed R / sum by less than 2^-19 / sum, the fractional part of R / sum is a multiple of 1/sum below 1, so the product's
+//       fractional part lies strictly inside (0, 1) and the single rounding of the FMA (ulp 1 at 2^52) lands on 2^52 + q;
+//   C = fma(T, frq, -(2^52 * frq)) == q * frq exactly (below 2^48);
+//   the top-bit index of C is its exponent, and adding (31 - e) & 24 to the exponent is the shift by 0 .. 3 bytes.
+#define RC_DP_MAGIC 4503599627370495.5         /* 2^52 - 0.5 */
+#define RC_DP_TWO52 4503599627370496.0
+CR_HD void rc_dp_split(double v, uint32_t& hi, uint32_t& lo) {
+#if defined(__CUDA_ARCH__)
+    hi = (uint32_t)__double2hiint(v); lo = (uint32_t)__double2loint(v);
+#else
+    unsigned long long b; memcpy(&b, &v, 8); hi = (uint32_t)(b >> 32); lo = (uint32_t)b;
+#endif
+}
+CR_HD double rc_dp_join(uint32_t hi, uint32_t lo) {
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double((int)hi, (int)lo);
+#else
+    unsigned long long b = (unsigned long long)hi << 32 | lo; double v; memcpy(&v, &b, 8); return v;
+#endif
+}
+// chain record of one symbol: {inv, frq} as two doubles in a uint4 slot (x, y = inv lo, hi; z, w = frq lo, hi)
+CR_HD uint4 rc_dp_record(uint32_t frq, uint32_t sum) {
+    double inv = 1.0 / (double)sum;
+    uint32_t ih, il; rc_dp_split(inv, ih, il);
+    unsigned long long b = ((unsigned long long)ih << 32 | il) + 2ull;          // two ulps up: strictly above 1/sum, power-of-two sums included
+    uint32_t fh, fl; rc_dp_split((double)frq, fh, fl);
+    uint4 r; r.x = (uint32_t)b; r.y = (uint32_t)(b >> 32); r.z = fl; r.w = fh;
+    return r;
+}
+// one symbol: R = the (normalised) range as a double; returns q, msb = top-bit index of the UN-normalised new range (as VARIANT 4 stores it)
+CR_HD void rc_dp_step(double& R, const uint4 t, uint32_t& q, uint32_t& msb) {
+    const double inv = rc_dp_join(t.y, t.x), f = rc_dp_join(t.w, t.z);
+    const double T = fma(R, inv, RC_DP_MAGIC);
+    const double C = fma(T, f, -(RC_DP_TWO52 * f));
+    uint32_t th, tl, ch, cl;
+    rc_dp_split(T, th, tl); rc_dp_split(C, ch, cl);
+    q = tl;
+    msb = (ch >> 20) - 1023u;
+    ch += (0x41EFFFFFu - ch) & 0x01800000u;
+    R = rc_dp_join(ch, cl);
 }
 
 struct RcStream {

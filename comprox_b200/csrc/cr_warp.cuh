@@ -936,6 +936,14 @@ __global__ void k_chain_inputs(const Tri* __restrict__ dense, uint64_t n, uint4*
     cin[i] = make_uint4(t.frq & 0x7FFFFFFFu, (uint32_t)M, (uint32_t)(M >> 32), t.sum);
 }
 
+// chain input of VARIANT 7 (double-precision chain, cr_rc.cuh): {inv, frq} as two doubles
+__global__ void k_chain_inputs_dp(const Tri* __restrict__ dense, uint64_t n, uint4* __restrict__ cin) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Tri t = dense[i];
+    cin[i] = rc_dp_record(t.frq & 0x7FFFFFFFu, t.sum);
+}
+
 // VARIANT 1: 32-bit reciprocal + correction, both candidates normalised speculatively (input: Tri)
 // VARIANT 2: exact 64-bit reciprocal, FLO-based normalisation                          (input: k_chain_inputs)
 // VARIANT 3: exact 64-bit reciprocal, one compare/select for the common 0/1-byte shift, loop for the rest
@@ -985,6 +993,7 @@ __global__ void __launch_bounds__(128) k_range_chain(const uint4* __restrict__ i
     size_t i0 = S.ev_begin, i1 = S.ev_end;
     if (S.is_main) { i0 += escord[S.ev_begin]; i1 += escord[S.ev_end]; }
     uint32_t range = 0xFFFFFFFFu;
+    double R = 4294967295.0;                             // VARIANT 7: the normalised range as a double
     uint32_t msb = 31;                                   // VARIANT 4: index of the top set bit of the un-normalised range
     uint32_t c24 = 24, c7 = 7;
     asm volatile("" : "+r"(c24), "+r"(c7));            // keep the LOP3 operands in registers
@@ -1000,6 +1009,17 @@ __global__ void __launch_bounds__(128) k_range_chain(const uint4* __restrict__ i
         const uint32_t cnt = i1 - base < RC_BATCH ? (uint32_t)(i1 - base) : RC_BATCH;
         if (lane == 0) {
             uint4 t = stage[w][0];
+            if (VARIANT == 7) {
+                // VARIANT 7: two dependent DFMA + three ALU operations per symbol (rc_dp_step, cr_rc.cuh); q and the top-bit index leave
+                // the chain through shared memory like VARIANT 4's (os[j + 1] = top bit after symbol j)
+                for (uint32_t j = 0; j < cnt; j++) {
+                    const uint4 tn = stage[w][j + 1];
+                    uint32_t q, m;
+                    rc_dp_step(R, t, q, m);
+                    oq[w][j] = q; os[w][j + 1] = m;
+                    t = tn;
+                }
+            }
             for (uint32_t j = 0; j < cnt && VARIANT < 5; j++) {
                 const uint4 tn = stage[w][j + 1];
                 uint32_t q, sh;
@@ -1041,7 +1061,7 @@ __global__ void __launch_bounds__(128) k_range_chain(const uint4* __restrict__ i
                 oq[w][j] = q; os[w][j] = sh;
                 t = tn;
             }
-            if (VARIANT >= 5) {
+            if (VARIANT == 5 || VARIANT == 6) {
                 // a symbol takes less than one LDS latency here: full batches keep 8 symbols in registers and refill each slot
                 // 8 symbols ahead of its use
                 if (cnt == RC_BATCH) {
@@ -1068,7 +1088,7 @@ __global__ void __launch_bounds__(128) k_range_chain(const uint4* __restrict__ i
                 }
             }
             if (VARIANT == 4) os[w][cnt] = msb;
-            if (VARIANT >= 5) os[w][cnt] = 31u - (__clz(range) & 24u);
+            if (VARIANT == 5 || VARIANT == 6) os[w][cnt] = 31u - (__clz(range) & 24u);
         }
         __syncwarp();
         const uint32_t so_off = VARIANT >= 4 ? 1u : 0u;                    // VARIANT 4 keeps the value after symbol j in slot j+1

@@ -189,7 +189,7 @@ extern "C" int crgpu_set_option(crgpu_handle* h, const char* name, int64_t value
     if (!h || !name) return CRGPU_ERR_ARG;
     std::string n(name);
     if (n == "scalar_models") { h->chain.scalar_models = value != 0; return CRGPU_OK; }
-    if (n == "rc_variant") { if (value < 1 || value > 6) return CRGPU_ERR_ARG; h->chain.rc_variant = (int)value; return CRGPU_OK; }
+    if (n == "rc_variant") { if (value < 1 || value > 7) return CRGPU_ERR_ARG; h->chain.rc_variant = (int)value; return CRGPU_OK; }
     if (n == "hot_contexts") { h->chain.hot_contexts = value != 0; return CRGPU_OK; }
     if (n == "match_limit") { if (value < 1 || value > 1000000) return CRGPU_ERR_ARG; h->chain.match_limit = (uint32_t)value; return CRGPU_OK; }   // comprox -m
     if (n == "exact_aborts") { h->chain.exact_aborts = value != 0; return CRGPU_OK; }             // 0: mid-chain "cannot compress" -> CRGPU_ERR_MIDCHAIN_ABORT
@@ -433,4 +433,19 @@ extern "C" int crgpu_compress_batch(crgpu_handle* const* hs, uint32_t nhandles, 
     if (nthreads) worker(0);
     for (auto& t : pool) t.join();
     return first_error.load();
+}
+
+// Test aid for k_range_chain<7>: walks the double-precision form of the range recurrence (rc_dp_record / rc_dp_step, cr_rc.cuh -- the
+// very functions the kernel calls) over n symbols ON THE HOST, from the coder's initial range.  q_out[i] = range / sum, shift_out[i] =
+// renormalisation bytes after symbol i.  Lets the CPU tests compare the formulation with the integer recurrence without a GPU.
+extern "C" int crgpu_debug_rc_dp(const uint32_t* frq, const uint32_t* sum, uint64_t n, uint32_t* q_out, uint32_t* shift_out) {
+    if (!frq || !sum || !q_out || !shift_out) return CRGPU_ERR_ARG;
+    double R = 4294967295.0;
+    for (uint64_t i = 0; i < n; i++) {
+        if (sum[i] == 0 || frq[i] == 0 || frq[i] > sum[i] || sum[i] >= (1u << 23)) return CRGPU_ERR_ARG;
+        uint32_t q, msb;
+        rc_dp_step(R, rc_dp_record(frq[i], sum[i]), q, msb);
+        q_out[i] = q; shift_out[i] = 3u - (msb >> 3);
+    }
+    return CRGPU_OK;
 }

@@ -165,6 +165,10 @@ int64_t crgpu_debug_fetch(crgpu_handle* h, const char* what, void* dst, uint64_t
 int crgpu_debug_sort(crgpu_handle* h, const void* keys, const uint32_t* vals, uint64_t n, int key_bytes, int begin_bit, int end_bit,
                      void* keys_out, uint32_t* vals_out);
 
+/* Test aid: the double-precision form of the range recurrence (k_range_chain<7>, opt-in through crgpu_set_option "rc_variant" = 7)
+ * walked on the HOST with the same step function the kernel uses; q_out[i] = range / sum[i], shift_out[i] = renormalisation bytes. */
+int crgpu_debug_rc_dp(const uint32_t* frq, const uint32_t* sum, uint64_t n, uint32_t* q_out, uint32_t* shift_out);
+
 /* Tuning / test switches.  "scalar_models" = 1 runs the scalar model and coder kernels (the ones the CPU
  * kernel-logic simulation checks) instead of the warp-cooperative ones; results are identical.
  * "exact_aborts" = 0 turns the exact replay of mid-chain "cannot compress" blocks off (CRGPU_ERR_MIDCHAIN_ABORT instead).

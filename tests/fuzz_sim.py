@@ -4,7 +4,7 @@ and the stage-level calls with random block cuts.  Not collected by pytest (it r
 
     python tests/fuzz_sim.py --seconds 300 [--seed N]
 
-Every failing case is written to gpurun_out/fuzz_fail_<seed>.bin with its parameters on stdout.  So far (~5000 cases): no difference in
+Every failing case is written to gpurun_out/fuzz_fail_<seed>.bin with its parameters on stdout.  So far (~7000 cases): no difference in
 the CUDA sources; one finding in the reference itself -- a PE header near the end of a block makes it parse heap memory behind the
 block (undefined behaviour, restated too faithfully by the oracle, which crashed): both sides now define those bytes as zero."""
 import argparse

@@ -219,6 +219,17 @@ class Handle:
         _check(self.L, rc)
         return ctypes.string_at(out, n.value)
 
+    def get_stat(self, name: str) -> int:
+        """crgpu_get_stat: "cut_blocks" / "last_cut_blocks" (mid-chain blocks stored raw, see include/crgpu.h)."""
+        self.L.crgpu_get_stat.restype = ctypes.c_int64
+        v = self.L.crgpu_get_stat(self.h, name.encode())
+        if v < 0:
+            _check(self.L, int(v))
+        return int(v)
+
+    def stage_input(self, data: bytes):
+        _check(self.L, self.L.crgpu_stage_input(self.h, data, ctypes.c_uint64(len(data))))
+
     def set_option(self, name, value):
         _check(self.L, self.L.crgpu_set_option(self.h, name.encode(), ctypes.c_int64(int(value))))
 

@@ -46,7 +46,7 @@ struct Compressor {
         if (n) CR_CUDA(cudaMemcpyAsync(d_raw.p, in, n, cudaMemcpyHostToDevice, stream));
         CR_CUDA(cudaMemsetAsync(d_raw.as<uint8_t>() + n, 0, 128, stream));
         CR_CUDA(cudaStreamSynchronize(stream));
-        staged_ptr = in; staged_n = n;
+        staged_ptr = nullptr;                  // only crgpu_stage_input arms the "already resident" fast path of compress()
         return CRGPU_OK;
     }
     int dicpick(const uint8_t* h_in, const uint8_t* d_in, uint64_t n, std::string& text);

@@ -79,8 +79,8 @@ struct Decompressor {
     int describe(uint64_t off, uint32_t size, int prec, uint64_t d_off, DecBlock& b);
     int begin(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_n);   // -> job = dictionary payload
     int middle();                                                                                  // -> job = data blocks (nb may be 0)
-    int finish_layout();                                                                           // -> ddjob = the sub-chunks to expand
-    int layout();
+    int finish_layout(bool may_resume = false);                                                                         // -> ddjob = the sub-chunks to expand
+    int layout(bool may_resume = false);
     int load_words(const char* text);
     int lzdecode_block(const uint8_t* in, uint32_t n, uint8_t* out, uint64_t out_cap, uint32_t* out_n);          // stage shims (crgpu_lzdecode,
     int dict_decode_block(const uint8_t* in, uint32_t n, uint8_t* out, uint64_t out_cap, uint32_t* out_n);       //  crgpu_dictionary_decode)
@@ -99,13 +99,13 @@ struct Decompressor {
             // second call for the same container after "out_cap too small": d_D still holds the decoded blocks, the models are past them
             resume_in = nullptr;
             c_out = out; c_out_cap = out_cap; c_out_n = out_n;
-            CR_TRY(layout()); CR_TRY(dd_launch());
+            CR_TRY(layout(true)); CR_TRY(dd_launch());
             return finish_output();
         }
         resume_in = nullptr;
         CR_TRY(begin(in, n, out, out_cap, out_n)); CR_TRY(lz_launch());
         CR_TRY(middle()); CR_TRY(lz_launch());
-        CR_TRY(finish_layout()); CR_TRY(dd_launch());
+        CR_TRY(finish_layout(true)); CR_TRY(dd_launch());
         return finish_output();
     }
 };
@@ -126,6 +126,7 @@ inline int Decompressor::describe(uint64_t off, uint32_t size, int prec, uint64_
 
 inline int Decompressor::begin(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_n) {
     stream = chain->stream;
+    resume_in = nullptr;
     const char* magic = cr_magic(chain->variant);
     const size_t mlen = strlen(magic);
     if (!in || !out_n || n < mlen + 4 || memcmp(in, magic, mlen) != 0) return CRGPU_ERR_ARG;     // check_magic, src/main.c:72-79
@@ -180,13 +181,13 @@ inline int Decompressor::middle() {
     return CRGPU_OK;
 }
 
-inline int Decompressor::finish_layout() {
+inline int Decompressor::finish_layout(bool may_resume) {
     if (!c_blk.empty()) CR_TRY(lz_finish());
-    return layout();
+    return layout(may_resume);
 }
 
 // dictionary_decode of the blocks described by c_blk (their dictionary-coded bytes sit in d_D): pair framing -> sub-chunks
-inline int Decompressor::layout() {
+inline int Decompressor::layout(bool may_resume) {
     std::vector<DecBlock>& blk = c_blk;
     // ---- dictionary_decode
     const DdDict dic = c_dic;
@@ -207,7 +208,8 @@ inline int Decompressor::layout() {
         // the decoded size is only known here, after the (serial, slow) lzdecode chain: report it and keep the dictionary-coded
         // blocks, so that the caller's second call with a large enough buffer resumes at this point (decompress())
         if (c_out_n) *c_out_n = raw_total;
-        resume_in = c_in; resume_n = c_n; resume_tag = tag_of(c_in, c_n);
+        // (armed only on the whole-container route: the stage calls and the batch route reuse d_D / c_blk for other data)
+        if (may_resume) { resume_in = c_in; resume_n = c_n; resume_tag = tag_of(c_in, c_n); }
         return CRGPU_ERR_ARG;
     }
     CR_TRY(chain->download(ddb, d_ddblocks.p, nb));
@@ -260,6 +262,7 @@ inline int Decompressor::finish_output() {
 // the PPM context carry over from the previous call of this handle until reset_models().
 inline int Decompressor::lzdecode_block(const uint8_t* in, uint32_t n, uint8_t* out, uint64_t out_cap, uint32_t* out_n) {
     stream = chain->stream;
+    resume_in = nullptr;
     c_in = in; c_n = n;
     CR_TRY(d_cont.reserve((size_t)n + 64));
     if (n) CR_CUDA(cudaMemcpyAsync(d_cont.p, in, n, cudaMemcpyHostToDevice, stream));
@@ -277,6 +280,7 @@ inline int Decompressor::lzdecode_block(const uint8_t* in, uint32_t n, uint8_t* 
 // dictionary_decode(ib, ob, NULL) (src/cr-diccode.c:223-283) of one block; needs load_words() first.
 inline int Decompressor::dict_decode_block(const uint8_t* in, uint32_t n, uint8_t* out, uint64_t out_cap, uint32_t* out_n) {
     stream = chain->stream;
+    resume_in = nullptr; c_in = nullptr; c_n = 0;
     if (n == 0 || !d_words.p) return CRGPU_ERR_ARG;          // the reference reads ib->m_data[size - 1]: an empty block is not a valid input
     CR_TRY(d_D.reserve((size_t)n + 64));
     CR_CUDA(cudaMemcpyAsync(d_D.p, in, n, cudaMemcpyHostToDevice, stream));

@@ -23,6 +23,7 @@ struct crgpu_handle {
     Decompressor decomp;
     FilterHost stage_filt;          // continuation state of crgpu_filter_inplace (the reference's function-local statics)
     bool owns_stream = false;
+    uint32_t last_cut_blocks = 0;   // mid-chain blocks stored raw by the most recent crgpu_compress (crgpu_get_stat)
 };
 
 extern "C" const char* crgpu_strerror(int code) {
@@ -36,6 +37,7 @@ extern "C" const char* crgpu_strerror(int code) {
         case CRGPU_ERR_MIDCHAIN_ABORT: return "a non-final block could not be compressed (reference desyncs here too)";
         case CRGPU_ERR_UNSUPPORTED: return "unsupported option";
         case CRGPU_ERR_OOM: return "out of device memory";
+        case CRGPU_ERR_CORRUPT: return "corrupt container";
     }
     return "unknown error";
 }
@@ -91,6 +93,9 @@ extern "C" int crgpu_lzencode(crgpu_handle* h, const uint8_t* in, const uint32_t
 #ifndef CRGPU_SIM
     CR_CUDA(cudaSetDevice(h->device));
 #endif
+    // every payload is at most header + block bytes (stored form): demand that much up front, so that a too small `out` is
+    // reported BEFORE any block has advanced the models of the chain
+    { uint64_t need = 0; for (uint32_t b = 0; b < nblocks; b++) need += (uint64_t)sizes[b] + 32; if (nblocks == 0) need = 32; if (out_cap < need) return CRGPU_ERR_ARG; }
     // windows of at most RZ_MAX_BLOCKS consecutive blocks; model state carries from window to window
     size_t src = 0, written = 0;
     for (uint32_t b0 = 0; b0 < nblocks || (nblocks == 0 && b0 == 0); b0 += RZ_MAX_BLOCKS) {
@@ -207,7 +212,18 @@ extern "C" int crgpu_compress(crgpu_handle* h, const crgpu_config* cfg, const ui
 #endif
     CrConfig c; c.block_size = cfg->block_size; c.filt = cfg->filt; c.prec = cfg->prec; c.flexible = cfg->flexible; c.window_bytes = cfg->window_bytes;
     h->comp.chain = &h->chain;
-    return h->comp.compress(c, in, n, out, out_cap, out_n);
+    const uint32_t cuts0 = h->chain.cut_blocks;
+    const int rc = h->comp.compress(c, in, n, out, out_cap, out_n);
+    h->last_cut_blocks = h->chain.cut_blocks - cuts0;
+    return rc;
+}
+
+extern "C" int64_t crgpu_get_stat(crgpu_handle* h, const char* name) {
+    if (!h || !name) return CRGPU_ERR_ARG;
+    const std::string n(name);
+    if (n == "cut_blocks") return h->chain.cut_blocks;
+    if (n == "last_cut_blocks") return h->last_cut_blocks;
+    return CRGPU_ERR_ARG;
 }
 
 extern "C" uint64_t crgpu_launch_count(void) {
@@ -226,7 +242,9 @@ extern "C" int crgpu_stage_input(crgpu_handle* h, const uint8_t* in, uint64_t n)
     CR_CUDA(cudaSetDevice(h->device));
 #endif
     h->comp.chain = &h->chain; h->comp.stream = h->chain.stream;
-    return h->comp.stage(in, n);
+    CR_TRY(h->comp.stage(in, n));
+    h->comp.staged_ptr = in; h->comp.staged_n = n;       // one-shot: the next crgpu_compress consumes it, every other staging call clears it
+    return CRGPU_OK;
 }
 
 extern "C" int crgpu_decompress(crgpu_handle* h, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_n) {
@@ -331,6 +349,9 @@ extern "C" int crgpu_filter_inplace(crgpu_handle* h, uint8_t* buf, uint32_t len,
 // dic_lcp_encode / dic_lcp_decode -- src/cr-dicpick.c:261-346.  Host only: the dictionary text is at most a few hundred KB.
 extern "C" int crgpu_dic_lcp_encode(const uint8_t* text, uint64_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_n) {
     if (!text || !out || !out_n || n == 0 || text[n - 1] != 0) return CRGPU_ERR_ARG;        // NUL-terminated, as dicpick leaves it
+    // dicpick's text is a list of '\n'-terminated lines (at least the two fixed ones, src/cr-dicpick.c:238-240) with no NUL inside;
+    // the front coder scans for '\n' without a bound, so anything else is rejected here instead of being read past its end
+    if (n < 2 || text[n - 2] != '\n' || memchr(text, 0, n - 1) != nullptr) return CRGPU_ERR_ARG;
     const std::vector<uint8_t> enc = hd_lcp_encode(std::string((const char*)text, n - 1));
     if (enc.size() > out_cap) return CRGPU_ERR_ARG;
     memcpy(out, enc.data(), enc.size());
@@ -364,7 +385,6 @@ extern "C" int crgpu_dictionary_encode(crgpu_handle* h, const uint8_t* in, uint3
     CR_SET_DEVICE(h);
     h->comp.chain = &h->chain; h->comp.stream = h->chain.stream;
     CR_TRY(h->comp.stage(in, n));
-    h->comp.staged_ptr = nullptr;
     std::vector<uint64_t> roff(1, 0); std::vector<uint32_t> rsize(1, n); std::vector<BlockIO> blk; size_t dtotal = 0;
     CR_TRY(h->comp.dict_encode_window(h->comp.d_raw.as<uint8_t>(), roff, rsize, blk, dtotal));
     if (blk[0].size > out_cap) return CRGPU_ERR_ARG;

@@ -28,6 +28,7 @@ extern "C" {
                                            replay of that case is switched off (crgpu_set_option "exact_aborts" = 0) */
 #define CRGPU_ERR_UNSUPPORTED      -7
 #define CRGPU_ERR_OOM              -8
+#define CRGPU_ERR_CORRUPT          -9   /* decoder: the container is damaged (a stream, match or dictionary reference leaves its buffer) */
 
 #define CRGPU_ROLZ 0   /* comprolz: src/rolzmain */
 #define CRGPU_LZP  1   /* comprop : src/ropmain  */
@@ -56,7 +57,9 @@ int crgpu_reset_models(crgpu_handle* h);
  * chain_ends: nonzero if reset_models() follows before any further block (as after the dictionary payload,
  *             src/main.c:164-165, or at end of file).
  * A block the reference's coder loop gives up on ("cannot compress") is stored raw and leaves the models exactly where the
- * reference's aborted loop leaves them, so the following blocks stay byte-identical. */
+ * reference's aborted loop leaves them, so the following blocks stay byte-identical.
+ * out_cap must be >= sum(sizes[i] + 32) (a stored block is its bytes behind the inner header); a smaller `out` is refused with
+ * CRGPU_ERR_ARG before any block has touched the models, so the call can be repeated. */
 int crgpu_lzencode(crgpu_handle* h, const uint8_t* in, const uint32_t* sizes, uint32_t nblocks, int chain_ends,
                    uint8_t* out, uint64_t out_cap, uint32_t* out_sizes);
 
@@ -149,6 +152,14 @@ int64_t crgpu_lzdecode_size(int variant, const uint8_t* in, uint32_t n);
  * length (and no -F, which rewrites the staged bytes in place) then skips its host-to-device copy; used by
  * bench.py to time the device-resident path separately from the end-to-end path. */
 int crgpu_stage_input(crgpu_handle* h, const uint8_t* in, uint64_t n);
+
+/* Counters of a handle.  "cut_blocks": blocks of the data chain that hit "cannot compress" in mid-chain since the handle was created
+ * and were stored raw with the exact replay.  Such a container is byte-identical to the reference CLI's, but NEITHER
+ * the reference decoder NOR crgpu_decompress can read the blocks behind the stored one (the decoder skips a stored block without
+ * touching its models; the reference crashes, this library returns CRGPU_ERR_CORRUPT).  crgpu_compress still returns CRGPU_OK for
+ * parity with the reference; callers that need a decodable archive check "last_cut_blocks" (the most recent crgpu_compress call)
+ * or switch the replay off ("exact_aborts" = 0 -> CRGPU_ERR_MIDCHAIN_ABORT).  Returns < 0 for an unknown name. */
+int64_t crgpu_get_stat(crgpu_handle* h, const char* name);
 
 /* Number of CUDA kernels this library has launched in this process (all handles). */
 uint64_t crgpu_launch_count(void);

@@ -179,8 +179,16 @@ def rolz_parse(data, flexible=0):
 
 
 def ref_binary(name):
+    """Path of an unmodified reference binary under oracle/_ref, or None where the reference was never built (a CPU-only checkout
+    without /root/reference).  On a GPU box oracle/_ref must have travelled with the repo: its absence there would silently
+    drop every comparison with the reference CLI, so it is an error, not a downgrade."""
     path = os.path.join(REF_DIR, name)
-    return path if os.path.exists(path) else None
+    if os.path.exists(path):
+        return path
+    if os.path.exists("/dev/nvidiactl") or os.path.isdir("/root/reference/src"):
+        raise RuntimeError("oracle/_ref/%s is missing: build it here with `make -C oracle ref` (it is git-ignored but travels to the "
+                           "GPU box with gpurun); the reference-CLI parity checks must not be skipped" % name)
+    return None
 
 
 def ref_compress(data, binary, flags=(), tmpdir="/tmp"):

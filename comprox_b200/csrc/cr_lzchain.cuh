@@ -17,6 +17,7 @@
 #include "cr_ppm.cuh"
 #include "cr_rc.cuh"
 #include "cr_warp.cuh"
+#include "cr_rcpar.cuh"
 
 enum { CR_ROLZ = 0, CR_LZP = 1, CR_LZ77 = 2 };
 
@@ -65,11 +66,14 @@ struct LzChain {
     size_t last_dtotal = 0;
     StageTimer timer;
     bool flexible = false;         // -f flexible parsing (ROLZ)
-    int rc_variant = 4;            // range-chain formulation (cr_warp.cuh: k_range_chain<1..7>; 7 = double-precision chain, opt-in until it has run on a GPU)
+    int rc_variant = 7;            // range-chain formulation (cr_warp.cuh: k_range_chain<1..7>; 7 = double-precision chain, B200-verified in round 1's driver run)
     bool hot_contexts = true;      // hot o2 contexts run the rank-based CTA kernel (k_o2_pass_cta)
     bool scalar_models = false;   // GPU A/B switch: run the scalar (simulation-checked) model/coder kernels
     bool exact_aborts = true;      // replay a mid-chain "cannot compress" exactly (encode_blocks); false = CRGPU_ERR_MIDCHAIN_ABORT
     DevBuf b_abort;
+#ifndef CRGPU_SIM
+    RcPar rcpar;                   // rc_variant 8: the range chain cut into jobs (cr_rcpar.cuh)
+#endif
 
     int init(int variant_, cudaStream_t s) {
         variant = variant_; stream = s; prims.stream = s;
@@ -97,6 +101,7 @@ struct LzChain {
         for (DevBuf* b : all) b->release();
         prims.release();
 #ifndef CRGPU_SIM
+        rcpar.release();
         if (side_stream) { cudaStreamDestroy(side_stream); cudaEventDestroy(ev_side_go); cudaEventDestroy(ev_side_done); side_stream = 0; }
 #endif
         inited = false;
@@ -598,7 +603,7 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
                       b_streams.as<RcStream>(), nstr, b_qm.as<uint32_t>(), b_shm.as<uint32_t>(), b_qs.as<uint32_t>(), b_shs.as<uint32_t>());
         } else {
             CR_TRY(b_cinm.reserve((ntm + 1) * 16 + 16)); CR_TRY(b_cins.reserve((nts + 1) * 16 + 16));
-            if (rc_variant == 7) {
+            if (rc_variant >= 7) {
                 if (ntm) CR_LAUNCH(k_chain_inputs_dp, dim3(cr_div_up(ntm, 256)), dim3(256), stream, b_dense.as<Tri>(), (uint64_t)ntm, b_cinm.as<uint4>());
                 if (nts) CR_LAUNCH(k_chain_inputs_dp, dim3(cr_div_up(nts, 256)), dim3(256), stream, b_denseside.as<Tri>(), (uint64_t)nts, b_cins.as<uint4>());
             } else {
@@ -606,7 +611,17 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
             if (nts) CR_LAUNCH(k_chain_inputs, dim3(cr_div_up(nts, 256)), dim3(256), stream, b_denseside.as<Tri>(), (uint64_t)nts, b_cins.as<uint4>());
             }
             timer.mark("expand");
-            if (rc_variant == 7) CR_LAUNCH(k_range_chain<7>, gchain, dim3(128), stream, b_cinm.as<uint4>(), b_cins.as<uint4>(), b_escord.as<uint32_t>(),
+            if (rc_variant == 8) {
+                CR_TRY(rcpar.run(stream, b_streams.as<RcStream>(), nstr, b_escord.as<uint32_t>(), ntm, nts, b_dense.as<Tri>(), b_denseside.as<Tri>(),
+                                 b_cinm.as<uint4>(), b_cins.as<uint4>(), b_qm.as<uint32_t>(), b_shm.as<uint32_t>(), b_qs.as<uint32_t>(), b_shs.as<uint32_t>(), timer.enabled));
+                if (timer.enabled) {
+                    timer.count("#rcp_state_steps", (double)rcpar.last.state_steps); timer.count("#rcp_live_jobs", rcpar.last.live_jobs);
+                    timer.count("#rcp_merged_jobs", rcpar.last.merged_jobs); timer.count("#rcp_seed_retries", rcpar.last.seed_retries);
+                    timer.count("#rcp_failed_seeds", rcpar.last.failed_seeds); timer.count("#rcp_flagged_streams", rcpar.last.flagged_streams);
+                    timer.count("#rcp_max_exit_set", rcpar.last.max_e);
+                }
+            }
+            else if (rc_variant == 7) CR_LAUNCH(k_range_chain<7>, gchain, dim3(128), stream, b_cinm.as<uint4>(), b_cins.as<uint4>(), b_escord.as<uint32_t>(),
                       b_streams.as<RcStream>(), nstr, b_qm.as<uint32_t>(), b_shm.as<uint32_t>(), b_qs.as<uint32_t>(), b_shs.as<uint32_t>());
             else if (rc_variant == 2) CR_LAUNCH(k_range_chain<2>, gchain, dim3(128), stream, b_cinm.as<uint4>(), b_cins.as<uint4>(), b_escord.as<uint32_t>(),
                       b_streams.as<RcStream>(), nstr, b_qm.as<uint32_t>(), b_shm.as<uint32_t>(), b_qs.as<uint32_t>(), b_shs.as<uint32_t>());

@@ -1,0 +1,490 @@
+// cr_rcpar.cuh -- the range recurrence of one coder stream, cut into jobs that run side by side (rc_variant 8).
+//
+// Replaces the serial walk of `range` in range_encoder_encode (src/cr-rangecoder.c:60-70: range /= sum; range *= frq; renormalise)
+// for a whole (block, stream).  The recurrence  r' = norm(floor(r / sum) * frq)  cannot be speculated from a guessed state, but it
+// FORGETS: floor(r / sum) merges every r of one quotient bucket, so the image of ALL 2^32 - 2^24 possible states shrinks to a few
+// hundred values within some thousand symbols (measured on the text workload: ~60000 / sqrt(symbols), profiles/round2_rcpar.md).
+// That makes the exit state of a piece of the stream a function of its entry state with a small, enumerable range:
+//
+//   plan    the stream is cut into jobs of ~T symbols; job c >= 1 starts at the symbol with the LARGEST sum near its nominal start
+//           (a_c): behind that symbol only  2^32 / sum  states are possible, whatever came before.
+//   seed    (A1) job c enumerates those states implicitly (q = qlo .. qhi), runs S symbols on each, drops equal neighbours.
+//   track   (A2, A3) the surviving states are stepped in registers to the start of the next job, merged values dropped as they
+//           appear: E_c = every state the coder can possibly be in at a_(c+1).
+//   follow  (B) job c steps every candidate of E_(c-1) through its own symbols: F_c[j] = where candidate j ends up.
+//   resolve (C) one walk over the jobs of a stream: entry_(c+1) = F_c[ index of entry_c in E_(c-1) ].
+//   emit    (D) every job re-walks its symbols from its true entry state and writes the quotient and the top-bit index of every
+//           symbol (what k_range_chain<7> writes), then CHECKS that it arrives at the entry state of the next job.
+//
+// Exactness does not rest on the set tracking: phase D is the same step function as the serial chain, and a stream whose jobs do
+// not link up (or whose seeds outgrow their buffers) is flagged and re-done by the serial walk (k_rcp_emit in whole-stream mode).
+// Streams whose sums are all small (BMP data through the LZP coder: sums below 2^14) never shrink far enough; their jobs are
+// merged at plan time and the stream runs as one serial job, i.e. exactly as before.
+//
+// Arithmetic: the double-precision form of the step (rc_dp_step, cr_rc.cuh): two dependent DFMA and three integer operations per
+// state and symbol, states kept as doubles with exact integer values in [2^24, 2^32).
+#pragma once
+#include "cr_rc.cuh"
+
+#ifndef CRGPU_SIM
+#define RCP_MMAX      262144u      // most states a seed may enumerate (2^32 / sum at the seed symbol: sum >= 2^14)
+#define RCP_CAP_A     16384u       // most states a seed may hand to the tracking kernels
+#define RCP_CAP_E     2048u        // most states of an exit set E_c
+#define RCP_S0        64u          // symbols a seed runs before it counts its survivors (doubled while they exceed RCP_CAP_A)
+#define RCP_SMAX      512u
+#define RCP_WINDOW    2048u        // a job's start is the largest sum among this many symbols behind its nominal start
+#define RCP_R0        4294967295.0 // the coder's initial range (src/cr-rangecoder.c:36)
+
+enum { RCP_LIVE = 1, RCP_MERGED = 2 };
+struct RcpStream { unsigned long long i0, i1; uint32_t first_job, njobs, is_main, flags; };   // flags != 0: redo serially
+struct RcpJob {
+    unsigned long long nominal, a, pos;   // nominal start, real start (seed symbol; stream start for job 0), next symbol of the tracked set
+    uint32_t stream, status, count, ecount;   // count: states handed from A1 to A2/A3; ecount: |E_c|
+    double entry;                             // true state on entry (phase C)
+    uint32_t seed_steps, pad;
+};
+struct RcpStats { unsigned long long state_steps; uint32_t live_jobs, merged_jobs, seed_retries, failed_seeds, flagged_streams, max_e; };
+
+CR_D void rcp_step(double& R, const double inv, const double f, const double nf) {
+    const double T = fma(R, inv, RC_DP_MAGIC);
+    const double C = fma(T, f, nf);
+    uint32_t ch = (uint32_t)__double2hiint(C);
+    ch += (0x41EFFFFFu - ch) & 0x01800000u;
+    R = __hiloint2double((int)ch, __double2loint(C));
+}
+CR_D bool rcp_same(double a, double b) { return __double_as_longlong(a) == __double_as_longlong(b); }
+CR_D double rcp_seed_state(uint32_t q, double f) {           // norm(q * frq), exact: q * frq < 2^53
+    const double C = (double)q * f;
+    uint32_t ch = (uint32_t)__double2hiint(C);
+    ch += (0x41EFFFFFu - ch) & 0x01800000u;
+    return __hiloint2double((int)ch, __double2loint(C));
+}
+CR_D void rcp_rec(const uint4 t, double& inv, double& f, double& nf) {
+    inv = __hiloint2double((int)t.y, (int)t.x); f = __hiloint2double((int)t.w, (int)t.z); nf = -(RC_DP_TWO52 * f);
+}
+
+// ---- plan: job table from the stream table.  One CTA; job counts per stream, exclusive scan, nominal starts.
+__global__ void __launch_bounds__(256) k_rcp_plan(const RcStream* __restrict__ streams, uint32_t nstreams, const uint32_t* __restrict__ escord,
+                                                  uint32_t job_symbols, uint32_t max_jobs, RcpStream* __restrict__ ps, RcpJob* __restrict__ jobs,
+                                                  uint32_t* __restrict__ njobs_total) {
+    __shared__ uint32_t wsum[8]; __shared__ uint32_t base;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    for (uint32_t s0 = 0; s0 < nstreams; s0 += 256) {
+        const uint32_t s = s0 + threadIdx.x;
+        unsigned long long i0 = 0, i1 = 0; uint32_t nj = 0, is_main = 0;
+        if (s < nstreams) {
+            const RcStream S = streams[s];
+            i0 = S.ev_begin; i1 = S.ev_end; is_main = S.is_main;
+            if (S.is_main) { i0 += escord[S.ev_begin]; i1 += escord[S.ev_end]; }
+            const unsigned long long n = i1 - i0;
+            nj = (uint32_t)(n / job_symbols); if (nj < 2) nj = 1;
+        }
+        // block exclusive scan of nj
+        const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        uint32_t incl = nj;
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += v; }
+        if (lane == 31) wsum[w] = incl;
+        __syncthreads();
+        uint32_t woff = 0, tot = 0;
+        for (uint32_t k = 0; k < 8; k++) { if (k < w) woff += wsum[k]; tot += wsum[k]; }
+        const uint32_t first = base + woff + incl - nj;
+        if (s < nstreams) {
+            RcpStream P; P.i0 = i0; P.i1 = i1; P.first_job = first; P.is_main = is_main; P.flags = 0;
+            if (first + nj > max_jobs) { nj = 1; P.flags = 1; if (first >= max_jobs) P.first_job = 0; }      // cannot happen (host bound); be safe
+            P.njobs = nj;
+            ps[s] = P;
+            const unsigned long long n = i1 - i0;
+            for (uint32_t c = 0; c < nj && P.flags == 0; c++) {
+                RcpJob J; memset(&J, 0, sizeof J);
+                J.nominal = i0 + n * c / nj; J.a = J.nominal; J.pos = J.nominal; J.stream = s; J.status = c == 0 ? RCP_LIVE : 0;
+                jobs[first + c] = J;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) base += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *njobs_total = base < max_jobs ? base : max_jobs;
+}
+
+// ---- bounds: one warp per job c >= 1: the symbol with the largest sum in the window behind the nominal start becomes the seed.
+__global__ void __launch_bounds__(128) k_rcp_bounds(const RcpStream* __restrict__ ps, RcpJob* __restrict__ jobs, const uint32_t* __restrict__ njobs_total,
+                                                    const Tri* __restrict__ dense_main, const Tri* __restrict__ dense_side, RcpStats* __restrict__ stats) {
+    const uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (j >= *njobs_total) return;
+    RcpJob J = jobs[j];
+    const RcpStream P = ps[J.stream];
+    if (P.flags || j == P.first_job) return;
+    const Tri* tri = P.is_main ? dense_main : dense_side;
+    // this job ends where the next nominal job starts; keep the seed in the first quarter of the job
+    const unsigned long long nxt = (j + 1 < P.first_job + P.njobs) ? jobs[j + 1].nominal : P.i1;
+    unsigned long long W = (nxt - J.nominal) / 4; if (W > RCP_WINDOW) W = RCP_WINDOW;
+    uint32_t best = 0; unsigned long long at = J.nominal;
+    for (unsigned long long i = J.nominal + lane; i < J.nominal + W; i += 32) { const uint32_t s = tri[i].sum; if (s > best) { best = s; at = i; } }
+    for (int d = 16; d; d >>= 1) {
+        const uint32_t ob = __shfl_down_sync(0xFFFFFFFFu, best, d); const unsigned long long oa = __shfl_down_sync(0xFFFFFFFFu, at, d);
+        if (ob > best || (ob == best && oa < at)) { best = ob; at = oa; }
+    }
+    if (lane == 0) {
+        const uint32_t M = best ? 0xFFFFFFFFu / best - (1u << 24) / best + 1 : 0xFFFFFFFFu;
+        const bool ok = best != 0 && M <= RCP_MMAX;
+        jobs[j].a = at; jobs[j].pos = at; jobs[j].status = ok ? RCP_LIVE : RCP_MERGED;
+        if (ok) atomicAdd(&stats->live_jobs, 1u); else atomicAdd(&stats->merged_jobs, 1u);
+    }
+}
+
+// end of job j's symbols = start of the next live job of its stream (or the stream's end); *next = that job (0xFFFFFFFF: none)
+CR_D unsigned long long rcp_job_end(const RcpStream& P, const RcpJob* __restrict__ jobs, uint32_t j, uint32_t* next) {
+    for (uint32_t k = j + 1; k < P.first_job + P.njobs; k++) if (jobs[k].status == RCP_LIVE) { *next = k; return jobs[k].a; }
+    *next = 0xFFFFFFFFu;
+    return P.i1;
+}
+CR_D uint32_t rcp_prev_live(const RcpStream& P, const RcpJob* __restrict__ jobs, uint32_t j) {
+    for (uint32_t k = j; k-- > P.first_job;) if (jobs[k].status == RCP_LIVE) return k;
+    return 0xFFFFFFFFu;
+}
+
+// block-wide exclusive scan of one value per thread (THREADS <= 1024); returns the offset, *total = sum.  Two barriers.
+template <int THREADS> CR_D uint32_t rcp_block_scan(uint32_t v, uint32_t* __restrict__ swarp, uint32_t* total) {
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += o; }
+    __syncthreads();                       // swarp may still be read from the previous scan
+    if (lane == 31) swarp[w] = incl;
+    __syncthreads();
+    uint32_t woff = 0, tot = 0;
+#pragma unroll
+    for (int k = 0; k < THREADS / 32; k++) { const uint32_t x = swarp[k]; if (k < (int)w) woff += x; tot += x; }
+    *total = tot;
+    return woff + incl - v;
+}
+
+// ---- A1 seed: the states possible behind the seed symbol, enumerated implicitly, S symbols each, equal neighbours dropped.
+#define RCP_SEED_THREADS 1024
+__global__ void __launch_bounds__(RCP_SEED_THREADS) k_rcp_seed(const RcpStream* __restrict__ ps, RcpJob* __restrict__ jobs, const uint32_t* __restrict__ njobs_total,
+                                                               const Tri* __restrict__ dense_main, const Tri* __restrict__ dense_side,
+                                                               const uint4* __restrict__ cin_main, const uint4* __restrict__ cin_side,
+                                                               double* __restrict__ listA, RcpStats* __restrict__ stats) {
+    __shared__ uint4 srec[RCP_SMAX];
+    __shared__ uint32_t swarp[32];
+    __shared__ double sfirst;
+    const uint32_t j = blockIdx.x, tid = threadIdx.x;
+    if (j >= *njobs_total) return;
+    const RcpJob J = jobs[j];
+    const RcpStream P = ps[J.stream];
+    if (P.flags || J.status != RCP_LIVE || j == P.first_job) return;
+    uint32_t nextj;
+    const unsigned long long end = rcp_job_end(P, jobs, j, &nextj);
+    if (nextj == 0xFFFFFFFFu) return;                               // last live job of its stream: nobody needs its exit set
+    const Tri seed = (P.is_main ? dense_main : dense_side)[J.a];
+    const uint4* cin = P.is_main ? cin_main : cin_side;
+    const uint32_t sum = seed.sum, qlo = (1u << 24) / sum, qhi = 0xFFFFFFFFu / sum, M = qhi - qlo + 1;
+    const double f0 = (double)(seed.frq & 0x7FFFFFFFu);
+    const uint32_t per = (M + RCP_SEED_THREADS - 1) / RCP_SEED_THREADS;
+    const uint32_t lo = tid * per < M ? tid * per : M, hi = lo + per < M ? lo + per : M;
+    double* out = listA + (size_t)j * RCP_CAP_A;
+    uint32_t S = RCP_S0, staged = 0;
+    unsigned long long work = 0;
+    for (;;) {
+        if (J.a + 1 + S > end) S = (uint32_t)(end - J.a - 1);
+        for (uint32_t i = staged + tid; i < S; i += RCP_SEED_THREADS) srec[i] = cin[J.a + 1 + i];
+        staged = S;
+        __syncthreads();
+        // state of element 0 after S symbols (the seam: the last elements wrap around onto the first)
+        if (tid == 0) {
+            double r = rcp_seed_state(qlo, f0);
+            for (uint32_t s = 0; s < S; s++) { double inv, f, nf; rcp_rec(srec[s], inv, f, nf); rcp_step(r, inv, f, nf); }
+            sfirst = r;
+        }
+        __syncthreads();
+        const double first = sfirst;
+        uint32_t off = 0, total = 0;
+        for (int pass = 0; pass < 2; pass++) {
+            uint32_t cnt = 0;
+            double prev = first;
+            if (lo > 0 && lo < hi) {                                 // the element in front of this thread's slice
+                prev = rcp_seed_state(qlo + lo - 1, f0);
+                for (uint32_t s = 0; s < S; s++) { double inv, f, nf; rcp_rec(srec[s], inv, f, nf); rcp_step(prev, inv, f, nf); }
+            }
+            for (uint32_t b = lo; b < hi; b += 8) {
+                double d[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) d[k] = rcp_seed_state(qlo + (b + k < hi ? b + k : hi - 1), f0);
+                for (uint32_t s = 0; s < S; s++) {
+                    double inv, f, nf; rcp_rec(srec[s], inv, f, nf);
+#pragma unroll
+                    for (int k = 0; k < 8; k++) rcp_step(d[k], inv, f, nf);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const bool uniq = b + k < hi && (b + k == 0 || (!rcp_same(d[k], prev) && !rcp_same(d[k], first)));
+                    if (uniq) { if (pass) out[off + cnt] = d[k]; cnt++; }
+                    prev = d[k];
+                }
+            }
+            if (pass == 0) {
+                off = rcp_block_scan<RCP_SEED_THREADS>(cnt, swarp, &total);
+                if (total > RCP_CAP_A) break;
+            }
+        }
+        work += 2ull * (hi - lo) * S;
+        if (total <= RCP_CAP_A) {
+            if (tid == 0) { jobs[j].count = total; jobs[j].pos = J.a + 1 + S; jobs[j].seed_steps = S; }
+            break;
+        }
+        if (S >= RCP_SMAX || J.a + 1 + S >= end) {                   // does not shrink: give the stream to the serial walk
+            if (tid == 0) { atomicOr((uint32_t*)&ps[J.stream].flags, 2u); atomicAdd(&stats->failed_seeds, 1u); jobs[j].count = 0; }
+            break;
+        }
+        if (tid == 0) atomicAdd(&stats->seed_retries, 1u);
+        S *= 2;
+        __syncthreads();
+    }
+    if (work) atomicAdd(&stats->state_steps, work);
+}
+
+// ---- A2 / A3 / B: explicit state lists stepped in registers (K per thread, blocked layout), merged values dropped.
+//   mode 0 (A2): listA[j] (count states at pos) -> until count <= RCP_CAP_E (or the job's end), back into listA[j]
+//   mode 1 (A3): listA[j] (or the single start state for the first job of a stream) -> to the job's end, E[j]
+//   mode 2 (B) : E[previous live job] stepped through this job's symbols WITHOUT merging -> F[j][i] = where candidate i ends up
+enum { RCP_MODE_MID = 0, RCP_MODE_LATE = 1, RCP_MODE_FOLLOW = 2 };
+template <int THREADS, int K, int BATCH, bool DEDUP>
+__global__ void __launch_bounds__(THREADS) k_rcp_track(const RcpStream* __restrict__ ps, RcpJob* __restrict__ jobs, const uint32_t* __restrict__ njobs_total,
+                                                       const uint4* __restrict__ cin_main, const uint4* __restrict__ cin_side,
+                                                       double* __restrict__ listA, double* __restrict__ E, double* __restrict__ F, int mode, RcpStats* __restrict__ stats) {
+    extern __shared__ double sbuf[];                 // DEDUP: THREADS * K doubles for the compaction
+    __shared__ uint4 srec[BATCH];
+    __shared__ uint32_t swarp[32];
+    __shared__ double slast[32];
+    __shared__ double sfirst;
+    const uint32_t j = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (j >= *njobs_total) return;
+    const RcpJob J = jobs[j];
+    const RcpStream P = ps[J.stream];
+    if (P.flags || J.status != RCP_LIVE) return;
+    uint32_t nextj;
+    const unsigned long long end = rcp_job_end(P, jobs, j, &nextj);
+    if (nextj == 0xFFFFFFFFu) return;                // last live job of the stream
+    const bool first_job = j == P.first_job;
+    const double* in; uint32_t n; unsigned long long pos;
+    if (mode == RCP_MODE_FOLLOW) {
+        if (first_job) return;
+        const uint32_t pj = rcp_prev_live(P, jobs, j);
+        in = E + (size_t)pj * RCP_CAP_E; n = jobs[pj].ecount; pos = J.a;
+    } else if (first_job) {
+        if (mode == RCP_MODE_MID) return;
+        in = nullptr; n = 1; pos = P.i0;
+    } else {
+        in = listA + (size_t)j * RCP_CAP_A; n = J.count; pos = J.pos;
+        if (mode == RCP_MODE_MID && n <= RCP_CAP_E) return;
+        if (mode == RCP_MODE_LATE && n > RCP_CAP_E) {                  // A2 could not shrink it far enough
+            if (tid == 0) atomicOr((uint32_t*)&ps[J.stream].flags, 4u);
+            return;
+        }
+    }
+    if (n == 0 || n > (uint32_t)THREADS * K) { if (tid == 0) atomicOr((uint32_t*)&ps[J.stream].flags, 8u); return; }
+    const uint4* cin = P.is_main ? cin_main : cin_side;
+    double d[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) { const uint32_t i = tid * K + k; d[k] = in ? in[i < n ? i : n - 1] : RCP_R0; }
+    unsigned long long work = 0;
+    uint4 nxt = make_uint4(0, 0, 0, 0x3FF00000u);
+    if (tid < BATCH && pos + tid < end) nxt = cin[pos + tid];
+    while (pos < end) {
+        __syncthreads();                                               // the previous batch has been consumed
+        if (tid < BATCH) srec[tid] = nxt;
+        __syncthreads();
+        const uint32_t nb = end - pos < BATCH ? (uint32_t)(end - pos) : BATCH;
+        if (tid < BATCH && pos + BATCH + tid < end) nxt = cin[pos + BATCH + tid];
+        if (tid * K < n) {
+            for (uint32_t s = 0; s < nb; s++) {
+                double inv, f, nf; rcp_rec(srec[s], inv, f, nf);
+#pragma unroll
+                for (int k = 0; k < K; k++) rcp_step(d[k], inv, f, nf);
+            }
+            if (lane == 0) work += (unsigned long long)nb * (n - tid * K < 32u * K ? n - tid * K : 32u * K);
+        }
+        pos += nb;
+        if (DEDUP) {
+            // drop every element equal to its predecessor (or, wrapping around, to element 0); order is kept
+            if (lane == 31) slast[w] = d[K - 1];
+            if (tid == 0) sfirst = d[0];
+            __syncthreads();
+            const double first = sfirst;
+            double prev = __shfl_up_sync(0xFFFFFFFFu, d[K - 1], 1);
+            if (lane == 0) prev = w ? slast[w - 1] : first;
+            uint32_t keep = 0, cnt = 0;
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                const uint32_t i = tid * K + k;
+                const bool uniq = i < n && (i == 0 || (!rcp_same(d[k], prev) && !rcp_same(d[k], first)));
+                keep |= (uint32_t)uniq << k; cnt += uniq;
+                prev = d[k];
+            }
+            uint32_t total;
+            uint32_t off = rcp_block_scan<THREADS>(cnt, swarp, &total);
+            if (total < n) {
+#pragma unroll
+                for (int k = 0; k < K; k++) if (keep >> k & 1) sbuf[off++] = d[k];
+                __syncthreads();
+                n = total;
+#pragma unroll
+                for (int k = 0; k < K; k++) { const uint32_t i = tid * K + k; d[k] = sbuf[i < n ? i : n - 1]; }
+            }
+            if (mode == RCP_MODE_MID && n <= RCP_CAP_E) break;
+        }
+    }
+    // hand over
+    double* out = mode == RCP_MODE_MID ? listA + (size_t)j * RCP_CAP_A : mode == RCP_MODE_LATE ? E + (size_t)j * RCP_CAP_E : F + (size_t)j * RCP_CAP_E;
+    if (mode != RCP_MODE_MID && n > RCP_CAP_E) { if (tid == 0) atomicOr((uint32_t*)&ps[J.stream].flags, 16u); return; }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; k++) { const uint32_t i = tid * K + k; if (i < n) out[i] = d[k]; }
+    if (tid == 0) {
+        if (mode == RCP_MODE_MID) { jobs[j].count = n; jobs[j].pos = pos; }
+        else if (mode == RCP_MODE_LATE) { jobs[j].ecount = n; atomicMax(&stats->max_e, n); }
+    }
+    if (lane == 0 && work) atomicAdd(&stats->state_steps, work);
+}
+
+// ---- C resolve: one warp per stream walks its live jobs: entry of the next job = F[this job][index of this job's entry in E[previous]]
+__global__ void __launch_bounds__(32) k_rcp_resolve(RcpStream* __restrict__ ps, uint32_t nstreams, RcpJob* __restrict__ jobs,
+                                                    const double* __restrict__ E, const double* __restrict__ F) {
+    const uint32_t s = blockIdx.x, lane = threadIdx.x;
+    if (s >= nstreams) return;
+    const RcpStream P = ps[s];
+    if (P.flags) return;
+    uint32_t cur = P.first_job, prev = 0xFFFFFFFFu;
+    double entry = RCP_R0;
+    if (lane == 0) jobs[cur].entry = entry;
+    for (;;) {
+        uint32_t nxt;
+        rcp_job_end(P, jobs, cur, &nxt);
+        if (nxt == 0xFFFFFFFFu) break;
+        double ne = 0.0; bool ok = false;
+        if (prev == 0xFFFFFFFFu) {                     // first job: its exit set is the one state the known start leads to
+            ok = jobs[cur].ecount == 1; ne = E[(size_t)cur * RCP_CAP_E];
+        } else {
+            const uint32_t n = jobs[prev].ecount;
+            const double* e = E + (size_t)prev * RCP_CAP_E;
+            uint32_t found = 0xFFFFFFFFu;
+            for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+                const bool hit = i0 + lane < n && rcp_same(e[i0 + lane], entry);
+                const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
+                if (m) { found = i0 + __ffs(m) - 1; break; }
+            }
+            if (found != 0xFFFFFFFFu) { ok = true; ne = F[(size_t)cur * RCP_CAP_E + found]; }
+        }
+        if (!ok) { if (lane == 0) atomicOr(&ps[s].flags, 32u); return; }
+        entry = ne; prev = cur; cur = nxt;
+        if (lane == 0) jobs[cur].entry = entry;
+    }
+}
+
+// ---- D emit: the serial walk (k_range_chain<7>'s loop) per job from its true entry state; checks the link to the next job.
+// whole_streams != 0: the fallback -- one warp per FLAGGED stream walks the whole stream from the coder's initial range.
+__global__ void __launch_bounds__(128) k_rcp_emit(RcpStream* __restrict__ ps, uint32_t nstreams, const RcpJob* __restrict__ jobs, const uint32_t* __restrict__ njobs_total,
+                                                  const uint4* __restrict__ cin_main, const uint4* __restrict__ cin_side,
+                                                  uint32_t* __restrict__ q_main, uint32_t* __restrict__ sh_main, uint32_t* __restrict__ q_side, uint32_t* __restrict__ sh_side,
+                                                  int whole_streams, RcpStats* __restrict__ stats) {
+    __shared__ uint4 stage[4][RC_BATCH + 8];
+    __shared__ uint32_t oq[4][RC_BATCH], os[4][RC_BATCH + 1];
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    unsigned long long i0, i1; double R; uint32_t sidx, nextj = 0xFFFFFFFFu; bool is_main;
+    if (whole_streams) {
+        if (g >= nstreams) return;
+        const RcpStream P = ps[g];
+        if (!P.flags) return;
+        if (lane == 0) atomicAdd(&stats->flagged_streams, 1u);
+        i0 = P.i0; i1 = P.i1; R = RCP_R0; sidx = g; is_main = P.is_main != 0;
+    } else {
+        if (g >= *njobs_total) return;
+        const RcpJob J = jobs[g];
+        const RcpStream P = ps[J.stream];
+        if (P.flags || J.status != RCP_LIVE) return;
+        i1 = rcp_job_end(P, jobs, g, &nextj);
+        i0 = g == P.first_job ? P.i0 : J.a; R = J.entry; sidx = J.stream; is_main = P.is_main != 0;
+    }
+    const uint4* tri = is_main ? cin_main : cin_side;
+    uint32_t* qo = is_main ? q_main : q_side;
+    uint32_t* so = is_main ? sh_main : sh_side;
+    uint4 r0 = make_uint4(1, 1, 1, 1), r1 = r0;
+    if (i0 + lane < i1) r0 = tri[i0 + lane];
+    if (i0 + 32 + lane < i1) r1 = tri[i0 + 32 + lane];
+    for (unsigned long long base = i0; base < i1; base += RC_BATCH) {
+        stage[w][lane] = r0; stage[w][lane + 32] = r1;
+        __syncwarp();
+        const unsigned long long nb = base + RC_BATCH;
+        if (nb + lane < i1) r0 = tri[nb + lane];
+        if (nb + 32 + lane < i1) r1 = tri[nb + 32 + lane];
+        const uint32_t cnt = i1 - base < RC_BATCH ? (uint32_t)(i1 - base) : RC_BATCH;
+        if (lane == 0) {
+            uint4 t = stage[w][0];
+            for (uint32_t j = 0; j < cnt; j++) {
+                const uint4 tn = stage[w][j + 1];
+                uint32_t q, m;
+                rc_dp_step(R, t, q, m);
+                oq[w][j] = q; os[w][j] = m;
+                t = tn;
+            }
+        }
+        __syncwarp();
+        if (lane < cnt) { qo[base + lane] = oq[w][lane]; so[base + lane] = os[w][lane]; }
+        if (lane + 32 < cnt) { qo[base + lane + 32] = oq[w][lane + 32]; so[base + lane + 32] = os[w][lane + 32]; }
+        __syncwarp();
+    }
+    if (!whole_streams && lane == 0 && nextj != 0xFFFFFFFFu && !rcp_same(R, jobs[nextj].entry)) atomicOr(&ps[sidx].flags, 64u);   // the jobs do not link up
+}
+
+// host side: all buffers of the parallel chain
+struct RcPar {
+    DevBuf b_ps, b_jobs, b_njobs, b_listA, b_E, b_F, b_stats;
+    uint32_t job_symbols = 49152;
+    bool attr_done = false;
+    RcpStats last = {};
+    void release() { DevBuf* all[] = { &b_ps, &b_jobs, &b_njobs, &b_listA, &b_E, &b_F, &b_stats }; for (DevBuf* b : all) b->release(); }
+    // q / top-bit index of every symbol of every stream, as k_range_chain<7> writes them
+    int run(cudaStream_t stream, const RcStream* d_streams, uint32_t nstreams, const uint32_t* d_escord, uint64_t ntm, uint64_t nts,
+            const Tri* dense_main, const Tri* dense_side, const uint4* cin_main, const uint4* cin_side,
+            uint32_t* q_main, uint32_t* sh_main, uint32_t* q_side, uint32_t* sh_side, bool want_stats) {
+        if (nstreams == 0) return CRGPU_OK;
+        const uint32_t T = job_symbols < 4096 ? 4096 : job_symbols;
+        const uint64_t maxjobs64 = nstreams + (ntm + nts) / T + 1;
+        if (maxjobs64 > (1u << 20)) return CRGPU_ERR_UNSUPPORTED;
+        const uint32_t maxjobs = (uint32_t)maxjobs64;
+        CR_TRY(b_ps.reserve((size_t)nstreams * sizeof(RcpStream))); CR_TRY(b_jobs.reserve((size_t)maxjobs * sizeof(RcpJob)));
+        CR_TRY(b_njobs.reserve(16)); CR_TRY(b_stats.reserve(sizeof(RcpStats)));
+        CR_TRY(b_listA.reserve((size_t)maxjobs * RCP_CAP_A * 8)); CR_TRY(b_E.reserve((size_t)maxjobs * RCP_CAP_E * 8)); CR_TRY(b_F.reserve((size_t)maxjobs * RCP_CAP_E * 8));
+        CR_CUDA(cudaMemsetAsync(b_stats.p, 0, sizeof(RcpStats), stream));
+        RcpStream* ps = b_ps.as<RcpStream>(); RcpJob* jobs = b_jobs.as<RcpJob>(); uint32_t* nj = b_njobs.as<uint32_t>(); RcpStats* st = b_stats.as<RcpStats>();
+        double* LA = b_listA.as<double>(); double* E = b_E.as<double>(); double* F = b_F.as<double>();
+        CR_LAUNCH(k_rcp_plan, dim3(1), dim3(256), stream, d_streams, nstreams, d_escord, T, maxjobs, ps, jobs, nj);
+        CR_LAUNCH(k_rcp_bounds, dim3(cr_div_up((size_t)maxjobs * 32, 128)), dim3(128), stream, ps, jobs, nj, dense_main, dense_side, st);
+        CR_LAUNCH(k_rcp_seed, dim3(maxjobs), dim3(RCP_SEED_THREADS), stream, ps, jobs, nj, dense_main, dense_side, cin_main, cin_side, LA, st);
+        if (!attr_done) {                            // per handle: a handle is bound to one device
+            CR_CUDA(cudaFuncSetAttribute(k_rcp_track<512, 32, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * 32 * 8));
+            attr_done = true;
+        }
+        { __atomic_fetch_add(&g_cr_launches, 1ull, __ATOMIC_RELAXED);
+          k_rcp_track<512, 32, 16, true><<<dim3(maxjobs), dim3(512), 512 * 32 * 8, stream>>>(ps, jobs, nj, cin_main, cin_side, LA, E, F, RCP_MODE_MID, st);
+          CR_CUDA(cudaGetLastError()); }
+        { __atomic_fetch_add(&g_cr_launches, 1ull, __ATOMIC_RELAXED);
+          k_rcp_track<256, 8, 128, true><<<dim3(maxjobs), dim3(256), 256 * 8 * 8, stream>>>(ps, jobs, nj, cin_main, cin_side, LA, E, F, RCP_MODE_LATE, st);
+          CR_CUDA(cudaGetLastError()); }
+        { __atomic_fetch_add(&g_cr_launches, 1ull, __ATOMIC_RELAXED);
+          k_rcp_track<256, 8, 128, false><<<dim3(maxjobs), dim3(256), 0, stream>>>(ps, jobs, nj, cin_main, cin_side, LA, E, F, RCP_MODE_FOLLOW, st);
+          CR_CUDA(cudaGetLastError()); }
+        CR_LAUNCH(k_rcp_resolve, dim3(nstreams), dim3(32), stream, ps, nstreams, jobs, E, F);
+        CR_LAUNCH(k_rcp_emit, dim3(cr_div_up((size_t)maxjobs * 32, 128)), dim3(128), stream, ps, nstreams, jobs, nj, cin_main, cin_side, q_main, sh_main, q_side, sh_side, 0, st);
+        CR_LAUNCH(k_rcp_emit, dim3(cr_div_up((size_t)nstreams * 32, 128)), dim3(128), stream, ps, nstreams, jobs, nj, cin_main, cin_side, q_main, sh_main, q_side, sh_side, 1, st);
+        if (want_stats) {
+            CR_CUDA(cudaMemcpyAsync(&last, st, sizeof(RcpStats), cudaMemcpyDeviceToHost, stream));
+            CR_CUDA(cudaStreamSynchronize(stream));
+        }
+        return CRGPU_OK;
+    }
+};
+#endif

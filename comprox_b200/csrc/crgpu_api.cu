@@ -194,7 +194,12 @@ extern "C" int crgpu_set_option(crgpu_handle* h, const char* name, int64_t value
     if (!h || !name) return CRGPU_ERR_ARG;
     std::string n(name);
     if (n == "scalar_models") { h->chain.scalar_models = value != 0; return CRGPU_OK; }
-    if (n == "rc_variant") { if (value < 1 || value > 7) return CRGPU_ERR_ARG; h->chain.rc_variant = (int)value; return CRGPU_OK; }
+    if (n == "rc_variant") { if (value < 1 || value > 8) return CRGPU_ERR_ARG; h->chain.rc_variant = (int)value; return CRGPU_OK; }
+#ifndef CRGPU_SIM
+    if (n == "rc_job_symbols") { if (value < 4096 || value > (1 << 24)) return CRGPU_ERR_ARG; h->chain.rcpar.job_symbols = (uint32_t)value; return CRGPU_OK; }
+#else
+    if (n == "rc_job_symbols") return CRGPU_OK;
+#endif
     if (n == "hot_contexts") { h->chain.hot_contexts = value != 0; return CRGPU_OK; }
     if (n == "match_limit") { if (value < 1 || value > 1000000) return CRGPU_ERR_ARG; h->chain.match_limit = (uint32_t)value; return CRGPU_OK; }   // comprox -m
     if (n == "exact_aborts") { h->chain.exact_aborts = value != 0; return CRGPU_OK; }             // 0: mid-chain "cannot compress" -> CRGPU_ERR_MIDCHAIN_ABORT

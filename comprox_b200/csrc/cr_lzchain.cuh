@@ -66,7 +66,7 @@ struct LzChain {
     size_t last_dtotal = 0;
     StageTimer timer;
     bool flexible = false;         // -f flexible parsing (ROLZ)
-    int rc_variant = 7;            // range-chain formulation (cr_warp.cuh: k_range_chain<1..7>; 7 = double-precision chain, B200-verified in round 1's driver run)
+    int rc_variant = 8;            // range-chain formulation: 8 = cut into jobs that run side by side (cr_rcpar.cuh); 1..7 = one serial walk per stream (cr_warp.cuh: k_range_chain<1..7>)
     bool hot_contexts = true;      // hot o2 contexts run the rank-based CTA kernel (k_o2_pass_cta)
     bool scalar_models = false;   // GPU A/B switch: run the scalar (simulation-checked) model/coder kernels
     bool exact_aborts = true;      // replay a mid-chain "cannot compress" exactly (encode_blocks); false = CRGPU_ERR_MIDCHAIN_ABORT
@@ -617,7 +617,7 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
                 if (timer.enabled) {
                     timer.count("#rcp_state_steps", (double)rcpar.last.state_steps); timer.count("#rcp_live_jobs", rcpar.last.live_jobs);
                     timer.count("#rcp_merged_jobs", rcpar.last.merged_jobs); timer.count("#rcp_seed_retries", rcpar.last.seed_retries);
-                    timer.count("#rcp_failed_seeds", rcpar.last.failed_seeds); timer.count("#rcp_flagged_streams", rcpar.last.flagged_streams);
+                    timer.count("#rcp_demoted_jobs", rcpar.last.demoted_jobs); timer.count("#rcp_flagged_streams", rcpar.last.flagged_streams);
                     timer.count("#rcp_max_exit_set", rcpar.last.max_e);
                 }
             }

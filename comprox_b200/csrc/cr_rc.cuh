@@ -59,16 +59,22 @@ __global__ void k_expand_side(const uint64_t* __restrict__ TS, uint32_t n, Tri* 
     dense[i] = a;
 }
 
-// ------------------------------------------------------------------ double-precision form of the range recurrence (k_range_chain<7>)
-// q = floor(r / sum); r' = q * frq; byte renormalisation -- as two dependent FMAs and three integer operations (tests/micro/chain_dp.cu,
-// profiles/round1_chain_latency.md: 39.1 cycles per symbol against 44.0 for the integer chain on B200):
-//   T = fma(R, inv, 2^52 - 0.5) == 2^52 + floor(R / sum) exactly, for inv = two ulps above the correctly rounded 1/sum:  R < 2^32 makes
-//       R * inv exceed R / sum by less than 2^-19 / sum, the fractional part of R / sum is a multiple of 1/sum below 1, so the product's
-//       fractional part lies strictly inside (0, 1) and the single rounding of the FMA (ulp 1 at 2^52) lands on 2^52 + q;
-//   C = fma(T, frq, -(2^52 * frq)) == q * frq exactly (below 2^48);
-//   the top-bit index of C is its exponent, and adding (31 - e) & 24 to the exponent is the shift by 0 .. 3 bytes.
+// ------------------------------------------------------------------ double-precision form of the range recurrence (k_range_chain<7>, cr_rcpar.cuh)
+// q = floor(r / sum); r' = q * frq; byte renormalisation -- as two dependent FMAs and ONE integer operation.  The state is kept as
+// R = 2 * range (a double with an exact integer value in [2^25, 2^33)); the records hold inv/2 and 2*frq, both exact scalings:
+//   T = fma(R, inv/2, 2^52 - 0.5) == 2^52 + floor(range / sum) exactly, for inv = two ulps above the correctly rounded 1/sum:  range < 2^32
+//       makes range * inv exceed range / sum by less than 2^-19 / sum, the fractional part of range / sum is a multiple of 1/sum below 1, so
+//       the product's fractional part lies strictly inside (0, 1) and the single rounding of the FMA (ulp 1 at 2^52) lands on 2^52 + q;
+//   C = fma(T, 2*frq, -(2^52 * 2*frq)) == 2 * q * frq exactly (below 2^49);
+//   renormalisation: with e = top-bit index of q * frq, the coder shifts by whole bytes until the top bit sits at 24 + (e & 7).  The
+//       exponent field of C is 1024 + e, whose low three bits ARE e & 7, so  hi' = (hi & 0x007FFFFF) | 0x41800000  (exponent field
+//       1048 + (e & 7), i.e. 2 * range' with range' in [2^24, 2^32)) is the whole renormalisation: one LOP3.  That is why the state
+//       carries the factor two: 1047 is not a multiple of eight, 1048 is.
+// Measured on B200: see profiles/round2_rcpar.md (the chain with the three-operation renormalisation: 39.1 cycles per symbol,
+// profiles/round1_chain_latency.md).
 #define RC_DP_MAGIC 4503599627370495.5         /* 2^52 - 0.5 */
 #define RC_DP_TWO52 4503599627370496.0
+#define RC_DP_R0    8589934590.0               /* 2 * 0xFFFFFFFF: the coder's initial range (src/cr-rangecoder.c:36) */
 CR_HD void rc_dp_split(double v, uint32_t& hi, uint32_t& lo) {
 #if defined(__CUDA_ARCH__)
     hi = (uint32_t)__double2hiint(v); lo = (uint32_t)__double2loint(v);
@@ -83,16 +89,29 @@ CR_HD double rc_dp_join(uint32_t hi, uint32_t lo) {
     unsigned long long b = (unsigned long long)hi << 32 | lo; double v; memcpy(&v, &b, 8); return v;
 #endif
 }
-// chain record of one symbol: {inv, frq} as two doubles in a uint4 slot (x, y = inv lo, hi; z, w = frq lo, hi)
+// the renormalisation on the high word: (hi & 0x007FFFFF) | 0x41800000.  The compiler emits two LOP3 for two immediates; with the
+// second constant in a register it is one (measured: 27.3 instead of 31.1 cycles per symbol, tests/micro/dpstep.cu)
+CR_HD uint32_t rc_dp_renorm(uint32_t ch) {
+#if defined(__CUDA_ARCH__)
+    uint32_t c = 0x41800000u, r;
+    asm volatile("" : "+r"(c));
+    asm("lop3.b32 %0, %1, 0x007FFFFF, %2, 0xEA;" : "=r"(r) : "r"(ch), "r"(c));
+    return r;
+#else
+    return (ch & 0x007FFFFFu) | 0x41800000u;
+#endif
+}
+// chain record of one symbol: {inv / 2, 2 * frq} as two doubles in a uint4 slot (x, y = lo, hi of the first; z, w = lo, hi of the second)
 CR_HD uint4 rc_dp_record(uint32_t frq, uint32_t sum) {
     double inv = 1.0 / (double)sum;
     uint32_t ih, il; rc_dp_split(inv, ih, il);
     unsigned long long b = ((unsigned long long)ih << 32 | il) + 2ull;          // two ulps up: strictly above 1/sum, power-of-two sums included
-    uint32_t fh, fl; rc_dp_split((double)frq, fh, fl);
+    b -= 1ull << 52;                                                            // halve (sum < 2^23: far from the subnormals)
+    uint32_t fh, fl; rc_dp_split(2.0 * (double)frq, fh, fl);
     uint4 r; r.x = (uint32_t)b; r.y = (uint32_t)(b >> 32); r.z = fl; r.w = fh;
     return r;
 }
-// one symbol: R = the (normalised) range as a double; returns q, msb = top-bit index of the UN-normalised new range (as VARIANT 4 stores it)
+// one symbol: R = 2 * (normalised range) as a double; returns q, msb = top-bit index of the UN-normalised new range (as VARIANT 4 stores it)
 CR_HD void rc_dp_step(double& R, const uint4 t, uint32_t& q, uint32_t& msb) {
     const double inv = rc_dp_join(t.y, t.x), f = rc_dp_join(t.w, t.z);
     const double T = fma(R, inv, RC_DP_MAGIC);
@@ -100,9 +119,8 @@ CR_HD void rc_dp_step(double& R, const uint4 t, uint32_t& q, uint32_t& msb) {
     uint32_t th, tl, ch, cl;
     rc_dp_split(T, th, tl); rc_dp_split(C, ch, cl);
     q = tl;
-    msb = (ch >> 20) - 1023u;
-    ch += (0x41EFFFFFu - ch) & 0x01800000u;
-    R = rc_dp_join(ch, cl);
+    msb = (ch >> 20) - 1024u;
+    R = rc_dp_join(rc_dp_renorm(ch), cl);
 }
 
 struct RcStream {

@@ -33,34 +33,43 @@
 #define RCP_S0        64u          // symbols a seed runs before it counts its survivors (doubled while they exceed RCP_CAP_A)
 #define RCP_SMAX      512u
 #define RCP_WINDOW    2048u        // a job's start is the largest sum among this many symbols behind its nominal start
-#define RCP_R0        4294967295.0 // the coder's initial range (src/cr-rangecoder.c:36)
+#define RCP_NONE      0xFFFFFFFFu
 
 enum { RCP_LIVE = 1, RCP_MERGED = 2 };
 struct RcpStream { unsigned long long i0, i1; uint32_t first_job, njobs, is_main, flags; };   // flags != 0: redo serially
 struct RcpJob {
-    unsigned long long nominal, a, pos;   // nominal start, real start (seed symbol; stream start for job 0), next symbol of the tracked set
+    unsigned long long nominal, a, pos, end;  // nominal start; real start (seed symbol; stream start for job 0); next symbol of the tracked set; end (k_rcp_links)
     uint32_t stream, status, count, ecount;   // count: states handed from A1 to A2/A3; ecount: |E_c|
+    uint32_t next, prev;                      // neighbouring live jobs of the stream (k_rcp_links)
     double entry;                             // true state on entry (phase C)
-    uint32_t seed_steps, pad;
 };
-struct RcpStats { unsigned long long state_steps; uint32_t live_jobs, merged_jobs, seed_retries, failed_seeds, flagged_streams, max_e; };
+struct RcpStats { unsigned long long state_steps; uint32_t live_jobs, merged_jobs, seed_retries, demoted_jobs, flagged_streams, max_e; };
 
+// one symbol on one state: two dependent DFMA and one LOP3 (rc_dp_step, cr_rc.cuh, without the outputs)
 CR_D void rcp_step(double& R, const double inv, const double f, const double nf) {
     const double T = fma(R, inv, RC_DP_MAGIC);
     const double C = fma(T, f, nf);
-    uint32_t ch = (uint32_t)__double2hiint(C);
-    ch += (0x41EFFFFFu - ch) & 0x01800000u;
-    R = __hiloint2double((int)ch, __double2loint(C));
+    R = __hiloint2double((int)rc_dp_renorm((uint32_t)__double2hiint(C)), __double2loint(C));
 }
 CR_D bool rcp_same(double a, double b) { return __double_as_longlong(a) == __double_as_longlong(b); }
-CR_D double rcp_seed_state(uint32_t q, double f) {           // norm(q * frq), exact: q * frq < 2^53
-    const double C = (double)q * f;
-    uint32_t ch = (uint32_t)__double2hiint(C);
-    ch += (0x41EFFFFFu - ch) & 0x01800000u;
-    return __hiloint2double((int)ch, __double2loint(C));
+CR_D double rcp_seed_state(uint32_t q, double f2) {          // 2 * norm(q * frq), exact: 2 * q * frq < 2^53
+    const double C = (double)q * f2;
+    return __hiloint2double((int)rc_dp_renorm((uint32_t)__double2hiint(C)), __double2loint(C));
 }
-CR_D void rcp_rec(const uint4 t, double& inv, double& f, double& nf) {
-    inv = __hiloint2double((int)t.y, (int)t.x); f = __hiloint2double((int)t.w, (int)t.z); nf = -(RC_DP_TWO52 * f);
+struct RcpRecA { double inv, f; };
+CR_D void rcp_unpack(const uint4 t, RcpRecA& a, double& nf) {
+    a.inv = __hiloint2double((int)t.y, (int)t.x); a.f = __hiloint2double((int)t.w, (int)t.z); nf = -(RC_DP_TWO52 * a.f);
+}
+// nb symbols on K states; the records sit in shared memory (padded by one), the next one is fetched while this one is applied
+template <int K> CR_D void rcp_run(double (&d)[K], const RcpRecA* __restrict__ sa, const double* __restrict__ sn, uint32_t nb) {
+    RcpRecA a = sa[0]; double nf = sn[0];
+#pragma unroll 2
+    for (uint32_t s = 0; s < nb; s++) {
+        const RcpRecA na = sa[s + 1]; const double nn = sn[s + 1];
+#pragma unroll
+        for (int k = 0; k < K; k++) rcp_step(d[k], a.inv, a.f, nf);
+        a = na; nf = nn;
+    }
 }
 
 // ---- plan: job table from the stream table.  One CTA; job counts per stream, exclusive scan, nominal starts.
@@ -80,7 +89,6 @@ __global__ void __launch_bounds__(256) k_rcp_plan(const RcStream* __restrict__ s
             const unsigned long long n = i1 - i0;
             nj = (uint32_t)(n / job_symbols); if (nj < 2) nj = 1;
         }
-        // block exclusive scan of nj
         const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
         uint32_t incl = nj;
         for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += v; }
@@ -91,13 +99,14 @@ __global__ void __launch_bounds__(256) k_rcp_plan(const RcStream* __restrict__ s
         const uint32_t first = base + woff + incl - nj;
         if (s < nstreams) {
             RcpStream P; P.i0 = i0; P.i1 = i1; P.first_job = first; P.is_main = is_main; P.flags = 0;
-            if (first + nj > max_jobs) { nj = 1; P.flags = 1; if (first >= max_jobs) P.first_job = 0; }      // cannot happen (host bound); be safe
+            if (first + nj > max_jobs) { nj = 0; P.flags = 1; P.first_job = 0; }      // cannot happen (host bound); the serial walk takes it
             P.njobs = nj;
             ps[s] = P;
             const unsigned long long n = i1 - i0;
-            for (uint32_t c = 0; c < nj && P.flags == 0; c++) {
+            for (uint32_t c = 0; c < nj; c++) {
                 RcpJob J; memset(&J, 0, sizeof J);
-                J.nominal = i0 + n * c / nj; J.a = J.nominal; J.pos = J.nominal; J.stream = s; J.status = c == 0 ? RCP_LIVE : 0;
+                J.nominal = i0 + n * c / nj; J.a = J.nominal; J.pos = J.nominal; J.end = i1; J.stream = s; J.status = c == 0 ? RCP_LIVE : 0;
+                J.next = RCP_NONE; J.prev = RCP_NONE;
                 jobs[first + c] = J;
             }
         }
@@ -113,19 +122,26 @@ __global__ void __launch_bounds__(128) k_rcp_bounds(const RcpStream* __restrict_
                                                     const Tri* __restrict__ dense_main, const Tri* __restrict__ dense_side, RcpStats* __restrict__ stats) {
     const uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (j >= *njobs_total) return;
-    RcpJob J = jobs[j];
+    const RcpJob J = jobs[j];
     const RcpStream P = ps[J.stream];
     if (P.flags || j == P.first_job) return;
     const Tri* tri = P.is_main ? dense_main : dense_side;
-    // this job ends where the next nominal job starts; keep the seed in the first quarter of the job
+    // this job ends where the next nominal job starts.  The seed is the largest sum among the first RCP_WINDOW symbols; if even that
+    // one leaves too many states (fresh models at the start of a chain have small sums) the search goes on through the first half
     const unsigned long long nxt = (j + 1 < P.first_job + P.njobs) ? jobs[j + 1].nominal : P.i1;
-    unsigned long long W = (nxt - J.nominal) / 4; if (W > RCP_WINDOW) W = RCP_WINDOW;
+    const unsigned long long half = (nxt - J.nominal) / 2;
+    const unsigned long long W = half < RCP_WINDOW ? half : RCP_WINDOW;
     uint32_t best = 0; unsigned long long at = J.nominal;
-    for (unsigned long long i = J.nominal + lane; i < J.nominal + W; i += 32) { const uint32_t s = tri[i].sum; if (s > best) { best = s; at = i; } }
-    for (int d = 16; d; d >>= 1) {
-        const uint32_t ob = __shfl_down_sync(0xFFFFFFFFu, best, d); const unsigned long long oa = __shfl_down_sync(0xFFFFFFFFu, at, d);
-        if (ob > best || (ob == best && oa < at)) { best = ob; at = oa; }
-    }
+    auto scan = [&](unsigned long long lo, unsigned long long hi) {
+        for (unsigned long long i = lo + lane; i < hi; i += 32) { const uint32_t s = tri[i].sum; if (s > best) { best = s; at = i; } }
+        for (int d = 16; d; d >>= 1) {
+            const uint32_t ob = __shfl_down_sync(0xFFFFFFFFu, best, d); const unsigned long long oa = __shfl_down_sync(0xFFFFFFFFu, at, d);
+            if (ob > best || (ob == best && oa < at)) { best = ob; at = oa; }
+        }
+        best = __shfl_sync(0xFFFFFFFFu, best, 0); at = __shfl_sync(0xFFFFFFFFu, at, 0);
+    };
+    scan(J.nominal, J.nominal + W);
+    if (best < (1u << 14) && half > W) scan(J.nominal + W, J.nominal + half);
     if (lane == 0) {
         const uint32_t M = best ? 0xFFFFFFFFu / best - (1u << 24) / best + 1 : 0xFFFFFFFFu;
         const bool ok = best != 0 && M <= RCP_MMAX;
@@ -134,15 +150,24 @@ __global__ void __launch_bounds__(128) k_rcp_bounds(const RcpStream* __restrict_
     }
 }
 
-// end of job j's symbols = start of the next live job of its stream (or the stream's end); *next = that job (0xFFFFFFFF: none)
-CR_D unsigned long long rcp_job_end(const RcpStream& P, const RcpJob* __restrict__ jobs, uint32_t j, uint32_t* next) {
-    for (uint32_t k = j + 1; k < P.first_job + P.njobs; k++) if (jobs[k].status == RCP_LIVE) { *next = k; return jobs[k].a; }
-    *next = 0xFFFFFFFFu;
+// end of job j's symbols = start of the next live job of its stream (or the stream's end).  A1 and A2 may demote jobs while
+// other CTAs of the same launch call this: a stale answer only makes a job stop early, the later phases use k_rcp_links.
+CR_D unsigned long long rcp_job_end(const RcpStream& P, const RcpJob* jobs, uint32_t j, uint32_t* next) {
+    for (uint32_t k = j + 1; k < P.first_job + P.njobs; k++) if (((volatile const RcpJob*)jobs)[k].status == RCP_LIVE) { *next = k; return jobs[k].a; }
+    *next = RCP_NONE;
     return P.i1;
 }
-CR_D uint32_t rcp_prev_live(const RcpStream& P, const RcpJob* __restrict__ jobs, uint32_t j) {
-    for (uint32_t k = j; k-- > P.first_job;) if (jobs[k].status == RCP_LIVE) return k;
-    return 0xFFFFFFFFu;
+// ---- links: once A1 and A2 are through, the set of live jobs is final
+__global__ void k_rcp_links(const RcpStream* __restrict__ ps, RcpJob* __restrict__ jobs, const uint32_t* __restrict__ njobs_total) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= *njobs_total) return;
+    const RcpJob J = jobs[j];
+    if (J.status != RCP_LIVE) return;
+    const RcpStream P = ps[J.stream];
+    uint32_t nx = RCP_NONE, pv = RCP_NONE;
+    const unsigned long long end = rcp_job_end(P, jobs, j, &nx);
+    for (uint32_t k = j; k-- > P.first_job;) if (jobs[k].status == RCP_LIVE) { pv = k; break; }
+    jobs[j].end = end; jobs[j].next = nx; jobs[j].prev = pv;
 }
 
 // block-wide exclusive scan of one value per thread (THREADS <= 1024); returns the offset, *total = sum.  Two barriers.
@@ -163,11 +188,12 @@ template <int THREADS> CR_D uint32_t rcp_block_scan(uint32_t v, uint32_t* __rest
 
 // ---- A1 seed: the states possible behind the seed symbol, enumerated implicitly, S symbols each, equal neighbours dropped.
 #define RCP_SEED_THREADS 1024
-__global__ void __launch_bounds__(RCP_SEED_THREADS) k_rcp_seed(const RcpStream* __restrict__ ps, RcpJob* __restrict__ jobs, const uint32_t* __restrict__ njobs_total,
+__global__ void __launch_bounds__(RCP_SEED_THREADS) k_rcp_seed(const RcpStream* __restrict__ ps, RcpJob* jobs, const uint32_t* __restrict__ njobs_total,
                                                                const Tri* __restrict__ dense_main, const Tri* __restrict__ dense_side,
                                                                const uint4* __restrict__ cin_main, const uint4* __restrict__ cin_side,
                                                                double* __restrict__ listA, RcpStats* __restrict__ stats) {
-    __shared__ uint4 srec[RCP_SMAX];
+    __shared__ RcpRecA sa[RCP_SMAX + 1];
+    __shared__ double sn[RCP_SMAX + 1];
     __shared__ uint32_t swarp[32];
     __shared__ double sfirst;
     const uint32_t j = blockIdx.x, tid = threadIdx.x;
@@ -177,11 +203,11 @@ __global__ void __launch_bounds__(RCP_SEED_THREADS) k_rcp_seed(const RcpStream* 
     if (P.flags || J.status != RCP_LIVE || j == P.first_job) return;
     uint32_t nextj;
     const unsigned long long end = rcp_job_end(P, jobs, j, &nextj);
-    if (nextj == 0xFFFFFFFFu) return;                               // last live job of its stream: nobody needs its exit set
+    if (nextj == RCP_NONE) return;                                  // last live job of its stream: nobody needs its exit set
     const Tri seed = (P.is_main ? dense_main : dense_side)[J.a];
     const uint4* cin = P.is_main ? cin_main : cin_side;
     const uint32_t sum = seed.sum, qlo = (1u << 24) / sum, qhi = 0xFFFFFFFFu / sum, M = qhi - qlo + 1;
-    const double f0 = (double)(seed.frq & 0x7FFFFFFFu);
+    const double f0 = 2.0 * (double)(seed.frq & 0x7FFFFFFFu);
     const uint32_t per = (M + RCP_SEED_THREADS - 1) / RCP_SEED_THREADS;
     const uint32_t lo = tid * per < M ? tid * per : M, hi = lo + per < M ? lo + per : M;
     double* out = listA + (size_t)j * RCP_CAP_A;
@@ -189,34 +215,27 @@ __global__ void __launch_bounds__(RCP_SEED_THREADS) k_rcp_seed(const RcpStream* 
     unsigned long long work = 0;
     for (;;) {
         if (J.a + 1 + S > end) S = (uint32_t)(end - J.a - 1);
-        for (uint32_t i = staged + tid; i < S; i += RCP_SEED_THREADS) srec[i] = cin[J.a + 1 + i];
-        staged = S;
+        for (uint32_t i = staged + tid; i < S + 1; i += RCP_SEED_THREADS) {
+            RcpRecA a; double nf;
+            rcp_unpack(J.a + 1 + i < end ? cin[J.a + 1 + i] : make_uint4(0, 0x3FE00000u, 0, 0x40000000u), a, nf);
+            sa[i] = a; sn[i] = nf;
+        }
+        staged = S + 1;
         __syncthreads();
         // state of element 0 after S symbols (the seam: the last elements wrap around onto the first)
-        if (tid == 0) {
-            double r = rcp_seed_state(qlo, f0);
-            for (uint32_t s = 0; s < S; s++) { double inv, f, nf; rcp_rec(srec[s], inv, f, nf); rcp_step(r, inv, f, nf); }
-            sfirst = r;
-        }
+        if (tid == 0) { double r[1] = { rcp_seed_state(qlo, f0) }; rcp_run<1>(r, sa, sn, S); sfirst = r[0]; }
         __syncthreads();
         const double first = sfirst;
         uint32_t off = 0, total = 0;
         for (int pass = 0; pass < 2; pass++) {
             uint32_t cnt = 0;
             double prev = first;
-            if (lo > 0 && lo < hi) {                                 // the element in front of this thread's slice
-                prev = rcp_seed_state(qlo + lo - 1, f0);
-                for (uint32_t s = 0; s < S; s++) { double inv, f, nf; rcp_rec(srec[s], inv, f, nf); rcp_step(prev, inv, f, nf); }
-            }
+            if (lo > 0 && lo < hi) { double r[1] = { rcp_seed_state(qlo + lo - 1, f0) }; rcp_run<1>(r, sa, sn, S); prev = r[0]; }   // the element in front of this slice
             for (uint32_t b = lo; b < hi; b += 8) {
                 double d[8];
 #pragma unroll
                 for (int k = 0; k < 8; k++) d[k] = rcp_seed_state(qlo + (b + k < hi ? b + k : hi - 1), f0);
-                for (uint32_t s = 0; s < S; s++) {
-                    double inv, f, nf; rcp_rec(srec[s], inv, f, nf);
-#pragma unroll
-                    for (int k = 0; k < 8; k++) rcp_step(d[k], inv, f, nf);
-                }
+                rcp_run<8>(d, sa, sn, S);
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
                     const bool uniq = b + k < hi && (b + k == 0 || (!rcp_same(d[k], prev) && !rcp_same(d[k], first)));
@@ -231,11 +250,11 @@ __global__ void __launch_bounds__(RCP_SEED_THREADS) k_rcp_seed(const RcpStream* 
         }
         work += 2ull * (hi - lo) * S;
         if (total <= RCP_CAP_A) {
-            if (tid == 0) { jobs[j].count = total; jobs[j].pos = J.a + 1 + S; jobs[j].seed_steps = S; }
+            if (tid == 0) { jobs[j].count = total; jobs[j].pos = J.a + 1 + S; }
             break;
         }
-        if (S >= RCP_SMAX || J.a + 1 + S >= end) {                   // does not shrink: give the stream to the serial walk
-            if (tid == 0) { atomicOr((uint32_t*)&ps[J.stream].flags, 2u); atomicAdd(&stats->failed_seeds, 1u); jobs[j].count = 0; }
+        if (S >= RCP_SMAX || J.a + 1 + S >= end) {                   // does not shrink: this job is merged into the one in front of it
+            if (tid == 0) { jobs[j].status = RCP_MERGED; jobs[j].count = 0; atomicAdd(&stats->demoted_jobs, 1u); }
             break;
         }
         if (tid == 0) atomicAdd(&stats->seed_retries, 1u);
@@ -246,64 +265,62 @@ __global__ void __launch_bounds__(RCP_SEED_THREADS) k_rcp_seed(const RcpStream* 
 }
 
 // ---- A2 / A3 / B: explicit state lists stepped in registers (K per thread, blocked layout), merged values dropped.
-//   mode 0 (A2): listA[j] (count states at pos) -> until count <= RCP_CAP_E (or the job's end), back into listA[j]
+//   mode 0 (A2): listA[j] (count states at pos) -> until count <= RCP_CAP_E, back into listA[j]; a job that reaches its end with
+//                more states than that is merged into the job in front of it
 //   mode 1 (A3): listA[j] (or the single start state for the first job of a stream) -> to the job's end, E[j]
 //   mode 2 (B) : E[previous live job] stepped through this job's symbols WITHOUT merging -> F[j][i] = where candidate i ends up
 enum { RCP_MODE_MID = 0, RCP_MODE_LATE = 1, RCP_MODE_FOLLOW = 2 };
 template <int THREADS, int K, int BATCH, bool DEDUP>
-__global__ void __launch_bounds__(THREADS) k_rcp_track(const RcpStream* __restrict__ ps, RcpJob* __restrict__ jobs, const uint32_t* __restrict__ njobs_total,
+__global__ void __launch_bounds__(THREADS) k_rcp_track(RcpStream* ps, RcpJob* jobs, const uint32_t* __restrict__ njobs_total,
                                                        const uint4* __restrict__ cin_main, const uint4* __restrict__ cin_side,
                                                        double* __restrict__ listA, double* __restrict__ E, double* __restrict__ F, int mode, RcpStats* __restrict__ stats) {
     extern __shared__ double sbuf[];                 // DEDUP: THREADS * K doubles for the compaction
-    __shared__ uint4 srec[BATCH];
+    __shared__ RcpRecA sa[BATCH + 1];
+    __shared__ double sn[BATCH + 1];
     __shared__ uint32_t swarp[32];
     __shared__ double slast[32];
     __shared__ double sfirst;
     const uint32_t j = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     if (j >= *njobs_total) return;
     const RcpJob J = jobs[j];
+    if (J.status != RCP_LIVE) return;
     const RcpStream P = ps[J.stream];
-    if (P.flags || J.status != RCP_LIVE) return;
-    uint32_t nextj;
-    const unsigned long long end = rcp_job_end(P, jobs, j, &nextj);
-    if (nextj == 0xFFFFFFFFu) return;                // last live job of the stream
+    if (P.flags) return;
     const bool first_job = j == P.first_job;
-    const double* in; uint32_t n; unsigned long long pos;
-    if (mode == RCP_MODE_FOLLOW) {
-        if (first_job) return;
-        const uint32_t pj = rcp_prev_live(P, jobs, j);
-        in = E + (size_t)pj * RCP_CAP_E; n = jobs[pj].ecount; pos = J.a;
-    } else if (first_job) {
-        if (mode == RCP_MODE_MID) return;
-        in = nullptr; n = 1; pos = P.i0;
-    } else {
+    const double* in; uint32_t n; unsigned long long pos, end;
+    if (mode == RCP_MODE_MID) {
+        if (first_job || J.count <= RCP_CAP_E) return;
+        uint32_t nextj;
+        end = rcp_job_end(P, jobs, j, &nextj);
+        if (nextj == RCP_NONE) return;
         in = listA + (size_t)j * RCP_CAP_A; n = J.count; pos = J.pos;
-        if (mode == RCP_MODE_MID && n <= RCP_CAP_E) return;
-        if (mode == RCP_MODE_LATE && n > RCP_CAP_E) {                  // A2 could not shrink it far enough
-            if (tid == 0) atomicOr((uint32_t*)&ps[J.stream].flags, 4u);
-            return;
-        }
+    } else {
+        if (J.next == RCP_NONE) return;              // last live job of the stream: nobody needs its exit set
+        end = J.end;
+        if (mode == RCP_MODE_FOLLOW) {
+            if (first_job) return;
+            in = E + (size_t)J.prev * RCP_CAP_E; n = jobs[J.prev].ecount; pos = J.a;
+        } else if (first_job) { in = nullptr; n = 1; pos = P.i0; }
+        else { in = listA + (size_t)j * RCP_CAP_A; n = J.count; pos = J.pos; }
     }
-    if (n == 0 || n > (uint32_t)THREADS * K) { if (tid == 0) atomicOr((uint32_t*)&ps[J.stream].flags, 8u); return; }
+    if (n == 0 || n > (uint32_t)THREADS * K || pos > end) { if (tid == 0) atomicOr(&ps[J.stream].flags, 8u); return; }
     const uint4* cin = P.is_main ? cin_main : cin_side;
     double d[K];
 #pragma unroll
-    for (int k = 0; k < K; k++) { const uint32_t i = tid * K + k; d[k] = in ? in[i < n ? i : n - 1] : RCP_R0; }
+    for (int k = 0; k < K; k++) { const uint32_t i = tid * K + k; d[k] = in ? in[i < n ? i : n - 1] : RC_DP_R0; }
     unsigned long long work = 0;
-    uint4 nxt = make_uint4(0, 0, 0, 0x3FF00000u);
-    if (tid < BATCH && pos + tid < end) nxt = cin[pos + tid];
+    const uint4 idle = make_uint4(0, 0x3FE00000u, 0, 0x40000000u);
+    uint4 nxt = idle;
+    if (tid <= BATCH && pos + tid < end) nxt = cin[pos + tid];
     while (pos < end) {
         __syncthreads();                                               // the previous batch has been consumed
-        if (tid < BATCH) srec[tid] = nxt;
+        if (tid <= BATCH) { RcpRecA a; double nf; rcp_unpack(nxt, a, nf); sa[tid] = a; sn[tid] = nf; }
         __syncthreads();
         const uint32_t nb = end - pos < BATCH ? (uint32_t)(end - pos) : BATCH;
-        if (tid < BATCH && pos + BATCH + tid < end) nxt = cin[pos + BATCH + tid];
+        nxt = idle;
+        if (tid <= BATCH && pos + BATCH + tid < end) nxt = cin[pos + BATCH + tid];
         if (tid * K < n) {
-            for (uint32_t s = 0; s < nb; s++) {
-                double inv, f, nf; rcp_rec(srec[s], inv, f, nf);
-#pragma unroll
-                for (int k = 0; k < K; k++) rcp_step(d[k], inv, f, nf);
-            }
+            rcp_run<K>(d, sa, sn, nb);
             if (lane == 0) work += (unsigned long long)nb * (n - tid * K < 32u * K ? n - tid * K : 32u * K);
         }
         pos += nb;
@@ -336,9 +353,11 @@ __global__ void __launch_bounds__(THREADS) k_rcp_track(const RcpStream* __restri
             if (mode == RCP_MODE_MID && n <= RCP_CAP_E) break;
         }
     }
-    // hand over
+    if (mode == RCP_MODE_MID && n > RCP_CAP_E) {                        // did not shrink far enough within the job: merge it
+        if (tid == 0) { jobs[j].status = RCP_MERGED; atomicAdd(&stats->demoted_jobs, 1u); }
+        return;
+    }
     double* out = mode == RCP_MODE_MID ? listA + (size_t)j * RCP_CAP_A : mode == RCP_MODE_LATE ? E + (size_t)j * RCP_CAP_E : F + (size_t)j * RCP_CAP_E;
-    if (mode != RCP_MODE_MID && n > RCP_CAP_E) { if (tid == 0) atomicOr((uint32_t*)&ps[J.stream].flags, 16u); return; }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < K; k++) { const uint32_t i = tid * K + k; if (i < n) out[i] = d[k]; }
@@ -350,32 +369,32 @@ __global__ void __launch_bounds__(THREADS) k_rcp_track(const RcpStream* __restri
 }
 
 // ---- C resolve: one warp per stream walks its live jobs: entry of the next job = F[this job][index of this job's entry in E[previous]]
-__global__ void __launch_bounds__(32) k_rcp_resolve(RcpStream* __restrict__ ps, uint32_t nstreams, RcpJob* __restrict__ jobs,
-                                                    const double* __restrict__ E, const double* __restrict__ F) {
+__global__ void __launch_bounds__(32) k_rcp_resolve(RcpStream* ps, uint32_t nstreams, RcpJob* jobs, const double* __restrict__ E, const double* __restrict__ F) {
     const uint32_t s = blockIdx.x, lane = threadIdx.x;
     if (s >= nstreams) return;
     const RcpStream P = ps[s];
-    if (P.flags) return;
-    uint32_t cur = P.first_job, prev = 0xFFFFFFFFu;
-    double entry = RCP_R0;
+    if (P.flags || P.njobs == 0) return;
+    uint32_t cur = P.first_job, prev = RCP_NONE;
+    double entry = RC_DP_R0;
     if (lane == 0) jobs[cur].entry = entry;
     for (;;) {
-        uint32_t nxt;
-        rcp_job_end(P, jobs, cur, &nxt);
-        if (nxt == 0xFFFFFFFFu) break;
+        const uint32_t nxt = jobs[cur].next;
+        if (nxt == RCP_NONE) break;
         double ne = 0.0; bool ok = false;
-        if (prev == 0xFFFFFFFFu) {                     // first job: its exit set is the one state the known start leads to
+        if (prev == RCP_NONE) {                        // first job: its exit set is the one state the known start leads to
             ok = jobs[cur].ecount == 1; ne = E[(size_t)cur * RCP_CAP_E];
         } else {
             const uint32_t n = jobs[prev].ecount;
             const double* e = E + (size_t)prev * RCP_CAP_E;
-            uint32_t found = 0xFFFFFFFFu;
-            for (uint32_t i0 = 0; i0 < n; i0 += 32) {
-                const bool hit = i0 + lane < n && rcp_same(e[i0 + lane], entry);
-                const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
-                if (m) { found = i0 + __ffs(m) - 1; break; }
+            uint32_t found = RCP_NONE;
+            for (uint32_t i0 = 0; i0 < n && found == RCP_NONE; i0 += 128) {
+                bool hit[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) hit[u] = i0 + 32 * u + lane < n && rcp_same(e[i0 + 32 * u + lane], entry);
+#pragma unroll
+                for (int u = 0; u < 4; u++) { const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit[u]); if (m && found == RCP_NONE) found = i0 + 32 * u + __ffs(m) - 1; }
             }
-            if (found != 0xFFFFFFFFu) { ok = true; ne = F[(size_t)cur * RCP_CAP_E + found]; }
+            if (found != RCP_NONE) { ok = true; ne = F[(size_t)cur * RCP_CAP_E + found]; }
         }
         if (!ok) { if (lane == 0) atomicOr(&ps[s].flags, 32u); return; }
         entry = ne; prev = cur; cur = nxt;
@@ -385,7 +404,7 @@ __global__ void __launch_bounds__(32) k_rcp_resolve(RcpStream* __restrict__ ps, 
 
 // ---- D emit: the serial walk (k_range_chain<7>'s loop) per job from its true entry state; checks the link to the next job.
 // whole_streams != 0: the fallback -- one warp per FLAGGED stream walks the whole stream from the coder's initial range.
-__global__ void __launch_bounds__(128) k_rcp_emit(RcpStream* __restrict__ ps, uint32_t nstreams, const RcpJob* __restrict__ jobs, const uint32_t* __restrict__ njobs_total,
+__global__ void __launch_bounds__(128) k_rcp_emit(RcpStream* ps, uint32_t nstreams, const RcpJob* jobs, const uint32_t* __restrict__ njobs_total,
                                                   const uint4* __restrict__ cin_main, const uint4* __restrict__ cin_side,
                                                   uint32_t* __restrict__ q_main, uint32_t* __restrict__ sh_main, uint32_t* __restrict__ q_side, uint32_t* __restrict__ sh_side,
                                                   int whole_streams, RcpStats* __restrict__ stats) {
@@ -393,19 +412,20 @@ __global__ void __launch_bounds__(128) k_rcp_emit(RcpStream* __restrict__ ps, ui
     __shared__ uint32_t oq[4][RC_BATCH], os[4][RC_BATCH + 1];
     const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    unsigned long long i0, i1; double R; uint32_t sidx, nextj = 0xFFFFFFFFu; bool is_main;
+    unsigned long long i0, i1; double R; uint32_t sidx, nextj = RCP_NONE; bool is_main;
     if (whole_streams) {
         if (g >= nstreams) return;
         const RcpStream P = ps[g];
         if (!P.flags) return;
         if (lane == 0) atomicAdd(&stats->flagged_streams, 1u);
-        i0 = P.i0; i1 = P.i1; R = RCP_R0; sidx = g; is_main = P.is_main != 0;
+        i0 = P.i0; i1 = P.i1; R = RC_DP_R0; sidx = g; is_main = P.is_main != 0;
     } else {
         if (g >= *njobs_total) return;
         const RcpJob J = jobs[g];
+        if (J.status != RCP_LIVE) return;
         const RcpStream P = ps[J.stream];
-        if (P.flags || J.status != RCP_LIVE) return;
-        i1 = rcp_job_end(P, jobs, g, &nextj);
+        if (P.flags) return;
+        i1 = J.end; nextj = J.next;
         i0 = g == P.first_job ? P.i0 : J.a; R = J.entry; sidx = J.stream; is_main = P.is_main != 0;
     }
     const uint4* tri = is_main ? cin_main : cin_side;
@@ -436,13 +456,14 @@ __global__ void __launch_bounds__(128) k_rcp_emit(RcpStream* __restrict__ ps, ui
         if (lane + 32 < cnt) { qo[base + lane + 32] = oq[w][lane + 32]; so[base + lane + 32] = os[w][lane + 32]; }
         __syncwarp();
     }
-    if (!whole_streams && lane == 0 && nextj != 0xFFFFFFFFu && !rcp_same(R, jobs[nextj].entry)) atomicOr(&ps[sidx].flags, 64u);   // the jobs do not link up
+    if (!whole_streams && lane == 0 && nextj != RCP_NONE && !rcp_same(R, jobs[nextj].entry)) atomicOr(&ps[sidx].flags, 64u);   // the jobs do not link up
 }
 
 // host side: all buffers of the parallel chain
 struct RcPar {
     DevBuf b_ps, b_jobs, b_njobs, b_listA, b_E, b_F, b_stats;
-    uint32_t job_symbols = 49152;
+    uint32_t job_symbols = 0;        // symbols per job; 0 = chosen from the window's size
+    int late_cfg = 0;                // tuning: thread / register layout of the A3 and B kernels
     bool attr_done = false;
     RcpStats last = {};
     void release() { DevBuf* all[] = { &b_ps, &b_jobs, &b_njobs, &b_listA, &b_E, &b_F, &b_stats }; for (DevBuf* b : all) b->release(); }
@@ -451,7 +472,12 @@ struct RcPar {
             const Tri* dense_main, const Tri* dense_side, const uint4* cin_main, const uint4* cin_side,
             uint32_t* q_main, uint32_t* sh_main, uint32_t* q_side, uint32_t* sh_side, bool want_stats) {
         if (nstreams == 0) return CRGPU_OK;
-        const uint32_t T = job_symbols < 4096 ? 4096 : job_symbols;
+        uint32_t T = job_symbols;
+        if (T == 0) {                // about eight jobs per SM when the window is large; a job of fewer than 16384 symbols does not pay for its seed
+            const uint64_t t = (ntm + nts) / 1184;
+            T = t < 16384 ? 16384u : t > 65536 ? 65536u : (uint32_t)((t + 4095) & ~4095ull);
+        }
+        if (T < 4096) T = 4096;
         const uint64_t maxjobs64 = nstreams + (ntm + nts) / T + 1;
         if (maxjobs64 > (1u << 20)) return CRGPU_ERR_UNSUPPORTED;
         const uint32_t maxjobs = (uint32_t)maxjobs64;
@@ -468,15 +494,15 @@ struct RcPar {
             CR_CUDA(cudaFuncSetAttribute(k_rcp_track<512, 32, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * 32 * 8));
             attr_done = true;
         }
-        { __atomic_fetch_add(&g_cr_launches, 1ull, __ATOMIC_RELAXED);
-          k_rcp_track<512, 32, 16, true><<<dim3(maxjobs), dim3(512), 512 * 32 * 8, stream>>>(ps, jobs, nj, cin_main, cin_side, LA, E, F, RCP_MODE_MID, st);
-          CR_CUDA(cudaGetLastError()); }
-        { __atomic_fetch_add(&g_cr_launches, 1ull, __ATOMIC_RELAXED);
-          k_rcp_track<256, 8, 128, true><<<dim3(maxjobs), dim3(256), 256 * 8 * 8, stream>>>(ps, jobs, nj, cin_main, cin_side, LA, E, F, RCP_MODE_LATE, st);
-          CR_CUDA(cudaGetLastError()); }
-        { __atomic_fetch_add(&g_cr_launches, 1ull, __ATOMIC_RELAXED);
-          k_rcp_track<256, 8, 128, false><<<dim3(maxjobs), dim3(256), 0, stream>>>(ps, jobs, nj, cin_main, cin_side, LA, E, F, RCP_MODE_FOLLOW, st);
-          CR_CUDA(cudaGetLastError()); }
+#define RCP_TRACK(TH, KK, BB, DD, SMEM, MODE)                                                                                       \
+        do { __atomic_fetch_add(&g_cr_launches, 1ull, __ATOMIC_RELAXED);                                                             \
+             k_rcp_track<TH, KK, BB, DD><<<dim3(maxjobs), dim3(TH), (SMEM), stream>>>(ps, jobs, nj, cin_main, cin_side, LA, E, F, MODE, st); \
+             CR_CUDA(cudaGetLastError()); } while (0)
+        RCP_TRACK(512, 32, 16, true, 512 * 32 * 8, RCP_MODE_MID);
+        CR_LAUNCH(k_rcp_links, dim3(cr_div_up(maxjobs, 128)), dim3(128), stream, ps, jobs, nj);
+        if (late_cfg == 1) { RCP_TRACK(256, 8, 128, true, 2048 * 8, RCP_MODE_LATE); RCP_TRACK(256, 8, 128, false, 0, RCP_MODE_FOLLOW); }
+        else { RCP_TRACK(512, 4, 128, true, 2048 * 8, RCP_MODE_LATE); RCP_TRACK(512, 4, 128, false, 0, RCP_MODE_FOLLOW); }
+#undef RCP_TRACK
         CR_LAUNCH(k_rcp_resolve, dim3(nstreams), dim3(32), stream, ps, nstreams, jobs, E, F);
         CR_LAUNCH(k_rcp_emit, dim3(cr_div_up((size_t)maxjobs * 32, 128)), dim3(128), stream, ps, nstreams, jobs, nj, cin_main, cin_side, q_main, sh_main, q_side, sh_side, 0, st);
         CR_LAUNCH(k_rcp_emit, dim3(cr_div_up((size_t)nstreams * 32, 128)), dim3(128), stream, ps, nstreams, jobs, nj, cin_main, cin_side, q_main, sh_main, q_side, sh_side, 1, st);

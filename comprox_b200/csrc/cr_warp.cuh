@@ -993,7 +993,7 @@ __global__ void __launch_bounds__(128) k_range_chain(const uint4* __restrict__ i
     size_t i0 = S.ev_begin, i1 = S.ev_end;
     if (S.is_main) { i0 += escord[S.ev_begin]; i1 += escord[S.ev_end]; }
     uint32_t range = 0xFFFFFFFFu;
-    double R = 4294967295.0;                             // VARIANT 7: the normalised range as a double
+    double R = RC_DP_R0;                                 // VARIANT 7: twice the normalised range as a double (cr_rc.cuh)
     uint32_t msb = 31;                                   // VARIANT 4: index of the top set bit of the un-normalised range
     uint32_t c24 = 24, c7 = 7;
     asm volatile("" : "+r"(c24), "+r"(c7));            // keep the LOP3 operands in registers

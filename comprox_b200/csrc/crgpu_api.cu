@@ -196,9 +196,10 @@ extern "C" int crgpu_set_option(crgpu_handle* h, const char* name, int64_t value
     if (n == "scalar_models") { h->chain.scalar_models = value != 0; return CRGPU_OK; }
     if (n == "rc_variant") { if (value < 1 || value > 8) return CRGPU_ERR_ARG; h->chain.rc_variant = (int)value; return CRGPU_OK; }
 #ifndef CRGPU_SIM
-    if (n == "rc_job_symbols") { if (value < 4096 || value > (1 << 24)) return CRGPU_ERR_ARG; h->chain.rcpar.job_symbols = (uint32_t)value; return CRGPU_OK; }
+    if (n == "rc_job_symbols") { if (value != 0 && (value < 4096 || value > (1 << 24))) return CRGPU_ERR_ARG; h->chain.rcpar.job_symbols = (uint32_t)value; return CRGPU_OK; }
+    if (n == "rc_late_cfg") { h->chain.rcpar.late_cfg = (int)value; return CRGPU_OK; }
 #else
-    if (n == "rc_job_symbols") return CRGPU_OK;
+    if (n == "rc_job_symbols" || n == "rc_late_cfg") return CRGPU_OK;
 #endif
     if (n == "hot_contexts") { h->chain.hot_contexts = value != 0; return CRGPU_OK; }
     if (n == "match_limit") { if (value < 1 || value > 1000000) return CRGPU_ERR_ARG; h->chain.match_limit = (uint32_t)value; return CRGPU_OK; }   // comprox -m
@@ -465,7 +466,7 @@ extern "C" int crgpu_compress_batch(crgpu_handle* const* hs, uint32_t nhandles, 
 // renormalisation bytes after symbol i.  Lets the CPU tests compare the formulation with the integer recurrence without a GPU.
 extern "C" int crgpu_debug_rc_dp(const uint32_t* frq, const uint32_t* sum, uint64_t n, uint32_t* q_out, uint32_t* shift_out) {
     if (!frq || !sum || !q_out || !shift_out) return CRGPU_ERR_ARG;
-    double R = 4294967295.0;
+    double R = RC_DP_R0;
     for (uint64_t i = 0; i < n; i++) {
         if (sum[i] == 0 || frq[i] == 0 || frq[i] > sum[i] || sum[i] >= (1u << 23)) return CRGPU_ERR_ARG;
         uint32_t q, msb;
@@ -473,4 +474,61 @@ extern "C" int crgpu_debug_rc_dp(const uint32_t* frq, const uint32_t* sum, uint6
         q_out[i] = q; shift_out[i] = 3u - (msb >> 3);
     }
     return CRGPU_OK;
+}
+
+// Test aid for the parallel range chain (cr_rcpar.cuh, rc_variant 8): runs it ON THE GPU over caller-supplied (frq, sum) symbols cut
+// into `nstreams` consecutive streams of lens[] symbols, each starting from the coder's initial range.  q_out[i] = range / sum[i],
+// shift_out[i] = renormalisation bytes after symbol i; stats_out (8 x u64): state steps, live jobs, merged jobs, seed retries, failed
+// seeds, streams re-done serially, largest exit set, 0.
+extern "C" int crgpu_debug_rc_parallel(crgpu_handle* h, const uint32_t* frq, const uint32_t* sum, uint64_t n, const uint64_t* lens, uint32_t nstreams,
+                                       uint32_t job_symbols, uint32_t* q_out, uint32_t* shift_out, uint64_t* stats_out) {
+#ifdef CRGPU_SIM
+    (void)h; (void)frq; (void)sum; (void)n; (void)lens; (void)nstreams; (void)job_symbols; (void)q_out; (void)shift_out; (void)stats_out;
+    return CRGPU_ERR_UNSUPPORTED;
+#else
+    if (!h || !frq || !sum || !lens || !q_out || !shift_out || n == 0 || n >= (1ull << 32) || nstreams == 0) return CRGPU_ERR_ARG;
+    CR_CUDA(cudaSetDevice(h->device));
+    LzChain& c = h->chain;
+    cudaStream_t stream = c.stream;
+    std::vector<Tri> tri(n);
+    for (uint64_t i = 0; i < n; i++) {
+        if (sum[i] == 0 || frq[i] == 0 || frq[i] > sum[i] || sum[i] >= (1u << 23)) return CRGPU_ERR_ARG;
+        tri[i].cum = 0; tri[i].frq = frq[i]; tri[i].sum = sum[i]; tri[i].magic = rc_magic(sum[i]);
+    }
+    std::vector<RcStream> streams(nstreams);
+    uint64_t at = 0;
+    for (uint32_t s = 0; s < nstreams; s++) {
+        memset(&streams[s], 0, sizeof(RcStream));
+        streams[s].ev_begin = (uint32_t)at; at += lens[s]; streams[s].ev_end = (uint32_t)at; streams[s].is_main = 0; streams[s].limit = 0xFFFFFFFFu;
+    }
+    if (at != n) return CRGPU_ERR_ARG;
+    DevBuf d_tri, d_cin, d_q, d_sh, d_str;
+    int rc = CRGPU_OK;
+    auto run = [&]() -> int {
+        CR_TRY(d_tri.reserve(n * sizeof(Tri) + 64)); CR_TRY(d_cin.reserve((n + 1) * 16 + 64)); CR_TRY(d_q.reserve(n * 4 + 64)); CR_TRY(d_sh.reserve(n * 4 + 64));
+        CR_TRY(d_str.reserve(nstreams * sizeof(RcStream) + 64));
+        CR_CUDA(cudaMemcpyAsync(d_tri.p, tri.data(), n * sizeof(Tri), cudaMemcpyHostToDevice, stream));
+        CR_CUDA(cudaMemcpyAsync(d_str.p, streams.data(), nstreams * sizeof(RcStream), cudaMemcpyHostToDevice, stream));
+        CR_LAUNCH(k_chain_inputs_dp, dim3(cr_div_up(n, 256)), dim3(256), stream, d_tri.as<Tri>(), (uint64_t)n, d_cin.as<uint4>());
+        const uint32_t keep = c.rcpar.job_symbols;
+        if (job_symbols) c.rcpar.job_symbols = job_symbols;
+        const int r = c.rcpar.run(stream, d_str.as<RcStream>(), nstreams, d_q.as<uint32_t>() /* unused: no main streams */, 0, n, d_tri.as<Tri>(), d_tri.as<Tri>(),
+                                  d_cin.as<uint4>(), d_cin.as<uint4>(), d_q.as<uint32_t>(), d_sh.as<uint32_t>(), d_q.as<uint32_t>(), d_sh.as<uint32_t>(), true);
+        c.rcpar.job_symbols = keep;
+        CR_TRY(r);
+        CR_LAUNCH(k_msb_to_shifts, dim3(cr_div_up(n, 256)), dim3(256), stream, d_sh.as<uint32_t>(), (uint64_t)n);
+        CR_CUDA(cudaMemcpyAsync(q_out, d_q.p, n * 4, cudaMemcpyDeviceToHost, stream));
+        CR_CUDA(cudaMemcpyAsync(shift_out, d_sh.p, n * 4, cudaMemcpyDeviceToHost, stream));
+        CR_CUDA(cudaStreamSynchronize(stream));
+        return CRGPU_OK;
+    };
+    rc = run();
+    d_tri.release(); d_cin.release(); d_q.release(); d_sh.release(); d_str.release();
+    if (rc == CRGPU_OK && stats_out) {
+        const RcpStats& st = c.rcpar.last;
+        stats_out[0] = st.state_steps; stats_out[1] = st.live_jobs; stats_out[2] = st.merged_jobs; stats_out[3] = st.seed_retries;
+        stats_out[4] = st.demoted_jobs; stats_out[5] = st.flagged_streams; stats_out[6] = st.max_e; stats_out[7] = 0;
+    }
+    return rc;
+#endif
 }

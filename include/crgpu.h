@@ -180,6 +180,13 @@ int crgpu_debug_sort(crgpu_handle* h, const void* keys, const uint32_t* vals, ui
  * walked on the HOST with the same step function the kernel uses; q_out[i] = range / sum[i], shift_out[i] = renormalisation bytes. */
 int crgpu_debug_rc_dp(const uint32_t* frq, const uint32_t* sum, uint64_t n, uint32_t* q_out, uint32_t* shift_out);
 
+/* Test aid for the parallel range chain (cr_rcpar.cuh, "rc_variant" = 8): runs it on the GPU over caller-supplied (frq, sum) symbols cut
+ * into `nstreams` consecutive streams of lens[] symbols, each from the coder's initial range.  q_out / shift_out as above;
+ * stats_out (8 x u64, may be NULL): state steps, live jobs, merged jobs, seed retries, failed seeds, streams re-done serially, largest
+ * exit set, 0.  job_symbols = 0 keeps the handle's setting. */
+int crgpu_debug_rc_parallel(crgpu_handle* h, const uint32_t* frq, const uint32_t* sum, uint64_t n, const uint64_t* lens, uint32_t nstreams,
+                            uint32_t job_symbols, uint32_t* q_out, uint32_t* shift_out, uint64_t* stats_out);
+
 /* Tuning / test switches.  "scalar_models" = 1 runs the scalar model and coder kernels (the ones the CPU
  * kernel-logic simulation checks) instead of the warp-cooperative ones; results are identical.
  * "exact_aborts" = 0 turns the exact replay of mid-chain "cannot compress" blocks off (CRGPU_ERR_MIDCHAIN_ABORT instead).

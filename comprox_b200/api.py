@@ -16,6 +16,7 @@ ROLZ, LZP, LZ77 = 0, 1, 2
 OWN_STREAM = 1   # pass as `stream`: private stream per handle (several handles then overlap on one GPU)
 
 _lib = None
+last_batch_call_s = 0.0
 
 
 class CrgpuError(RuntimeError):
@@ -58,7 +59,11 @@ def decompress_batch(handles, containers, out_caps):
     outp = (ctypes.c_void_p * k)(*[ctypes.addressof(o) for o in outs])
     caps = (ctypes.c_uint64 * k)(*[int(c) for c in out_caps])
     lens = (ctypes.c_uint64 * k)()
-    _check(L, L.crgpu_decompress_batch(hs, ctypes.c_uint32(k), ins, in_lens, outp, caps, lens))
+    global last_batch_call_s
+    t0 = time.perf_counter()
+    rc = L.crgpu_decompress_batch(hs, ctypes.c_uint32(k), ins, in_lens, outp, caps, lens)
+    last_batch_call_s = time.perf_counter() - t0           # the C ABI call alone
+    _check(L, rc)
     return [outs[i].raw[:lens[i]] for i in range(k)]
 
 

@@ -37,18 +37,28 @@ struct DecJob {           // everything one decode chain (the consecutive blocks
     int variant; uint32_t nb;
     const uint8_t* cont; const DecBlock* blocks;
     PpmState st; DecTables T;
-    uint32_t* ctx_io; uint8_t* D;
+    uint32_t* ctx_io; uint8_t* D;      // ctx_io[0]: PPM context in / out; ctx_io[1]: error code out (0 = fine)
 };
 
 // ------------------------------------------------------------------ range decoder (cr-rangecoder.c:81-104)
+// Untrusted input: a stream never reads behind `end` (the end of its payload), a zero divisor / zero range / zero frequency (only a
+// damaged stream produces them) sets `err` instead of dividing by zero or spinning in the renormalisation loop.  The decoders test
+// `err` once per symbol and give the container up (CRGPU_ERR_CORRUPT); the reference crashes on such input.
+enum { DEC_ERR_STREAM = 1, DEC_ERR_MATCH = 2, DEC_ERR_DICT = 3 };
 struct RcDec {
-    uint32_t range, code;
-    const uint8_t* in;
-    CR_D void init(const uint8_t* p) { range = 0xFFFFFFFFu; code = 0; in = p; for (int i = 0; i < 5; i++) code = (code << 8) + *in++; }
-    CR_D uint32_t target(uint32_t sum) { range /= sum; return code / range; }
+    uint32_t range, code, err;
+    const uint8_t* in; const uint8_t* end;
+    CR_D uint32_t next() { if (in < end) return *in++; err = DEC_ERR_STREAM; return 0; }
+    CR_D void init(const uint8_t* p, const uint8_t* e) { range = 0xFFFFFFFFu; code = 0; err = 0; in = p; end = e; if (p > e) { err = DEC_ERR_STREAM; in = e; } for (int i = 0; i < 5; i++) code = (code << 8) + next(); }
+    CR_D uint32_t target(uint32_t sum) {
+        if (sum == 0 || range < sum) { err = DEC_ERR_STREAM; range = 1u << 24; return 0; }
+        range /= sum; return code / range;
+    }
     CR_D void consume(uint32_t cum, uint32_t frq) {
+        if (frq == 0) { err = DEC_ERR_STREAM; frq = 1; }
         code -= cum * range; range *= frq;
-        while (range < (1u << 24)) { code = (code << 8) + *in++; range <<= 8; }
+        if (range == 0) { err = DEC_ERR_STREAM; range = 1u << 24; }
+        while (range < (1u << 24)) { code = (code << 8) + next(); range <<= 8; }
     }
 };
 
@@ -167,16 +177,18 @@ template <class F> CR_D uint32_t x_decode_distance(F next) {
 __global__ void k_lzdecode_serial(int variant, const uint8_t* __restrict__ cont, const DecBlock* __restrict__ blocks, uint32_t nb,
                                   PpmState st, DecTables tabs, uint32_t* __restrict__ ctx_io, uint8_t* __restrict__ D) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    uint32_t ctx = *ctx_io;
-    for (uint32_t b = 0; b < nb; b++) {
+    uint32_t ctx = *ctx_io, err = 0;
+    for (uint32_t b = 0; b < nb && !err; b++) {
         const DecBlock B = blocks[b];
         if (!B.coded) continue;
         const uint8_t* in = cont + B.in_off;
+        const uint8_t* in_end = in + B.in_size;
         uint8_t* out = D + B.d_off;
         const uint32_t orig = B.d_size;
+        if (orig == 0) continue;
         if (variant == 0) {                                                    // src/rolzmain/cr-coder.c:287-379
             const uint32_t esc = in[2], off_idx = cr_ld32(in + 12);
-            RcDec rc, side; rc.init(in + 16); side.init(in + off_idx);
+            RcDec rc, side; rc.init(in + 16, in_end); side.init(in + (off_idx <= B.in_size ? off_idx : B.in_size), in_end);
             RzDec m; m.begin(tabs, B.epoch, orig >= 4194304);
             uint32_t n = 0;
             out[n++] = in[0];
@@ -190,14 +202,17 @@ __global__ void k_lzdecode_serial(int variant, const uint8_t* __restrict__ cont,
                         const uint32_t idx = dec_m0(st.m0 + 256, side);
                         const uint32_t q = m.getpos(idx);
                         len = l;
+                        if (q >= n || len > orig - n) { err = DEC_ERR_MATCH; break; }          // a slot no position of this block was stored in
                         for (uint32_t i = 0; i < len; i++) { out[n] = out[q + i]; n++; }
                     }
                 } else out[n++] = (uint8_t)s;
+                if ((err = rc.err | side.err) != 0) break;
                 for (; len; len--) { const uint32_t p = n - len; m.insert(out, p); ctx = ctx << 8 | out[p]; }
             }
         } else if (variant == 2) {                                             // src/roxmain/cr-coder.c:388-526
             const uint32_t mm = in[1], esc = in[2];
-            RcDec rc, rs, rp, rl; rc.init(in + 32); rs.init(in + cr_ld32(in + 20)); rp.init(in + cr_ld32(in + 24)); rl.init(in + cr_ld32(in + 28));
+            auto at = [&](uint32_t off) { return in + (off <= B.in_size ? off : B.in_size); };
+            RcDec rc, rs, rp, rl; rc.init(in + 32, in_end); rs.init(at(cr_ld32(in + 20)), in_end); rp.init(at(cr_ld32(in + 24)), in_end); rl.init(at(cr_ld32(in + 28)), in_end);
             uint32_t n = 0, last = 0;
             while (n < orig) {
                 uint32_t len = 1;
@@ -212,16 +227,18 @@ __global__ void k_lzdecode_serial(int variant, const uint8_t* __restrict__ cont,
                         else dist = x_decode_distance([&](uint32_t j) { return dec_m0(st.m0 + (2 + j) * 256, rp, 1u << (2 * j)); });
                         if (dist == 0) dist = last;
                         last = dist; len = l;
+                        if (dist == 0 || dist > n || len > orig - n) { err = DEC_ERR_MATCH; break; }
                         const uint32_t q = n - dist;
                         for (uint32_t i = 0; i < len; i++) { out[n] = out[q + i]; n++; }
                     }
                 }
+                if ((err = rc.err | rs.err | rp.err | rl.err) != 0) break;
                 for (; len; len--) ctx = ctx << 8 | out[n - len];
             }
         } else {                                                               // src/ropmain/cr-coder.c:231-292
             const uint32_t esc = in[8];
-            for (int i = 0; i < 9; i++) out[i] = in[9 + i];
-            RcDec rc; rc.init(in + 20);
+            for (uint32_t i = 0; i < 9 && i < orig; i++) out[i] = in[9 + i];
+            RcDec rc; rc.init(in + 20, in_end);
             LzpDec m; m.begin(tabs, B.epoch);
             uint32_t n = 9;
             while (n < orig) {
@@ -232,23 +249,29 @@ __global__ void k_lzdecode_serial(int variant, const uint8_t* __restrict__ cont,
                     ctx = ctx << 8 | esc;
                     len = dec_ppm(st, ctx, rc);
                     if (len == 0) { len = 1; out[n++] = (uint8_t)esc; }
-                    else { const uint32_t q = m.getpos(out, n); for (uint32_t i = 0; i < len; i++) { out[n] = out[q + i]; n++; } }
+                    else {
+                        const uint32_t q = m.getpos(out, n);
+                        if (q >= n || len > orig - n) { err = DEC_ERR_MATCH; break; }
+                        for (uint32_t i = 0; i < len; i++) { out[n] = out[q + i]; n++; }
+                    }
                 }
+                if ((err = rc.err) != 0) break;
                 for (; len; len--) { const uint32_t p = n - len; ctx = ctx << 8 | out[p]; m.insert(out, p); }
             }
         }
     }
-    *ctx_io = ctx;
+    ctx_io[0] = ctx; ctx_io[1] = err;
 }
 
 // ------------------------------------------------------------------ dictionary_decode (cr-diccode.c:223-283)
 struct DdSub { uint64_t src; uint32_t size; uint32_t block; uint64_t dst; uint32_t orig; uint32_t pad; };   // one sub-chunk
 struct DdBlock { uint64_t d_off; uint32_t d_size; uint32_t first_sub; uint64_t raw_off; uint32_t raw_size; uint32_t nsub; };
 // Walks the pair framing of every dictionary-coded block (serial over a few hundred headers) and lays out the output.
+// totals[2] != 0: the framing of a block is damaged (sizes that leave the block, sub-chunks above 1 000 000 bytes).
 __global__ void k_dd_layout(const uint8_t* __restrict__ D, DdBlock* __restrict__ blocks, uint32_t nb, DdSub* __restrict__ subs, uint32_t sub_cap,
                             uint64_t out_base, uint64_t* __restrict__ totals) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    uint64_t raw = out_base; uint32_t ns = 0;
+    uint64_t raw = out_base; uint32_t ns = 0; uint64_t bad = 0;
     for (uint32_t b = 0; b < nb; b++) {
         DdBlock& B = blocks[b];
         const uint8_t* d = D + B.d_off;
@@ -256,11 +279,15 @@ __global__ void k_dd_layout(const uint8_t* __restrict__ D, DdBlock* __restrict__
         if (B.d_size == 0) { B.raw_size = 0; continue; }
         if (d[B.d_size - 1] == 0) { B.raw_size = B.d_size - 1; raw += B.raw_size; continue; }      // stored (:237-241)
         uint32_t size = 0;
+        if (B.d_size < 11) { bad = 1; B.raw_size = 0; continue; }
         for (uint32_t pos = 0; pos + 11 < B.d_size;) {
             const uint32_t s1 = cr_ld32(d + pos), s2 = cr_ld32(d + pos + 4);
+            // a pair is  u32 len1, u32 len2, codes1 + u32 orig1, codes2 + u32 orig2  and the block ends with esc[10], 1 (cr-diccode.c:173-207)
+            if (s1 < 4 || s2 < 4 || (uint64_t)pos + 8 + s1 + s2 + 11 > B.d_size) { bad = 1; break; }
             const uint32_t sz[2] = { s1, s2 }; uint64_t src = B.d_off + pos + 8;
             for (int k = 0; k < 2; k++) {
                 const uint32_t orig = cr_ld32(D + src + sz[k] - 4);
+                if (orig > 1000000u) bad = 1;                                   // sub-chunks are at most 1 000 000 bytes (cr-diccode.c:174)
                 if (ns < sub_cap) { DdSub S; S.src = src; S.size = sz[k]; S.block = b; S.dst = raw + size; S.orig = orig; S.pad = 0; subs[ns] = S; }
                 ns++; B.nsub++; size += orig; src += sz[k];
             }
@@ -268,12 +295,14 @@ __global__ void k_dd_layout(const uint8_t* __restrict__ D, DdBlock* __restrict__
         }
         B.raw_size = size; raw += size;
     }
-    totals[0] = raw - out_base; totals[1] = ns;
+    totals[0] = raw - out_base; totals[1] = ns; totals[2] = bad;
 }
 struct DdDict { const char* words; const uint8_t* lens; int32_t nentries, level1; };   // words: [nentries][24]
 CR_HD bool dd_sentence_start(const uint8_t* s, uint32_t i) { return i >= 3 && s[i - 1] == ' ' && (s[i - 2] == '.' || (s[i - 2] == ' ' && s[i - 3] == '.')); }
 // dictionary_decode_imp (cr-diccode.c:364-425): each sub-chunk is expanded back to front by one thread
-CR_D void dd_sub_body(const uint8_t* __restrict__ D, const DdBlock* __restrict__ blocks, const DdSub S, const DdDict dic, uint8_t* __restrict__ out) {
+// Untrusted input: the code bytes are read back to front from index size-4; a damaged sub-chunk (a code cut off at the front, a word
+// index the dictionary does not have, more bytes than `orig` says) sets *err and stops instead of leaving its buffers.
+CR_D void dd_sub_body(const uint8_t* __restrict__ D, const DdBlock* __restrict__ blocks, const DdSub S, const DdDict dic, uint8_t* __restrict__ out, uint32_t* __restrict__ err) {
     const DdBlock B = blocks[S.block];
     const uint8_t* esc = D + B.d_off + B.d_size - 11;
     uint8_t escmap[256];
@@ -284,15 +313,20 @@ CR_D void dd_sub_body(const uint8_t* __restrict__ D, const DdBlock* __restrict__
     const int L1 = dic.level1;
     uint32_t src = S.orig, rev = 0xFFFFFFFFu; int dst = (int)S.size - 4;
     while (src > 0) {
+        if (dst < 1) { *err = DEC_ERR_DICT; return; }
         const uint32_t ch = d[--dst];
         if (!escmap[ch]) { o[--src] = (uint8_t)ch; continue; }
+        if (dst < 1) { *err = DEC_ERR_DICT; return; }
         int id = d[--dst];
         if (id >= L1) {
+            if (dst < 1) { *err = DEC_ERR_DICT; return; }
             id = d[--dst] * (256 - L1) + (id - L1);
             if (id == dic.nentries) { o[--src] = (uint8_t)ch; continue; }
         }
+        if (id < 0 || id >= dic.nentries) { *err = DEC_ERR_DICT; return; }
         const uint32_t wl = dic.lens[id];
         const char* w = dic.words + (size_t)id * 24;
+        if (wl == 0 || wl > 24 || wl > src) { *err = DEC_ERR_DICT; return; }
         src -= wl;
         for (uint32_t i = 0; i < wl; i++) o[src + i] = (uint8_t)w[i];
         const uint32_t e = escmap[ch];
@@ -306,18 +340,18 @@ CR_D void dd_sub_body(const uint8_t* __restrict__ D, const DdBlock* __restrict__
     }
     if (rev != 0xFFFFFFFFu && dd_sentence_start(o, rev)) o[rev] ^= 0x20;
 }
-__global__ void k_dd_subs(const uint8_t* __restrict__ D, const DdBlock* __restrict__ blocks, const DdSub* __restrict__ subs, uint32_t nsub, DdDict dic, uint8_t* __restrict__ out) {
+__global__ void k_dd_subs(const uint8_t* __restrict__ D, const DdBlock* __restrict__ blocks, const DdSub* __restrict__ subs, uint32_t nsub, DdDict dic, uint8_t* __restrict__ out, uint32_t* __restrict__ err) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nsub) return;
-    dd_sub_body(D, blocks, subs[t], dic, out);
+    dd_sub_body(D, blocks, subs[t], dic, out, err);
 }
 // the same over the sub-chunks of many containers (crgpu_decompress_batch): first[j] = index of job j's first sub-chunk
-struct DdJob { const uint8_t* D; const DdBlock* blocks; const DdSub* subs; DdDict dic; uint8_t* out; };
+struct DdJob { const uint8_t* D; const DdBlock* blocks; const DdSub* subs; DdDict dic; uint8_t* out; uint32_t* err; };
 __global__ void k_dd_subs_jobs(const DdJob* __restrict__ jobs, const uint32_t* __restrict__ first, uint32_t njobs, uint32_t nsub) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nsub) return;
     uint32_t lo = 0, hi = njobs;
     while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (first[mid] <= t) lo = mid; else hi = mid; }
     const DdJob J = jobs[lo];
-    dd_sub_body(J.D, J.blocks, J.subs[t - first[lo]], J.dic, J.out);
+    dd_sub_body(J.D, J.blocks, J.subs[t - first[lo]], J.dic, J.out, J.err);
 }

@@ -6,13 +6,13 @@
 struct Decompressor {
     LzChain* chain = nullptr;
     cudaStream_t stream = 0;
-    DevBuf d_cont, d_D, d_out, d_blocks, d_ctx, d_ddblocks, d_subs, d_totals, d_words, d_lens, d_copy, d_jobs, d_first;
+    DevBuf d_cont, d_D, d_out, d_blocks, d_ctx, d_ddblocks, d_subs, d_totals, d_words, d_lens, d_copy, d_jobs, d_first, d_err;
     DevBuf t_meta, t_items, t_short, t_l8, t_l4, t_l2;
     FilterHost filt;
     uint32_t epoch = 0;
 
     void release() {
-        DevBuf* all[] = { &d_cont, &d_D, &d_out, &d_blocks, &d_ctx, &d_ddblocks, &d_subs, &d_totals, &d_words, &d_lens, &d_copy, &d_jobs, &d_first, &t_meta, &t_items, &t_short, &t_l8, &t_l4, &t_l2 };
+        DevBuf* all[] = { &d_cont, &d_D, &d_out, &d_blocks, &d_ctx, &d_ddblocks, &d_subs, &d_totals, &d_words, &d_lens, &d_copy, &d_jobs, &d_first, &d_err, &t_meta, &t_items, &t_short, &t_l8, &t_l4, &t_l2 };
         for (DevBuf* b : all) b->release();
         filt.release();
     }
@@ -46,7 +46,7 @@ struct Decompressor {
             if (!b.coded && b.d_size) { CopyDesc c = { b.in_off + (b.in_size - b.d_size), b.d_off, b.d_size, 0 }; copies.push_back(c); }
         }
         CR_TRY(chain->upload(d_blocks, blk));
-        std::vector<uint32_t> c(1, chain->chain_ctx);
+        std::vector<uint32_t> c(2, 0); c[0] = chain->chain_ctx;            // [context in/out, error code out]
         CR_TRY(chain->upload(d_ctx, c));
         if (!copies.empty()) {
             CR_TRY(chain->upload(d_copy, copies));
@@ -68,9 +68,9 @@ struct Decompressor {
     }
     int lz_finish() {
         std::vector<uint32_t> c;
-        CR_TRY(chain->download(c, d_ctx.p, 1));
+        CR_TRY(chain->download(c, d_ctx.p, 2));
         chain->chain_ctx = c[0];
-        return CRGPU_OK;
+        return c[1] ? CRGPU_ERR_CORRUPT : CRGPU_OK;       // a damaged stream / match (cr_decode.cuh): nothing outside the block was touched
     }
     // one container in three phases; between the phases the decode chain `job` must have run (lz_launch() or a batched launch)
     const uint8_t* c_in = nullptr; uint64_t c_n = 0; uint8_t* c_out = nullptr; uint64_t c_out_cap = 0; uint64_t* c_out_n = nullptr;
@@ -117,10 +117,15 @@ inline int Decompressor::describe(uint64_t off, uint32_t size, int prec, uint64_
     memset(&b, 0, sizeof b);
     b.in_off = off; b.in_size = size; b.d_off = d_off;
     if (prec) { b.coded = 0; b.d_size = size; return CRGPU_OK; }
-    if (size < hdr) return CRGPU_ERR_ARG;
+    if (size < hdr) return CRGPU_ERR_CORRUPT;
     const int compressed = variant == CR_ROLZ ? c_in[off + 1] : c_in[off];
     if (!compressed) { b.coded = 0; b.d_size = size - hdr; return CRGPU_OK; }
     b.coded = 1; memcpy(&b.d_size, c_in + off + 4, 4);
+    // stream offsets of the inner header must lie inside the payload (the reference trusts them: src/rolzmain/cr-coder.c:300-303)
+    auto ld = [&](uint32_t at) { uint32_t v; memcpy(&v, c_in + off + at, 4); return v; };
+    if (variant == CR_ROLZ) { const uint32_t o1 = ld(12); if (o1 < 16 || o1 > size) return CRGPU_ERR_CORRUPT; }
+    if (variant == CR_LZ77) { const uint32_t o1 = ld(20), o2 = ld(24), o3 = ld(28); if (o1 < 32 || o1 > o2 || o2 > o3 || o3 > size) return CRGPU_ERR_CORRUPT; }
+    if (variant == CR_LZP && b.d_size < 9 && b.d_size != 0) return CRGPU_ERR_CORRUPT;          // a coded LZP block carries its first nine bytes in the header
     return CRGPU_OK;
 }
 
@@ -136,10 +141,11 @@ inline int Decompressor::begin(const uint8_t* in, uint64_t n, uint8_t* out, uint
     // ---- static dictionary (src/main.c:244-259)
     uint64_t p = mlen;
     uint32_t dict_len; memcpy(&dict_len, in + p, 4); p += 4;
-    if (p + dict_len > n) return CRGPU_ERR_ARG;
+    if (p + dict_len > n) return CRGPU_ERR_CORRUPT;
     c_dblk.assign(1, DecBlock());
     CR_TRY(describe(p, dict_len, 0, 0, c_dblk[0]));
     c_p = p + dict_len;
+    if (c_dblk[0].d_size > (8u << 20)) return CRGPU_ERR_CORRUPT;              // the front-coded dictionary text is a few hundred KB at most
     // the data blocks are parsed here too, so that every device buffer of the call is sized before any chain runs
     c_blk.clear(); c_filt.clear();
     uint64_t dtotal = 0;
@@ -147,7 +153,7 @@ inline int Decompressor::begin(const uint8_t* in, uint64_t n, uint8_t* out, uint
     while (p + 6 <= n) {
         uint32_t size; memcpy(&size, in + p, 4); const int f = in[p + 4], prec = in[p + 5];
         p += 6;
-        if (p + size > n) return CRGPU_ERR_ARG;
+        if (p + size > n) return CRGPU_ERR_CORRUPT;
         DecBlock b; CR_TRY(describe(p, size, prec, dtotal, b));
         c_blk.push_back(b); c_filt.push_back((uint8_t)f);
         dtotal += ((uint64_t)b.d_size + 15) & ~15ull;
@@ -161,8 +167,12 @@ inline int Decompressor::begin(const uint8_t* in, uint64_t n, uint8_t* out, uint
 // dictionary_load(dicstr, 0) (src/cr-diccode.c:76-104): the word table the expansion kernel indexes
 inline int Decompressor::load_words(const char* text) {
     const std::vector<std::string> entries = hd_entries(text);
+    if (entries.size() > 25000 + 2) return CRGPU_ERR_CORRUPT;                  // dic[25000][22] in the reference (src/cr-diccode.c:33-35)
     std::vector<char> words(entries.size() * 24 + 24, 0); std::vector<uint8_t> lens(entries.size() + 1, 0);
-    for (size_t i = 0; i < entries.size(); i++) { lens[i] = (uint8_t)entries[i].size(); memcpy(&words[i * 24], entries[i].data(), entries[i].size() < 24 ? entries[i].size() : 24); }
+    for (size_t i = 0; i < entries.size(); i++) {
+        if (entries[i].size() > 24) return CRGPU_ERR_CORRUPT;                  // the expansion kernel's word slots are 24 bytes
+        lens[i] = (uint8_t)entries[i].size(); memcpy(&words[i * 24], entries[i].data(), entries[i].size());
+    }
     CR_TRY(chain->upload(d_words, words)); CR_TRY(chain->upload(d_lens, lens));
     c_dic = DdDict{ d_words.as<char>(), d_lens.as<uint8_t>(), (int32_t)entries.size(), HD_LEVEL1((int)entries.size()) };
     return CRGPU_OK;
@@ -201,9 +211,9 @@ inline int Decompressor::layout(bool may_resume) {
     CR_TRY(d_subs.reserve(sub_cap * sizeof(DdSub))); CR_TRY(d_totals.reserve(64));
     CR_LAUNCH(k_dd_layout, dim3(1), dim3(1), stream, d_D.as<uint8_t>(), d_ddblocks.as<DdBlock>(), nb, d_subs.as<DdSub>(), (uint32_t)sub_cap, (uint64_t)0, d_totals.as<uint64_t>());
     std::vector<uint64_t> totals;
-    CR_TRY(chain->download(totals, d_totals.p, 2));
+    CR_TRY(chain->download(totals, d_totals.p, 3));
     const uint64_t raw_total = totals[0]; const uint32_t nsub = (uint32_t)totals[1];
-    if (nsub > sub_cap) return CRGPU_ERR_ARG;
+    if (totals[2] || nsub > sub_cap) return CRGPU_ERR_CORRUPT;
     if (raw_total > out_cap) {
         // the decoded size is only known here, after the (serial, slow) lzdecode chain: report it and keep the dictionary-coded
         // blocks, so that the caller's second call with a large enough buffer resumes at this point (decompress())
@@ -214,7 +224,7 @@ inline int Decompressor::layout(bool may_resume) {
     }
     CR_TRY(chain->download(ddb, d_ddblocks.p, nb));
     CR_TRY(d_out.reserve(raw_total + 256));
-    CR_CUDA(cudaMemsetAsync(d_out.as<uint8_t>() + raw_total, 0, 128, stream));
+    CR_CUDA(cudaMemsetAsync(d_out.p, 0, raw_total + 128, stream));      // (bytes a damaged sub-chunk never reaches stay defined)
     std::vector<CopyDesc> copies;
     for (uint32_t b = 0; b < nb; b++) if (ddb[b].nsub == 0 && ddb[b].raw_size) { CopyDesc c = { ddb[b].d_off, ddb[b].raw_off, ddb[b].raw_size, 0 }; copies.push_back(c); }
     if (!copies.empty()) {
@@ -222,13 +232,15 @@ inline int Decompressor::layout(bool may_resume) {
         CR_LAUNCH(k_copy_segments, dim3(64, (unsigned)copies.size()), dim3(256), stream, d_copy.as<CopyDesc>(), d_D.as<uint8_t>(), d_D.as<uint8_t>(), d_out.as<uint8_t>());
     }
     c_ddb = ddb; c_raw_total = raw_total;
-    ddjob = DdJob{ d_D.as<uint8_t>(), d_ddblocks.as<DdBlock>(), d_subs.as<DdSub>(), dic, d_out.as<uint8_t>() };
+    CR_TRY(d_err.reserve(16));
+    CR_CUDA(cudaMemsetAsync(d_err.p, 0, 4, stream));
+    ddjob = DdJob{ d_D.as<uint8_t>(), d_ddblocks.as<DdBlock>(), d_subs.as<DdSub>(), dic, d_out.as<uint8_t>(), d_err.as<uint32_t>() };
     dd_nsub = nsub;
     return CRGPU_OK;
 }
 
 inline int Decompressor::dd_launch() {
-    if (dd_nsub) CR_LAUNCH(k_dd_subs, dim3(cr_div_up(dd_nsub, 32)), dim3(32), stream, ddjob.D, ddjob.blocks, ddjob.subs, dd_nsub, ddjob.dic, ddjob.out);
+    if (dd_nsub) CR_LAUNCH(k_dd_subs, dim3(cr_div_up(dd_nsub, 32)), dim3(32), stream, ddjob.D, ddjob.blocks, ddjob.subs, dd_nsub, ddjob.dic, ddjob.out, ddjob.err);
     return CRGPU_OK;
 }
 
@@ -238,6 +250,11 @@ inline int Decompressor::finish_output() {
     const std::vector<uint8_t>& filt_flags = c_filt;
     const uint32_t nb = (uint32_t)c_blk.size();
     uint8_t* out = c_out;
+    if (dd_nsub) {                                                     // a sub-chunk that left its buffers stopped and said so
+        std::vector<uint32_t> e;
+        CR_TRY(chain->download(e, d_err.p, 1));
+        if (e[0]) return CRGPU_ERR_CORRUPT;
+    }
 
     // ---- inverse filters (src/main.c:284-286): the state machine needs the decoded headers on the host
     bool any_filt = false;

@@ -77,10 +77,10 @@ static inline std::string hd_lcp_decode(const uint8_t* d, size_t n) {
     wi++; o.push_back('\n');
     while (wi < n && d[wi] != 255) {
         int lcp = d[wi++];
-        while (lcp-- > 0) o.push_back(o[wo++]);
+        while (lcp-- > 0 && wo < o.size()) o.push_back(o[wo++]);          // (wo < size always holds for a well-formed text; damaged input must not read past the end)
         while (wi < n && d[wi] != '\n') o.push_back((char)d[wi++]);
         wi++; o.push_back('\n');
-        while (o[wo] != '\n') wo++;
+        while (wo < o.size() && o[wo] != '\n') wo++;
         wo++;
     }
     return o;

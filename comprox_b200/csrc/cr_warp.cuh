@@ -1165,13 +1165,20 @@ __global__ void k_stream_totals(const RcStream* __restrict__ streams, uint32_t n
 // 256-wide loop of ppm_decode / model_get_decode_symbol runs across the lanes: lane l owns symbols 8l..8l+7 of the
 // current o2 row / o1 row / order-0 model, cumulative frequencies come from a warp scan, the symbol search is a
 // ballot.  The range decoder state is replicated in all lanes (uniform control flow, no divergence).
+// (bounds and error state as in RcDec, cr_decode.cuh: untrusted input never reads behind `end`, divides by zero or spins)
 struct WRc {
-    uint32_t range, code; const uint8_t* in;
-    CR_D void init(const uint8_t* p) { range = 0xFFFFFFFFu; code = 0; in = p; for (int i = 0; i < 5; i++) code = (code << 8) + __ldg(in++); }
-    CR_D uint32_t target(uint32_t sum) { range /= sum; return code / range; }
+    uint32_t range, code, err; const uint8_t* in; const uint8_t* end;
+    CR_D uint32_t next() { if (in < end) return __ldg(in++); err = DEC_ERR_STREAM; return 0; }
+    CR_D void init(const uint8_t* p, const uint8_t* e) { range = 0xFFFFFFFFu; code = 0; err = 0; in = p; end = e; if (p > e) { err = DEC_ERR_STREAM; in = e; } for (int i = 0; i < 5; i++) code = (code << 8) + next(); }
+    CR_D uint32_t target(uint32_t sum) {
+        if (sum == 0 || range < sum) { err = DEC_ERR_STREAM; range = 1u << 24; return 0; }
+        range /= sum; return code / range;
+    }
     CR_D void consume(uint32_t cum, uint32_t frq) {
+        if (frq == 0) { err = DEC_ERR_STREAM; frq = 1; }
         code -= cum * range; range *= frq;
-        while (range < (1u << 24)) { code = (code << 8) + __ldg(in++); range <<= 8; }
+        if (range == 0) { err = DEC_ERR_STREAM; range = 1u << 24; }
+        while (range < (1u << 24)) { code = (code << 8) + next(); range <<= 8; }
     }
 };
 CR_D uint32_t wscan_incl(uint32_t v, uint32_t lane) {
@@ -1329,21 +1336,23 @@ CR_D void wcopy_match(uint8_t* out, uint32_t n, uint32_t q, uint32_t len, uint32
 __device__ __forceinline__ void lzdecode_warp_body(int variant, const uint8_t* __restrict__ cont, const DecBlock* __restrict__ blocks, uint32_t nb,
                                                    PpmState st, DecTables T, uint32_t* __restrict__ ctx_io, uint8_t* __restrict__ D) {
     const uint32_t lane = threadIdx.x & 31;
-    uint32_t ctx = *ctx_io;
+    uint32_t ctx = *ctx_io, err = 0;
     uint32_t fa[4], fb[4];
     { const uint4 v = ((const uint4*)(st.m0))[lane]; fa[0] = v.x; fa[1] = v.y; fa[2] = v.z; fa[3] = v.w;
       const uint4 u = ((const uint4*)(st.m0 + 256))[lane]; fb[0] = u.x; fb[1] = u.y; fb[2] = u.z; fb[3] = u.w; }
     uint32_t tota = __reduce_add_sync(FULLMASK, side_part(fa, 8)), totb = __reduce_add_sync(FULLMASK, side_part(fb, 8));
-    for (uint32_t b = 0; b < nb; b++) {
+    for (uint32_t b = 0; b < nb && !err; b++) {
         const DecBlock B = blocks[b];
         if (!B.coded) continue;
         const uint8_t* in = cont + B.in_off;
+        const uint8_t* in_end = in + B.in_size;
         uint8_t* out = D + B.d_off;
         const uint32_t orig = B.d_size;
+        if (orig == 0) continue;
         if (variant == 0) {
             const uint32_t esc = in[2], off_idx = cr_ld32(in + 12);
             const int ctx4 = orig >= 4194304;
-            WRc rc, side; rc.init(in + 16); side.init(in + off_idx);
+            WRc rc, side; rc.init(in + 16, in_end); side.init(in + (off_idx <= B.in_size ? off_idx : B.in_size), in_end);
             for (uint32_t i = lane; i < 256 * 16; i += 32) T.rz_short[i] = 0;
             __syncwarp();
             uint32_t bucket = 0, sbucket = 0, n = 0, hist = 0;                 // hist: last four bytes written
@@ -1370,10 +1379,12 @@ __device__ __forceinline__ void lzdecode_warp_body(int variant, const uint8_t* _
                             q = T.rz_short[sbucket * 16 + ((hd + 64 + 16 - idx) & 15)];              // idx - 64 steps back from the newest
                         }
                         len = l;
+                        if (q >= n || len > orig - n) { err = DEC_ERR_MATCH; break; }        // a slot no position of this block was stored in
                         wcopy_match(out, n, q, len, lane);
                         n += len;
                     }
                 } else { if (lane == 0) out[n] = (uint8_t)s; n++; }
+                if ((err = rc.err | side.err) != 0) break;
                 __syncwarp();
                 for (uint32_t p = n - len; p < n; p++) {                        // matcher_update + ppm_update_context per byte
                     const uint32_t byte = len == 1 ? (s == esc ? esc : s) : out[p];
@@ -1403,7 +1414,8 @@ __device__ __forceinline__ void lzdecode_warp_body(int variant, const uint8_t* _
             }
         } else if (variant == 2) {                                             // LZ77, src/roxmain/cr-coder.c:388-526
             const uint32_t mm = in[1], esc = in[2];
-            WRc rc, rs, rp, rl; rc.init(in + 32); rs.init(in + cr_ld32(in + 20)); rp.init(in + cr_ld32(in + 24)); rl.init(in + cr_ld32(in + 28));
+            auto at = [&](uint32_t off) { return in + (off <= B.in_size ? off : B.in_size); };
+            WRc rc, rs, rp, rl; rc.init(in + 32, in_end); rs.init(at(cr_ld32(in + 20)), in_end); rp.init(at(cr_ld32(in + 24)), in_end); rl.init(at(cr_ld32(in + 28)), in_end);
             // the two ROLZ models cached in registers above alias slots 0 and 1: write them through memory instead
             uint32_t n = 0, last = 0;
             while (n < orig) {
@@ -1419,19 +1431,21 @@ __device__ __forceinline__ void lzdecode_warp_body(int variant, const uint8_t* _
                         else dist = x_decode_distance([&](uint32_t j) { return wdec_m0g(st.m0 + (2 + j) * 256, rp, 1u << (2 * j), lane); });
                         if (dist == 0) dist = last;
                         last = dist; len = l;
+                        if (dist == 0 || dist > n || len > orig - n) { err = DEC_ERR_MATCH; break; }
                         wcopy_match(out, n, n - dist, len, lane);
                         n += len;
                         __syncwarp();
                         for (uint32_t i = len < 4 ? len : 4; i; i--) ctx = ctx << 8 | out[n - i];
                     }
                 }
+                if ((err = rc.err | rs.err | rp.err | rl.err) != 0) break;
                 __syncwarp();
             }
         } else {
             const uint32_t esc = in[8];
-            if (lane < 9) out[lane] = in[9 + lane];
+            if (lane < 9 && lane < orig) out[lane] = in[9 + lane];
             __syncwarp();
-            WRc rc; rc.init(in + 20);
+            WRc rc; rc.init(in + 20, in_end);
             const unsigned long long tag = (unsigned long long)B.epoch << 32;
             unsigned long long h8 = 0;                                          // last eight bytes written (most recent in the top byte)
             for (int i = 1; i < 9; i++) h8 = h8 >> 8 | (unsigned long long)in[9 + i] << 56;
@@ -1447,10 +1461,12 @@ __device__ __forceinline__ void lzdecode_warp_body(int variant, const uint8_t* _
                     else {
                         LzpDec m; m.T = T; m.tag = tag;
                         const uint32_t q = m.getpos(out, n);
+                        if (q >= n || len > orig - n) { err = DEC_ERR_MATCH; break; }
                         wcopy_match(out, n, q, len, lane);
                         n += len;
                     }
                 } else { if (lane == 0) out[n] = (uint8_t)s; n++; }
+                if ((err = rc.err) != 0) break;
                 __syncwarp();
                 for (uint32_t p = n - len; p < n; p++) {
                     const uint32_t byte = len == 1 ? lit : out[p];
@@ -1472,7 +1488,7 @@ __device__ __forceinline__ void lzdecode_warp_body(int variant, const uint8_t* _
         ((uint4*)(st.m0))[lane] = make_uint4(fa[0], fa[1], fa[2], fa[3]);
         ((uint4*)(st.m0 + 256))[lane] = make_uint4(fb[0], fb[1], fb[2], fb[3]);
     }
-    if (lane == 0) *ctx_io = ctx;
+    if (lane == 0) { ctx_io[0] = ctx; ctx_io[1] = err; }
 }
 __global__ void __launch_bounds__(32) k_lzdecode_warp(int variant, const uint8_t* __restrict__ cont, const DecBlock* __restrict__ blocks, uint32_t nb,
                                                        PpmState st, DecTables T, uint32_t* __restrict__ ctx_io, uint8_t* __restrict__ D) {

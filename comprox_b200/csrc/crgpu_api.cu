@@ -271,40 +271,53 @@ extern "C" int crgpu_decompress_batch(crgpu_handle* const* hs, uint32_t count, c
         for (uint32_t k = 0; k < i; k++) if (hs[k] == hs[i]) return CRGPU_ERR_ARG;
         hs[i]->decomp.chain = &hs[i]->chain;
     }
+    // one container after the other (the simulation, and the scalar kernels on the GPU); a damaged container fails alone
+    auto one_by_one = [&]() -> int {
+        int first_err = CRGPU_OK;
+        for (uint32_t i = 0; i < count; i++) {
+            out_lens[i] = 0;
+            const int rc = hs[i]->decomp.decompress(ins[i], in_lens[i], outs[i], out_caps[i], &out_lens[i]);
+            if (rc != CRGPU_OK && rc != CRGPU_ERR_CORRUPT && rc != CRGPU_ERR_ARG) return rc;
+            if (rc != CRGPU_OK) { out_lens[i] = 0; if (first_err == CRGPU_OK) first_err = rc; }
+        }
+        return first_err;
+    };
 #ifdef CRGPU_SIM
-    for (uint32_t i = 0; i < count; i++) CR_TRY(hs[i]->decomp.decompress(ins[i], in_lens[i], outs[i], out_caps[i], &out_lens[i]));
-    return CRGPU_OK;
+    return one_by_one();
 #else
     CR_CUDA(cudaSetDevice(hs[0]->device));
-    if (hs[0]->chain.scalar_models) {
-        for (uint32_t i = 0; i < count; i++) CR_TRY(hs[i]->decomp.decompress(ins[i], in_lens[i], outs[i], out_caps[i], &out_lens[i]));
-        return CRGPU_OK;
-    }
+    if (hs[0]->chain.scalar_models) return one_by_one();
     cudaStream_t stream = hs[0]->stream;
     DevBuf& d_jobs = hs[0]->decomp.d_jobs;
     std::vector<DecJob> jobs(count);
+    // a damaged container is given up on its own: the others are decoded, its out_lens[i] is 0 and the call returns the first error
+    std::vector<int> st(count, CRGPU_OK);
     auto launch = [&]() -> int {
-        for (uint32_t i = 0; i < count; i++) jobs[i] = hs[i]->decomp.job;
+        for (uint32_t i = 0; i < count; i++) { jobs[i] = hs[i]->decomp.job; if (st[i] != CRGPU_OK) jobs[i].nb = 0; }
         CR_TRY(hs[0]->chain.upload(d_jobs, jobs));
         CR_LAUNCH(k_lzdecode_jobs, dim3(count), dim3(32), stream, d_jobs.as<DecJob>(), count);
         return CRGPU_OK;
     };
-    for (uint32_t i = 0; i < count; i++) CR_TRY(hs[i]->decomp.begin(ins[i], in_lens[i], outs[i], out_caps[i], &out_lens[i]));
+    auto hard = [](int rc) { return rc != CRGPU_OK && rc != CRGPU_ERR_CORRUPT && rc != CRGPU_ERR_ARG; };     // CUDA / memory errors end the call
+    for (uint32_t i = 0; i < count; i++) { out_lens[i] = 0; st[i] = hs[i]->decomp.begin(ins[i], in_lens[i], outs[i], out_caps[i], &out_lens[i]); if (hard(st[i])) return st[i]; }
     CR_TRY(launch());
-    for (uint32_t i = 0; i < count; i++) CR_TRY(hs[i]->decomp.middle());
+    for (uint32_t i = 0; i < count; i++) if (st[i] == CRGPU_OK) { st[i] = hs[i]->decomp.middle(); if (hard(st[i])) return st[i]; }
     CR_TRY(launch());
     // dictionary_decode: the sub-chunks of all containers in one launch (each is a serial back-to-front expansion)
     std::vector<DdJob> ddjobs(count); std::vector<uint32_t> first(count + 1, 0);
     for (uint32_t i = 0; i < count; i++) {
-        CR_TRY(hs[i]->decomp.finish_layout());
-        ddjobs[i] = hs[i]->decomp.ddjob; first[i + 1] = first[i] + hs[i]->decomp.dd_nsub;
+        if (st[i] == CRGPU_OK) { st[i] = hs[i]->decomp.finish_layout(); if (hard(st[i])) return st[i]; }
+        const bool ok = st[i] == CRGPU_OK;
+        if (ok) ddjobs[i] = hs[i]->decomp.ddjob; else memset(&ddjobs[i], 0, sizeof(DdJob));
+        first[i + 1] = first[i] + (ok ? hs[i]->decomp.dd_nsub : 0);
     }
     if (first[count]) {
         DevBuf& d_first = hs[0]->decomp.d_first;
         CR_TRY(hs[0]->chain.upload(d_jobs, ddjobs)); CR_TRY(hs[0]->chain.upload(d_first, first));
         CR_LAUNCH(k_dd_subs_jobs, dim3(cr_div_up(first[count], 32)), dim3(32), stream, d_jobs.as<DdJob>(), d_first.as<uint32_t>(), count, first[count]);
     }
-    for (uint32_t i = 0; i < count; i++) CR_TRY(hs[i]->decomp.finish_output());
+    for (uint32_t i = 0; i < count; i++) if (st[i] == CRGPU_OK) { st[i] = hs[i]->decomp.finish_output(); if (hard(st[i])) return st[i]; }
+    for (uint32_t i = 0; i < count; i++) if (st[i] != CRGPU_OK) { out_lens[i] = 0; return st[i]; }
     return CRGPU_OK;
 #endif
 }

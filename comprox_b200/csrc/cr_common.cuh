@@ -97,14 +97,30 @@ static inline unsigned cr_div_up(size_t a, size_t b) { return (unsigned)((a + b 
 
 // ------------------------------------------------------------------ device memory arena-ish helper
 // A growable device buffer: keeps its allocation between calls so steady-state runs do no cudaMalloc.
+// Growth goes through the stream-ordered allocator (cudaMallocAsync / cudaFreeAsync on the stream the calling thread's handle works on,
+// bound by CR_SET_DEVICE): cudaFree synchronises the whole device, which stalled every other handle of a crgpu_compress_batch call each
+// time one of them met a larger container (mixed corpus, 8 handles: 9.7 s -> see profiles/round2_corpus.md).
+#ifndef CRGPU_SIM
+extern thread_local cudaStream_t g_cr_alloc_stream;
+extern thread_local bool g_cr_alloc_async;
+#endif
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
     int reserve(size_t n) {
         if (n <= cap) return CRGPU_OK;
+        const size_t want = n + n / 4 + 256;
+#ifndef CRGPU_SIM
+        if (g_cr_alloc_async) {
+            if (p) cudaFreeAsync(p, g_cr_alloc_stream);
+            p = nullptr; cap = 0;
+            if (cudaMallocAsync(&p, want, g_cr_alloc_stream) != cudaSuccess) { p = nullptr; cudaGetLastError(); return CRGPU_ERR_OOM; }
+            cap = want;
+            return CRGPU_OK;
+        }
+#endif
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
-        size_t want = n + n / 8 + 256;
         if (cudaMalloc(&p, want) != cudaSuccess) { p = nullptr; return CRGPU_ERR_OOM; }
         cap = want;
         return CRGPU_OK;

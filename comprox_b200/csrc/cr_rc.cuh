@@ -123,6 +123,18 @@ CR_HD void rc_dp_step(double& R, const uint4 t, uint32_t& q, uint32_t& msb) {
     R = rc_dp_join(rc_dp_renorm(ch), cl);
 }
 
+// the same with -(2^52 * 2 frq) supplied by the caller (k_rcp_emit computes it while staging, off the chain)
+CR_HD void rc_dp_step_nf(double& R, const uint4 t, const double nf, uint32_t& q, uint32_t& msb) {
+    const double inv = rc_dp_join(t.y, t.x), f = rc_dp_join(t.w, t.z);
+    const double T = fma(R, inv, RC_DP_MAGIC);
+    const double C = fma(T, f, nf);
+    uint32_t th, tl, ch, cl;
+    rc_dp_split(T, th, tl); rc_dp_split(C, ch, cl);
+    q = tl;
+    msb = (ch >> 20) - 1024u;
+    R = rc_dp_join(rc_dp_renorm(ch), cl);
+}
+
 struct RcStream {
     uint32_t ev_begin, ev_end;   // main: event range (dense range = + escord); side: dense range directly
     uint32_t is_main;

@@ -43,7 +43,7 @@ struct RcpJob {
     uint32_t next, prev;                      // neighbouring live jobs of the stream (k_rcp_links)
     double entry;                             // true state on entry (phase C)
 };
-struct RcpStats { unsigned long long state_steps; uint32_t live_jobs, merged_jobs, seed_retries, demoted_jobs, flagged_streams, max_e; };
+struct RcpStats { unsigned long long state_steps; uint32_t live_jobs, merged_jobs, seed_retries, demoted_jobs, flagged_streams, max_e; unsigned long long phase_steps[4]; };   // phase_steps: seed, mid, late, follow
 
 // one symbol on one state: two dependent DFMA and one LOP3 (rc_dp_step, cr_rc.cuh, without the outputs)
 CR_D void rcp_step(double& R, const double inv, const double f, const double nf) {
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(RCP_SEED_THREADS) k_rcp_seed(const RcpStream* 
         S *= 2;
         __syncthreads();
     }
-    if (work) atomicAdd(&stats->state_steps, work);
+    if (work) { atomicAdd(&stats->state_steps, work); atomicAdd(&stats->phase_steps[0], work); }
 }
 
 // ---- A2 / A3 / B: explicit state lists stepped in registers (K per thread, blocked layout), merged values dropped.
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(THREADS) k_rcp_track(RcpStream* ps, RcpJob* jo
         if (mode == RCP_MODE_FOLLOW) {
             if (first_job) return;
             in = E + (size_t)J.prev * RCP_CAP_E; n = jobs[J.prev].ecount; pos = J.a;
-        } else if (first_job) { in = nullptr; n = 1; pos = P.i0; }
+        } else if (first_job) return;                 // k_rcp_emit(RCP_EMIT_FIRST) has written its one-element exit set
         else { in = listA + (size_t)j * RCP_CAP_A; n = J.count; pos = J.pos; }
     }
     if (n == 0 || n > (uint32_t)THREADS * K || pos > end) { if (tid == 0) atomicOr(&ps[J.stream].flags, 8u); return; }
@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(THREADS) k_rcp_track(RcpStream* ps, RcpJob* jo
         if (mode == RCP_MODE_MID) { jobs[j].count = n; jobs[j].pos = pos; }
         else if (mode == RCP_MODE_LATE) { jobs[j].ecount = n; atomicMax(&stats->max_e, n); }
     }
-    if (lane == 0 && work) atomicAdd(&stats->state_steps, work);
+    if (lane == 0 && work) { atomicAdd(&stats->state_steps, work); atomicAdd(&stats->phase_steps[1 + mode], work); }
 }
 
 // ---- C resolve: one warp per stream walks its live jobs: entry of the next job = F[this job][index of this job's entry in E[previous]]
@@ -402,18 +402,32 @@ __global__ void __launch_bounds__(32) k_rcp_resolve(RcpStream* ps, uint32_t nstr
     }
 }
 
-// ---- D emit: the serial walk (k_range_chain<7>'s loop) per job from its true entry state; checks the link to the next job.
-// whole_streams != 0: the fallback -- one warp per FLAGGED stream walks the whole stream from the coder's initial range.
-__global__ void __launch_bounds__(128) k_rcp_emit(RcpStream* ps, uint32_t nstreams, const RcpJob* jobs, const uint32_t* __restrict__ njobs_total,
+// ---- D emit: the serial walk per job from its true entry state; checks the link to the next job.
+//   RCP_EMIT_JOBS   every live job but the first of its stream
+//   RCP_EMIT_WHOLE  the fallback: one warp per FLAGGED stream walks the whole stream from the coder's initial range
+//   RCP_EMIT_FIRST  the first job of every stream (its entry is the coder's initial range); its exit state becomes E[job] (one element),
+//                   so no tracking pass has to walk these symbols a second time
+// Lane 0 runs the chain and nothing else: per symbol two dependent DFMA, one LOP3 on the high word and one 8-byte store of T (whose low
+// word is the quotient).  Records come from shared memory four symbols ahead; -(2^52 * 2 frq) is computed by the staging lanes; the
+// top-bit index is recomputed from T by all lanes afterwards (C = fma(T, 2 frq, nf) again, off the chain).  A full batch is straight-line
+// code.  Measured: profiles/round2_emit_loop.md.
+enum { RCP_EMIT_JOBS = 0, RCP_EMIT_WHOLE = 1, RCP_EMIT_FIRST = 2 };
+CR_D void rcp_chain_step(double& R, const uint4 t, const double nf, double& T) {
+    T = fma(R, rc_dp_join(t.y, t.x), RC_DP_MAGIC);
+    const double C = fma(T, rc_dp_join(t.w, t.z), nf);
+    R = __hiloint2double((int)rc_dp_renorm((uint32_t)__double2hiint(C)), __double2loint(C));
+}
+__global__ void __launch_bounds__(128) k_rcp_emit(RcpStream* ps, uint32_t nstreams, RcpJob* jobs, const uint32_t* __restrict__ njobs_total,
                                                   const uint4* __restrict__ cin_main, const uint4* __restrict__ cin_side,
                                                   uint32_t* __restrict__ q_main, uint32_t* __restrict__ sh_main, uint32_t* __restrict__ q_side, uint32_t* __restrict__ sh_side,
-                                                  int whole_streams, RcpStats* __restrict__ stats) {
+                                                  int which, double* __restrict__ E, RcpStats* __restrict__ stats) {
     __shared__ uint4 stage[4][RC_BATCH + 8];
-    __shared__ uint32_t oq[4][RC_BATCH], os[4][RC_BATCH + 1];
+    __shared__ double snf[4][RC_BATCH + 8];
+    __shared__ double sT[4][RC_BATCH];
     const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     unsigned long long i0, i1; double R; uint32_t sidx, nextj = RCP_NONE; bool is_main;
-    if (whole_streams) {
+    if (which == RCP_EMIT_WHOLE) {
         if (g >= nstreams) return;
         const RcpStream P = ps[g];
         if (!P.flags) return;
@@ -425,8 +439,10 @@ __global__ void __launch_bounds__(128) k_rcp_emit(RcpStream* ps, uint32_t nstrea
         if (J.status != RCP_LIVE) return;
         const RcpStream P = ps[J.stream];
         if (P.flags) return;
+        const bool first = g == P.first_job;
+        if (first != (which == RCP_EMIT_FIRST)) return;
         i1 = J.end; nextj = J.next;
-        i0 = g == P.first_job ? P.i0 : J.a; R = J.entry; sidx = J.stream; is_main = P.is_main != 0;
+        i0 = first ? P.i0 : J.a; R = first ? RC_DP_R0 : J.entry; sidx = J.stream; is_main = P.is_main != 0;
     }
     const uint4* tri = is_main ? cin_main : cin_side;
     uint32_t* qo = is_main ? q_main : q_side;
@@ -434,29 +450,66 @@ __global__ void __launch_bounds__(128) k_rcp_emit(RcpStream* ps, uint32_t nstrea
     uint4 r0 = make_uint4(1, 1, 1, 1), r1 = r0;
     if (i0 + lane < i1) r0 = tri[i0 + lane];
     if (i0 + 32 + lane < i1) r1 = tri[i0 + 32 + lane];
+    if (lane < 8) { stage[w][RC_BATCH + lane] = make_uint4(0, 0x3FE00000u, 0, 0x40000000u); snf[w][RC_BATCH + lane] = 0.0; }    // read ahead only, never applied
     for (unsigned long long base = i0; base < i1; base += RC_BATCH) {
         stage[w][lane] = r0; stage[w][lane + 32] = r1;
+        const double nfa = -(RC_DP_TWO52 * rc_dp_join(r0.w, r0.z)), nfb = -(RC_DP_TWO52 * rc_dp_join(r1.w, r1.z));
+        const double fa = rc_dp_join(r0.w, r0.z), fb = rc_dp_join(r1.w, r1.z);
+        snf[w][lane] = nfa; snf[w][lane + 32] = nfb;
         __syncwarp();
         const unsigned long long nb = base + RC_BATCH;
         if (nb + lane < i1) r0 = tri[nb + lane];
         if (nb + 32 + lane < i1) r1 = tri[nb + 32 + lane];
         const uint32_t cnt = i1 - base < RC_BATCH ? (uint32_t)(i1 - base) : RC_BATCH;
         if (lane == 0) {
-            uint4 t = stage[w][0];
-            for (uint32_t j = 0; j < cnt; j++) {
-                const uint4 tn = stage[w][j + 1];
-                uint32_t q, m;
-                rc_dp_step(R, t, q, m);
-                oq[w][j] = q; os[w][j] = m;
-                t = tn;
+            const uint4* st = stage[w]; const double* sn = snf[w]; double* so_t = sT[w];
+            if (cnt == RC_BATCH) {
+                uint4 c0 = st[0], c1 = st[1], c2 = st[2], c3 = st[3];
+                double n0 = sn[0], n1 = sn[1], n2 = sn[2], n3 = sn[3];
+#pragma unroll
+                for (uint32_t j = 0; j < RC_BATCH; j += 4) {
+                    const uint4 d0 = st[j + 4], d1 = st[j + 5], d2 = st[j + 6], d3 = st[j + 7];
+                    const double m0 = sn[j + 4], m1 = sn[j + 5], m2 = sn[j + 6], m3 = sn[j + 7];
+                    double T0, T1, T2, T3;
+                    rcp_chain_step(R, c0, n0, T0); so_t[j] = T0;
+                    rcp_chain_step(R, c1, n1, T1); so_t[j + 1] = T1;
+                    rcp_chain_step(R, c2, n2, T2); so_t[j + 2] = T2;
+                    rcp_chain_step(R, c3, n3, T3); so_t[j + 3] = T3;
+                    c0 = d0; c1 = d1; c2 = d2; c3 = d3; n0 = m0; n1 = m1; n2 = m2; n3 = m3;
+                }
+            } else {
+                for (uint32_t j = 0; j < cnt; j++) { double T; rcp_chain_step(R, st[j], sn[j], T); so_t[j] = T; }
             }
         }
         __syncwarp();
-        if (lane < cnt) { qo[base + lane] = oq[w][lane]; so[base + lane] = os[w][lane]; }
-        if (lane + 32 < cnt) { qo[base + lane + 32] = oq[w][lane + 32]; so[base + lane + 32] = os[w][lane + 32]; }
+        {   // quotient = low word of T; top-bit index of q * frq = exponent of C
+            const double Ta = sT[w][lane], Tb = sT[w][lane + 32];
+            const double Ca = fma(Ta, fa, nfa), Cb = fma(Tb, fb, nfb);
+            if (lane < cnt) { qo[base + lane] = (uint32_t)__double2loint(Ta); so[base + lane] = ((uint32_t)__double2hiint(Ca) >> 20) - 1024u; }
+            if (lane + 32 < cnt) { qo[base + lane + 32] = (uint32_t)__double2loint(Tb); so[base + lane + 32] = ((uint32_t)__double2hiint(Cb) >> 20) - 1024u; }
+        }
         __syncwarp();
     }
-    if (!whole_streams && lane == 0 && nextj != RCP_NONE && !rcp_same(R, jobs[nextj].entry)) atomicOr(&ps[sidx].flags, 64u);   // the jobs do not link up
+    if (lane != 0) return;
+    if (which == RCP_EMIT_FIRST) { if (nextj != RCP_NONE) { E[(size_t)g * RCP_CAP_E] = R; jobs[g].ecount = 1; } }
+    else if (which == RCP_EMIT_JOBS && nextj != RCP_NONE && !rcp_same(R, jobs[nextj].entry)) atomicOr(&ps[sidx].flags, 64u);   // the jobs do not link up
+}
+
+// ---- prune: a stream whose live jobs leave a span longer than a third of the stream gains little from the cut and pays for the
+// tracking of the jobs around it (BMP data: sums below 2^14 almost everywhere, a handful of seeds survive): it becomes one serial job.
+__global__ void k_rcp_prune(const RcpStream* __restrict__ ps, uint32_t nstreams, RcpJob* jobs, int force_serial, RcpStats* __restrict__ stats) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nstreams) return;
+    const RcpStream P = ps[s];
+    if (P.flags || P.njobs < 2) return;
+    unsigned long long last = P.i0, longest = 0; uint32_t live = 0;
+    for (uint32_t k = P.first_job + 1; k < P.first_job + P.njobs; k++) if (jobs[k].status == RCP_LIVE) {
+        if (jobs[k].a - last > longest) longest = jobs[k].a - last;
+        last = jobs[k].a; live++;
+    }
+    if (P.i1 - last > longest) longest = P.i1 - last;
+    if (!live || (!force_serial && longest * 3 <= P.i1 - P.i0)) return;
+    for (uint32_t k = P.first_job + 1; k < P.first_job + P.njobs; k++) if (jobs[k].status == RCP_LIVE) { jobs[k].status = RCP_MERGED; atomicAdd(&stats->demoted_jobs, 1u); }
 }
 
 // host side: all buffers of the parallel chain
@@ -464,6 +517,8 @@ struct RcPar {
     DevBuf b_ps, b_jobs, b_njobs, b_listA, b_E, b_F, b_stats;
     uint32_t job_symbols = 0;        // symbols per job; 0 = chosen from the window's size
     int late_cfg = 0;                // tuning: thread / register layout of the A3 and B kernels
+    int serial_only = -1;            // 1: one serial job per stream; 0: always cut; -1: cut unless `crowded` (several handles share the device)
+    bool crowded = false;            // set by crgpu_compress_batch: the serial walks of different handles overlap, the tracking kernels do not
     bool attr_done = false;
     RcpStats last = {};
     void release() { DevBuf* all[] = { &b_ps, &b_jobs, &b_njobs, &b_listA, &b_E, &b_F, &b_stats }; for (DevBuf* b : all) b->release(); }
@@ -472,22 +527,26 @@ struct RcPar {
             const Tri* dense_main, const Tri* dense_side, const uint4* cin_main, const uint4* cin_side,
             uint32_t* q_main, uint32_t* sh_main, uint32_t* q_side, uint32_t* sh_side, bool want_stats) {
         if (nstreams == 0) return CRGPU_OK;
+        const bool serial = serial_only == 1 || (serial_only < 0 && crowded);
         uint32_t T = job_symbols;
         if (T == 0) {                // about eight jobs per SM when the window is large; a job of fewer than 16384 symbols does not pay for its seed
             const uint64_t t = (ntm + nts) / 1184;
             T = t < 16384 ? 16384u : t > 65536 ? 65536u : (uint32_t)((t + 4095) & ~4095ull);
         }
         if (T < 4096) T = 4096;
-        const uint64_t maxjobs64 = nstreams + (ntm + nts) / T + 1;
+        if (serial) T = 0xFFFFFFFFu;                                   // one job per stream
+        const uint64_t maxjobs64 = nstreams + (serial ? 0 : (ntm + nts) / T) + 1;
         if (maxjobs64 > (1u << 20)) return CRGPU_ERR_UNSUPPORTED;
         const uint32_t maxjobs = (uint32_t)maxjobs64;
         CR_TRY(b_ps.reserve((size_t)nstreams * sizeof(RcpStream))); CR_TRY(b_jobs.reserve((size_t)maxjobs * sizeof(RcpJob)));
         CR_TRY(b_njobs.reserve(16)); CR_TRY(b_stats.reserve(sizeof(RcpStats)));
-        CR_TRY(b_listA.reserve((size_t)maxjobs * RCP_CAP_A * 8)); CR_TRY(b_E.reserve((size_t)maxjobs * RCP_CAP_E * 8)); CR_TRY(b_F.reserve((size_t)maxjobs * RCP_CAP_E * 8));
+        if (!serial) { CR_TRY(b_listA.reserve((size_t)maxjobs * RCP_CAP_A * 8)); CR_TRY(b_F.reserve((size_t)maxjobs * RCP_CAP_E * 8)); }
+        CR_TRY(b_E.reserve((size_t)maxjobs * RCP_CAP_E * 8));
         CR_CUDA(cudaMemsetAsync(b_stats.p, 0, sizeof(RcpStats), stream));
         RcpStream* ps = b_ps.as<RcpStream>(); RcpJob* jobs = b_jobs.as<RcpJob>(); uint32_t* nj = b_njobs.as<uint32_t>(); RcpStats* st = b_stats.as<RcpStats>();
         double* LA = b_listA.as<double>(); double* E = b_E.as<double>(); double* F = b_F.as<double>();
         CR_LAUNCH(k_rcp_plan, dim3(1), dim3(256), stream, d_streams, nstreams, d_escord, T, maxjobs, ps, jobs, nj);
+        if (!serial) {
         CR_LAUNCH(k_rcp_bounds, dim3(cr_div_up((size_t)maxjobs * 32, 128)), dim3(128), stream, ps, jobs, nj, dense_main, dense_side, st);
         CR_LAUNCH(k_rcp_seed, dim3(maxjobs), dim3(RCP_SEED_THREADS), stream, ps, jobs, nj, dense_main, dense_side, cin_main, cin_side, LA, st);
         if (!attr_done) {                            // per handle: a handle is bound to one device
@@ -499,13 +558,20 @@ struct RcPar {
              k_rcp_track<TH, KK, BB, DD><<<dim3(maxjobs), dim3(TH), (SMEM), stream>>>(ps, jobs, nj, cin_main, cin_side, LA, E, F, MODE, st); \
              CR_CUDA(cudaGetLastError()); } while (0)
         RCP_TRACK(512, 32, 16, true, 512 * 32 * 8, RCP_MODE_MID);
+        CR_LAUNCH(k_rcp_prune, dim3(cr_div_up(nstreams, 64)), dim3(64), stream, ps, nstreams, jobs, 0, st);
+        }
         CR_LAUNCH(k_rcp_links, dim3(cr_div_up(maxjobs, 128)), dim3(128), stream, ps, jobs, nj);
+        const dim3 gemit(cr_div_up((size_t)maxjobs * 32, 128));
+        // first jobs: their entry is known, the walk that emits them also yields their exit state
+        CR_LAUNCH(k_rcp_emit, gemit, dim3(128), stream, ps, nstreams, jobs, nj, cin_main, cin_side, q_main, sh_main, q_side, sh_side, (int)RCP_EMIT_FIRST, E, st);
+        if (!serial) {
         if (late_cfg == 1) { RCP_TRACK(256, 8, 128, true, 2048 * 8, RCP_MODE_LATE); RCP_TRACK(256, 8, 128, false, 0, RCP_MODE_FOLLOW); }
         else { RCP_TRACK(512, 4, 128, true, 2048 * 8, RCP_MODE_LATE); RCP_TRACK(512, 4, 128, false, 0, RCP_MODE_FOLLOW); }
-#undef RCP_TRACK
         CR_LAUNCH(k_rcp_resolve, dim3(nstreams), dim3(32), stream, ps, nstreams, jobs, E, F);
-        CR_LAUNCH(k_rcp_emit, dim3(cr_div_up((size_t)maxjobs * 32, 128)), dim3(128), stream, ps, nstreams, jobs, nj, cin_main, cin_side, q_main, sh_main, q_side, sh_side, 0, st);
-        CR_LAUNCH(k_rcp_emit, dim3(cr_div_up((size_t)nstreams * 32, 128)), dim3(128), stream, ps, nstreams, jobs, nj, cin_main, cin_side, q_main, sh_main, q_side, sh_side, 1, st);
+        CR_LAUNCH(k_rcp_emit, gemit, dim3(128), stream, ps, nstreams, jobs, nj, cin_main, cin_side, q_main, sh_main, q_side, sh_side, (int)RCP_EMIT_JOBS, E, st);
+        }
+#undef RCP_TRACK
+        CR_LAUNCH(k_rcp_emit, dim3(cr_div_up((size_t)nstreams * 32, 128)), dim3(128), stream, ps, nstreams, jobs, nj, cin_main, cin_side, q_main, sh_main, q_side, sh_side, (int)RCP_EMIT_WHOLE, E, st);
         if (want_stats) {
             CR_CUDA(cudaMemcpyAsync(&last, st, sizeof(RcpStats), cudaMemcpyDeviceToHost, stream));
             CR_CUDA(cudaStreamSynchronize(stream));

@@ -9,8 +9,13 @@
 
 #ifdef CRGPU_SIM
 thread_local crsim_dim3 threadIdx, blockIdx, blockDim, gridDim;
+#define CR_SET_DEVICE(h) do { } while (0)
 #else
 unsigned long long g_cr_launches = 0;
+thread_local cudaStream_t g_cr_alloc_stream = 0;
+thread_local bool g_cr_alloc_async = false;
+// every entry point that touches the device: select the handle's GPU and bind DevBuf growth (cr_common.cuh) to the handle's stream
+#define CR_SET_DEVICE(h) do { CR_CUDA(cudaSetDevice((h)->device)); g_cr_alloc_stream = (h)->stream; g_cr_alloc_async = true; } while (0)
 #endif
 
 struct crgpu_handle {
@@ -63,6 +68,13 @@ extern "C" int crgpu_create(crgpu_handle** out, int variant, int device, void* s
 #else
     if (stream == CRGPU_OWN_STREAM) h->stream = 0;
 #endif
+#ifndef CRGPU_SIM
+    {   // keep freed blocks in the stream-ordered pool instead of returning them to the driver at every synchronisation
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) { uint64_t keep = ~0ull; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep); }
+        g_cr_alloc_stream = h->stream; g_cr_alloc_async = true;
+    }
+#endif
     int rc = h->chain.init(variant, h->stream);
     if (rc != CRGPU_OK) { delete h; return rc; }
     *out = h;
@@ -84,6 +96,7 @@ extern "C" void crgpu_destroy(crgpu_handle* h) {
 
 extern "C" int crgpu_reset_models(crgpu_handle* h) {
     if (!h) return CRGPU_ERR_ARG;
+    CR_SET_DEVICE(h);
     return h->chain.reset_models();
 }
 
@@ -91,7 +104,7 @@ extern "C" int crgpu_lzencode(crgpu_handle* h, const uint8_t* in, const uint32_t
                               uint8_t* out, uint64_t out_cap, uint32_t* out_sizes) {
     if (!h || !sizes || !out_sizes || (nblocks && !in)) return CRGPU_ERR_ARG;
 #ifndef CRGPU_SIM
-    CR_CUDA(cudaSetDevice(h->device));
+    CR_SET_DEVICE(h);
 #endif
     // every payload is at most header + block bytes (stored form): demand that much up front, so that a too small `out` is
     // reported BEFORE any block has advanced the models of the chain
@@ -198,8 +211,9 @@ extern "C" int crgpu_set_option(crgpu_handle* h, const char* name, int64_t value
 #ifndef CRGPU_SIM
     if (n == "rc_job_symbols") { if (value != 0 && (value < 4096 || value > (1 << 24))) return CRGPU_ERR_ARG; h->chain.rcpar.job_symbols = (uint32_t)value; return CRGPU_OK; }
     if (n == "rc_late_cfg") { h->chain.rcpar.late_cfg = (int)value; return CRGPU_OK; }
+    if (n == "rc_serial") { if (value < -1 || value > 1) return CRGPU_ERR_ARG; h->chain.rcpar.serial_only = (int)value; return CRGPU_OK; }
 #else
-    if (n == "rc_job_symbols" || n == "rc_late_cfg") return CRGPU_OK;
+    if (n == "rc_job_symbols" || n == "rc_late_cfg" || n == "rc_serial") return CRGPU_OK;
 #endif
     if (n == "hot_contexts") { h->chain.hot_contexts = value != 0; return CRGPU_OK; }
     if (n == "match_limit") { if (value < 1 || value > 1000000) return CRGPU_ERR_ARG; h->chain.match_limit = (uint32_t)value; return CRGPU_OK; }   // comprox -m
@@ -214,7 +228,7 @@ extern "C" uint64_t crgpu_compress_bound(uint64_t n, uint32_t block_size) { retu
 extern "C" int crgpu_compress(crgpu_handle* h, const crgpu_config* cfg, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_n) {
     if (!h || !cfg) return CRGPU_ERR_ARG;
 #ifndef CRGPU_SIM
-    CR_CUDA(cudaSetDevice(h->device));
+    CR_SET_DEVICE(h);
 #endif
     CrConfig c; c.block_size = cfg->block_size; c.filt = cfg->filt; c.prec = cfg->prec; c.flexible = cfg->flexible; c.window_bytes = cfg->window_bytes;
     h->comp.chain = &h->chain;
@@ -245,7 +259,7 @@ extern "C" uint64_t crgpu_launch_count(void) {
 extern "C" int crgpu_stage_input(crgpu_handle* h, const uint8_t* in, uint64_t n) {
     if (!h || (n && !in)) return CRGPU_ERR_ARG;
 #ifndef CRGPU_SIM
-    CR_CUDA(cudaSetDevice(h->device));
+    CR_SET_DEVICE(h);
 #endif
     h->comp.chain = &h->chain; h->comp.stream = h->chain.stream;
     CR_TRY(h->comp.stage(in, n));
@@ -256,7 +270,7 @@ extern "C" int crgpu_stage_input(crgpu_handle* h, const uint8_t* in, uint64_t n)
 extern "C" int crgpu_decompress(crgpu_handle* h, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_n) {
     if (!h) return CRGPU_ERR_ARG;
 #ifndef CRGPU_SIM
-    CR_CUDA(cudaSetDevice(h->device));
+    CR_SET_DEVICE(h);
 #endif
     h->decomp.chain = &h->chain;
     return h->decomp.decompress(in, n, out, out_cap, out_n);
@@ -285,7 +299,7 @@ extern "C" int crgpu_decompress_batch(crgpu_handle* const* hs, uint32_t count, c
 #ifdef CRGPU_SIM
     return one_by_one();
 #else
-    CR_CUDA(cudaSetDevice(hs[0]->device));
+    CR_SET_DEVICE(hs[0]);
     if (hs[0]->chain.scalar_models) return one_by_one();
     cudaStream_t stream = hs[0]->stream;
     DevBuf& d_jobs = hs[0]->decomp.d_jobs;
@@ -327,7 +341,7 @@ extern "C" int crgpu_dicpick(crgpu_handle* h, const uint8_t* in, uint64_t n, uin
     if (!h || (n && !in) || !out || !out_n) return CRGPU_ERR_ARG;
     if (n > (1ull << 32)) return CRGPU_ERR_UNSUPPORTED;                        // word positions of the table are 32 bit
 #ifndef CRGPU_SIM
-    CR_CUDA(cudaSetDevice(h->device));
+    CR_SET_DEVICE(h);
 #endif
     h->comp.chain = &h->chain; h->comp.stream = h->chain.stream;
     CR_TRY(h->comp.stage(in, n));
@@ -342,11 +356,6 @@ extern "C" int crgpu_dicpick(crgpu_handle* h, const uint8_t* in, uint64_t n, uin
 // ------------------------------------------------------------------ stage-level entry points: one block per call, with the
 // argument meaning of the reference's cr-* functions.  host/cr_shim.c wraps them into the reference's
 // own signatures so that the UNMODIFIED src/main.c links against this library.
-#ifndef CRGPU_SIM
-#define CR_SET_DEVICE(h) CR_CUDA(cudaSetDevice((h)->device))
-#else
-#define CR_SET_DEVICE(h) do { } while (0)
-#endif
 
 // filter_inplace(buf, len, en_de) -- src/cr-filter.c:33-73
 extern "C" int crgpu_filter_inplace(crgpu_handle* h, uint8_t* buf, uint32_t len, int en_de) {
@@ -456,6 +465,15 @@ extern "C" int crgpu_compress_batch(crgpu_handle* const* hs, uint32_t nhandles, 
 #endif
         }
     }
+#ifndef CRGPU_SIM
+    // three or more handles on one device: the serial range walks of different containers overlap each other and everything else, while
+    // the tracking kernels of the cut chain (cr_rcpar.cuh) fill the device and do not -- unless the caller chose with "rc_serial"
+    for (uint32_t i = 0; i < nhandles; i++) {
+        uint32_t same = 0;
+        for (uint32_t k = 0; k < nhandles; k++) same += hs[k]->device == hs[i]->device;
+        hs[i]->chain.rcpar.crowded = same >= 3 && count >= 3;
+    }
+#endif
     std::atomic<uint32_t> next(0);
     std::atomic<int> first_error(CRGPU_OK);
     auto worker = [&](uint32_t j) {
@@ -471,6 +489,9 @@ extern "C" int crgpu_compress_batch(crgpu_handle* const* hs, uint32_t nhandles, 
     for (uint32_t j = 1; j < nthreads; j++) pool.emplace_back(worker, j);
     if (nthreads) worker(0);
     for (auto& t : pool) t.join();
+#ifndef CRGPU_SIM
+    for (uint32_t i = 0; i < nhandles; i++) hs[i]->chain.rcpar.crowded = false;
+#endif
     return first_error.load();
 }
 
@@ -500,7 +521,7 @@ extern "C" int crgpu_debug_rc_parallel(crgpu_handle* h, const uint32_t* frq, con
     return CRGPU_ERR_UNSUPPORTED;
 #else
     if (!h || !frq || !sum || !lens || !q_out || !shift_out || n == 0 || n >= (1ull << 32) || nstreams == 0) return CRGPU_ERR_ARG;
-    CR_CUDA(cudaSetDevice(h->device));
+    CR_SET_DEVICE(h);
     LzChain& c = h->chain;
     cudaStream_t stream = c.stream;
     std::vector<Tri> tri(n);

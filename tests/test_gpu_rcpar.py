@@ -89,6 +89,31 @@ def test_gpu_rcpar_seeds_that_do_not_shrink_are_merged(gpulib):
     assert st["demoted"] > 0 and st["flagged"] == 0, st
 
 
+def test_gpu_rcpar_serial_mode_and_pruned_streams(gpulib):
+    """rc_serial = 1 (what crgpu_compress_batch picks when handles share a device): one job per stream, same numbers.  A stream with
+    only a couple of usable seeds is pruned to one serial job instead of tracking sets around a long serial span."""
+    rng = np.random.default_rng(77)
+    lens = [300000, 3, 200000]
+    f, s = _symbols(rng, sum(lens), "textlike")
+    want_q, want_sh = _serial(gpulib, f, s, lens)
+    with api.Handle(api.ROLZ, lib=gpulib) as h:
+        h.set_option("rc_serial", 1)
+        q, sh, st = _parallel(gpulib, h, f, s, lens, 8192)
+        assert np.array_equal(q, want_q) and np.array_equal(sh, want_sh), st
+        assert st["live"] == 0 and st["flagged"] == 0, st
+        h.set_option("rc_serial", -1)
+        q, sh, st = _parallel(gpulib, h, f, s, lens, 8192)
+        assert np.array_equal(q, want_q) and np.array_equal(sh, want_sh) and st["live"] > 0, st
+    n = 400000
+    f, s = _symbols(rng, n, "small")
+    s[150000:150040] = 200000; f[150000:150040] = 150000          # the only place a seed can stand
+    want_q, want_sh = _serial(gpulib, f, s, [n])
+    with api.Handle(api.ROLZ, lib=gpulib) as h:
+        q, sh, st = _parallel(gpulib, h, f, s, [n], 8192)
+    assert np.array_equal(q, want_q) and np.array_equal(sh, want_sh), st
+    assert st["demoted"] >= 1 and st["flagged"] == 0, st
+
+
 def test_gpu_rcpar_on_real_triples(gpulib):
     """(frq, sum) of a real ROLZ main stream and side stream (oracle trace of 6 MiB of text)."""
     data = synth.markov_text(6 * MiB, seed=31)

@@ -33,6 +33,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# handles that share a GPU need their own hardware work queues (crgpu_api.cu: cr_more_work_queues); the variable only counts before the
+# CUDA context exists, and torch creates that before libcrgpu.so is loaded
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 MiB = 1 << 20
 WORKLOAD_BYTES = 100 * MiB

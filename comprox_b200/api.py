@@ -9,6 +9,9 @@ import ctypes
 import os
 import time
 
+# see crgpu_api.cu: cr_more_work_queues (only counts if no CUDA context exists yet in this process)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcrgpu.so")
 

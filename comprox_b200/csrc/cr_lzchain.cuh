@@ -53,6 +53,7 @@ struct LzChain {
     DevBuf b_escrec, b_esccount, b_k64a, b_k64b, b_ord, b_flag, b_escord;
     DevBuf b_lensym, b_lenpos, b_idxsym, b_idxpos;
     DevBuf b_hits;
+    DevBuf b_o1ctx, b_o1steps, b_o1snaps;
     DevBuf b_o1info, b_o1ord, b_o1incl, b_bounds, b_o3hot, b_cinm, b_cins, b_segstart, b_segkey, b_rank, b_flexlen;
     DevBuf b_qm, b_shm, b_bm, b_qs, b_shs, b_bs, b_stot, b_dsum, b_lsm, b_lss, b_rsm, b_rss, b_fb;
     DevBuf b_dense, b_denseside, b_streams, b_rcres, b_rcout, b_copy, b_hdr;
@@ -68,6 +69,9 @@ struct LzChain {
     bool flexible = false;         // -f flexible parsing (ROLZ)
     int rc_variant = 8;            // range-chain formulation: 8 = cut into jobs that run side by side (cr_rcpar.cuh); 1..7 = one serial walk per stream (cr_warp.cuh: k_range_chain<1..7>)
     bool hot_contexts = true;      // hot o2 contexts run the rank-based CTA kernel (k_o2_pass_cta)
+    int o1_hot_variant = 2;        // 2 = k_o1_skel + k_o1_eval (the chain of steps carries only the counts), 1 = k_o1_pass_cta
+    int o2_hot_variant = 2;        // 2 = k_o2_hot (event ring, ballot ranks), 1 = k_o2_pass_cta
+    bool o2_attr_done = false;
     bool scalar_models = false;   // GPU A/B switch: run the scalar (simulation-checked) model/coder kernels
     bool exact_aborts = true;      // replay a mid-chain "cannot compress" exactly (encode_blocks); false = CRGPU_ERR_MIDCHAIN_ABORT
     DevBuf b_abort;
@@ -95,7 +99,7 @@ struct LzChain {
         DevBuf* all[] = { &s_o3b, &s_o3c, &s_o2, &s_o1, &s_m0, &b_blocks, &b_segoff, &b_seglen, &b_hist, &b_esc1, &b_first, &b_ctxout,
             &b_k0, &b_k1, &b_v0, &b_v1, &b_ks0, &b_M, &b_S, &b_span, &b_tidx, &b_segs, &b_xt, &b_entry, &b_cnt, &b_scan, &b_chainwork,
             &b_evctx, &b_evsym, &b_tokend, &b_pred, &b_T1, &b_T2, &b_TS, &b_side, &b_escrec, &b_esccount, &b_k64a, &b_k64b, &b_ord,
-            &b_flag, &b_escord, &b_lensym, &b_lenpos, &b_idxsym, &b_idxpos, &b_hits, &b_o1info, &b_o1ord, &b_o1incl, &b_bounds, &b_o3hot, &b_cinm, &b_cins, &b_segstart, &b_segkey, &b_rank, &b_flexlen, &b_qm, &b_shm, &b_bm, &b_qs, &b_shs, &b_bs, &b_stot, &b_dsum, &b_lsm, &b_lss, &b_rsm, &b_rss, &b_fb, &b_dense, &b_denseside, &b_streams, &b_rcres, &b_rcout, &b_copy, &b_hdr,
+            &b_flag, &b_escord, &b_lensym, &b_lenpos, &b_idxsym, &b_idxpos, &b_hits, &b_o1ctx, &b_o1steps, &b_o1snaps, &b_o1info, &b_o1ord, &b_o1incl, &b_bounds, &b_o3hot, &b_cinm, &b_cins, &b_segstart, &b_segkey, &b_rank, &b_flexlen, &b_qm, &b_shm, &b_bm, &b_qs, &b_shs, &b_bs, &b_stot, &b_dsum, &b_lsm, &b_lss, &b_rsm, &b_rss, &b_fb, &b_dense, &b_denseside, &b_streams, &b_rcres, &b_rcout, &b_copy, &b_hdr,
             &x_npos, &x_nlen, &x_sdist, &x_slen, &x_G, &x_tdist, &x_h16, &x_rank, &x_mpos0, &x_mlen0, &x_clast, &x_ckey, &x_cmax, &x_lastin, &x_mism, &x_msym, &x_mpos,
             &snap_o3b, &snap_o3c, &snap_o2, &snap_o1, &snap_m0, &b_abort };
         for (DevBuf* b : all) b->release();
@@ -488,7 +492,18 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
                 std::vector<uint32_t> hh;
                 CR_TRY(download(hh, b_hits.p, 1));
                 timer.count("#o3_hits", hh[0]);
-                if ((double)hh[0] > 0.25 * (double)nev)
+                const bool narrow = (double)hh[0] > 0.25 * (double)nev;
+                if (o2_hot_variant == 2) {
+                    if (!o2_attr_done) {
+                        CR_CUDA(cudaFuncSetAttribute(k_o2_hot<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(O2HotSmem<256>)));
+                        CR_CUDA(cudaFuncSetAttribute(k_o2_hot<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(O2HotSmem<1024>)));
+                        o2_attr_done = true;
+                    }
+                    __atomic_fetch_add(&g_cr_launches, 1ull, __ATOMIC_RELAXED);
+                    if (narrow) k_o2_hot<256><<<dim3(65536), dim3(256), sizeof(O2HotSmem<256>), stream>>>(b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nev, st, b_T1.as<uint64_t>(), b_escrec.as<EscRec>(), b_esccount.as<uint32_t>(), b_bounds.as<uint32_t>());
+                    else k_o2_hot<1024><<<dim3(65536), dim3(1024), sizeof(O2HotSmem<1024>), stream>>>(b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nev, st, b_T1.as<uint64_t>(), b_escrec.as<EscRec>(), b_esccount.as<uint32_t>(), b_bounds.as<uint32_t>());
+                    CR_CUDA(cudaGetLastError());
+                } else if (narrow)
                     CR_LAUNCH(k_o2_pass_cta<256>, dim3(65536), dim3(256), stream, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nev, st, b_T1.as<uint64_t>(), b_escrec.as<EscRec>(), b_esccount.as<uint32_t>(), b_bounds.as<uint32_t>());
                 else
                     CR_LAUNCH(k_o2_pass_cta<1024>, dim3(65536), dim3(1024), stream, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nev, st, b_T1.as<uint64_t>(), b_escrec.as<EscRec>(), b_esccount.as<uint32_t>(), b_bounds.as<uint32_t>());
@@ -514,6 +529,14 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
             if (!scalar_models) {
                 CR_TRY(b_o1info.reserve((size_t)nesc * 4 + 16)); CR_TRY(b_o1ord.reserve((size_t)nesc * 4 + 16)); CR_TRY(b_o1incl.reserve((size_t)nesc * 32 + 32));
                 CR_LAUNCH(k_o1_gather, gx, te, stream, b_v1.as<uint32_t>(), nesc, b_escrec.as<EscRec>(), b_ord.as<uint32_t>(), b_o1info.as<uint32_t>(), b_o1ord.as<uint32_t>(), b_o1incl.as<uint4>());
+                if (hot_contexts && o1_hot_variant == 2) {
+                    const uint32_t max_rec = nesc / O1S_TH + nesc / 127u + 2u * 256u;
+                    CR_TRY(b_o1ctx.reserve(256 * sizeof(O1Ctx))); CR_TRY(b_o1steps.reserve((size_t)max_rec * sizeof(O1Step))); CR_TRY(b_o1snaps.reserve((size_t)max_rec * 256));
+                    CR_LAUNCH(k_o1_plan, dim3(1), dim3(256), stream, b_k64b.as<uint64_t>(), nesc, b_o1ctx.as<O1Ctx>());
+                    CR_LAUNCH(k_o1_skel, dim3(256), dim3(O1S_TH), stream, b_o1ctx.as<O1Ctx>(), b_o1info.as<uint32_t>(), st, b_o1steps.as<O1Step>(), b_o1snaps.as<uint8_t>());
+                    CR_LAUNCH(k_o1_eval, dim3(max_rec), dim3(O1C_THREADS), stream, b_o1ctx.as<O1Ctx>(), b_o1steps.as<O1Step>(), b_o1snaps.as<uint8_t>(),
+                              b_o1info.as<uint32_t>(), b_o1ord.as<uint32_t>(), b_o1incl.as<uint4>(), b_T2.as<uint64_t>());
+                } else
                 if (hot_contexts) CR_LAUNCH(k_o1_pass_cta, dim3(256), dim3(O1C_THREADS), stream, b_k64b.as<uint64_t>(), nesc, b_o1info.as<uint32_t>(), b_o1ord.as<uint32_t>(), b_o1incl.as<uint4>(), st, b_T2.as<uint64_t>());
                 CR_LAUNCH(k_o1_pass_warp, dim3(256 * 32 / 128), dim3(128), stream, b_k64b.as<uint64_t>(), nesc, b_o1info.as<uint32_t>(), b_o1ord.as<uint32_t>(), b_o1incl.as<uint4>(), st, b_T2.as<uint64_t>(), hot_contexts ? O1C_MIN : 0xFFFFFFFFu);
             } else

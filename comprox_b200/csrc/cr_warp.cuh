@@ -480,6 +480,218 @@ __global__ void __launch_bounds__(O2C_THREADS) k_o2_pass_cta(const uint32_t* __r
     if (tid == 0) { row[256] = (uint8_t)s_f256; row[257] = (uint8_t)s_f257; }
 }
 
+// ------------------------------------------------------------------ o2 pass for HOT contexts, second form (default)
+// Same step as k_o2_pass_cta -- every quantity of ppm_encode is a start-of-step value plus a rank, the first event whose update would
+// rescale ends the step -- with the per-step latency cut (the hottest context is one chain of ~events / 200 steps and sets the time of the
+// whole pass, profiles/round2_o2_pass.md):
+//   * the events of the next two steps sit in a shared-memory ring filled by cp.async two steps ahead: no global load on the chain;
+//   * ranks inside a warp come from eight ballots of the symbol bits (lanes with a smaller / the same symbol, lanes whose symbol is my
+//     predicted byte) instead of a 32-step shuffle loop;
+//   * the per-warp histogram is written by one leader lane per distinct symbol (no shared-memory atomics, no bank conflicts), and the
+//     counts are bumped once per (warp, symbol);
+//   * warp 0 rebuilds the cumulative table while the other warps already rank the next step; six barriers per step instead of ten.
+CR_D void cr_cp_async4(void* smem, const void* gmem) {
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(sa), "l"(gmem) : "memory");
+}
+CR_D void cr_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> CR_D void cr_cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+template <int TH> struct O2HotSmem {
+    static constexpr int NW = TH / 32, RING = 2 * TH;
+    uint32_t ringK[RING], ringV[RING];
+    uint32_t cnt[256], cumt[256], zmask[8];
+    uint32_t wtot[3][32];
+    uint32_t s_f256, s_f257, s_body, s_first;
+    uint16_t hexcl[NW][256];           // nonhit events of earlier warps of the step, per symbol
+    uint16_t below[NW][256];           // the same summed over smaller symbols
+    uint8_t hraw[NW][256];             // nonhit events of this warp, per symbol (written by the leader lanes, cleared by them)
+    uint16_t ssym[TH];
+    uint8_t esc_sym[TH];
+};
+template <int TH>
+__global__ void __launch_bounds__(TH) k_o2_hot(const uint32_t* __restrict__ K, const uint32_t* __restrict__ V, uint32_t n, PpmState st,
+                                               uint64_t* __restrict__ T1, EscRec* __restrict__ esc_rec, uint32_t* __restrict__ esc_count, const uint32_t* __restrict__ bounds) {
+    extern __shared__ __align__(16) unsigned char o2hot_raw[];
+    O2HotSmem<TH>& S = *reinterpret_cast<O2HotSmem<TH>*>(o2hot_raw);
+    constexpr int NW = TH / 32, RING = 2 * TH;
+    const uint32_t c16 = blockIdx.x;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const uint32_t r0 = bounds[c16], r1 = bounds[c16 + 1];
+    if (r1 - r0 < O2C_MIN) return;
+    uint8_t* row = st.o2 + (size_t)c16 * PPM_O2_STRIDE;
+    for (uint32_t i = tid; i < 256; i += TH) S.cnt[i] = row[i];
+    for (uint32_t i = tid; i < NW * 64; i += TH) ((uint32_t*)&S.hraw[0][0])[i] = 0;
+    if (tid == 0) { S.s_f256 = row[256]; S.s_f257 = row[257]; S.s_first = 0xFFFFFFFFu; }
+    for (uint32_t i = tid; i < RING; i += TH) if (r0 + i < r1) { cr_cp_async4(&S.ringK[i], K + r0 + i); cr_cp_async4(&S.ringV[i], V + r0 + i); }
+    cr_cp_async_commit();
+    cr_cp_async_wait<0>();
+    __syncthreads();
+
+    const uint32_t before = (1u << lane) - 1u;
+    uint32_t pos = r0;
+    // an escape's record is written one step late: its slot comes from a global atomic whose round trip (~1000 cycles) would
+    // otherwise sit on the chain of steps.  The thread keeps the record in registers and stores it in the next step (or after the loop).
+    bool pend = false; uint32_t pend_slot = 0, pend_e = 0, pend_info = 0, pm0 = 0, pm1 = 0, pm2 = 0, pm3 = 0, pm4 = 0, pm5 = 0, pm6 = 0, pm7 = 0;
+    auto flush = [&]() {
+        if (pend) {
+            EscRec* rec = esc_rec + pend_slot;
+            rec->e = pend_e; rec->info = pend_info;
+            rec->incl[0] = pm0; rec->incl[1] = pm1; rec->incl[2] = pm2; rec->incl[3] = pm3; rec->incl[4] = pm4; rec->incl[5] = pm5; rec->incl[6] = pm6; rec->incl[7] = pm7;
+            pend = false;
+        }
+    };
+    while (pos < r1) {
+        const uint32_t step = r1 - pos < (uint32_t)TH ? r1 - pos : (uint32_t)TH;
+        const uint32_t nw = (step + 31) >> 5;
+        // ---- 1: warp 0 derives cumt / body / zero mask from cnt; everybody ranks its event inside its warp
+        if (w == 0) {
+            uint32_t v[8], sum = 0, zb = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { v[k] = S.cnt[lane * 8 + k]; sum += v[k]; zb |= (uint32_t)(v[k] == 0) << k; }
+            uint32_t inc = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(FULLMASK, inc, d); if (lane >= d) inc += t; }
+            uint32_t run = inc - sum;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { S.cumt[lane * 8 + k] = run; run += v[k]; }
+            if (lane == 31) S.s_body = inc;
+            uint32_t z = zb << (8 * (lane & 3));
+            z |= __shfl_xor_sync(FULLMASK, z, 1); z |= __shfl_xor_sync(FULLMASK, z, 2);
+            if ((lane & 3) == 0) S.zmask[lane >> 2] = z;
+        }
+        const bool active = tid < step;
+        const uint32_t slot = (pos - r0 + tid) % RING;
+        uint32_t k = 0, ev = 0;
+        if (active) { k = S.ringK[slot]; ev = S.ringV[slot]; }
+        const uint32_t sym = k >> 24, pr = (k >> 16) & 255;
+        const bool hit = active && sym == pr, nonhit = active && sym != pr;
+        const uint32_t b_nh = __ballot_sync(FULLMASK, nonhit);
+        uint32_t mL = 0, mE = b_nh, mP = b_nh;        // nonhit lanes with a smaller symbol / my symbol / my predicted byte as their symbol
+#pragma unroll
+        for (int b = 7; b >= 0; b--) {
+            const uint32_t Bb = __ballot_sync(FULLMASK, (sym >> b) & 1u);
+            if ((sym >> b) & 1u) { mL |= mE & ~Bb; mE &= Bb; } else mE &= ~Bb;
+            mP &= ((pr >> b) & 1u) ? Bb : ~Bb;
+        }
+        const uint32_t lt = __popc(mL & before), eq = __popc(mE & before), peq = __popc(mP & before);
+        const bool leader = nonhit && (mE & before) == 0;
+        if (leader) S.hraw[w][sym] = (uint8_t)__popc(mE);
+        S.ssym[tid] = nonhit ? (uint16_t)sym : (uint16_t)0x100;
+        __syncthreads();                                                             // B1
+        // ---- 2a: per symbol, exclusive prefix over the warps of the step
+        if (tid < 256) { uint32_t run = 0; for (uint32_t q = 0; q < nw; q++) { const uint32_t h = S.hraw[q][tid]; S.hexcl[q][tid] = (uint16_t)run; run += h; } }
+        __syncthreads();                                                             // B2
+        // ---- 2b: per warp, prefix over the symbols; frequencies of my symbol and of my predicted byte as of my event
+        if (w < nw) {
+            if (leader) S.hraw[w][sym] = 0;
+            uint32_t v[8], sum = 0;
+            const uint4 hv = *(const uint4*)&S.hexcl[w][lane * 8];
+            v[0] = hv.x & 0xffff; v[1] = hv.x >> 16; v[2] = hv.y & 0xffff; v[3] = hv.y >> 16; v[4] = hv.z & 0xffff; v[5] = hv.z >> 16; v[6] = hv.w & 0xffff; v[7] = hv.w >> 16;
+#pragma unroll
+            for (int q = 0; q < 8; q++) sum += v[q];
+            uint32_t inc = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(FULLMASK, inc, d); if (lane >= d) inc += t; }
+            uint32_t run = inc - sum, o[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) { o[q] = run; run += v[q]; }
+            *(uint4*)&S.below[w][lane * 8] = make_uint4(o[0] | o[1] << 16, o[2] | o[3] << 16, o[4] | o[5] << 16, o[6] | o[7] << 16);
+        }
+        __syncwarp();
+        uint32_t fs = 0, pf = 0;
+        if (active) { fs = S.cnt[sym] + S.hexcl[w][sym] + eq; pf = S.cnt[pr] + S.hexcl[w][pr] + peq; }
+        const bool esc = nonhit && fs == 0, two = nonhit && fs == 1;
+        const uint32_t b_es = __ballot_sync(FULLMASK, esc), b_tw = __ballot_sync(FULLMASK, two);
+        if (lane == 0) { S.wtot[0][w] = __popc(b_nh); S.wtot[1][w] = __popc(b_es); S.wtot[2][w] = __popc(b_tw); }
+        __syncthreads();                                                             // B3
+        // ---- 3: totals of the earlier warps; does my event's update rescale the table?
+        uint32_t p0 = 0, p1 = 0, p2 = 0;
+        if (lane < w) { p0 = S.wtot[0][lane]; p1 = S.wtot[1][lane]; p2 = S.wtot[2][lane]; }
+        p0 = __reduce_add_sync(FULLMASK, p0); p1 = __reduce_add_sync(FULLMASK, p1); p2 = __reduce_add_sync(FULLMASK, p2);
+        const uint32_t A = p0 + __popc(b_nh & before);            // non-hits before this event
+        const uint32_t ES = p1 + __popc(b_es & before);           // escapes before
+        const uint32_t TW = p2 + __popc(b_tw & before);           // 1->2 transitions before
+        const uint32_t f256 = S.s_f256 + (tid - A), f257 = S.s_f257 + ES - TW, body = S.s_body + A;
+        bool trig = false;
+        if (hit) trig = f256 + 1 > 250;
+        else if (esc) trig = f257 + 1 > 250;
+        else if (nonhit) trig = (fs + 1 > 250) || (fs == 1 && f257 == 0);
+        const uint32_t b_tr = __ballot_sync(FULLMASK, trig);
+        if (lane == 0 && b_tr) atomicMin(&S.s_first, w * 32 + __ffs(b_tr) - 1);
+        if (esc) S.esc_sym[ES] = (uint8_t)sym;
+        __syncthreads();                                                             // B4
+        // ---- 4: results of the events up to and including the first trigger; their counts
+        const uint32_t first = S.s_first;
+        const bool valid = active && tid <= first;
+        flush();                                                                     // the record of an earlier step: its slot has arrived
+        if (valid) {
+            const uint32_t sum = body + f256 + f257 - pf;
+            if (hit) T1[ev] = ppm_pack(body - pf, f256, sum, 0);
+            else if (!esc) T1[ev] = ppm_pack(S.cumt[sym] + S.below[w][sym] + lt - (sym >= pr ? pf : 0), fs, sum, 0);
+            else {
+                T1[ev] = ppm_pack(body + f256 - pf, f257, sum, 1);
+                uint32_t m0, m1, m2, m3, m4, m5, m6, m7;
+                if (trig) {
+                    // the escape update rescales BEFORE the mask is taken (cr-ppm.c:146-151): zero <=> count <= 1 now
+                    auto word = [&](uint32_t q) {
+                        uint32_t r = 0;
+                        for (uint32_t bb = 0; bb < 32; bb++) {
+                            const uint32_t x = q * 32 + bb;
+                            uint32_t c = S.cnt[x] + S.hexcl[w][x];
+                            for (uint32_t j = w * 32; j < tid && c < 2; j++) c += S.ssym[j] == x;
+                            if (c < 2) r |= 1u << bb;
+                        }
+                        return r;
+                    };
+                    m0 = word(0); m1 = word(1); m2 = word(2); m3 = word(3); m4 = word(4); m5 = word(5); m6 = word(6); m7 = word(7);
+                } else {
+                    m0 = S.zmask[0]; m1 = S.zmask[1]; m2 = S.zmask[2]; m3 = S.zmask[3]; m4 = S.zmask[4]; m5 = S.zmask[5]; m6 = S.zmask[6]; m7 = S.zmask[7];
+                }
+                auto drop = [&](uint32_t x) {                      // clear bit x (no indexed registers: no local memory)
+                    const uint32_t q = x >> 5, bit = ~(1u << (x & 31));
+                    m0 &= q == 0 ? bit : ~0u; m1 &= q == 1 ? bit : ~0u; m2 &= q == 2 ? bit : ~0u; m3 &= q == 3 ? bit : ~0u;
+                    m4 &= q == 4 ? bit : ~0u; m5 &= q == 5 ? bit : ~0u; m6 &= q == 6 ? bit : ~0u; m7 &= q == 7 ? bit : ~0u;
+                };
+                if (!trig) for (uint32_t e = 0; e < ES; e++) drop(S.esc_sym[e]);
+                drop(pr);
+                pend = true; pend_slot = atomicAdd(esc_count, 1u); pend_e = ev; pend_info = (c16 & 0xff) | sym << 8;
+                pm0 = m0; pm1 = m1; pm2 = m2; pm3 = m3; pm4 = m4; pm5 = m5; pm6 = m6; pm7 = m7;
+            }
+        }
+        const uint32_t applied = first == 0xFFFFFFFFu ? step : first + 1;
+        // events that enter their symbol's count: valid non-hits (an escape that rescaled does not); one bump per (warp, symbol)
+        const uint32_t b_ap = __ballot_sync(FULLMASK, valid && nonhit && !(esc && trig));
+        if (leader && (mE & b_ap)) atomicAdd(&S.cnt[sym], (uint32_t)__popc(mE & b_ap));
+        if (tid == applied - 1) {                                                    // totals through the last applied event
+            const uint32_t hits_incl = (tid - A) + (hit ? 1 : 0);
+            if (first == 0xFFFFFFFFu) { S.s_f256 = S.s_f256 + hits_incl; S.s_f257 = f257 + (esc ? 1 : 0) - (two ? 1 : 0); }
+            else S.s_f256 = (S.s_f256 + hits_incl + 1) >> 1;                         // flag 256 -> (f+1)/2 (cr-o2model.c:67)
+        }
+        // the slots this step has consumed take the events two windows ahead
+        if (tid < applied) {
+            const uint32_t p = pos + RING + tid;
+            if (p < r1) { cr_cp_async4(&S.ringK[slot], K + p); cr_cp_async4(&S.ringV[slot], V + p); }
+        }
+        cr_cp_async_commit();
+        __syncthreads();                                                             // B5
+        if (tid == 0) S.s_first = 0xFFFFFFFFu;
+        cr_cp_async_wait<1>();                                                       // everything but the group just issued has landed
+        if (first != 0xFFFFFFFFu) {                                                  // rescale: halve, count the ones (cr-o2model.c:55-68)
+            uint32_t one = 0;
+            if (tid < 256) { const uint32_t c = S.cnt[tid] >> 1; S.cnt[tid] = c; one = c == 1; }
+            const uint32_t ones = __syncthreads_count(one);                          // B6
+            if (tid == 0) S.s_f257 = (1 + ones) & 255;
+        } else __syncthreads();                                                      // B6
+        pos += applied;
+    }
+    flush();
+    cr_cp_async_wait<0>();
+    __syncthreads();
+    if (tid < 256) row[tid] = (uint8_t)S.cnt[tid];
+    if (tid == 0) { row[256] = (uint8_t)S.s_f256; row[257] = (uint8_t)S.s_f257; }
+}
+
 // ------------------------------------------------------------------ o1 pass, one warp per ctx8
 // Escapes arrive sorted by (ctx8, time).  k_o1_gather first makes that order physical, so the pass streams its
 // input: 32 records per batch, loaded one batch ahead and staged through shared memory.
@@ -638,6 +850,168 @@ __global__ void __launch_bounds__(O1C_THREADS) k_o1_pass_cta(const uint64_t* __r
         __syncthreads();
     }
     if (tid < 256) row[tid] = (uint8_t)cnt[tid];
+}
+
+// ------------------------------------------------------------------ o1 pass for HOT ctx8 rows, split form (default)
+// k_o1_pass_cta spends ~1300 instructions per thread and step on the masked sums, and the hottest row (the context "space" of a text
+// holds more than half of all escapes) walks its steps one after the other on ONE SM while the others idle (ncu: sm__cycles_active
+// avg 66 K vs max 5.6 M, profiles/round2_o1_pass.md).  But the masked sums do not feed the chain: what carries from step to step is only
+// the row of counts and where it is halved, and that depends on the escapes' SYMBOLS alone.  So:
+//   k_o1_plan   per ctx8: its range of sorted escapes and where its step records start (bound: n/512 + n/127 + 2 steps);
+//   k_o1_skel   one CTA per hot row walks the steps -- symbols from a cp.async ring, ranks from ballots, per-warp counts by leader lanes,
+//               the first escape whose update halves the row ends the step -- and records (position, length, row of counts) per step;
+//   k_o1_eval   one CTA per RECORDED STEP, all rows, all steps at once: the masked sums of k_o1_pass_cta from the recorded row.
+#define O1S_TH 512
+#define O1S_RING 1024
+struct O1Ctx { uint32_t r0, r1, rec_base, nsteps; };
+struct O1Step { uint32_t pos, applied; };
+CR_HD uint32_t o1_max_steps(uint32_t n) { return n / O1S_TH + n / 127u + 2u; }
+__global__ void __launch_bounds__(256) k_o1_plan(const uint64_t* __restrict__ K, uint32_t n, O1Ctx* __restrict__ ctx) {
+    __shared__ uint32_t wsum[8];
+    const uint32_t c8 = threadIdx.x, lane = c8 & 31, w = c8 >> 5;
+    auto keyof = [](uint64_t k) { return (uint32_t)(k >> 32) & 0xffu; };
+    const uint32_t r0 = lower_bound_key(K, n, c8, keyof), r1 = lower_bound_key(K, n, c8 + 1, keyof);
+    const uint32_t need = r1 - r0 >= O1C_MIN ? o1_max_steps(r1 - r0) : 0u;
+    uint32_t incl = need;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(FULLMASK, incl, d); if (lane >= d) incl += t; }
+    if (lane == 31) wsum[w] = incl;
+    __syncthreads();
+    uint32_t off = 0;
+    for (uint32_t q = 0; q < w; q++) off += wsum[q];
+    O1Ctx c; c.r0 = r0; c.r1 = r1; c.rec_base = off + incl - need; c.nsteps = 0;
+    ctx[c8] = c;
+}
+__global__ void __launch_bounds__(O1S_TH) k_o1_skel(O1Ctx* __restrict__ ctx, const uint32_t* __restrict__ info_s, PpmState st,
+                                                     O1Step* __restrict__ steps, uint8_t* __restrict__ snaps) {
+    constexpr int NW = O1S_TH / 32;
+    const uint32_t c8 = blockIdx.x;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const O1Ctx C = ctx[c8];
+    const uint32_t r0 = C.r0, r1 = C.r1;
+    if (r1 - r0 < O1C_MIN) return;
+    __shared__ uint32_t ring[O1S_RING];
+    __shared__ uint32_t cnt[256];
+    __shared__ uint16_t hexcl[NW][256];
+    __shared__ uint8_t hraw[NW][256];
+    __shared__ uint32_t s_first;
+    uint8_t* row = st.o1 + c8 * 256;
+    if (tid < 256) cnt[tid] = row[tid];
+    for (uint32_t i = tid; i < NW * 64; i += O1S_TH) ((uint32_t*)&hraw[0][0])[i] = 0;
+    if (tid == 0) s_first = 0xFFFFFFFFu;
+    for (uint32_t i = tid; i < O1S_RING; i += O1S_TH) if (r0 + i < r1) cr_cp_async4(&ring[i], info_s + r0 + i);
+    cr_cp_async_commit();
+    cr_cp_async_wait<0>();
+    __syncthreads();
+    const uint32_t before = (1u << lane) - 1u;
+    uint32_t pos = r0, nrec = 0;
+    while (pos < r1) {
+        const uint32_t step = r1 - pos < (uint32_t)O1S_TH ? r1 - pos : (uint32_t)O1S_TH;
+        const uint32_t nw = (step + 31) >> 5;
+        // the row as of the start of this step
+        if (tid < 64) {
+            const uint4 a = *(const uint4*)&cnt[tid * 4];
+            ((uint32_t*)(snaps + (size_t)(C.rec_base + nrec) * 256))[tid] = a.x | a.y << 8 | a.z << 16 | a.w << 24;
+        }
+        const bool active = tid < step;
+        const uint32_t slot = (pos - r0 + tid) % O1S_RING;
+        const uint32_t sym = active ? (ring[slot] >> 8) & 255u : 0u;
+        uint32_t mE = __ballot_sync(FULLMASK, active);
+#pragma unroll
+        for (int b = 7; b >= 0; b--) {
+            const uint32_t Bb = __ballot_sync(FULLMASK, (sym >> b) & 1u);
+            mE &= ((sym >> b) & 1u) ? Bb : ~Bb;
+        }
+        const uint32_t eq = __popc(mE & before);
+        const bool leader = active && eq == 0;
+        if (leader) hraw[w][sym] = (uint8_t)__popc(mE);
+        __syncthreads();
+        if (tid < 256) { uint32_t run = 0; for (uint32_t q = 0; q < nw; q++) { const uint32_t h = hraw[q][tid]; hexcl[q][tid] = (uint16_t)run; run += h; } }
+        __syncthreads();
+        if (leader) hraw[w][sym] = 0;
+        const uint32_t count_s = active ? cnt[sym] + hexcl[w][sym] + eq : 0u;
+        const uint32_t b_tr = __ballot_sync(FULLMASK, active && count_s + 1 >= 255);          // ++o1[c] >= 255 halves the row (cr-ppm.c:91)
+        if (lane == 0 && b_tr) atomicMin(&s_first, w * 32 + __ffs(b_tr) - 1);
+        __syncthreads();
+        const uint32_t first = s_first;
+        const uint32_t applied = first == 0xFFFFFFFFu ? step : first + 1;
+        const uint32_t b_ap = __ballot_sync(FULLMASK, active && tid < applied);
+        if (leader && (mE & b_ap)) atomicAdd(&cnt[sym], (uint32_t)__popc(mE & b_ap));
+        if (tid == 0) { O1Step r; r.pos = pos; r.applied = applied; steps[C.rec_base + nrec] = r; }
+        if (tid < applied) { const uint32_t p = pos + O1S_RING + tid; if (p < r1) cr_cp_async4(&ring[slot], info_s + p); }
+        cr_cp_async_commit();
+        __syncthreads();
+        if (tid == 0) s_first = 0xFFFFFFFFu;
+        cr_cp_async_wait<1>();
+        if (first != 0xFFFFFFFFu && tid < 256) cnt[tid] -= cnt[tid] / 2;                        // cr-ppm.c:92-94
+        __syncthreads();
+        pos += applied; nrec++;
+    }
+    cr_cp_async_wait<0>();
+    if (tid < 256) row[tid] = (uint8_t)cnt[tid];
+    if (tid == 0) ctx[c8].nsteps = nrec;
+}
+__global__ void __launch_bounds__(O1C_THREADS) k_o1_eval(const O1Ctx* __restrict__ ctx, const O1Step* __restrict__ steps, const uint8_t* __restrict__ snaps,
+                                                         const uint32_t* __restrict__ info_s, const uint32_t* __restrict__ ord_s, const uint4* __restrict__ incl_s,
+                                                         uint64_t* __restrict__ T2) {
+    static_assert(O1C_THREADS == O1S_TH, "one evaluation CTA per recorded step");
+    const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    // which row does this record belong to?  rec_base is ascending over ctx8 (rows that are not hot own no records)
+    uint32_t lo = 0, hi = 256;
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (ctx[mid].rec_base <= blockIdx.x) lo = mid; else hi = mid; }
+    // several rows may share a base (rows without records): the owner is the last one that starts here and has steps
+    const O1Ctx C = ctx[lo];
+    if (blockIdx.x - C.rec_base >= C.nsteps) return;
+    const O1Step R = steps[blockIdx.x];
+    __shared__ uint32_t cnt[256];
+    __shared__ __align__(4) uint16_t hist[O1C_WARPS][256];
+    __shared__ uint16_t basew[O1C_WARPS][256];
+    __shared__ uint32_t smask[O1C_THREADS][8];
+    if (tid < 256) cnt[tid] = snaps[(size_t)blockIdx.x * 256 + tid];
+    for (uint32_t i = tid; i < O1C_WARPS * 128; i += O1C_THREADS) ((uint32_t*)&hist[0][0])[i] = 0;
+    __syncthreads();
+    const bool active = tid < R.applied;
+    uint32_t sym = 0x1FF, ord = 0;
+    uint32_t m[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (active) {
+        const size_t x = R.pos + tid;
+        sym = (info_s[x] >> 8) & 255; ord = ord_s[x];
+        const uint4 a = incl_s[2 * x], b = incl_s[2 * x + 1];
+        m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w; m[4] = b.x; m[5] = b.y; m[6] = b.z; m[7] = b.w;
+        atomicAdd((uint32_t*)&hist[w][0] + (sym >> 1), (sym & 1u) ? 0x10000u : 1u);
+    }
+#pragma unroll
+    for (int q = 0; q < 8; q++) smask[tid][q] = m[q];
+    __syncthreads();
+    if (tid < 256) {
+        uint32_t run = 0;
+        for (int q = 0; q < O1C_WARPS; q++) { uint32_t h = hist[q][tid]; hist[q][tid] = (uint16_t)run; basew[q][tid] = (uint16_t)(8 * (cnt[tid] + run) - 7); run += h; }
+    }
+    __syncthreads();
+    uint32_t eq = 0, in_all = 0, in_lt = 0;
+#pragma unroll 8
+    for (uint32_t j = 0; j < 32; j++) {
+        const uint32_t sj = __shfl_sync(FULLMASK, sym, j);
+        if (j < lane && sj < 256) {
+            const uint32_t in = (smask[tid][sj >> 5] >> (sj & 31)) & 1u;
+            eq += sj == sym; in_all += in; in_lt += in & (uint32_t)(sj < sym);
+        }
+    }
+    if (active) {
+        uint32_t sum = 0, cum = 0;
+#pragma unroll
+        for (uint32_t q = 0; q < 8; q++) {
+            const uint32_t mq = m[q];
+            for (uint32_t b = 0; b < 32; b++) {
+                const uint32_t x = q * 32 + b;
+                const uint32_t v = (mq >> b & 1u) ? (uint32_t)basew[w][x] : 0u;
+                sum += v; cum += x < sym ? v : 0u;
+            }
+        }
+        sum += 8 * in_all; cum += 8 * in_lt;
+        const uint32_t count_s = cnt[sym] + hist[w][sym] + eq;
+        T2[ord] = ppm_pack(cum, 8 * count_s - 7, sum, 0);
+    }
 }
 
 // ------------------------------------------------------------------ order-0 side models, one warp

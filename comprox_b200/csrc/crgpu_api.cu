@@ -12,6 +12,11 @@ thread_local crsim_dim3 threadIdx, blockIdx, blockDim, gridDim;
 #define CR_SET_DEVICE(h) do { } while (0)
 #else
 unsigned long long g_cr_launches = 0;
+// Handles that share a GPU work on private streams, and a chain's serial range walk is one kernel that runs for tens to hundreds of
+// milliseconds.  With the default of 8 hardware work queues, streams alias onto the same queue and wait behind each other's long kernels
+// (measured: 24 shards, 8 handles: 3.8 s with 8 queues, 2.0 s with 32; profiles/round2_corpus.md).  The variable only counts before the
+// CUDA context exists, so it is set when the library is loaded -- unless the caller has chosen a value.
+__attribute__((constructor)) static void cr_more_work_queues() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
 thread_local cudaStream_t g_cr_alloc_stream = 0;
 thread_local bool g_cr_alloc_async = false;
 // every entry point that touches the device: select the handle's GPU and bind DevBuf growth (cr_common.cuh) to the handle's stream
@@ -207,6 +212,8 @@ extern "C" int crgpu_set_option(crgpu_handle* h, const char* name, int64_t value
     if (!h || !name) return CRGPU_ERR_ARG;
     std::string n(name);
     if (n == "scalar_models") { h->chain.scalar_models = value != 0; return CRGPU_OK; }
+    if (n == "o1_hot_variant") { if (value < 1 || value > 2) return CRGPU_ERR_ARG; h->chain.o1_hot_variant = (int)value; return CRGPU_OK; }
+    if (n == "o2_hot_variant") { if (value < 1 || value > 2) return CRGPU_ERR_ARG; h->chain.o2_hot_variant = (int)value; return CRGPU_OK; }
     if (n == "rc_variant") { if (value < 1 || value > 8) return CRGPU_ERR_ARG; h->chain.rc_variant = (int)value; return CRGPU_OK; }
 #ifndef CRGPU_SIM
     if (n == "rc_job_symbols") { if (value != 0 && (value < 4096 || value > (1 << 24))) return CRGPU_ERR_ARG; h->chain.rcpar.job_symbols = (uint32_t)value; return CRGPU_OK; }

@@ -53,7 +53,7 @@ struct LzChain {
     DevBuf b_escrec, b_esccount, b_k64a, b_k64b, b_ord, b_flag, b_escord;
     DevBuf b_lensym, b_lenpos, b_idxsym, b_idxpos;
     DevBuf b_hits;
-    DevBuf b_o1ctx, b_o1steps, b_o1snaps;
+    DevBuf b_o1ctx, b_o1steps, b_o1snaps, b_o2ctl, b_o2hot, b_o2todo, b_o2steps, b_o2snaps;
     DevBuf b_o1info, b_o1ord, b_o1incl, b_bounds, b_o3hot, b_cinm, b_cins, b_segstart, b_segkey, b_rank, b_flexlen;
     DevBuf b_qm, b_shm, b_bm, b_qs, b_shs, b_bs, b_stot, b_dsum, b_lsm, b_lss, b_rsm, b_rss, b_fb;
     DevBuf b_dense, b_denseside, b_streams, b_rcres, b_rcout, b_copy, b_hdr;
@@ -70,8 +70,9 @@ struct LzChain {
     int rc_variant = 8;            // range-chain formulation: 8 = cut into jobs that run side by side (cr_rcpar.cuh); 1..7 = one serial walk per stream (cr_warp.cuh: k_range_chain<1..7>)
     bool hot_contexts = true;      // hot o2 contexts run the rank-based CTA kernel (k_o2_pass_cta)
     int o1_hot_variant = 2;        // 2 = k_o1_skel + k_o1_eval (the chain of steps carries only the counts), 1 = k_o1_pass_cta
-    int o2_hot_variant = 2;        // 2 = k_o2_hot (event ring, ballot ranks), 1 = k_o2_pass_cta
+    int o2_hot_variant = 3;        // 3 = k_o2_skel + k_o2_eval (the chain of steps carries only counts and flags), 2 = k_o2_hot (event ring, ballot ranks), 1 = k_o2_pass_cta
     bool o2_attr_done = false;
+    uint32_t o2_rec_cap_test = 0;  // tests only: capacity of the step-record table (0 = the bound)
     bool scalar_models = false;   // GPU A/B switch: run the scalar (simulation-checked) model/coder kernels
     bool exact_aborts = true;      // replay a mid-chain "cannot compress" exactly (encode_blocks); false = CRGPU_ERR_MIDCHAIN_ABORT
     DevBuf b_abort;
@@ -99,7 +100,7 @@ struct LzChain {
         DevBuf* all[] = { &s_o3b, &s_o3c, &s_o2, &s_o1, &s_m0, &b_blocks, &b_segoff, &b_seglen, &b_hist, &b_esc1, &b_first, &b_ctxout,
             &b_k0, &b_k1, &b_v0, &b_v1, &b_ks0, &b_M, &b_S, &b_span, &b_tidx, &b_segs, &b_xt, &b_entry, &b_cnt, &b_scan, &b_chainwork,
             &b_evctx, &b_evsym, &b_tokend, &b_pred, &b_T1, &b_T2, &b_TS, &b_side, &b_escrec, &b_esccount, &b_k64a, &b_k64b, &b_ord,
-            &b_flag, &b_escord, &b_lensym, &b_lenpos, &b_idxsym, &b_idxpos, &b_hits, &b_o1ctx, &b_o1steps, &b_o1snaps, &b_o1info, &b_o1ord, &b_o1incl, &b_bounds, &b_o3hot, &b_cinm, &b_cins, &b_segstart, &b_segkey, &b_rank, &b_flexlen, &b_qm, &b_shm, &b_bm, &b_qs, &b_shs, &b_bs, &b_stot, &b_dsum, &b_lsm, &b_lss, &b_rsm, &b_rss, &b_fb, &b_dense, &b_denseside, &b_streams, &b_rcres, &b_rcout, &b_copy, &b_hdr,
+            &b_flag, &b_escord, &b_lensym, &b_lenpos, &b_idxsym, &b_idxpos, &b_hits, &b_o1ctx, &b_o1steps, &b_o1snaps, &b_o2ctl, &b_o2hot, &b_o2todo, &b_o2steps, &b_o2snaps, &b_o1info, &b_o1ord, &b_o1incl, &b_bounds, &b_o3hot, &b_cinm, &b_cins, &b_segstart, &b_segkey, &b_rank, &b_flexlen, &b_qm, &b_shm, &b_bm, &b_qs, &b_shs, &b_bs, &b_stot, &b_dsum, &b_lsm, &b_lss, &b_rsm, &b_rss, &b_fb, &b_dense, &b_denseside, &b_streams, &b_rcres, &b_rcout, &b_copy, &b_hdr,
             &x_npos, &x_nlen, &x_sdist, &x_slen, &x_G, &x_tdist, &x_h16, &x_rank, &x_mpos0, &x_mlen0, &x_clast, &x_ckey, &x_cmax, &x_lastin, &x_mism, &x_msym, &x_mpos,
             &snap_o3b, &snap_o3c, &snap_o2, &snap_o1, &snap_m0, &b_abort };
         for (DevBuf* b : all) b->release();
@@ -493,16 +494,44 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
                 CR_TRY(download(hh, b_hits.p, 1));
                 timer.count("#o3_hits", hh[0]);
                 const bool narrow = (double)hh[0] > 0.25 * (double)nev;
-                if (o2_hot_variant == 2) {
+                if (o2_hot_variant >= 2) {
                     if (!o2_attr_done) {
                         CR_CUDA(cudaFuncSetAttribute(k_o2_hot<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(O2HotSmem<256>)));
                         CR_CUDA(cudaFuncSetAttribute(k_o2_hot<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(O2HotSmem<1024>)));
+                        CR_CUDA(cudaFuncSetAttribute(k_o2_eval<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(O2EvalSmem<256>)));
+                        CR_CUDA(cudaFuncSetAttribute(k_o2_eval<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(O2EvalSmem<1024>)));
                         o2_attr_done = true;
                     }
-                    __atomic_fetch_add(&g_cr_launches, 1ull, __ATOMIC_RELAXED);
-                    if (narrow) k_o2_hot<256><<<dim3(65536), dim3(256), sizeof(O2HotSmem<256>), stream>>>(b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nev, st, b_T1.as<uint64_t>(), b_escrec.as<EscRec>(), b_esccount.as<uint32_t>(), b_bounds.as<uint32_t>());
-                    else k_o2_hot<1024><<<dim3(65536), dim3(1024), sizeof(O2HotSmem<1024>), stream>>>(b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nev, st, b_T1.as<uint64_t>(), b_escrec.as<EscRec>(), b_esccount.as<uint32_t>(), b_bounds.as<uint32_t>());
-                    CR_CUDA(cudaGetLastError());
+                    const uint32_t* nolist = nullptr; const O2SplitCtl* noctl = nullptr; const uint8_t* notodo = nullptr;
+#define CR_O2_LAUNCH(KERNEL, GRID, TH, SMEM, ...) do { __atomic_fetch_add(&g_cr_launches, 1ull, __ATOMIC_RELAXED); \
+                        KERNEL<TH><<<dim3(GRID), dim3(TH), (SMEM), stream>>>(__VA_ARGS__); CR_CUDA(cudaGetLastError()); } while (0)
+                    if (o2_hot_variant == 2) {
+                        if (narrow) CR_O2_LAUNCH(k_o2_hot, 65536, 256, sizeof(O2HotSmem<256>), b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nev, st, b_T1.as<uint64_t>(), b_escrec.as<EscRec>(), b_esccount.as<uint32_t>(), b_bounds.as<uint32_t>(), nolist, noctl, notodo);
+                        else CR_O2_LAUNCH(k_o2_hot, 65536, 1024, sizeof(O2HotSmem<1024>), b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nev, st, b_T1.as<uint64_t>(), b_escrec.as<EscRec>(), b_esccount.as<uint32_t>(), b_bounds.as<uint32_t>(), nolist, noctl, notodo);
+                    } else {
+                        // split form: the chain of steps (k_o2_skel) records (position, length, flags, table) per step, k_o2_eval turns every record
+                        // into triples and escape records.  Records: one per TH events plus one per rescale; a rescale needs 125 hits or 125
+                        // occurrences of one symbol since the last one (short cascades aside), so n / 120 bounds them with room to spare; a context
+                        // that still runs out is redone by k_o2_hot (nothing of it has been written by then)
+                        const uint32_t th = narrow ? 256u : 1024u;
+                        const uint32_t hot_bound = nev / O2C_MIN + 1 < 65536u ? nev / O2C_MIN + 1 : 65536u;
+                        const uint32_t cap = o2_rec_cap_test ? o2_rec_cap_test : nev / th + nev / 120u + 2u * hot_bound + 256u;
+                        CR_TRY(b_o2hot.reserve(65536 * 4)); CR_TRY(b_o2todo.reserve(65536)); CR_TRY(b_o2steps.reserve((size_t)cap * sizeof(O2Step))); CR_TRY(b_o2snaps.reserve((size_t)cap * 256));
+                        std::vector<uint32_t> ctl0 = { 0u, 0u, cap, 0u };
+                        CR_TRY(upload(b_o2ctl, ctl0));
+                        CR_LAUNCH(k_o2_hotlist, dim3(256), dim3(256), stream, b_bounds.as<uint32_t>(), b_o2hot.as<uint32_t>(), b_o2ctl.as<O2SplitCtl>(), b_o2todo.as<uint8_t>());
+                        const uint32_t geval = narrow ? 148u * 8u : 148u * 2u;
+                        if (narrow) {
+                            CR_O2_LAUNCH(k_o2_skel, hot_bound, 256, 0, b_k1.as<uint32_t>(), st, b_bounds.as<uint32_t>(), b_o2hot.as<uint32_t>(), b_o2ctl.as<O2SplitCtl>(), b_o2todo.as<uint8_t>(), b_o2steps.as<O2Step>(), b_o2snaps.as<uint8_t>());
+                            CR_O2_LAUNCH(k_o2_eval, geval, 256, sizeof(O2EvalSmem<256>), b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), b_o2ctl.as<O2SplitCtl>(), b_o2todo.as<uint8_t>(), b_o2steps.as<O2Step>(), b_o2snaps.as<uint8_t>(), b_T1.as<uint64_t>(), b_escrec.as<EscRec>(), b_esccount.as<uint32_t>());
+                            CR_O2_LAUNCH(k_o2_hot, hot_bound, 256, sizeof(O2HotSmem<256>), b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nev, st, b_T1.as<uint64_t>(), b_escrec.as<EscRec>(), b_esccount.as<uint32_t>(), b_bounds.as<uint32_t>(), b_o2hot.as<uint32_t>(), b_o2ctl.as<O2SplitCtl>(), b_o2todo.as<uint8_t>());
+                        } else {
+                            CR_O2_LAUNCH(k_o2_skel, hot_bound, 1024, 0, b_k1.as<uint32_t>(), st, b_bounds.as<uint32_t>(), b_o2hot.as<uint32_t>(), b_o2ctl.as<O2SplitCtl>(), b_o2todo.as<uint8_t>(), b_o2steps.as<O2Step>(), b_o2snaps.as<uint8_t>());
+                            CR_O2_LAUNCH(k_o2_eval, geval, 1024, sizeof(O2EvalSmem<1024>), b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), b_o2ctl.as<O2SplitCtl>(), b_o2todo.as<uint8_t>(), b_o2steps.as<O2Step>(), b_o2snaps.as<uint8_t>(), b_T1.as<uint64_t>(), b_escrec.as<EscRec>(), b_esccount.as<uint32_t>());
+                            CR_O2_LAUNCH(k_o2_hot, hot_bound, 1024, sizeof(O2HotSmem<1024>), b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nev, st, b_T1.as<uint64_t>(), b_escrec.as<EscRec>(), b_esccount.as<uint32_t>(), b_bounds.as<uint32_t>(), b_o2hot.as<uint32_t>(), b_o2ctl.as<O2SplitCtl>(), b_o2todo.as<uint8_t>());
+                        }
+                    }
+#undef CR_O2_LAUNCH
                 } else if (narrow)
                     CR_LAUNCH(k_o2_pass_cta<256>, dim3(65536), dim3(256), stream, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nev, st, b_T1.as<uint64_t>(), b_escrec.as<EscRec>(), b_esccount.as<uint32_t>(), b_bounds.as<uint32_t>());
                 else

@@ -497,25 +497,31 @@ CR_D void cr_cp_async4(void* smem, const void* gmem) {
 CR_D void cr_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> CR_D void cr_cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
+struct O2Step { uint32_t c16, pos, applied, f256, f257, pad[3]; };
+struct O2SplitCtl { uint32_t hot_count, rec_count, rec_cap, overflowed; };
 template <int TH> struct O2HotSmem {
     static constexpr int NW = TH / 32, RING = 2 * TH;
     uint32_t ringK[RING], ringV[RING];
     uint32_t cnt[256], cumt[256], zmask[8];
     uint32_t wtot[3][32];
     uint32_t s_f256, s_f257, s_body, s_first;
-    uint16_t hexcl[NW][256];           // nonhit events of earlier warps of the step, per symbol
-    uint16_t below[NW][256];           // the same summed over smaller symbols
+    alignas(16) uint16_t hexcl[NW][256];           // nonhit events of earlier warps of the step, per symbol
+    alignas(16) uint16_t below[NW][256];           // the same summed over smaller symbols
     uint8_t hraw[NW][256];             // nonhit events of this warp, per symbol (written by the leader lanes, cleared by them)
     uint16_t ssym[TH];
     uint8_t esc_sym[TH];
 };
 template <int TH>
 __global__ void __launch_bounds__(TH) k_o2_hot(const uint32_t* __restrict__ K, const uint32_t* __restrict__ V, uint32_t n, PpmState st,
-                                               uint64_t* __restrict__ T1, EscRec* __restrict__ esc_rec, uint32_t* __restrict__ esc_count, const uint32_t* __restrict__ bounds) {
+                                               uint64_t* __restrict__ T1, EscRec* __restrict__ esc_rec, uint32_t* __restrict__ esc_count, const uint32_t* __restrict__ bounds,
+                                               const uint32_t* __restrict__ hotlist, const O2SplitCtl* __restrict__ ctl, const uint8_t* __restrict__ todo) {
     extern __shared__ __align__(16) unsigned char o2hot_raw[];
     O2HotSmem<TH>& S = *reinterpret_cast<O2HotSmem<TH>*>(o2hot_raw);
     constexpr int NW = TH / 32, RING = 2 * TH;
-    const uint32_t c16 = blockIdx.x;
+    // hotlist == nullptr: one CTA per ctx16; otherwise: the contexts k_o2_skel has marked as not done (ran out of step records)
+    if (hotlist && (blockIdx.x >= ctl->hot_count || !ctl->overflowed)) return;
+    const uint32_t c16 = hotlist ? hotlist[blockIdx.x] : blockIdx.x;
+    if (hotlist && !todo[c16]) return;
     const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const uint32_t r0 = bounds[c16], r1 = bounds[c16 + 1];
     if (r1 - r0 < O2C_MIN) return;
@@ -690,6 +696,257 @@ __global__ void __launch_bounds__(TH) k_o2_hot(const uint32_t* __restrict__ K, c
     __syncthreads();
     if (tid < 256) row[tid] = (uint8_t)S.cnt[tid];
     if (tid == 0) { row[256] = (uint8_t)S.s_f256; row[257] = (uint8_t)S.s_f257; }
+}
+
+// ------------------------------------------------------------------ o2 pass for HOT contexts, split form (default)
+// As for o1 (k_o1_skel / k_o1_eval below): what carries from step to step is the table of counts, flags 256 / 257 and where the table is
+// rescaled -- and that needs, per event, only "is it a hit", the count of its own symbol and whether it is an escape or a 1 -> 2
+// transition.  Cumulative frequencies, the predicted byte's count, exclusion masks and the triples themselves do not feed the chain.
+//   k_o2_hotlist  the contexts with at least O2C_MIN events, as a list (the grids below cover the list, not all 65536 contexts)
+//   k_o2_skel     one CTA per hot context walks the steps and records (position, length, flags, table) per step; the record index
+//                 comes from a global counter one step ahead.  Out of records (cannot happen within the bound the host allocates, see
+//                 LzChain): the context is marked, its row left untouched, and k_o2_hot redoes it
+//   k_o2_eval     one CTA per RECORDED STEP: the triples and escape records of k_o2_hot's step, from the recorded table
+__global__ void k_o2_hotlist(const uint32_t* __restrict__ bounds, uint32_t* __restrict__ hotlist, O2SplitCtl* __restrict__ ctl, uint8_t* __restrict__ todo) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= 65536) return;
+    todo[c] = 0;
+    if (bounds[c + 1] - bounds[c] >= O2C_MIN) hotlist[atomicAdd(&ctl->hot_count, 1u)] = c;
+}
+template <int TH>
+__global__ void __launch_bounds__(TH) k_o2_skel(const uint32_t* __restrict__ K, PpmState st, const uint32_t* __restrict__ bounds, const uint32_t* __restrict__ hotlist,
+                                                O2SplitCtl* __restrict__ ctl, uint8_t* __restrict__ todo, O2Step* __restrict__ steps, uint8_t* __restrict__ snaps) {
+    constexpr int NW = TH / 32, RING = 2 * TH;
+    if (blockIdx.x >= ctl->hot_count) return;
+    const uint32_t c16 = hotlist[blockIdx.x];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const uint32_t r0 = bounds[c16], r1 = bounds[c16 + 1];
+    __shared__ uint32_t ringK[RING];
+    __shared__ __align__(16) uint32_t cnt[256];
+    __shared__ uint32_t wtot[3][32];
+    __shared__ uint32_t s_f256, s_f257, s_first, s_idx;
+    __shared__ uint16_t hexcl[NW][256];
+    __shared__ uint8_t hraw[NW][256];
+    uint8_t* row = st.o2 + (size_t)c16 * PPM_O2_STRIDE;
+    for (uint32_t i = tid; i < 256; i += TH) cnt[i] = row[i];
+    for (uint32_t i = tid; i < NW * 64; i += TH) ((uint32_t*)&hraw[0][0])[i] = 0;
+    uint32_t next_idx = 0;
+    if (tid == 0) { s_f256 = row[256]; s_f257 = row[257]; s_first = 0xFFFFFFFFu; next_idx = atomicAdd(&ctl->rec_count, 1u); }
+    for (uint32_t i = tid; i < RING; i += TH) if (r0 + i < r1) cr_cp_async4(&ringK[i], K + r0 + i);
+    cr_cp_async_commit();
+    cr_cp_async_wait<0>();
+    __syncthreads();
+    const uint32_t before = (1u << lane) - 1u;
+    const uint32_t cap = ctl->rec_cap;
+    uint32_t pos = r0;
+    bool gave_up = false;
+    while (pos < r1) {
+        const uint32_t step = r1 - pos < (uint32_t)TH ? r1 - pos : (uint32_t)TH;
+        const uint32_t nw = (step + 31) >> 5;
+        if (tid == 0) { s_idx = next_idx; next_idx = atomicAdd(&ctl->rec_count, 1u); }       // the next step's record: its round trip hides behind this step
+        const bool active = tid < step;
+        const uint32_t slot = (pos - r0 + tid) % RING;
+        const uint32_t k = active ? ringK[slot] : 0u;
+        const uint32_t sym = k >> 24, pr = (k >> 16) & 255;
+        const bool hit = active && sym == pr, nonhit = active && sym != pr;
+        const uint32_t b_nh = __ballot_sync(FULLMASK, nonhit);
+        uint32_t mE = b_nh;
+#pragma unroll
+        for (int b = 7; b >= 0; b--) {
+            const uint32_t Bb = __ballot_sync(FULLMASK, (sym >> b) & 1u);
+            mE &= ((sym >> b) & 1u) ? Bb : ~Bb;
+        }
+        const uint32_t eq = __popc(mE & before);
+        const bool leader = nonhit && eq == 0;
+        if (leader) hraw[w][sym] = (uint8_t)__popc(mE);
+        __syncthreads();                                                             // B1
+        const uint32_t idx = s_idx;
+        if (idx >= cap) { gave_up = true; break; }                                   // uniform
+        if (tid < 64) {                                                              // the table as of the start of this step
+            const uint4 a = *(const uint4*)&cnt[tid * 4];
+            ((uint32_t*)(snaps + (size_t)idx * 256))[tid] = a.x | a.y << 8 | a.z << 16 | a.w << 24;
+        }
+        if (tid < 256) { uint32_t run = 0; for (uint32_t q = 0; q < nw; q++) { const uint32_t h = hraw[q][tid]; hexcl[q][tid] = (uint16_t)run; run += h; } }
+        __syncthreads();                                                             // B2
+        if (leader) hraw[w][sym] = 0;
+        const uint32_t fs = nonhit ? cnt[sym] + hexcl[w][sym] + eq : 0u;
+        const bool esc = nonhit && fs == 0, two = nonhit && fs == 1;
+        const uint32_t b_es = __ballot_sync(FULLMASK, esc), b_tw = __ballot_sync(FULLMASK, two);
+        if (lane == 0) { wtot[0][w] = __popc(b_nh); wtot[1][w] = __popc(b_es); wtot[2][w] = __popc(b_tw); }
+        __syncthreads();                                                             // B3
+        uint32_t p0 = 0, p1 = 0, p2 = 0;
+        if (lane < w) { p0 = wtot[0][lane]; p1 = wtot[1][lane]; p2 = wtot[2][lane]; }
+        p0 = __reduce_add_sync(FULLMASK, p0); p1 = __reduce_add_sync(FULLMASK, p1); p2 = __reduce_add_sync(FULLMASK, p2);
+        const uint32_t A = p0 + __popc(b_nh & before), ES = p1 + __popc(b_es & before), TW = p2 + __popc(b_tw & before);
+        const uint32_t f256_0 = s_f256, f257_0 = s_f257;
+        const uint32_t f256 = f256_0 + (tid - A), f257 = f257_0 + ES - TW;
+        bool trig = false;
+        if (hit) trig = f256 + 1 > 250;
+        else if (esc) trig = f257 + 1 > 250;
+        else if (nonhit) trig = (fs + 1 > 250) || (fs == 1 && f257 == 0);
+        const uint32_t b_tr = __ballot_sync(FULLMASK, trig);
+        if (lane == 0 && b_tr) atomicMin(&s_first, w * 32 + __ffs(b_tr) - 1);
+        __syncthreads();                                                             // B4
+        const uint32_t first = s_first;
+        const bool valid = active && tid <= first;
+        const uint32_t applied = first == 0xFFFFFFFFu ? step : first + 1;
+        const uint32_t b_ap = __ballot_sync(FULLMASK, valid && nonhit && !(esc && trig));
+        if (leader && (mE & b_ap)) atomicAdd(&cnt[sym], (uint32_t)__popc(mE & b_ap));
+        if (tid == applied - 1) {
+            const uint32_t hits_incl = (tid - A) + (hit ? 1 : 0);
+            if (first == 0xFFFFFFFFu) { s_f256 = f256_0 + hits_incl; s_f257 = f257 + (esc ? 1 : 0) - (two ? 1 : 0); }
+            else s_f256 = (f256_0 + hits_incl + 1) >> 1;
+        }
+        if (tid == 0) { O2Step r; r.c16 = c16; r.pos = pos; r.applied = applied; r.f256 = f256_0; r.f257 = f257_0; r.pad[0] = r.pad[1] = r.pad[2] = 0; steps[idx] = r; }
+        if (tid < applied) { const uint32_t p = pos + RING + tid; if (p < r1) cr_cp_async4(&ringK[slot], K + p); }
+        cr_cp_async_commit();
+        __syncthreads();                                                             // B5
+        if (tid == 0) s_first = 0xFFFFFFFFu;
+        cr_cp_async_wait<1>();
+        if (first != 0xFFFFFFFFu) {
+            uint32_t one = 0;
+            if (tid < 256) { const uint32_t c = cnt[tid] >> 1; cnt[tid] = c; one = c == 1; }
+            const uint32_t ones = __syncthreads_count(one);                          // B6
+            if (tid == 0) s_f257 = (1 + ones) & 255;
+        } else __syncthreads();                                                      // B6
+        pos += applied;
+    }
+    cr_cp_async_wait<0>();
+    __syncthreads();
+    if (tid == 0 && next_idx < cap) { O2Step r; memset(&r, 0, sizeof r); steps[next_idx] = r; }   // the record reserved ahead and not used
+    if (gave_up) { if (tid == 0) { todo[c16] = 1; ctl->overflowed = 1; } return; }
+    if (tid < 256) row[tid] = (uint8_t)cnt[tid];
+    if (tid == 0) { row[256] = (uint8_t)s_f256; row[257] = (uint8_t)s_f257; }
+}
+template <int TH> struct O2EvalSmem {
+    static constexpr int NW = TH / 32;
+    uint32_t cnt[256], cumt[256], zmask[8];
+    uint32_t wtot[3][32];
+    uint32_t s_body, pad_[3];
+    alignas(16) uint16_t hexcl[NW][256];
+    alignas(16) uint16_t below[NW][256];
+    uint8_t hraw[NW][256];
+    uint16_t ssym[TH];
+    uint8_t esc_sym[TH];
+};
+template <int TH>
+__global__ void __launch_bounds__(TH) k_o2_eval(const uint32_t* __restrict__ K, const uint32_t* __restrict__ V, const O2SplitCtl* __restrict__ ctl, const uint8_t* __restrict__ todo,
+                                                const O2Step* __restrict__ steps, const uint8_t* __restrict__ snaps,
+                                                uint64_t* __restrict__ T1, EscRec* __restrict__ esc_rec, uint32_t* __restrict__ esc_count) {
+    extern __shared__ __align__(16) unsigned char o2eval_raw[];
+    O2EvalSmem<TH>& S = *reinterpret_cast<O2EvalSmem<TH>*>(o2eval_raw);
+    constexpr int NW = TH / 32;
+    const uint32_t nrec = ctl->rec_count < ctl->rec_cap ? ctl->rec_count : ctl->rec_cap;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    for (uint32_t rec_i = blockIdx.x; rec_i < nrec; rec_i += gridDim.x) {
+    const O2Step R = steps[rec_i];
+    if (R.applied == 0 || todo[R.c16]) continue;                                     // uniform
+    __syncthreads();                                                                 // the previous record's tables are no longer read
+    const uint32_t c16 = R.c16, step = R.applied;
+    for (uint32_t i = tid; i < 256; i += TH) S.cnt[i] = snaps[(size_t)rec_i * 256 + i];
+    for (uint32_t i = tid; i < NW * 64; i += TH) ((uint32_t*)&S.hraw[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t nw = (step + 31) >> 5;
+    const uint32_t before = (1u << lane) - 1u;
+    if (w == 0) {
+        uint32_t v[8], sum = 0, zb = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { v[k] = S.cnt[lane * 8 + k]; sum += v[k]; zb |= (uint32_t)(v[k] == 0) << k; }
+        uint32_t inc = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(FULLMASK, inc, d); if (lane >= d) inc += t; }
+        uint32_t run = inc - sum;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { S.cumt[lane * 8 + k] = run; run += v[k]; }
+        if (lane == 31) S.s_body = inc;
+        uint32_t z = zb << (8 * (lane & 3));
+        z |= __shfl_xor_sync(FULLMASK, z, 1); z |= __shfl_xor_sync(FULLMASK, z, 2);
+        if ((lane & 3) == 0) S.zmask[lane >> 2] = z;
+    }
+    const bool active = tid < step;
+    uint32_t k = 0, ev = 0;
+    if (active) { k = K[R.pos + tid]; ev = V[R.pos + tid]; }
+    const uint32_t sym = k >> 24, pr = (k >> 16) & 255;
+    const bool hit = active && sym == pr, nonhit = active && sym != pr;
+    const uint32_t b_nh = __ballot_sync(FULLMASK, nonhit);
+    uint32_t mL = 0, mE = b_nh, mP = b_nh;
+#pragma unroll
+    for (int b = 7; b >= 0; b--) {
+        const uint32_t Bb = __ballot_sync(FULLMASK, (sym >> b) & 1u);
+        if ((sym >> b) & 1u) { mL |= mE & ~Bb; mE &= Bb; } else mE &= ~Bb;
+        mP &= ((pr >> b) & 1u) ? Bb : ~Bb;
+    }
+    const uint32_t lt = __popc(mL & before), eq = __popc(mE & before), peq = __popc(mP & before);
+    const bool leader = nonhit && (mE & before) == 0;
+    if (leader) S.hraw[w][sym] = (uint8_t)__popc(mE);
+    S.ssym[tid] = nonhit ? (uint16_t)sym : (uint16_t)0x100;
+    __syncthreads();
+    if (tid < 256) { uint32_t run = 0; for (uint32_t q = 0; q < nw; q++) { const uint32_t h = S.hraw[q][tid]; S.hexcl[q][tid] = (uint16_t)run; run += h; } }
+    __syncthreads();
+    if (w < nw) {
+        uint32_t v[8], sum = 0;
+        const uint4 hv = *(const uint4*)&S.hexcl[w][lane * 8];
+        v[0] = hv.x & 0xffff; v[1] = hv.x >> 16; v[2] = hv.y & 0xffff; v[3] = hv.y >> 16; v[4] = hv.z & 0xffff; v[5] = hv.z >> 16; v[6] = hv.w & 0xffff; v[7] = hv.w >> 16;
+#pragma unroll
+        for (int q = 0; q < 8; q++) sum += v[q];
+        uint32_t inc = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(FULLMASK, inc, d); if (lane >= d) inc += t; }
+        uint32_t run = inc - sum, o[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) { o[q] = run; run += v[q]; }
+        *(uint4*)&S.below[w][lane * 8] = make_uint4(o[0] | o[1] << 16, o[2] | o[3] << 16, o[4] | o[5] << 16, o[6] | o[7] << 16);
+    }
+    __syncwarp();
+    uint32_t fs = 0, pf = 0;
+    if (active) { fs = S.cnt[sym] + S.hexcl[w][sym] + eq; pf = S.cnt[pr] + S.hexcl[w][pr] + peq; }
+    const bool esc = nonhit && fs == 0, two = nonhit && fs == 1;
+    const uint32_t b_es = __ballot_sync(FULLMASK, esc), b_tw = __ballot_sync(FULLMASK, two);
+    if (lane == 0) { S.wtot[0][w] = __popc(b_nh); S.wtot[1][w] = __popc(b_es); S.wtot[2][w] = __popc(b_tw); }
+    __syncthreads();
+    uint32_t p0 = 0, p1 = 0, p2 = 0;
+    if (lane < w) { p0 = S.wtot[0][lane]; p1 = S.wtot[1][lane]; p2 = S.wtot[2][lane]; }
+    p0 = __reduce_add_sync(FULLMASK, p0); p1 = __reduce_add_sync(FULLMASK, p1); p2 = __reduce_add_sync(FULLMASK, p2);
+    const uint32_t A = p0 + __popc(b_nh & before), ES = p1 + __popc(b_es & before), TW = p2 + __popc(b_tw & before);
+    const uint32_t f256 = R.f256 + (tid - A), f257 = R.f257 + ES - TW, body = S.s_body + A;
+    if (esc) S.esc_sym[ES] = (uint8_t)sym;
+    __syncthreads();
+    if (!active) continue;
+    const uint32_t sum = body + f256 + f257 - pf;
+    if (hit) T1[ev] = ppm_pack(body - pf, f256, sum, 0);
+    else if (!esc) T1[ev] = ppm_pack(S.cumt[sym] + S.below[w][sym] + lt - (sym >= pr ? pf : 0), fs, sum, 0);
+    else {
+        T1[ev] = ppm_pack(body + f256 - pf, f257, sum, 1);
+        const bool trig = f257 + 1 > 250;
+        uint32_t m0, m1, m2, m3, m4, m5, m6, m7;
+        if (trig) {
+            // the escape update rescales BEFORE the mask is taken (cr-ppm.c:146-151): zero <=> count <= 1 now
+            auto word = [&](uint32_t q) {
+                uint32_t r = 0;
+                for (uint32_t bb = 0; bb < 32; bb++) {
+                    const uint32_t x = q * 32 + bb;
+                    uint32_t c = S.cnt[x] + S.hexcl[w][x];
+                    for (uint32_t j = w * 32; j < tid && c < 2; j++) c += S.ssym[j] == x;
+                    if (c < 2) r |= 1u << bb;
+                }
+                return r;
+            };
+            m0 = word(0); m1 = word(1); m2 = word(2); m3 = word(3); m4 = word(4); m5 = word(5); m6 = word(6); m7 = word(7);
+        } else {
+            m0 = S.zmask[0]; m1 = S.zmask[1]; m2 = S.zmask[2]; m3 = S.zmask[3]; m4 = S.zmask[4]; m5 = S.zmask[5]; m6 = S.zmask[6]; m7 = S.zmask[7];
+        }
+        auto drop = [&](uint32_t x) {
+            const uint32_t q = x >> 5, bit = ~(1u << (x & 31));
+            m0 &= q == 0 ? bit : ~0u; m1 &= q == 1 ? bit : ~0u; m2 &= q == 2 ? bit : ~0u; m3 &= q == 3 ? bit : ~0u;
+            m4 &= q == 4 ? bit : ~0u; m5 &= q == 5 ? bit : ~0u; m6 &= q == 6 ? bit : ~0u; m7 &= q == 7 ? bit : ~0u;
+        };
+        if (!trig) for (uint32_t e = 0; e < ES; e++) drop(S.esc_sym[e]);
+        drop(pr);
+        EscRec* rec = esc_rec + atomicAdd(esc_count, 1u);
+        rec->e = ev; rec->info = (c16 & 0xff) | sym << 8;
+        rec->incl[0] = m0; rec->incl[1] = m1; rec->incl[2] = m2; rec->incl[3] = m3; rec->incl[4] = m4; rec->incl[5] = m5; rec->incl[6] = m6; rec->incl[7] = m7;
+    }
+    }
 }
 
 // ------------------------------------------------------------------ o1 pass, one warp per ctx8
@@ -891,7 +1148,7 @@ __global__ void __launch_bounds__(O1S_TH) k_o1_skel(O1Ctx* __restrict__ ctx, con
     const uint32_t r0 = C.r0, r1 = C.r1;
     if (r1 - r0 < O1C_MIN) return;
     __shared__ uint32_t ring[O1S_RING];
-    __shared__ uint32_t cnt[256];
+    __shared__ __align__(16) uint32_t cnt[256];
     __shared__ uint16_t hexcl[NW][256];
     __shared__ uint8_t hraw[NW][256];
     __shared__ uint32_t s_first;

@@ -213,7 +213,8 @@ extern "C" int crgpu_set_option(crgpu_handle* h, const char* name, int64_t value
     std::string n(name);
     if (n == "scalar_models") { h->chain.scalar_models = value != 0; return CRGPU_OK; }
     if (n == "o1_hot_variant") { if (value < 1 || value > 2) return CRGPU_ERR_ARG; h->chain.o1_hot_variant = (int)value; return CRGPU_OK; }
-    if (n == "o2_hot_variant") { if (value < 1 || value > 2) return CRGPU_ERR_ARG; h->chain.o2_hot_variant = (int)value; return CRGPU_OK; }
+    if (n == "o2_hot_variant") { if (value < 1 || value > 3) return CRGPU_ERR_ARG; h->chain.o2_hot_variant = (int)value; return CRGPU_OK; }
+    if (n == "o2_rec_cap_test") { h->chain.o2_rec_cap_test = (uint32_t)value; return CRGPU_OK; }     // tests: force the out-of-records path
     if (n == "rc_variant") { if (value < 1 || value > 8) return CRGPU_ERR_ARG; h->chain.rc_variant = (int)value; return CRGPU_OK; }
 #ifndef CRGPU_SIM
     if (n == "rc_job_symbols") { if (value != 0 && (value < 4096 || value > (1 << 24))) return CRGPU_ERR_ARG; h->chain.rcpar.job_symbols = (uint32_t)value; return CRGPU_OK; }

@@ -101,3 +101,20 @@ def test_gpu_range_chain_variants_identical(gpulib, rcv):
             h.set_option("rc_variant", rcv)
             got = h.compress(data, MiB)
         assert got == O.compress(data, variant, MiB), "rc_variant %d differs from the oracle" % rcv
+
+
+@pytest.mark.parametrize("variant", [api.ROLZ, api.LZP])
+def test_gpu_model_pass_variants_agree(gpulib, variant):
+    """The hot-context passes in all their forms (o2: split chain / single kernel / first form; o1: split / single kernel) and the
+    split o2 pass when its table of step records is far too small (contexts are then redone by the single kernel): same container,
+    on text (hit-heavy: 256-event steps) and on skewed binary data (1024-event steps)."""
+    import numpy as np
+    rng = np.random.default_rng(5)
+    skew = rng.choice(np.arange(256, dtype=np.uint8), size=6 * MiB, p=np.r_[0.5, 0.2, np.full(254, 0.3 / 254)]).tobytes()
+    for data in (synth.markov_text(6 * MiB, seed=91), skew):
+        want = O.compress(data, variant, 4 * MiB)
+        for opts in ({}, {"o2_hot_variant": 2}, {"o2_hot_variant": 1, "o1_hot_variant": 1}, {"o2_rec_cap_test": 37}, {"o2_rec_cap_test": 1}):
+            with api.Handle(variant, lib=gpulib) as h:
+                for k, v in opts.items():
+                    h.set_option(k, v)
+                assert h.compress(data, 4 * MiB) == want, "options %r: container differs from the oracle" % (opts,)

@@ -69,6 +69,7 @@ struct LzChain {
     bool flexible = false;         // -f flexible parsing (ROLZ)
     int rc_variant = 8;            // range-chain formulation: 8 = cut into jobs that run side by side (cr_rcpar.cuh); 1..7 = one serial walk per stream (cr_warp.cuh: k_range_chain<1..7>)
     bool hot_contexts = true;      // hot o2 contexts run the rank-based CTA kernel (k_o2_pass_cta)
+    int rolz_match_variant = 2;    // 2 = k_rolz_match_main2 (five-byte filter in shared memory), 1 = k_rolz_match_main
     int o1_hot_variant = 2;        // 2 = k_o1_skel + k_o1_eval (the chain of steps carries only the counts), 1 = k_o1_pass_cta
     int o2_hot_variant = 3;        // 3 = k_o2_skel + k_o2_eval (the chain of steps carries only counts and flags), 2 = k_o2_hot (event ring, ballot ranks), 1 = k_o2_pass_cta
     bool o2_attr_done = false;
@@ -256,6 +257,12 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
             CR_LAUNCH(k_rolz_keys, dim3(cr_div_up(maxsize, 256), nb), dim3(256), stream, dD, d_blocks, b_k0.as<uint32_t>(), b_ks0.as<uint32_t>(), b_v0.as<uint32_t>());
             CR_TRY(cr_sort_pairs<uint32_t>(prims, b_k0.as<uint32_t>(), b_k1.as<uint32_t>(), b_v0.as<uint32_t>(), b_v1.as<uint32_t>(), nent, 0, RZ_BUCKET_BITS + bbits));
             if (flexible) { CR_TRY(b_rank.reserve((size_t)nent * 4 + 16)); CR_TRY(b_flexlen.reserve(nent + 16)); }
+#ifndef CRGPU_SIM
+            if (rolz_match_variant == 2)
+                CR_LAUNCH(k_rolz_match_main2, dim3(cr_div_up(nent, RZM_TH)), dim3(RZM_TH), stream, dD, d_blocks, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nent, b_M.as<uint16_t>(),
+                          flexible ? b_rank.as<uint32_t>() : (uint32_t*)nullptr);
+            else
+#endif
             CR_LAUNCH(k_rolz_match_main, dim3(cr_div_up(nent, 128)), dim3(128), stream, dD, d_blocks, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nent, b_M.as<uint16_t>(),
                       flexible ? b_rank.as<uint32_t>() : (uint32_t*)nullptr);
             if (flexible) CR_LAUNCH(k_rolz_flex, dim3(cr_div_up(maxsize, 128), nb), dim3(128), stream, dD, d_blocks, b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), b_rank.as<uint32_t>(), b_M.as<uint16_t>(), b_flexlen.as<uint8_t>());

@@ -120,6 +120,103 @@ __global__ void k_rolz_match_main(const uint8_t* __restrict__ D, const LzBlock* 
     for (int v = 1; v < 5; v++) M[(size_t)v * n + e] = best[v] >= RZ_MINLEN ? (uint16_t)(best[v] | idx[v] << 8) : (uint16_t)0;
 }
 
+#ifndef CRGPU_SIM
+// Main-table search, second form (default on the GPU; same results as k_rolz_match_main, which stays as the definition the CPU
+// kernel-logic simulation runs).  What changed, and why (ncu on x86 / BMP data: the first form moves 6x its algorithmic bytes, nearly
+// all of them 32-byte sectors fetched for one byte of a candidate that then fails, profiles/round2_match.md):
+//   * a candidate is only worth touching if its first FIVE bytes equal ours (a match shorter than RZ_MINLEN never wins).  Byte 0 is the
+//     key's tag; bytes 1..4 are gathered once per sorted entry while the CTA stages its window of the sorted list in shared memory,
+//     so the filter runs on shared memory alone and the data is read only for candidates that are real matches;
+//   * the window of keys (the CTA's 256 ranks and the 72 in front of them) is staged once instead of being re-read 64 times per rank;
+//   * the common prefix is counted four bytes per step (aligned words + funnel shift).
+#define RZM_TH   256
+#define RZM_BACK 72u        // RZ_WAYS + 4 look-ahead variants, rounded up
+CR_D uint32_t rz_ld32(const uint8_t* p) {               // four bytes at any alignment (reads up to 7 bytes past p: buffers carry slack)
+    const uintptr_t a = (uintptr_t)p;
+    const uint32_t* w = (const uint32_t*)(a & ~(uintptr_t)3);
+    return __funnelshift_r(w[0], w[1], (uint32_t)(a & 3) * 8);
+}
+CR_D uint32_t rz_cpl4(const uint8_t* a, const uint8_t* b, uint32_t from, uint32_t cap) {     // common prefix, known equal below `from`
+    uint32_t j = from;
+    while (j + 4 <= cap) {
+        const uint32_t x = rz_ld32(a + j) ^ rz_ld32(b + j);
+        if (x) return j + ((__ffs((int)x) - 1) >> 3);
+        j += 4;
+    }
+    while (j < cap && a[j] == b[j]) j++;
+    return j;
+}
+__global__ void __launch_bounds__(RZM_TH) k_rolz_match_main2(const uint8_t* __restrict__ D, const LzBlock* __restrict__ blocks,
+                                                              const uint32_t* __restrict__ K, const uint32_t* __restrict__ V, uint32_t n,
+                                                              uint16_t* __restrict__ M, uint32_t* __restrict__ rank_of) {
+    __shared__ uint32_t sK[RZM_TH + RZM_BACK], sX[RZM_TH + RZM_BACK];
+    const uint32_t base = blockIdx.x * RZM_TH;
+    for (uint32_t i = threadIdx.x; i < RZM_TH + RZM_BACK; i += RZM_TH) {
+        const long long g = (long long)base - RZM_BACK + i;
+        uint32_t k = 0, x = 0;
+        if (g >= 0 && g < (long long)n) {
+            k = K[g];
+            const LzBlock B = blocks[(k & RZ_KEY_MASK) >> RZ_BUCKET_BITS];
+            const uint32_t q = V[g];
+            if (q + 8 < B.size) x = rz_ld32(D + B.off + q + 1);          // a candidate of a looked-up position always has this much behind it
+        }
+        sK[i] = k; sX[i] = x;
+    }
+    __syncthreads();
+    const uint32_t r = base + threadIdx.x;
+    if (r >= n) return;
+    const uint32_t me = threadIdx.x + RZM_BACK;                              // my slot; candidate c sits at me - 1 - c
+    const uint32_t key = sK[me] & RZ_KEY_MASK, p = V[r];
+    const LzBlock B = blocks[key >> RZ_BUCKET_BITS];
+    if (rank_of) rank_of[B.eoff + p - 16] = r;
+    if (p + (RZ_LOOKAHEAD - 4) >= B.size) return;
+    const uint8_t* d = D + B.off;
+    const uint8_t* dp = d + p;
+    const uint32_t e = B.eoff + p - 16;
+    const uint32_t first = sK[me] >> RZ_TAG_SHIFT, myx = sX[me];
+
+    const bool simple = (r == 0) || (sK[me - 1] & RZ_KEY_MASK) != key || V[r - 1] + 4 < p;
+    if (simple) {
+        uint32_t best = RZ_MINLEN - 1, idx = 0;
+        for (uint32_t c = 0; c < RZ_WAYS && c < r && best < RZ_MAXLEN; c++) {
+            const uint32_t kc = sK[me - 1 - c];
+            if ((kc & RZ_KEY_MASK) != key) break;
+            if ((kc >> RZ_TAG_SHIFT) != first || sX[me - 1 - c] != myx) continue;
+            const uint8_t* dq = d + V[r - 1 - c];
+            if (best >= RZ_MINLEN && dq[best] != dp[best]) continue;
+            const uint32_t l = rz_cpl4(dp, dq, RZ_MINLEN, RZ_MAXLEN);
+            if (l > best) { best = l; idx = c; }
+        }
+        M[e] = best >= RZ_MINLEN ? (uint16_t)(best | idx << 8) : (uint16_t)0;
+        return;
+    }
+    uint32_t best[5], idx[5], skip[5];
+#pragma unroll
+    for (int v = 0; v < 5; v++) { best[v] = RZ_MINLEN - 1; idx[v] = 0; skip[v] = 0; }
+    for (uint32_t c = 0; c < RZ_WAYS + 4 && c < r; c++) {
+        const uint32_t kc = sK[me - 1 - c];
+        if ((kc & RZ_KEY_MASK) != key) break;
+        const uint32_t q = V[r - 1 - c];
+        bool use[5], any = false;
+#pragma unroll
+        for (int v = 0; v < 5; v++) {
+            const bool excluded = q + v >= p;                       // inserted at or after time p - v
+            if (excluded) skip[v]++;
+            use[v] = !excluded && (c - skip[v]) < RZ_WAYS && best[v] < RZ_MAXLEN;
+            any |= use[v];
+        }
+        if (!any) { if (c >= skip[4] + RZ_WAYS) break; continue; }
+        if ((kc >> RZ_TAG_SHIFT) != first || sX[me - 1 - c] != myx) continue;
+        const uint32_t l = rz_cpl4(dp, d + q, RZ_MINLEN, RZ_MAXLEN);
+#pragma unroll
+        for (int v = 0; v < 5; v++) if (use[v] && l > best[v]) { best[v] = l; idx[v] = c - skip[v]; }
+    }
+    M[e] = (uint16_t)((best[0] >= RZ_MINLEN ? (best[0] | idx[0] << 8) : 0u) | RZ_VARIANTS);
+#pragma unroll
+    for (int v = 1; v < 5; v++) M[(size_t)v * n + e] = best[v] >= RZ_MINLEN ? (uint16_t)(best[v] | idx[v] << 8) : (uint16_t)0;
+}
+#endif
+
 // Order-1 ("short") table, consulted only where the main table found nothing (cr-matcher.c:165-179).
 // Empty slots hold position 0 and ARE candidates (the table is zero-initialised, cr-matcher.c:53).
 __global__ void k_rolz_match_short(const uint8_t* __restrict__ D, const LzBlock* __restrict__ blocks,

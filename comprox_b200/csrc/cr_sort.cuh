@@ -190,6 +190,80 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const K* __restrict__
         __syncwarp();
     }
 }
+
+// 32-bit keys: the same ranking, but the tile is first put in digit order in shared memory and leaves in runs -- consecutive threads
+// write consecutive addresses of one digit's range (a run is ~16 elements with 256 digits and 4096 elements per tile), where
+// k_rs_scatter writes 32 scattered 4-byte words per warp and round (one 32-byte sector each).
+__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter_staged(const uint32_t* __restrict__ kin, const uint32_t* __restrict__ vin, uint32_t* __restrict__ kout, uint32_t* __restrict__ vout,
+                                                                  size_t n, int shift, uint32_t mask, uint32_t ntiles, const uint32_t* __restrict__ bases) {
+    __shared__ uint32_t wcnt[RS_WARPS][256];
+    __shared__ uint32_t sk[RS_TILE], sv[RS_TILE];
+    __shared__ uint32_t goff[256], wsum[RS_WARPS];
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (uint32_t i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&wcnt[0][0])[i] = 0;
+    __syncthreads();
+    const size_t tbase = (size_t)blockIdx.x * RS_TILE;
+    const size_t wbase = tbase + (size_t)w * (RS_ITEMS * 32);
+    uint32_t key[RS_ITEMS], val[RS_ITEMS], dig[RS_ITEMS];
+#pragma unroll
+    for (uint32_t r = 0; r < RS_ITEMS; r++) {
+        const size_t i = wbase + r * 32 + lane;
+        const bool ok = i < n;
+        key[r] = ok ? kin[i] : 0u; val[r] = ok ? vin[i] : 0u;
+        dig[r] = ok ? ((key[r] >> shift) & mask) : 0xFFFFFFFFu;
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, dig[r]);
+        if (ok && lane == (uint32_t)(__ffs(peers) - 1)) wcnt[w][dig[r]] += __popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    {   // per digit: prefix over warps; over digits: where the digit starts inside the tile
+        const uint32_t d = threadIdx.x;
+        uint32_t cq[RS_WARPS], tot = 0;
+#pragma unroll
+        for (uint32_t q = 0; q < RS_WARPS; q++) { cq[q] = wcnt[q][d]; tot += cq[q]; }
+        uint32_t inc = tot;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, s); if (lane >= (uint32_t)s) inc += t; }
+        if (lane == 31) wsum[w] = inc;
+        __syncthreads();
+        uint32_t off = 0;
+#pragma unroll
+        for (uint32_t q = 0; q < RS_WARPS; q++) if (q < w) off += wsum[q];
+        uint32_t run = off + inc - tot;                              // first local position of digit d
+        goff[d] = bases[(size_t)d * ntiles + blockIdx.x] - run;
+#pragma unroll
+        for (uint32_t q = 0; q < RS_WARPS; q++) { wcnt[q][d] = run; run += cq[q]; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (uint32_t r = 0; r < RS_ITEMS; r++) {
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, dig[r]);
+        const bool ok = dig[r] != 0xFFFFFFFFu;
+        uint32_t basepos = 0;
+        const uint32_t leader = __ffs(peers) - 1;
+        if (ok && lane == leader) { basepos = wcnt[w][dig[r]]; wcnt[w][dig[r]] = basepos + __popc(peers); }
+        basepos = __shfl_sync(0xFFFFFFFFu, basepos, leader);
+        if (ok) { const uint32_t loc = basepos + __popc(peers & ((1u << lane) - 1u)); sk[loc] = key[r]; sv[loc] = val[r]; }
+        __syncwarp();
+    }
+    __syncthreads();
+    const uint32_t tn = n - tbase < RS_TILE ? (uint32_t)(n - tbase) : RS_TILE;
+#pragma unroll
+    for (uint32_t j = 0; j < RS_ITEMS; j++) {
+        const uint32_t i = j * RS_THREADS + threadIdx.x;
+        if (i < tn) { const uint32_t k = sk[i]; const uint32_t dst = goff[(k >> shift) & mask] + i; kout[dst] = k; vout[dst] = sv[i]; }
+    }
+}
+template <class K> struct RsScatter {
+    static void launch(const K* ks, const uint32_t* vs, K* kd, uint32_t* vd, size_t n, int shift, uint32_t mask, uint32_t ntiles, const uint32_t* counts, cudaStream_t st) {
+        k_rs_scatter<K><<<dim3(ntiles), dim3(RS_THREADS), 0, st>>>(ks, vs, kd, vd, n, shift, mask, ntiles, counts);
+    }
+};
+template <> struct RsScatter<uint32_t> {
+    static void launch(const uint32_t* ks, const uint32_t* vs, uint32_t* kd, uint32_t* vd, size_t n, int shift, uint32_t mask, uint32_t ntiles, const uint32_t* counts, cudaStream_t st) {
+        k_rs_scatter_staged<<<dim3(ntiles), dim3(RS_THREADS), 0, st>>>(ks, vs, kd, vd, n, shift, mask, ntiles, counts);
+    }
+};
 #endif
 
 // Stable sort of (key, value) pairs on key bits [begin_bit, end_bit).  Full keys travel with the pairs; the inputs are
@@ -234,7 +308,9 @@ static int cr_sort_pairs(Prims& P, const K* kin, K* kout, const uint32_t* vin, u
         CR_TRY(cr_exclusive_sum(P, counts, counts, ncounts));
         const bool to_out = ((passes - 1 - p) & 1) == 0;          // the last pass writes the output
         K* kd = to_out ? kout : kalt; uint32_t* vd = to_out ? vout : valt;
-        CR_LAUNCH(k_rs_scatter<K>, dim3(ntiles), dim3(RS_THREADS), P.stream, ks, vs, kd, vd, n, shift, mask, ntiles, counts);
+        __atomic_fetch_add(&g_cr_launches, 1ull, __ATOMIC_RELAXED);
+        RsScatter<K>::launch(ks, vs, kd, vd, n, shift, mask, ntiles, counts, P.stream);
+        CR_CUDA(cudaGetLastError());
         ks = kd; vs = vd;
     }
     return CRGPU_OK;

@@ -7,6 +7,7 @@
 // blocks: filters -> dictionary substitution -> lzencode chain (cr_lzchain.cuh).  The container bytes are
 // assembled on the device and leave with a single copy.
 #pragma once
+#include <thread>
 #include "cr_lzchain.cuh"
 #include "cr_dict.cuh"
 #include "cr_filter.cuh"
@@ -31,12 +32,25 @@ struct Compressor {
     HdTrie trie;
     FilterHost filt;
     const uint8_t* staged_ptr = nullptr; uint64_t staged_n = 0;
+    // The dictionary payload is a model chain of its own: reset_models() stands before and after its lzencode (src/main.c:166-167).  It
+    // therefore runs on a second LzChain (own models, own buffers, own stream, driven by a helper thread) beside the data blocks: its
+    // range walk -- fresh models, small sums, nothing to cut: ~200 000 symbols one after the other, 2.6 ms -- no longer stands in front
+    // of them.  dict_mode 0 turns this off (the payload is then coded on the main chain first, as before).
+    LzChain* dict_chain = nullptr;
+    cudaStream_t dict_stream = 0;
+    DevBuf d_dictout;
+    int dict_mode = 1;
 
     void release() {
         DevBuf* all[] = { &d_raw, &d_D, &d_out, &d_dic, &t_key, &t_count, &t_first, &t_stats, &t_entries, &d_trie_key, &d_trie_val, &d_trie_id, &b_subs, &b_hist,
                           &b_esc10, &b_escmask, &b_span, &b_hit, &b_segs, &b_xt, &b_entry, &b_cnt, &b_scan, &b_chunk0, &b_hdr, &b_copy, &b_segoff, &b_seglen };
         for (DevBuf* b : all) b->release();
         filt.release();
+        d_dictout.release();
+        if (dict_chain) { dict_chain->release(); delete dict_chain; dict_chain = nullptr; }
+#ifndef CRGPU_SIM
+        if (dict_stream) { cudaStreamDestroy(dict_stream); dict_stream = 0; }
+#endif
     }
     template <class T> int upload(DevBuf& b, const std::vector<T>& v) { return chain->upload(b, v); }
     template <class T> int download(std::vector<T>& v, const void* src, size_t n) { return chain->download(v, src, n); }
@@ -319,14 +333,50 @@ inline int Compressor::compress(const CrConfig& cfg, const uint8_t* in, uint64_t
     if (tm.enabled) { CR_CUDA(cudaStreamSynchronize(stream)); tm.finish(); }
     CR_TRY(load_dictionary(text));
     std::vector<uint8_t> lcp = hd_lcp_encode(text);
-    CR_TRY(upload(d_dic, lcp));
     chain->flexible = cfg.flexible != 0;       // flexible_parsing is a process-wide switch: it also applies to the dictionary payload
-    CR_TRY(chain->reset_models());
     std::vector<BlockIO> dblk(1);
     memset(&dblk[0], 0, sizeof(BlockIO)); dblk[0].size = (uint32_t)lcp.size();
-    size_t out_pos = 0, wrote = 0;
-    CR_TRY(chain->encode_blocks(d_dic.as<uint8_t>(), dblk, 0, true, d_out, out_pos, wrote));
-    out_pos += wrote;
+    size_t out_pos = 0, wrote = 0, dict_wrote = 0;
+    bool dict_async = false;
+#ifndef CRGPU_SIM
+    std::thread dict_thread;
+    int dict_rc = CRGPU_OK;
+    if (dict_mode == 1) {
+        int dev = 0;
+        CR_CUDA(cudaGetDevice(&dev));
+        if (!dict_chain) {
+            CR_CUDA(cudaStreamCreateWithFlags(&dict_stream, cudaStreamNonBlocking));
+            const cudaStream_t keep = g_cr_alloc_stream;
+            g_cr_alloc_stream = dict_stream;
+            dict_chain = new LzChain();
+            const int rc = dict_chain->init(chain->variant, dict_stream);
+            g_cr_alloc_stream = keep;
+            if (rc != CRGPU_OK) return rc;
+        }
+        dict_chain->copy_options(*chain);
+        dict_async = true;
+        dict_thread = std::thread([&, dev]() {
+            dict_rc = [&]() -> int {
+                CR_CUDA(cudaSetDevice(dev));
+                g_cr_alloc_stream = dict_stream; g_cr_alloc_async = true;
+                CR_TRY(dict_chain->upload(d_dic, lcp));
+                CR_TRY(dict_chain->reset_models());
+                size_t w = 0;
+                CR_TRY(dict_chain->encode_blocks(d_dic.as<uint8_t>(), dblk, 0, true, d_dictout, 0, w));
+                CR_CUDA(cudaStreamSynchronize(dict_stream));
+                dict_wrote = w;
+                return CRGPU_OK;
+            }();
+        });
+    }
+    struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{dict_thread};      // every return path waits for the helper
+#endif
+    if (!dict_async) {
+        CR_TRY(upload(d_dic, lcp));
+        CR_TRY(chain->reset_models());
+        CR_TRY(chain->encode_blocks(d_dic.as<uint8_t>(), dblk, 0, true, d_out, out_pos, wrote));
+        out_pos += wrote;
+    }
     CR_TRY(chain->reset_models());
 
     // ---- data blocks, window by window.  A trailing empty block appears when n % block_size == 0 (F8).
@@ -381,9 +431,17 @@ inline int Compressor::compress(const CrConfig& cfg, const uint8_t* in, uint64_t
         }
         out_pos += wrote;
     }
-    if (mlen + out_pos > out_cap) return CRGPU_ERR_ARG;
-    CR_CUDA(cudaMemcpyAsync(out + mlen, d_out.p, out_pos, cudaMemcpyDeviceToHost, stream));
+#ifndef CRGPU_SIM
+    if (dict_async) {
+        dict_thread.join();
+        if (dict_rc != CRGPU_OK) return dict_rc;
+        if (mlen + dict_wrote + out_pos > out_cap) return CRGPU_ERR_ARG;
+        CR_CUDA(cudaMemcpyAsync(out + mlen, d_dictout.p, dict_wrote, cudaMemcpyDeviceToHost, stream));     // (the helper has synchronised its stream)
+    }
+#endif
+    if (mlen + dict_wrote + out_pos > out_cap) return CRGPU_ERR_ARG;
+    CR_CUDA(cudaMemcpyAsync(out + mlen + dict_wrote, d_out.p, out_pos, cudaMemcpyDeviceToHost, stream));
     CR_CUDA(cudaStreamSynchronize(stream));
-    *out_n = mlen + out_pos;
+    *out_n = mlen + dict_wrote + out_pos;
     return CRGPU_OK;
 }

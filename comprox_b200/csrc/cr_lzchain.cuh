@@ -81,6 +81,15 @@ struct LzChain {
     RcPar rcpar;                   // rc_variant 8: the range chain cut into jobs (cr_rcpar.cuh)
 #endif
 
+    // the switches a second chain of the same handle must share (Compressor's dictionary-payload chain)
+    void copy_options(const LzChain& o) {
+        match_limit = o.match_limit; x_max_iter = o.x_max_iter; flexible = o.flexible; rc_variant = o.rc_variant; hot_contexts = o.hot_contexts;
+        rolz_match_variant = o.rolz_match_variant; o1_hot_variant = o.o1_hot_variant; o2_hot_variant = o.o2_hot_variant; o2_rec_cap_test = o.o2_rec_cap_test;
+        scalar_models = o.scalar_models; exact_aborts = o.exact_aborts;
+#ifndef CRGPU_SIM
+        rcpar.job_symbols = o.rcpar.job_symbols; rcpar.late_cfg = o.rcpar.late_cfg; rcpar.serial_only = o.rcpar.serial_only; rcpar.crowded = o.rcpar.crowded;
+#endif
+    }
     int init(int variant_, cudaStream_t s) {
         variant = variant_; stream = s; prims.stream = s;
         CR_TRY(s_o3b.reserve(PPM_O3_SLOTS)); CR_TRY(s_o3c.reserve(PPM_O3_SLOTS));

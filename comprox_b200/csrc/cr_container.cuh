@@ -27,7 +27,7 @@ struct Compressor {
     cudaStream_t stream = 0;
     DevBuf d_raw, d_D, d_out, d_dic;
     DevBuf t_key, t_count, t_first, t_stats, t_entries;          // dicpick table
-    DevBuf d_trie_key, d_trie_val, d_trie_id;
+    DevBuf d_trie_edge, d_trie_id;
     DevBuf b_subs, b_hist, b_esc10, b_escmask, b_span, b_hit, b_segs, b_xt, b_entry, b_cnt, b_scan, b_chunk0, b_hdr, b_copy, b_segoff, b_seglen;
     HdTrie trie;
     FilterHost filt;
@@ -42,7 +42,7 @@ struct Compressor {
     int dict_mode = 1;
 
     void release() {
-        DevBuf* all[] = { &d_raw, &d_D, &d_out, &d_dic, &t_key, &t_count, &t_first, &t_stats, &t_entries, &d_trie_key, &d_trie_val, &d_trie_id, &b_subs, &b_hist,
+        DevBuf* all[] = { &d_raw, &d_D, &d_out, &d_dic, &t_key, &t_count, &t_first, &t_stats, &t_entries, &d_trie_edge, &d_trie_id, &b_subs, &b_hist,
                           &b_esc10, &b_escmask, &b_span, &b_hit, &b_segs, &b_xt, &b_entry, &b_cnt, &b_scan, &b_chunk0, &b_hdr, &b_copy, &b_segoff, &b_seglen };
         for (DevBuf* b : all) b->release();
         filt.release();
@@ -88,7 +88,7 @@ inline int Compressor::dicpick(const uint8_t* h_in, const uint8_t* d_in, uint64_
         uint64_t x1 = x0 + step < n ? x0 + step : n;
         CR_LAUNCH(k_dp_verify, dim3(cr_div_up(x1 - x0, 256)), dim3(256), stream, d_in, n, x0, x1, T);
     }
-    CR_LAUNCH(k_dp_collect, dim3(DP_SLOTS / 256), dim3(256), stream, T, t_entries.as<DpEntry>(), DP_MAXWORDS);
+    CR_LAUNCH(k_dp_collect, dim3(DP_SLOTS / 256), dim3(256), stream, T, d_in, n, t_entries.as<DpEntry>(), DP_MAXWORDS);
     chain->timer.mark("dp_kernels");
     auto t0 = std::chrono::steady_clock::now();
     auto lap = [&](const char* what) {
@@ -110,8 +110,10 @@ inline int Compressor::dicpick(const uint8_t* h_in, const uint8_t* d_in, uint64_
     CR_TRY(download(ent, t_entries.p, stats[2]));
     lap("dp entries d2h");
     std::vector<HdWord> words(ent.size());
-    for (size_t i = 0; i < ent.size(); i++) { words[i].set(h_in, n, ent[i].first); words[i].count = ent[i].count; }
+    for (size_t i = 0; i < ent.size(); i++) { words[i].k[0] = ent[i].k[0]; words[i].k[1] = ent[i].k[1]; words[i].k[2] = ent[i].k[2]; words[i].count = ent[i].count; words[i].len = ent[i].len; }
+    (void)h_in;
     lap("dp words");
+    if (getenv("CRGPU_TIMING")) fprintf(stderr, "crgpu timing: %zu words with count > 5\n", words.size());
     text = hd_dictionary_text(words);
     lap("dp text");
     chain->timer.mark("dp_host");
@@ -177,15 +179,17 @@ inline int Compressor::dicpick_epochs(const uint8_t* d_in, uint64_t n) {
     }
     DpTable T = { t_key.as<unsigned long long>(), t_count.as<uint32_t>(), t_first.as<uint32_t>(), t_stats.as<uint32_t>() };
     CR_CUDA(cudaMemsetAsync(t_stats.as<uint32_t>() + 2, 0, 4, stream));
-    CR_LAUNCH(k_dp_collect, dim3(DP_SLOTS / 256), dim3(256), stream, T, t_entries.as<DpEntry>(), DP_MAXWORDS);
+    CR_LAUNCH(k_dp_collect, dim3(DP_SLOTS / 256), dim3(256), stream, T, d_in, n, t_entries.as<DpEntry>(), DP_MAXWORDS);
     CR_CUDA(cudaStreamSynchronize(stream));
     k2.release(); c2.release(); f2.release(); list.release(); small.release();
     return rc;
 }
 
 inline int Compressor::load_dictionary(const std::string& text) {
+    auto t0 = std::chrono::steady_clock::now();
     trie.load(text.c_str());
-    CR_TRY(upload(d_trie_key, trie.ekey)); CR_TRY(upload(d_trie_val, trie.eval)); CR_TRY(upload(d_trie_id, trie.id));
+    if (getenv("CRGPU_TIMING")) fprintf(stderr, "crgpu timing: trie.load        %.3f ms (%zu nodes, table %u)\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), trie.id.size(), trie.mask + 1);
+    CR_TRY(upload(d_trie_edge, trie.edge)); CR_TRY(upload(d_trie_id, trie.id));
     return CRGPU_OK;
 }
 
@@ -232,7 +236,7 @@ inline int Compressor::dict_encode_window(const uint8_t* d_rawwin, const std::ve
     for (uint32_t s = 0; s < nsub; s++) chunk0[s] = segs[s].chunk0;
     chunk0[nsub] = nchunk;
     std::vector<uint32_t> hscan(nchunk + 1, 0);
-    DcTrie T = { d_trie_key.as<uint32_t>(), d_trie_val.as<uint32_t>(), d_trie_id.as<int32_t>(), trie.mask, trie.nentries, trie.level1() };
+    DcTrie T = { d_trie_edge.as<HdEdge>(), d_trie_id.as<int32_t>(), trie.mask, trie.nentries, trie.level1() };
     if (nsub) {
         CR_TRY(upload(b_subs, subs)); CR_TRY(upload(b_segs, segs)); CR_TRY(upload(b_chunk0, chunk0));
         CR_TRY(b_span.reserve(rawtotal + 16)); CR_TRY(b_hit.reserve(rawtotal * 4 + 16));
@@ -331,11 +335,19 @@ inline int Compressor::compress(const CrConfig& cfg, const uint8_t* in, uint64_t
     tm.begin(stream);
     CR_TRY(dicpick(in, d_raw.as<uint8_t>(), n, text));
     if (tm.enabled) { CR_CUDA(cudaStreamSynchronize(stream)); tm.finish(); }
+    auto th0 = std::chrono::steady_clock::now();
+    auto hlap = [&](const char* what) {
+        if (!getenv("CRGPU_TIMING")) return;
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "crgpu timing: %-16s %.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - th0).count());
+        th0 = t1;
+    };
     CR_TRY(load_dictionary(text));
-    std::vector<uint8_t> lcp = hd_lcp_encode(text);
+    hlap("trie load+upload");
+    std::vector<uint8_t> lcp;                  // front-coded dictionary text (made by whoever encodes it: the helper thread, or below)
     chain->flexible = cfg.flexible != 0;       // flexible_parsing is a process-wide switch: it also applies to the dictionary payload
     std::vector<BlockIO> dblk(1);
-    memset(&dblk[0], 0, sizeof(BlockIO)); dblk[0].size = (uint32_t)lcp.size();
+    memset(&dblk[0], 0, sizeof(BlockIO));
     size_t out_pos = 0, wrote = 0, dict_wrote = 0;
     bool dict_async = false;
 #ifndef CRGPU_SIM
@@ -359,6 +371,7 @@ inline int Compressor::compress(const CrConfig& cfg, const uint8_t* in, uint64_t
             dict_rc = [&]() -> int {
                 CR_CUDA(cudaSetDevice(dev));
                 g_cr_alloc_stream = dict_stream; g_cr_alloc_async = true;
+                lcp = hd_lcp_encode(text); dblk[0].size = (uint32_t)lcp.size();
                 CR_TRY(dict_chain->upload(d_dic, lcp));
                 CR_TRY(dict_chain->reset_models());
                 size_t w = 0;
@@ -372,12 +385,14 @@ inline int Compressor::compress(const CrConfig& cfg, const uint8_t* in, uint64_t
     struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{dict_thread};      // every return path waits for the helper
 #endif
     if (!dict_async) {
+        lcp = hd_lcp_encode(text); dblk[0].size = (uint32_t)lcp.size();
         CR_TRY(upload(d_dic, lcp));
         CR_TRY(chain->reset_models());
         CR_TRY(chain->encode_blocks(d_dic.as<uint8_t>(), dblk, 0, true, d_out, out_pos, wrote));
         out_pos += wrote;
     }
     CR_TRY(chain->reset_models());
+    hlap("dict chain start");
 
     // ---- data blocks, window by window.  A trailing empty block appears when n % block_size == 0 (F8).
     const uint64_t nblocks = n / cfg.block_size + 1;
@@ -431,6 +446,7 @@ inline int Compressor::compress(const CrConfig& cfg, const uint8_t* in, uint64_t
         }
         out_pos += wrote;
     }
+    hlap("data windows");
 #ifndef CRGPU_SIM
     if (dict_async) {
         dict_thread.join();
@@ -442,6 +458,7 @@ inline int Compressor::compress(const CrConfig& cfg, const uint8_t* in, uint64_t
     if (mlen + dict_wrote + out_pos > out_cap) return CRGPU_ERR_ARG;
     CR_CUDA(cudaMemcpyAsync(out + mlen + dict_wrote, d_out.p, out_pos, cudaMemcpyDeviceToHost, stream));
     CR_CUDA(cudaStreamSynchronize(stream));
+    hlap("d2h");
     *out_n = mlen + dict_wrote + out_pos;
     return CRGPU_OK;
 }

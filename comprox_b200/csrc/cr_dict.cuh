@@ -11,6 +11,7 @@
 //          scan of the per-position code sizes.
 #pragma once
 #include "cr_common.cuh"
+#include "cr_hostdict.h"
 
 // ------------------------------------------------------------------ dicpick
 #define DP_CHUNK      200000u            // fread granularity of the reference tokenizer (cr-dicpick.c:162)
@@ -136,22 +137,33 @@ __global__ void k_dp_rebuild(DpTable A, DpTable B, uint32_t threshold) {
     }
 }
 
-struct DpEntry { uint32_t first, count; };
-__global__ void k_dp_collect(DpTable T, DpEntry* __restrict__ out, uint32_t cap) {
+// a selected word leaves the device complete: first position, count, and its letters (first letter lower-cased, at most 20, zero padded)
+// as three big-endian 64-bit keys -- what HdWord::set (cr_hostdict.h) used to fetch from the host copy of the input, one cache miss per word
+struct DpEntry { uint32_t first, count; unsigned long long k[3]; uint32_t len, pad; };
+__global__ void k_dp_collect(DpTable T, const uint8_t* __restrict__ in, uint64_t n, DpEntry* __restrict__ out, uint32_t cap) {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= DP_SLOTS || T.key[s] == 0ull || T.count[s] <= 5) return;      // WORD_MIN_FREQ (:221)
     uint32_t i = atomicAdd(&T.stats[2], 1u);
-    if (i < cap) { out[i].first = T.first[s]; out[i].count = T.count[s]; }
+    if (i >= cap) return;
+    const uint64_t first = T.first[s];
+    uint8_t w[24];
+    for (int q = 0; q < 24; q++) w[q] = 0;
+    w[0] = (uint8_t)(in[first] | 32);
+    uint32_t len = 1;
+    for (uint64_t x = first + 1; x < n && in[x] >= 'a' && in[x] <= 'z' && len < 20; x++) w[len++] = in[x];      // copyword, cr-dicpick.c:88-94
+    DpEntry e; e.first = (uint32_t)first; e.count = T.count[s]; e.len = len; e.pad = 0;
+    for (int q = 0; q < 3; q++) { unsigned long long v = 0; for (int b = 0; b < 8; b++) v = v << 8 | w[q * 8 + b]; e.k[q] = v; }
+    out[i] = e;
 }
 
 // ------------------------------------------------------------------ diccode
 #define DC_SUB 1000000u                  // sub-chunk size (cr-diccode.c:177-180)
 
-struct DcTrie { const uint32_t* ekey; const uint32_t* eval; const int32_t* id; uint32_t mask; int32_t nentries; int32_t level1; };
+struct DcTrie { const HdEdge* edge; const int32_t* id; uint32_t mask; int32_t nentries; int32_t level1; };
 // child of `node` along byte `ch` (0 = none); same table as HdTrie (cr_hostdict.h)
 CR_D uint32_t dc_child(const DcTrie& T, uint32_t node, uint32_t ch) {
     const uint32_t key = ((node << 7) | ch) + 1;
-    for (uint32_t h = (key * 2654435761u) >> 8;; h++) { const uint32_t k = T.ekey[h & T.mask]; if (k == key) return T.eval[h & T.mask]; if (k == 0) return 0; }
+    for (uint32_t h = (key * 2654435761u) >> 8;; h++) { const HdEdge e = T.edge[h & T.mask]; if (e.key == key) return e.val; if (e.key == 0) return 0; }
 }
 struct DcSub {                           // one sub-chunk = one chain segment
     uint64_t off;                        // offset of the sub-chunk in the raw window

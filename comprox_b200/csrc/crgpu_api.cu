@@ -419,7 +419,7 @@ extern "C" int crgpu_dictionary_load(crgpu_handle* h, const char* dicstr, int in
 // dictionary_encode(ib, ob) -- src/cr-diccode.c:142-221
 extern "C" int crgpu_dictionary_encode(crgpu_handle* h, const uint8_t* in, uint32_t n, uint8_t* out, uint64_t out_cap, uint32_t* out_n) {
     if (!h || (n && !in) || !out || !out_n) return CRGPU_ERR_ARG;
-    if (!h->comp.d_trie_key.p) return CRGPU_ERR_ARG;                                         // crgpu_dictionary_load(.., 1) first
+    if (!h->comp.d_trie_edge.p) return CRGPU_ERR_ARG;                                         // crgpu_dictionary_load(.., 1) first
     CR_SET_DEVICE(h);
     h->comp.chain = &h->chain; h->comp.stream = h->chain.stream;
     CR_TRY(h->comp.stage(in, n));

@@ -99,7 +99,7 @@ static inline unsigned cr_div_up(size_t a, size_t b) { return (unsigned)((a + b 
 // A growable device buffer: keeps its allocation between calls so steady-state runs do no cudaMalloc.
 // Growth goes through the stream-ordered allocator (cudaMallocAsync / cudaFreeAsync on the stream the calling thread's handle works on,
 // bound by CR_SET_DEVICE): cudaFree synchronises the whole device, which stalled every other handle of a crgpu_compress_batch call each
-// time one of them met a larger container (mixed corpus, 8 handles: 9.7 s -> see profiles/round2_corpus.md).
+// time one of them met a larger container (mixed corpus, 8 handles: 9.7 s -> see profiles/round2_summary.md section 3).
 #ifndef CRGPU_SIM
 extern thread_local cudaStream_t g_cr_alloc_stream;
 extern thread_local bool g_cr_alloc_async;

@@ -70,7 +70,7 @@ __global__ void k_expand_side(const uint64_t* __restrict__ TS, uint32_t n, Tri* 
 //       exponent field of C is 1024 + e, whose low three bits ARE e & 7, so  hi' = (hi & 0x007FFFFF) | 0x41800000  (exponent field
 //       1048 + (e & 7), i.e. 2 * range' with range' in [2^24, 2^32)) is the whole renormalisation: one LOP3.  That is why the state
 //       carries the factor two: 1047 is not a multiple of eight, 1048 is.
-// Measured on B200: see profiles/round2_rcpar.md (the chain with the three-operation renormalisation: 39.1 cycles per symbol,
+// Measured on B200: see profiles/round2_summary.md (the chain with the three-operation renormalisation: 39.1 cycles per symbol,
 // profiles/round1_chain_latency.md).
 #define RC_DP_MAGIC 4503599627370495.5         /* 2^52 - 0.5 */
 #define RC_DP_TWO52 4503599627370496.0

@@ -3,7 +3,7 @@
 // Replaces the serial walk of `range` in range_encoder_encode (src/cr-rangecoder.c:60-70: range /= sum; range *= frq; renormalise)
 // for a whole (block, stream).  The recurrence  r' = norm(floor(r / sum) * frq)  cannot be speculated from a guessed state, but it
 // FORGETS: floor(r / sum) merges every r of one quotient bucket, so the image of ALL 2^32 - 2^24 possible states shrinks to a few
-// hundred values within some thousand symbols (measured on the text workload: ~60000 / sqrt(symbols), profiles/round2_rcpar.md).
+// hundred values within some thousand symbols (measured on the text workload: ~60000 / sqrt(symbols), profiles/round2_summary.md).
 // That makes the exit state of a piece of the stream a function of its entry state with a small, enumerable range:
 //
 //   plan    the stream is cut into jobs of ~T symbols; job c >= 1 starts at the symbol with the LARGEST sum near its nominal start
@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(32) k_rcp_resolve(RcpStream* ps, uint32_t nstr
 // Lane 0 runs the chain and nothing else: per symbol two dependent DFMA, one LOP3 on the high word and one 8-byte store of T (whose low
 // word is the quotient).  Records come from shared memory four symbols ahead; -(2^52 * 2 frq) is computed by the staging lanes; the
 // top-bit index is recomputed from T by all lanes afterwards (C = fma(T, 2 frq, nf) again, off the chain).  A full batch is straight-line
-// code.  Measured: profiles/round2_emit_loop.md.
+// code.  Measured: profiles/round2_summary.md section 1.
 enum { RCP_EMIT_JOBS = 0, RCP_EMIT_WHOLE = 1, RCP_EMIT_FIRST = 2 };
 CR_D void rcp_chain_step(double& R, const uint4 t, const double nf, double& T) {
     T = fma(R, rc_dp_join(t.y, t.x), RC_DP_MAGIC);

@@ -123,7 +123,7 @@ __global__ void k_rolz_match_main(const uint8_t* __restrict__ D, const LzBlock* 
 #ifndef CRGPU_SIM
 // Main-table search, second form (default on the GPU; same results as k_rolz_match_main, which stays as the definition the CPU
 // kernel-logic simulation runs).  What changed, and why (ncu on x86 / BMP data: the first form moves 6x its algorithmic bytes, nearly
-// all of them 32-byte sectors fetched for one byte of a candidate that then fails, profiles/round2_match.md):
+// all of them 32-byte sectors fetched for one byte of a candidate that then fails, profiles/round2_summary.md section 6):
 //   * a candidate is only worth touching if its first FIVE bytes equal ours (a match shorter than RZ_MINLEN never wins).  Byte 0 is the
 //     key's tag; bytes 1..4 are gathered once per sorted entry while the CTA stages its window of the sorted list in shared memory,
 //     so the filter runs on shared memory alone and the data is read only for candidates that are real matches;

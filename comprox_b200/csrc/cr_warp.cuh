@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(O2C_THREADS) k_o2_pass_cta(const uint32_t* __r
 // ------------------------------------------------------------------ o2 pass for HOT contexts, second form (default)
 // Same step as k_o2_pass_cta -- every quantity of ppm_encode is a start-of-step value plus a rank, the first event whose update would
 // rescale ends the step -- with the per-step latency cut (the hottest context is one chain of ~events / 200 steps and sets the time of the
-// whole pass, profiles/round2_o2_pass.md):
+// whole pass, profiles/round2_summary.md section 4):
 //   * the events of the next two steps sit in a shared-memory ring filled by cp.async two steps ahead: no global load on the chain;
 //   * ranks inside a warp come from eight ballots of the symbol bits (lanes with a smaller / the same symbol, lanes whose symbol is my
 //     predicted byte) instead of a 32-step shuffle loop;
@@ -1112,7 +1112,7 @@ __global__ void __launch_bounds__(O1C_THREADS) k_o1_pass_cta(const uint64_t* __r
 // ------------------------------------------------------------------ o1 pass for HOT ctx8 rows, split form (default)
 // k_o1_pass_cta spends ~1300 instructions per thread and step on the masked sums, and the hottest row (the context "space" of a text
 // holds more than half of all escapes) walks its steps one after the other on ONE SM while the others idle (ncu: sm__cycles_active
-// avg 66 K vs max 5.6 M, profiles/round2_o1_pass.md).  But the masked sums do not feed the chain: what carries from step to step is only
+// avg 66 K vs max 5.6 M, profiles/round2_summary.md section 5).  But the masked sums do not feed the chain: what carries from step to step is only
 // the row of counts and where it is halved, and that depends on the escapes' SYMBOLS alone.  So:
 //   k_o1_plan   per ctx8: its range of sorted escapes and where its step records start (bound: n/512 + n/127 + 2 steps);
 //   k_o1_skel   one CTA per hot row walks the steps -- symbols from a cp.async ring, ranks from ballots, per-warp counts by leader lanes,

@@ -14,7 +14,7 @@ thread_local crsim_dim3 threadIdx, blockIdx, blockDim, gridDim;
 unsigned long long g_cr_launches = 0;
 // Handles that share a GPU work on private streams, and a chain's serial range walk is one kernel that runs for tens to hundreds of
 // milliseconds.  With the default of 8 hardware work queues, streams alias onto the same queue and wait behind each other's long kernels
-// (measured: 24 shards, 8 handles: 3.8 s with 8 queues, 2.0 s with 32; profiles/round2_corpus.md).  The variable only counts before the
+// (measured: 24 shards, 8 handles: 3.8 s with 8 queues, 2.0 s with 32; profiles/round2_summary.md section 3).  The variable only counts before the
 // CUDA context exists, so it is set when the library is loaded -- unless the caller has chosen a value.
 __attribute__((constructor)) static void cr_more_work_queues() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
 thread_local cudaStream_t g_cr_alloc_stream = 0;

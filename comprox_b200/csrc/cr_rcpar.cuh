@@ -274,6 +274,7 @@ template <int THREADS, int K, int BATCH, bool DEDUP>
 __global__ void __launch_bounds__(THREADS) k_rcp_track(RcpStream* ps, RcpJob* jobs, const uint32_t* __restrict__ njobs_total,
                                                        const uint4* __restrict__ cin_main, const uint4* __restrict__ cin_side,
                                                        double* __restrict__ listA, double* __restrict__ E, double* __restrict__ F, int mode, RcpStats* __restrict__ stats) {
+    static_assert(THREADS >= BATCH, "one record per thread and batch");
     extern __shared__ double sbuf[];                 // DEDUP: THREADS * K doubles for the compaction
     __shared__ RcpRecA sa[BATCH + 1];
     __shared__ double sn[BATCH + 1];
@@ -309,6 +310,7 @@ __global__ void __launch_bounds__(THREADS) k_rcp_track(RcpStream* ps, RcpJob* jo
 #pragma unroll
     for (int k = 0; k < K; k++) { const uint32_t i = tid * K + k; d[k] = in ? in[i < n ? i : n - 1] : RC_DP_R0; }
     unsigned long long work = 0;
+    uint32_t batches = 0;
     const uint4 idle = make_uint4(0, 0x3FE00000u, 0, 0x40000000u);
     uint4 nxt = idle;
     if (tid <= BATCH && pos + tid < end) nxt = cin[pos + tid];
@@ -324,7 +326,11 @@ __global__ void __launch_bounds__(THREADS) k_rcp_track(RcpStream* ps, RcpJob* jo
             if (lane == 0) work += (unsigned long long)nb * (n - tid * K < 32u * K ? n - tid * K : 32u * K);
         }
         pos += nb;
-        if (DEDUP) {
+        batches++;
+        // merged states are dropped after every batch while the list still has to shrink (MID), otherwise after every fourth batch and
+        // at the end: the compaction (a block-wide scan and a trip through shared memory) costs as much as a batch of 128 symbols, and
+        // a set that is already small loses elements slowly (~1 / sqrt(symbols))
+        if (DEDUP && (mode == RCP_MODE_MID || (batches & 3u) == 0 || pos >= end)) {
             // drop every element equal to its predecessor (or, wrapping around, to element 0); order is kept
             if (lane == 31) slast[w] = d[K - 1];
             if (tid == 0) sfirst = d[0];
@@ -566,7 +572,10 @@ struct RcPar {
         CR_LAUNCH(k_rcp_emit, gemit, dim3(128), stream, ps, nstreams, jobs, nj, cin_main, cin_side, q_main, sh_main, q_side, sh_side, (int)RCP_EMIT_FIRST, E, st);
         if (!serial) {
         if (late_cfg == 1) { RCP_TRACK(256, 8, 128, true, 2048 * 8, RCP_MODE_LATE); RCP_TRACK(256, 8, 128, false, 0, RCP_MODE_FOLLOW); }
-        else { RCP_TRACK(512, 4, 128, true, 2048 * 8, RCP_MODE_LATE); RCP_TRACK(512, 4, 128, false, 0, RCP_MODE_FOLLOW); }
+        else if (late_cfg == 2) { RCP_TRACK(128, 16, 128, true, 2048 * 8, RCP_MODE_LATE); RCP_TRACK(128, 16, 128, false, 0, RCP_MODE_FOLLOW); }
+        else if (late_cfg == 3) { RCP_TRACK(256, 8, 256, true, 2048 * 8, RCP_MODE_LATE); RCP_TRACK(256, 8, 256, false, 0, RCP_MODE_FOLLOW); }
+        else if (late_cfg == 4) { RCP_TRACK(512, 4, 128, true, 2048 * 8, RCP_MODE_LATE); RCP_TRACK(512, 4, 128, false, 0, RCP_MODE_FOLLOW); }
+        else { RCP_TRACK(256, 8, 256, true, 2048 * 8, RCP_MODE_LATE); RCP_TRACK(256, 8, 256, false, 0, RCP_MODE_FOLLOW); }
         CR_LAUNCH(k_rcp_resolve, dim3(nstreams), dim3(32), stream, ps, nstreams, jobs, E, F);
         CR_LAUNCH(k_rcp_emit, gemit, dim3(128), stream, ps, nstreams, jobs, nj, cin_main, cin_side, q_main, sh_main, q_side, sh_side, (int)RCP_EMIT_JOBS, E, st);
         }

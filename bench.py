@@ -470,10 +470,10 @@ def decompress_leg(args, L, api, torch, raw, local_rank, peak):
 # algorithmic bytes of a stage per step, from the step's counters; the kernel that dominates the stage
 STAGE_MODEL = {
     "range_chain": ("k_rcp_track / k_rcp_seed / k_rcp_emit (cr_rcpar.cuh)", lambda c, n, cb: 12.0 * c["triples"] + cb),
-    "o2": ("k_o2_pass_cta (+ 16-bit radix sort of the events)", lambda c, n, cb: 20.0 * c["events"]),
-    "o1": ("k_o1_pass_cta (+ 64-bit radix sorts of the escapes)", lambda c, n, cb: 20.0 * c["escapes"]),
+    "o2": ("k_o2_skel / k_o2_eval / k_o2_pass_warp (+ 16-bit radix sort of the events)", lambda c, n, cb: 20.0 * c["events"]),
+    "o1": ("k_o1_skel / k_o1_eval / k_o1_pass_warp (+ 64-bit radix sorts of the escapes)", lambda c, n, cb: 20.0 * c["escapes"]),
     "o3": ("k_o3_hot_spec / k_o3_pass_sorted (+ 22-bit radix sort)", lambda c, n, cb: 20.0 * c["events"]),
-    "match": ("k_rolz_match_main (+ two radix sorts of the positions)", lambda c, n, cb: 0.36 * n + 8.0 * 0.36 * n),
+    "match": ("k_rolz_match_main2 (+ two radix sorts of the positions)", lambda c, n, cb: 0.36 * n + 8.0 * 0.36 * n),
     "diccode": ("k_dc_spans + skip-chain walk", lambda c, n, cb: 1.36 * n),
     "dp_kernels": ("k_dp_count / k_dp_verify", lambda c, n, cb: 2.0 * n),
 }
@@ -609,9 +609,9 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": kern, "stage": dom, "achieved": round(achieved, 3), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                          "frac": round(achieved / peak, 6), "traffic": traffic,
-                         "traffic_source": None if traffic is None else "ncu --set full captures, bytes per unit x units of this launch (profiles/round2_ncu_traffic.json)",
+                         "traffic_source": None if traffic is None else "ncu (dram__bytes_read.sum + dram__bytes_write.sum of every kernel of the stage, one launch each), bytes per unit x units of this step (profiles/round2_ncu_traffic.json)",
                          "algorithmic_bytes": int(alg), "launch_ms": round(stage_ms[dom], 2),
-                         "note": "the stage of the step with the largest CUDA-event time; a context-serial replay: latency bound, see DESIGN.md section 5"},
+                         "note": "the stage of the step with the largest CUDA-event time; bound by FP64 issue (tracking) and DFMA latency (serial emits), not by HBM: see DESIGN.md section 5"},
             "pipeline_roofline": {"achieved_gbs": round(pipe_gbs, 3), "frac": round(pipe_gbs / peak, 6), "algorithmic_bytes": "raw + container (SURVEY.md 8d)"},
             "stage_ms_per_step": {k: round(v, 2) for k, v in stage_ms.items()},
             "counters_per_step": {k: int(v) for k, v in counters.items()},

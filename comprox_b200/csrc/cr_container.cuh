@@ -36,6 +36,13 @@ struct Compressor {
     // therefore runs on a second LzChain (own models, own buffers, own stream, driven by a helper thread) beside the data blocks: its
     // range walk -- fresh models, small sums, nothing to cut: ~200 000 symbols one after the other, 2.6 ms -- no longer stands in front
     // of them.  dict_mode 0 turns this off (the payload is then coded on the main chain first, as before).
+    // the input arrives in pieces on a copy stream; the word count of a piece starts when the piece (and the one behind it: a word may
+    // straddle the border) has landed, so the H2D copy hides behind k_dp_count instead of standing in front of it
+#ifndef CRGPU_SIM
+    cudaStream_t copy_stream = 0;
+    std::vector<cudaEvent_t> copy_ev;
+#endif
+    uint64_t copy_chunk = 0;                // 0: the input is resident as a whole (no events to wait for)
     LzChain* dict_chain = nullptr;
     cudaStream_t dict_stream = 0;
     DevBuf d_dictout;
@@ -50,6 +57,9 @@ struct Compressor {
         if (dict_chain) { dict_chain->release(); delete dict_chain; dict_chain = nullptr; }
 #ifndef CRGPU_SIM
         if (dict_stream) { cudaStreamDestroy(dict_stream); dict_stream = 0; }
+        if (copy_stream) { cudaStreamDestroy(copy_stream); copy_stream = 0; }
+        for (cudaEvent_t e : copy_ev) cudaEventDestroy(e);
+        copy_ev.clear();
 #endif
     }
     template <class T> int upload(DevBuf& b, const std::vector<T>& v) { return chain->upload(b, v); }
@@ -80,6 +90,17 @@ inline int Compressor::dicpick(const uint8_t* h_in, const uint8_t* d_in, uint64_
     CR_CUDA(cudaMemsetAsync(t_stats.p, 0, 64, stream));
     DpTable T = { t_key.as<unsigned long long>(), t_count.as<uint32_t>(), t_first.as<uint32_t>(), t_stats.as<uint32_t>() };
     const uint64_t step = 1ull << 30;
+#ifndef CRGPU_SIM
+    if (copy_chunk) {
+        const uint64_t nchunks = (n + copy_chunk - 1) / copy_chunk;
+        for (uint64_t c = 0; c < nchunks; c++) {
+            CR_CUDA(cudaStreamWaitEvent(stream, copy_ev[c + 1 < nchunks ? c + 1 : c], 0));
+            const uint64_t x0 = c * copy_chunk, x1 = x0 + copy_chunk < n ? x0 + copy_chunk : n;
+            CR_LAUNCH(k_dp_count, dim3(cr_div_up(x1 - x0, 256)), dim3(256), stream, d_in, n, x0, x1, T);
+        }
+        copy_chunk = 0;
+    } else
+#endif
     for (uint64_t x0 = 0; x0 < n; x0 += step) {
         uint64_t x1 = x0 + step < n ? x0 + step : n;
         CR_LAUNCH(k_dp_count, dim3(cr_div_up(x1 - x0, 256)), dim3(256), stream, d_in, n, x0, x1, T);
@@ -324,10 +345,27 @@ inline int Compressor::compress(const CrConfig& cfg, const uint8_t* in, uint64_t
     // ---- whole input to HBM
     const bool staged = staged_ptr == in && staged_n == n && d_raw.p != nullptr && !cfg.filt;   // filters modify d_raw in place
     staged_ptr = nullptr;
+    copy_chunk = 0;
     if (!staged) {
         CR_TRY(d_raw.reserve(n + 256));
-        if (n) CR_CUDA(cudaMemcpyAsync(d_raw.p, in, n, cudaMemcpyHostToDevice, stream));
         CR_CUDA(cudaMemsetAsync(d_raw.as<uint8_t>() + n, 0, 128, stream));
+#ifndef CRGPU_SIM
+        const uint64_t CH = 16ull << 20;
+        if (n > 2 * CH) {
+            if (!copy_stream) CR_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+            const uint64_t nchunks = (n + CH - 1) / CH;
+            while (copy_ev.size() < nchunks + 1) { cudaEvent_t e; CR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); copy_ev.push_back(e); }
+            CR_CUDA(cudaEventRecord(copy_ev[nchunks], stream));                 // the buffer exists (stream-ordered allocation) and nothing reads it any more
+            CR_CUDA(cudaStreamWaitEvent(copy_stream, copy_ev[nchunks], 0));
+            for (uint64_t c = 0; c < nchunks; c++) {
+                const uint64_t x0 = c * CH, len = x0 + CH < n ? CH : n - x0;
+                CR_CUDA(cudaMemcpyAsync(d_raw.as<uint8_t>() + x0, in + x0, len, cudaMemcpyHostToDevice, copy_stream));
+                CR_CUDA(cudaEventRecord(copy_ev[c], copy_stream));
+            }
+            copy_chunk = CH;
+        } else
+#endif
+        if (n) CR_CUDA(cudaMemcpyAsync(d_raw.p, in, n, cudaMemcpyHostToDevice, stream));
     }
 
     // ---- static dictionary: build, load, emit as its own model chain (src/main.c:156-172)

@@ -83,8 +83,13 @@ int crgpu_compress(crgpu_handle* h, const crgpu_config* cfg, const uint8_t* in, 
  * per handle inside the call, containers dealt to whichever handle is idle; what `xargs -P` over the reference CLI does with host
  * cores.  All handles must be of one variant; they may sit on different devices (the multi-GPU form: no data-path collective, every
  * container goes straight from its GPU to outs[i]) or share a device on private streams (CRGPU_OWN_STREAM), where the serial range
- * chains of different containers overlap.  outs[i] / out_lens[i] receive container i, exactly the bytes crgpu_compress gives for
- * ins[i]; out_caps[i] >= crgpu_compress_bound(in_lens[i], cfg->block_size).  Returns the first error. */
+ * chains of different containers overlap.  With three or more handles on one device (and as many containers) the range chains are
+ * walked serially instead of cut into jobs -- one warp each, they overlap each other and all other work, where the tracking kernels
+ * of the cut chain fill the device; "rc_serial" (crgpu_set_option) overrides the choice.  Handles that share a device need their own
+ * hardware work queues: the library sets CUDA_DEVICE_MAX_CONNECTIONS=32 when it is loaded unless the variable is already set; a host
+ * program that creates its CUDA context BEFORE loading the library must export it itself.  outs[i] / out_lens[i] receive container
+ * i, exactly the bytes crgpu_compress gives for ins[i]; out_caps[i] >= crgpu_compress_bound(in_lens[i], cfg->block_size).  Returns
+ * the first error. */
 int crgpu_compress_batch(crgpu_handle* const* hs, uint32_t nhandles, const crgpu_config* cfg, uint32_t count,
                          const uint8_t* const* ins, const uint64_t* in_lens, uint8_t* const* outs, const uint64_t* out_caps, uint64_t* out_lens);
 
@@ -191,7 +196,12 @@ int crgpu_debug_rc_parallel(crgpu_handle* h, const uint32_t* frq, const uint32_t
  * kernel-logic simulation checks) instead of the warp-cooperative ones; results are identical.
  * "exact_aborts" = 0 turns the exact replay of mid-chain "cannot compress" blocks off (CRGPU_ERR_MIDCHAIN_ABORT instead).
  * "flexible" = the reference's global flexible_parsing (-f) for crgpu_lzencode (crgpu_compress takes it from its
- * config); "match_limit" = comprox -m. */
+ * config); "match_limit" = comprox -m.
+ * Formulation switches (every setting gives the same bytes; the defaults are the measured best, profiles/round2_summary.md):
+ * "rc_variant" 1..8 (8 = range chain cut into jobs), "rc_serial" -1 / 0 / 1 (automatic / always cut / one serial job per stream),
+ * "rc_job_symbols", "rc_late_cfg"; "o2_hot_variant" 1..3 and "o1_hot_variant" 1..2 (hot-context passes: 3 / 2 = chain of steps +
+ * parallel evaluation); "rolz_match_variant" 1..2; "dict_mode" 0 / 1 (1 = the dictionary payload is coded by a second model chain
+ * beside the data blocks). */
 int crgpu_set_option(crgpu_handle* h, const char* name, int64_t value);
 
 /* Stage timing (CUDA events on the handle's stream, accumulated over calls until reset).

@@ -77,6 +77,60 @@ __global__ void k_dp_count(const uint8_t* __restrict__ in, uint64_t n, uint64_t 
     }
     atomicOr(&T.stats[1], 1u);
 }
+#ifndef CRGPU_SIM
+// The same count with the hot words taken off the device-wide table: a CTA tokenizes a tile of DPS_TILE bytes, 256 positions per round;
+// the lanes of a warp that found the same word in a round are found with __match_any_sync and entered once (multiplicity = popcount,
+// first position = the lowest lane's); the tile's words are counted in a shared-memory open-addressing table and only the table's
+// distinct entries go to the global table -- one CAS / add / min per (tile, distinct word) instead of one per occurrence ("the" alone
+// is half a million serialised L2 atomics on a 100 MiB text).  A word that finds no slot within DPS_PROBES probes goes to the global
+// table directly.  Counts and first positions are sums and minima: the result does not depend on the order.
+#define DPS_TILE   16384u
+#define DPS_SLOTS  2048u
+#define DPS_PROBES 12u
+CR_D void dp_global_add(DpTable T, unsigned long long h, uint32_t count, uint32_t first) {
+    uint32_t slot = (uint32_t)h & (DP_SLOTS - 1);
+    for (uint32_t probe = 0; probe < DP_SLOTS; probe++) {
+        unsigned long long prev = atomicCAS(&T.key[slot], 0ull, h);
+        if (prev == 0ull) {
+            if (atomicAdd(&T.stats[0], 1u) + 1 >= DP_MAXWORDS) atomicOr(&T.stats[1], 1u);
+            prev = h;
+        }
+        if (prev == h) { atomicAdd(&T.count[slot], count); atomicMin(&T.first[slot], first); return; }
+        slot = (slot + 1) & (DP_SLOTS - 1);
+    }
+    atomicOr(&T.stats[1], 1u);
+}
+__global__ void __launch_bounds__(256) k_dp_count_tiles(const uint8_t* __restrict__ in, uint64_t n, uint64_t x0, uint64_t x1, DpTable T) {
+    __shared__ unsigned long long skey[DPS_SLOTS];
+    __shared__ uint32_t scount[DPS_SLOTS], sfirst[DPS_SLOTS];
+    for (uint32_t i = threadIdx.x; i < DPS_SLOTS; i += 256) { skey[i] = 0ull; scount[i] = 0; sfirst[i] = 0xFFFFFFFFu; }
+    __syncthreads();
+    const uint64_t tbase = x0 + (uint64_t)blockIdx.x * DPS_TILE;
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint32_t j = 0; j < DPS_TILE / 256; j++) {
+        const uint64_t x = tbase + j * 256 + threadIdx.x;
+        unsigned long long h = 0ull;
+        const bool word = x < x1 && dp_word_at(in, n, x, &h) != 0;
+        // lanes of this warp with the same word (lanes without a word carry distinct dummies: their own lane number, never a hash...
+        // a real hash below 32 would only merge the group with a lane that is masked out below)
+        const unsigned long long tag = word ? h : (unsigned long long)lane;
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, tag) & __ballot_sync(0xFFFFFFFFu, word);
+        if (word && lane == (uint32_t)(__ffs(peers) - 1)) {
+            const uint32_t mult = __popc(peers);
+            uint32_t slot = (uint32_t)(h >> 21) & (DPS_SLOTS - 1), probe = 0;
+            for (; probe < DPS_PROBES; probe++) {
+                unsigned long long prev = atomicCAS(&skey[slot], 0ull, h);
+                if (prev == 0ull || prev == h) { atomicAdd(&scount[slot], mult); atomicMin(&sfirst[slot], (uint32_t)x); break; }
+                slot = (slot + 1) & (DPS_SLOTS - 1);
+            }
+            if (probe == DPS_PROBES) dp_global_add(T, h, mult, (uint32_t)x);
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < DPS_SLOTS; i += 256) if (skey[i] != 0ull) dp_global_add(T, skey[i], scount[i], sfirst[i]);
+}
+#endif
+
 // every occurrence must spell the same word as the table entry's first occurrence (hash collisions are loud)
 __global__ void k_dp_verify(const uint8_t* __restrict__ in, uint64_t n, uint64_t x0, uint64_t x1, DpTable T) {
     uint64_t x = x0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -689,6 +689,8 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
                     timer.count("#rcp_max_exit_set", rcpar.last.max_e);
                     timer.count("#rcp_steps_seed", (double)rcpar.last.phase_steps[0]); timer.count("#rcp_steps_mid", (double)rcpar.last.phase_steps[1]);
                     timer.count("#rcp_steps_late", (double)rcpar.last.phase_steps[2]); timer.count("#rcp_steps_follow", (double)rcpar.last.phase_steps[3]);
+                    timer.count("#rcp_decided_serial", rcpar.last.decided_serial); timer.count("#rcp_pilot_jobs", rcpar.last.pilot_jobs);
+                    timer.count("#rcp_est_steps", (double)rcpar.last.est_steps); timer.count("#rcp_serial_equiv", (double)rcpar.last.serial_equiv);
                 }
             }
             else if (rc_variant == 7) CR_LAUNCH(k_range_chain<7>, gchain, dim3(128), stream, b_cinm.as<uint4>(), b_cins.as<uint4>(), b_escord.as<uint32_t>(),

@@ -43,7 +43,23 @@ struct RcpJob {
     uint32_t next, prev;                      // neighbouring live jobs of the stream (k_rcp_links)
     double entry;                             // true state on entry (phase C)
 };
-struct RcpStats { unsigned long long state_steps; uint32_t live_jobs, merged_jobs, seed_retries, demoted_jobs, flagged_streams, max_e; unsigned long long phase_steps[4]; };   // phase_steps: seed, mid, late, follow
+struct RcpStats { unsigned long long state_steps; uint32_t live_jobs, merged_jobs, seed_retries, demoted_jobs, flagged_streams, max_e; unsigned long long phase_steps[4];   // phase_steps: seed, mid, late, follow
+                  uint32_t decided_serial, pilot_jobs; unsigned long long est_steps, serial_equiv; };
+
+// The cut pays only while the tracked sets are small: the tracking passes step every possible state through every symbol (twice), and
+// their cost does not shrink with the number of jobs -- x86-256M: ~2000 states x 220 M symbols x 2 = 330 ms against 205 ms for the 16
+// serial walks side by side; BMP through the LZP coder: worse.  So one job in RCP_PILOT_EVERY is seeded and tracked first (the pilot),
+// k_rcp_decide extrapolates the cost of the whole cut from what the pilot spent and what it left, compares it with the serial walk of the
+// longest stream (state steps per second of the tracking kernels x seconds per symbol of the walk), and either lets the other jobs
+// follow or turns every stream into one serial job.  phase: 0 = pilot jobs, 1 = the others (nothing if the decision was "serial").
+#define RCP_PILOT_EVERY   16u
+#define RCP_STEPS_PER_SYM 41300ull      // 2.7e12 state steps per second (tracking kernels, text-100M) x 15.3 ns per symbol (serial walk)
+CR_D bool rcp_is_pilot(const RcpStream& P, uint32_t j) { return ((j - P.first_job) & (RCP_PILOT_EVERY - 1)) == RCP_PILOT_EVERY / 2; }
+CR_D bool rcp_phase_skips(const RcpStream& P, uint32_t j, int phase, const RcpStats* stats) {
+    if (phase == 2) return false;                                      // no pilot in this run: every job at once
+    if (phase == 0) return !rcp_is_pilot(P, j);
+    return rcp_is_pilot(P, j) || ((volatile const RcpStats*)stats)->decided_serial != 0;
+}
 
 // one symbol on one state: two dependent DFMA and one LOP3 (rc_dp_step, cr_rc.cuh, without the outputs)
 CR_D void rcp_step(double& R, const double inv, const double f, const double nf) {
@@ -191,7 +207,7 @@ template <int THREADS> CR_D uint32_t rcp_block_scan(uint32_t v, uint32_t* __rest
 __global__ void __launch_bounds__(RCP_SEED_THREADS) k_rcp_seed(const RcpStream* __restrict__ ps, RcpJob* jobs, const uint32_t* __restrict__ njobs_total,
                                                                const Tri* __restrict__ dense_main, const Tri* __restrict__ dense_side,
                                                                const uint4* __restrict__ cin_main, const uint4* __restrict__ cin_side,
-                                                               double* __restrict__ listA, RcpStats* __restrict__ stats) {
+                                                               double* __restrict__ listA, int phase, RcpStats* __restrict__ stats) {
     __shared__ RcpRecA sa[RCP_SMAX + 1];
     __shared__ double sn[RCP_SMAX + 1];
     __shared__ uint32_t swarp[32];
@@ -200,7 +216,7 @@ __global__ void __launch_bounds__(RCP_SEED_THREADS) k_rcp_seed(const RcpStream* 
     if (j >= *njobs_total) return;
     const RcpJob J = jobs[j];
     const RcpStream P = ps[J.stream];
-    if (P.flags || J.status != RCP_LIVE || j == P.first_job) return;
+    if (P.flags || J.status != RCP_LIVE || j == P.first_job || rcp_phase_skips(P, j, phase, stats)) return;
     uint32_t nextj;
     const unsigned long long end = rcp_job_end(P, jobs, j, &nextj);
     if (nextj == RCP_NONE) return;                                  // last live job of its stream: nobody needs its exit set
@@ -273,7 +289,7 @@ enum { RCP_MODE_MID = 0, RCP_MODE_LATE = 1, RCP_MODE_FOLLOW = 2 };
 template <int THREADS, int K, int BATCH, bool DEDUP>
 __global__ void __launch_bounds__(THREADS) k_rcp_track(RcpStream* ps, RcpJob* jobs, const uint32_t* __restrict__ njobs_total,
                                                        const uint4* __restrict__ cin_main, const uint4* __restrict__ cin_side,
-                                                       double* __restrict__ listA, double* __restrict__ E, double* __restrict__ F, int mode, RcpStats* __restrict__ stats) {
+                                                       double* __restrict__ listA, double* __restrict__ E, double* __restrict__ F, int mode, int phase, RcpStats* __restrict__ stats) {
     static_assert(THREADS >= BATCH, "one record per thread and batch");
     extern __shared__ double sbuf[];                 // DEDUP: THREADS * K doubles for the compaction
     __shared__ RcpRecA sa[BATCH + 1];
@@ -290,7 +306,7 @@ __global__ void __launch_bounds__(THREADS) k_rcp_track(RcpStream* ps, RcpJob* jo
     const bool first_job = j == P.first_job;
     const double* in; uint32_t n; unsigned long long pos, end;
     if (mode == RCP_MODE_MID) {
-        if (first_job || J.count <= RCP_CAP_E) return;
+        if (first_job || rcp_phase_skips(P, j, phase, stats) || J.count <= RCP_CAP_E) return;
         uint32_t nextj;
         end = rcp_job_end(P, jobs, j, &nextj);
         if (nextj == RCP_NONE) return;
@@ -501,6 +517,55 @@ __global__ void __launch_bounds__(128) k_rcp_emit(RcpStream* ps, uint32_t nstrea
     else if (which == RCP_EMIT_JOBS && nextj != RCP_NONE && !rcp_same(R, jobs[nextj].entry)) atomicOr(&ps[sidx].flags, 64u);   // the jobs do not link up
 }
 
+// ---- decide (one CTA): see RCP_PILOT_EVERY above
+__global__ void __launch_bounds__(256) k_rcp_decide(const RcpStream* __restrict__ ps, uint32_t nstreams, RcpJob* jobs, const uint32_t* __restrict__ njobs_total, uint32_t job_symbols, RcpStats* __restrict__ stats) {
+    __shared__ unsigned long long s_sum, s_total, s_longest; __shared__ uint32_t s_pilots, s_alive, s_serial;
+    if (threadIdx.x == 0) { s_sum = 0; s_total = 0; s_longest = 0; s_pilots = 0; s_alive = 0; s_serial = 0; }
+    __syncthreads();
+    const uint32_t nj = *njobs_total;
+    for (uint32_t j = threadIdx.x; j < nj; j += 256) {
+        const RcpJob J = jobs[j];
+        const RcpStream P = ps[J.stream];
+        if (P.flags || j == P.first_job || !rcp_is_pilot(P, j)) continue;
+        atomicAdd(&s_pilots, 1u);
+        // the average size of the set the tracking passes will carry through this job.  The set shrinks roughly as 1 / sqrt(symbols
+        // behind the seed) (profiles/round2_summary.md section 0): it had `count` states `t` symbols behind the seed, so over a job of
+        // T symbols it averages count * 2 sqrt(t / T) (at most count).  A job without a usable seed counts as a full set.
+        uint32_t left = RCP_CAP_E;
+        if (J.status == RCP_LIVE && J.count > 0) {
+            atomicAdd(&s_alive, 1u);
+            const uint32_t c = J.count < RCP_CAP_E ? J.count : RCP_CAP_E;
+            const float f = 2.0f * sqrtf((float)(J.pos - J.a + 1) / (float)job_symbols);
+            left = f < 1.0f ? (uint32_t)((float)c * f) + 1u : c;
+        }
+        atomicAdd(&s_sum, (unsigned long long)left);
+    }
+    for (uint32_t s = threadIdx.x; s < nstreams; s += 256) {
+        const RcpStream P = ps[s];
+        if (P.flags) continue;
+        atomicAdd(&s_total, P.i1 - P.i0);
+        atomicMax(&s_longest, P.i1 - P.i0);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        bool serial = false;
+        unsigned long long est = 0, ser = s_longest * RCP_STEPS_PER_SYM;
+        if (s_pilots >= 4) {                                           // (fewer: small windows, nothing to lose either way)
+            const unsigned long long spent = stats->phase_steps[0] + stats->phase_steps[1];
+            est = spent * RCP_PILOT_EVERY + 2ull * (s_sum / s_pilots) * s_total;
+            serial = est > ser || s_alive * 2 < s_pilots;
+        }
+        stats->decided_serial = serial ? 1u : 0u; stats->pilot_jobs = s_pilots; stats->est_steps = est; stats->serial_equiv = ser;
+        s_serial = serial ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_serial) return;
+    for (uint32_t j = threadIdx.x; j < nj; j += 256) {                 // one serial job per stream
+        const RcpStream P = ps[jobs[j].stream];
+        if (!P.flags && j != P.first_job && jobs[j].status == RCP_LIVE) jobs[j].status = RCP_MERGED;
+    }
+}
+
 // ---- prune: a stream whose live jobs leave a span longer than a third of the stream gains little from the cut and pays for the
 // tracking of the jobs around it (BMP data: sums below 2^14 almost everywhere, a handful of seeds survive): it becomes one serial job.
 __global__ void k_rcp_prune(const RcpStream* __restrict__ ps, uint32_t nstreams, RcpJob* jobs, int force_serial, RcpStats* __restrict__ stats) {
@@ -554,16 +619,25 @@ struct RcPar {
         CR_LAUNCH(k_rcp_plan, dim3(1), dim3(256), stream, d_streams, nstreams, d_escord, T, maxjobs, ps, jobs, nj);
         if (!serial) {
         CR_LAUNCH(k_rcp_bounds, dim3(cr_div_up((size_t)maxjobs * 32, 128)), dim3(128), stream, ps, jobs, nj, dense_main, dense_side, st);
-        CR_LAUNCH(k_rcp_seed, dim3(maxjobs), dim3(RCP_SEED_THREADS), stream, ps, jobs, nj, dense_main, dense_side, cin_main, cin_side, LA, st);
         if (!attr_done) {                            // per handle: a handle is bound to one device
             CR_CUDA(cudaFuncSetAttribute(k_rcp_track<512, 32, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * 32 * 8));
             attr_done = true;
         }
-#define RCP_TRACK(TH, KK, BB, DD, SMEM, MODE)                                                                                       \
+#define RCP_TRACK(TH, KK, BB, DD, SMEM, MODE, PHASE)                                                                                \
         do { __atomic_fetch_add(&g_cr_launches, 1ull, __ATOMIC_RELAXED);                                                             \
-             k_rcp_track<TH, KK, BB, DD><<<dim3(maxjobs), dim3(TH), (SMEM), stream>>>(ps, jobs, nj, cin_main, cin_side, LA, E, F, MODE, st); \
+             k_rcp_track<TH, KK, BB, DD><<<dim3(maxjobs), dim3(TH), (SMEM), stream>>>(ps, jobs, nj, cin_main, cin_side, LA, E, F, MODE, PHASE, st); \
              CR_CUDA(cudaGetLastError()); } while (0)
-        RCP_TRACK(512, 32, 16, true, 512 * 32 * 8, RCP_MODE_MID);
+        const bool pilot = serial_only < 0 && maxjobs >= 8 * RCP_PILOT_EVERY;       // "always cut" (rc_serial 0) and small windows: no pilot
+        if (pilot) {
+            CR_LAUNCH(k_rcp_seed, dim3(maxjobs), dim3(RCP_SEED_THREADS), stream, ps, jobs, nj, dense_main, dense_side, cin_main, cin_side, LA, 0, st);
+            RCP_TRACK(512, 32, 16, true, 512 * 32 * 8, RCP_MODE_MID, 0);
+            CR_LAUNCH(k_rcp_decide, dim3(1), dim3(256), stream, ps, nstreams, jobs, nj, T, st);
+            CR_LAUNCH(k_rcp_seed, dim3(maxjobs), dim3(RCP_SEED_THREADS), stream, ps, jobs, nj, dense_main, dense_side, cin_main, cin_side, LA, 1, st);
+            RCP_TRACK(512, 32, 16, true, 512 * 32 * 8, RCP_MODE_MID, 1);
+        } else {
+            CR_LAUNCH(k_rcp_seed, dim3(maxjobs), dim3(RCP_SEED_THREADS), stream, ps, jobs, nj, dense_main, dense_side, cin_main, cin_side, LA, 2, st);
+            RCP_TRACK(512, 32, 16, true, 512 * 32 * 8, RCP_MODE_MID, 2);
+        }
         CR_LAUNCH(k_rcp_prune, dim3(cr_div_up(nstreams, 64)), dim3(64), stream, ps, nstreams, jobs, 0, st);
         }
         CR_LAUNCH(k_rcp_links, dim3(cr_div_up(maxjobs, 128)), dim3(128), stream, ps, jobs, nj);
@@ -571,11 +645,11 @@ struct RcPar {
         // first jobs: their entry is known, the walk that emits them also yields their exit state
         CR_LAUNCH(k_rcp_emit, gemit, dim3(128), stream, ps, nstreams, jobs, nj, cin_main, cin_side, q_main, sh_main, q_side, sh_side, (int)RCP_EMIT_FIRST, E, st);
         if (!serial) {
-        if (late_cfg == 1) { RCP_TRACK(256, 8, 128, true, 2048 * 8, RCP_MODE_LATE); RCP_TRACK(256, 8, 128, false, 0, RCP_MODE_FOLLOW); }
-        else if (late_cfg == 2) { RCP_TRACK(128, 16, 128, true, 2048 * 8, RCP_MODE_LATE); RCP_TRACK(128, 16, 128, false, 0, RCP_MODE_FOLLOW); }
-        else if (late_cfg == 3) { RCP_TRACK(256, 8, 256, true, 2048 * 8, RCP_MODE_LATE); RCP_TRACK(256, 8, 256, false, 0, RCP_MODE_FOLLOW); }
-        else if (late_cfg == 4) { RCP_TRACK(512, 4, 128, true, 2048 * 8, RCP_MODE_LATE); RCP_TRACK(512, 4, 128, false, 0, RCP_MODE_FOLLOW); }
-        else { RCP_TRACK(256, 8, 256, true, 2048 * 8, RCP_MODE_LATE); RCP_TRACK(256, 8, 256, false, 0, RCP_MODE_FOLLOW); }
+        if (late_cfg == 1) { RCP_TRACK(256, 8, 128, true, 2048 * 8, RCP_MODE_LATE, 2); RCP_TRACK(256, 8, 128, false, 0, RCP_MODE_FOLLOW, 2); }
+        else if (late_cfg == 2) { RCP_TRACK(128, 16, 128, true, 2048 * 8, RCP_MODE_LATE, 2); RCP_TRACK(128, 16, 128, false, 0, RCP_MODE_FOLLOW, 2); }
+        else if (late_cfg == 3) { RCP_TRACK(256, 8, 256, true, 2048 * 8, RCP_MODE_LATE, 2); RCP_TRACK(256, 8, 256, false, 0, RCP_MODE_FOLLOW, 2); }
+        else if (late_cfg == 4) { RCP_TRACK(512, 4, 128, true, 2048 * 8, RCP_MODE_LATE, 2); RCP_TRACK(512, 4, 128, false, 0, RCP_MODE_FOLLOW, 2); }
+        else { RCP_TRACK(256, 8, 256, true, 2048 * 8, RCP_MODE_LATE, 2); RCP_TRACK(256, 8, 256, false, 0, RCP_MODE_FOLLOW, 2); }
         CR_LAUNCH(k_rcp_resolve, dim3(nstreams), dim3(32), stream, ps, nstreams, jobs, E, F);
         CR_LAUNCH(k_rcp_emit, gemit, dim3(128), stream, ps, nstreams, jobs, nj, cin_main, cin_side, q_main, sh_main, q_side, sh_side, (int)RCP_EMIT_JOBS, E, st);
         }

@@ -571,7 +571,7 @@ extern "C" int crgpu_debug_rc_parallel(crgpu_handle* h, const uint32_t* frq, con
     if (rc == CRGPU_OK && stats_out) {
         const RcpStats& st = c.rcpar.last;
         stats_out[0] = st.state_steps; stats_out[1] = st.live_jobs; stats_out[2] = st.merged_jobs; stats_out[3] = st.seed_retries;
-        stats_out[4] = st.demoted_jobs; stats_out[5] = st.flagged_streams; stats_out[6] = st.max_e; stats_out[7] = 0;
+        stats_out[4] = st.demoted_jobs; stats_out[5] = st.flagged_streams; stats_out[6] = st.max_e; stats_out[7] = st.decided_serial;
     }
     return rc;
 #endif

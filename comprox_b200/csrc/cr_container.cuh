@@ -47,6 +47,7 @@ struct Compressor {
     cudaStream_t dict_stream = 0;
     DevBuf d_dictout;
     int dict_mode = 1;
+    int dp_tiles = 0;                       // 1: k_dp_count_tiles (shared-memory table per tile) instead of k_dp_count; measured slower, see cr_dict.cuh
 
     void release() {
         DevBuf* all[] = { &d_raw, &d_D, &d_out, &d_dic, &t_key, &t_count, &t_first, &t_stats, &t_entries, &d_trie_edge, &d_trie_id, &b_subs, &b_hist,
@@ -96,7 +97,8 @@ inline int Compressor::dicpick(const uint8_t* h_in, const uint8_t* d_in, uint64_
         for (uint64_t c = 0; c < nchunks; c++) {
             CR_CUDA(cudaStreamWaitEvent(stream, copy_ev[c + 1 < nchunks ? c + 1 : c], 0));
             const uint64_t x0 = c * copy_chunk, x1 = x0 + copy_chunk < n ? x0 + copy_chunk : n;
-            CR_LAUNCH(k_dp_count_tiles, dim3(cr_div_up(x1 - x0, DPS_TILE)), dim3(256), stream, d_in, n, x0, x1, T);
+            if (dp_tiles) CR_LAUNCH(k_dp_count_tiles, dim3(cr_div_up(x1 - x0, DPS_TILE)), dim3(256), stream, d_in, n, x0, x1, T);
+            else CR_LAUNCH(k_dp_count, dim3(cr_div_up(x1 - x0, 256)), dim3(256), stream, d_in, n, x0, x1, T);
         }
         copy_chunk = 0;
     } else
@@ -104,10 +106,10 @@ inline int Compressor::dicpick(const uint8_t* h_in, const uint8_t* d_in, uint64_
     for (uint64_t x0 = 0; x0 < n; x0 += step) {
         uint64_t x1 = x0 + step < n ? x0 + step : n;
 #ifndef CRGPU_SIM
-        CR_LAUNCH(k_dp_count_tiles, dim3(cr_div_up(x1 - x0, DPS_TILE)), dim3(256), stream, d_in, n, x0, x1, T);
-#else
-        CR_LAUNCH(k_dp_count, dim3(cr_div_up(x1 - x0, 256)), dim3(256), stream, d_in, n, x0, x1, T);
+        if (dp_tiles) CR_LAUNCH(k_dp_count_tiles, dim3(cr_div_up(x1 - x0, DPS_TILE)), dim3(256), stream, d_in, n, x0, x1, T);
+        else
 #endif
+        CR_LAUNCH(k_dp_count, dim3(cr_div_up(x1 - x0, 256)), dim3(256), stream, d_in, n, x0, x1, T);
     }
     for (uint64_t x0 = 0; x0 < n; x0 += step) {
         uint64_t x1 = x0 + step < n ? x0 + step : n;

@@ -73,6 +73,7 @@ struct LzChain {
     int o1_hot_variant = 2;        // 2 = k_o1_skel + k_o1_eval (the chain of steps carries only the counts), 1 = k_o1_pass_cta
     int o2_hot_variant = 3;        // 3 = k_o2_skel + k_o2_eval (the chain of steps carries only counts and flags), 2 = k_o2_hot (event ring, ballot ranks), 1 = k_o2_pass_cta
     bool o2_attr_done = false;
+    uint32_t o2_width = 0;         // events per step of the split o2 pass: 0 = by the window's hit rate (256 / 1024), or 256 / 512 / 1024
     uint32_t o2_rec_cap_test = 0;  // tests only: capacity of the step-record table (0 = the bound)
     bool scalar_models = false;   // GPU A/B switch: run the scalar (simulation-checked) model/coder kernels
     bool exact_aborts = true;      // replay a mid-chain "cannot compress" exactly (encode_blocks); false = CRGPU_ERR_MIDCHAIN_ABORT
@@ -84,7 +85,7 @@ struct LzChain {
     // the switches a second chain of the same handle must share (Compressor's dictionary-payload chain)
     void copy_options(const LzChain& o) {
         match_limit = o.match_limit; x_max_iter = o.x_max_iter; flexible = o.flexible; rc_variant = o.rc_variant; hot_contexts = o.hot_contexts;
-        rolz_match_variant = o.rolz_match_variant; o1_hot_variant = o.o1_hot_variant; o2_hot_variant = o.o2_hot_variant; o2_rec_cap_test = o.o2_rec_cap_test;
+        rolz_match_variant = o.rolz_match_variant; o1_hot_variant = o.o1_hot_variant; o2_hot_variant = o.o2_hot_variant; o2_rec_cap_test = o.o2_rec_cap_test; o2_width = o.o2_width;
         scalar_models = o.scalar_models; exact_aborts = o.exact_aborts;
 #ifndef CRGPU_SIM
         rcpar.job_symbols = o.rcpar.job_symbols; rcpar.late_cfg = o.rcpar.late_cfg; rcpar.serial_only = o.rcpar.serial_only; rcpar.crowded = o.rcpar.crowded;
@@ -514,6 +515,8 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
                     if (!o2_attr_done) {
                         CR_CUDA(cudaFuncSetAttribute(k_o2_hot<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(O2HotSmem<256>)));
                         CR_CUDA(cudaFuncSetAttribute(k_o2_hot<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(O2HotSmem<1024>)));
+                        CR_CUDA(cudaFuncSetAttribute(k_o2_hot<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(O2HotSmem<512>)));
+                        CR_CUDA(cudaFuncSetAttribute(k_o2_eval<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(O2EvalSmem<512>)));
                         CR_CUDA(cudaFuncSetAttribute(k_o2_eval<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(O2EvalSmem<256>)));
                         CR_CUDA(cudaFuncSetAttribute(k_o2_eval<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(O2EvalSmem<1024>)));
                         o2_attr_done = true;
@@ -529,23 +532,19 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
                         // into triples and escape records.  Records: one per TH events plus one per rescale; a rescale needs 125 hits or 125
                         // occurrences of one symbol since the last one (short cascades aside), so n / 120 bounds them with room to spare; a context
                         // that still runs out is redone by k_o2_hot (nothing of it has been written by then)
-                        const uint32_t th = narrow ? 256u : 1024u;
+                        const uint32_t th = o2_width ? o2_width : narrow ? 256u : 1024u;
                         const uint32_t hot_bound = nev / O2C_MIN + 1 < 65536u ? nev / O2C_MIN + 1 : 65536u;
                         const uint32_t cap = o2_rec_cap_test ? o2_rec_cap_test : nev / th + nev / 120u + 2u * hot_bound + 256u;
                         CR_TRY(b_o2hot.reserve(65536 * 4)); CR_TRY(b_o2todo.reserve(65536)); CR_TRY(b_o2steps.reserve((size_t)cap * sizeof(O2Step))); CR_TRY(b_o2snaps.reserve((size_t)cap * 256));
                         std::vector<uint32_t> ctl0 = { 0u, 0u, cap, 0u };
                         CR_TRY(upload(b_o2ctl, ctl0));
                         CR_LAUNCH(k_o2_hotlist, dim3(256), dim3(256), stream, b_bounds.as<uint32_t>(), b_o2hot.as<uint32_t>(), b_o2ctl.as<O2SplitCtl>(), b_o2todo.as<uint8_t>());
-                        const uint32_t geval = narrow ? 148u * 8u : 148u * 2u;
-                        if (narrow) {
-                            CR_O2_LAUNCH(k_o2_skel, hot_bound, 256, 0, b_k1.as<uint32_t>(), st, b_bounds.as<uint32_t>(), b_o2hot.as<uint32_t>(), b_o2ctl.as<O2SplitCtl>(), b_o2todo.as<uint8_t>(), b_o2steps.as<O2Step>(), b_o2snaps.as<uint8_t>());
-                            CR_O2_LAUNCH(k_o2_eval, geval, 256, sizeof(O2EvalSmem<256>), b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), b_o2ctl.as<O2SplitCtl>(), b_o2todo.as<uint8_t>(), b_o2steps.as<O2Step>(), b_o2snaps.as<uint8_t>(), b_T1.as<uint64_t>(), b_escrec.as<EscRec>(), b_esccount.as<uint32_t>());
-                            CR_O2_LAUNCH(k_o2_hot, hot_bound, 256, sizeof(O2HotSmem<256>), b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nev, st, b_T1.as<uint64_t>(), b_escrec.as<EscRec>(), b_esccount.as<uint32_t>(), b_bounds.as<uint32_t>(), b_o2hot.as<uint32_t>(), b_o2ctl.as<O2SplitCtl>(), b_o2todo.as<uint8_t>());
-                        } else {
-                            CR_O2_LAUNCH(k_o2_skel, hot_bound, 1024, 0, b_k1.as<uint32_t>(), st, b_bounds.as<uint32_t>(), b_o2hot.as<uint32_t>(), b_o2ctl.as<O2SplitCtl>(), b_o2todo.as<uint8_t>(), b_o2steps.as<O2Step>(), b_o2snaps.as<uint8_t>());
-                            CR_O2_LAUNCH(k_o2_eval, geval, 1024, sizeof(O2EvalSmem<1024>), b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), b_o2ctl.as<O2SplitCtl>(), b_o2todo.as<uint8_t>(), b_o2steps.as<O2Step>(), b_o2snaps.as<uint8_t>(), b_T1.as<uint64_t>(), b_escrec.as<EscRec>(), b_esccount.as<uint32_t>());
-                            CR_O2_LAUNCH(k_o2_hot, hot_bound, 1024, sizeof(O2HotSmem<1024>), b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nev, st, b_T1.as<uint64_t>(), b_escrec.as<EscRec>(), b_esccount.as<uint32_t>(), b_bounds.as<uint32_t>(), b_o2hot.as<uint32_t>(), b_o2ctl.as<O2SplitCtl>(), b_o2todo.as<uint8_t>());
-                        }
+#define CR_O2_SPLIT(TH) do { \
+                            CR_O2_LAUNCH(k_o2_skel, hot_bound, TH, 0, b_k1.as<uint32_t>(), st, b_bounds.as<uint32_t>(), b_o2hot.as<uint32_t>(), b_o2ctl.as<O2SplitCtl>(), b_o2todo.as<uint8_t>(), b_o2steps.as<O2Step>(), b_o2snaps.as<uint8_t>()); \
+                            CR_O2_LAUNCH(k_o2_eval, 148u * (2048u / TH), TH, sizeof(O2EvalSmem<TH>), b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), b_o2ctl.as<O2SplitCtl>(), b_o2todo.as<uint8_t>(), b_o2steps.as<O2Step>(), b_o2snaps.as<uint8_t>(), b_T1.as<uint64_t>(), b_escrec.as<EscRec>(), b_esccount.as<uint32_t>()); \
+                            CR_O2_LAUNCH(k_o2_hot, hot_bound, TH, sizeof(O2HotSmem<TH>), b_k1.as<uint32_t>(), b_v1.as<uint32_t>(), nev, st, b_T1.as<uint64_t>(), b_escrec.as<EscRec>(), b_esccount.as<uint32_t>(), b_bounds.as<uint32_t>(), b_o2hot.as<uint32_t>(), b_o2ctl.as<O2SplitCtl>(), b_o2todo.as<uint8_t>()); } while (0)
+                        if (th == 256) CR_O2_SPLIT(256); else if (th == 512) CR_O2_SPLIT(512); else CR_O2_SPLIT(1024);
+#undef CR_O2_SPLIT
                     }
 #undef CR_O2_LAUNCH
                 } else if (narrow)

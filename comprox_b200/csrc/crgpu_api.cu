@@ -212,10 +212,12 @@ extern "C" int crgpu_set_option(crgpu_handle* h, const char* name, int64_t value
     if (!h || !name) return CRGPU_ERR_ARG;
     std::string n(name);
     if (n == "scalar_models") { h->chain.scalar_models = value != 0; return CRGPU_OK; }
+    if (n == "dp_tiles") { h->comp.dp_tiles = value != 0; return CRGPU_OK; }
     if (n == "dict_mode") { if (value < 0 || value > 1) return CRGPU_ERR_ARG; h->comp.dict_mode = (int)value; return CRGPU_OK; }
     if (n == "rolz_match_variant") { if (value < 1 || value > 2) return CRGPU_ERR_ARG; h->chain.rolz_match_variant = (int)value; return CRGPU_OK; }
     if (n == "o1_hot_variant") { if (value < 1 || value > 2) return CRGPU_ERR_ARG; h->chain.o1_hot_variant = (int)value; return CRGPU_OK; }
     if (n == "o2_hot_variant") { if (value < 1 || value > 3) return CRGPU_ERR_ARG; h->chain.o2_hot_variant = (int)value; return CRGPU_OK; }
+    if (n == "o2_width") { if (value != 0 && value != 256 && value != 512 && value != 1024) return CRGPU_ERR_ARG; h->chain.o2_width = (uint32_t)value; return CRGPU_OK; }
     if (n == "o2_rec_cap_test") { h->chain.o2_rec_cap_test = (uint32_t)value; return CRGPU_OK; }     // tests: force the out-of-records path
     if (n == "rc_variant") { if (value < 1 || value > 8) return CRGPU_ERR_ARG; h->chain.rc_variant = (int)value; return CRGPU_OK; }
 #ifndef CRGPU_SIM

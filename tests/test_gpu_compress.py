@@ -105,15 +105,18 @@ def test_gpu_range_chain_variants_identical(gpulib, rcv):
 
 @pytest.mark.parametrize("variant", [api.ROLZ, api.LZP])
 def test_gpu_model_pass_variants_agree(gpulib, variant):
-    """The hot-context passes in all their forms (o2: split chain / single kernel / first form; o1: split / single kernel) and the
-    split o2 pass when its table of step records is far too small (contexts are then redone by the single kernel): same container,
-    on text (hit-heavy: 256-event steps) and on skewed binary data (1024-event steps)."""
+    """The hot-context passes in all their forms (o2: split chain / single kernel / first form, 256 / 512 / 1024 events per step; o1:
+    split / single kernel), the split o2 pass when its table of step records is far too small (contexts are then redone by the single
+    kernel), the range chain forced serial / forced cut, the dictionary payload on the main chain, the first form of the match search:
+    same container, on text (hit-heavy) and on skewed binary data."""
     import numpy as np
     rng = np.random.default_rng(5)
     skew = rng.choice(np.arange(256, dtype=np.uint8), size=6 * MiB, p=np.r_[0.5, 0.2, np.full(254, 0.3 / 254)]).tobytes()
     for data in (synth.markov_text(6 * MiB, seed=91), skew):
         want = O.compress(data, variant, 4 * MiB)
-        for opts in ({}, {"o2_hot_variant": 2}, {"o2_hot_variant": 1, "o1_hot_variant": 1}, {"o2_rec_cap_test": 37}, {"o2_rec_cap_test": 1}):
+        for opts in ({}, {"o2_hot_variant": 2}, {"o2_hot_variant": 1, "o1_hot_variant": 1}, {"o2_rec_cap_test": 37}, {"o2_rec_cap_test": 1},
+                     {"o2_width": 256}, {"o2_width": 512}, {"o2_width": 1024}, {"rc_serial": 1}, {"rc_serial": 0}, {"dict_mode": 0},
+                     {"rolz_match_variant": 1}, {"dp_tiles": 1}):
             with api.Handle(variant, lib=gpulib) as h:
                 for k, v in opts.items():
                     h.set_option(k, v)

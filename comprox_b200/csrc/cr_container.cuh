@@ -41,6 +41,14 @@ struct Compressor {
 #ifndef CRGPU_SIM
     cudaStream_t copy_stream = 0;
     std::vector<cudaEvent_t> copy_ev;
+    cudaEvent_t ev_counted = 0;
+    // lowest priority: the check kernel that runs on it (k_dp_verify) must not hold up the kernels the host is waiting for
+    int make_copy_stream() {
+        int lo = 0, hi = 0;
+        CR_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CR_CUDA(cudaStreamCreateWithPriority(&copy_stream, cudaStreamNonBlocking, lo));
+        return CRGPU_OK;
+    }
 #endif
     uint64_t copy_chunk = 0;                // 0: the input is resident as a whole (no events to wait for)
     LzChain* dict_chain = nullptr;
@@ -61,6 +69,7 @@ struct Compressor {
         if (copy_stream) { cudaStreamDestroy(copy_stream); copy_stream = 0; }
         for (cudaEvent_t e : copy_ev) cudaEventDestroy(e);
         copy_ev.clear();
+        if (ev_counted) { cudaEventDestroy(ev_counted); ev_counted = 0; }
 #endif
     }
     template <class T> int upload(DevBuf& b, const std::vector<T>& v) { return chain->upload(b, v); }
@@ -111,10 +120,28 @@ inline int Compressor::dicpick(const uint8_t* h_in, const uint8_t* d_in, uint64_
 #endif
         CR_LAUNCH(k_dp_count, dim3(cr_div_up(x1 - x0, 256)), dim3(256), stream, d_in, n, x0, x1, T);
     }
+    // every occurrence must spell the word its table entry stands for (a 64-bit hash collision is an error, not a wrong dictionary).
+    // Nothing downstream waits for the answer, so the check runs on a second stream beside the collect kernel and the host's
+    // ordering of the words; its flag is read at the end of this function.
+    cudaStream_t vstream = stream;
+#ifndef CRGPU_SIM
+    if (!copy_stream) CR_TRY(make_copy_stream());
+    if (!ev_counted) CR_CUDA(cudaEventCreateWithFlags(&ev_counted, cudaEventDisableTiming));
+    CR_CUDA(cudaEventRecord(ev_counted, stream));
+    CR_CUDA(cudaStreamWaitEvent(copy_stream, ev_counted, 0));
+    vstream = copy_stream;
+#endif
     for (uint64_t x0 = 0; x0 < n; x0 += step) {
         uint64_t x1 = x0 + step < n ? x0 + step : n;
-        CR_LAUNCH(k_dp_verify, dim3(cr_div_up(x1 - x0, 256)), dim3(256), stream, d_in, n, x0, x1, T);
+        CR_LAUNCH(k_dp_verify, dim3(cr_div_up(x1 - x0, 256)), dim3(256), vstream, d_in, n, x0, x1, T);
     }
+    auto collided = [&](bool* yes) -> int {
+        uint32_t flag = 0;
+        CR_CUDA(cudaMemcpyAsync(&flag, t_stats.as<uint32_t>() + 8, 4, cudaMemcpyDeviceToHost, vstream));
+        CR_CUDA(cudaStreamSynchronize(vstream));
+        *yes = flag != 0;
+        return CRGPU_OK;
+    };
     CR_LAUNCH(k_dp_collect, dim3(DP_SLOTS / 256), dim3(256), stream, T, d_in, n, t_entries.as<DpEntry>(), DP_MAXWORDS);
     chain->timer.mark("dp_kernels");
     auto t0 = std::chrono::steady_clock::now();
@@ -128,6 +155,9 @@ inline int Compressor::dicpick(const uint8_t* h_in, const uint8_t* d_in, uint64_
     CR_TRY(download(stats, t_stats.p, 4));
     if (stats[1] & 1u) {
         // more than 325000 distinct words: replay the reference's prune epochs exactly (cr_dict.cuh)
+        bool bad = false;
+        CR_TRY(collided(&bad));                                          // (the epochs rebuild the tables the check reads)
+        if (bad) return CRGPU_ERR_HASH_COLLISION;
         CR_TRY(dicpick_epochs(d_in, n));
         CR_TRY(download(stats, t_stats.p, 4));
         if (stats[1] & 4u) return CRGPU_ERR_VOCAB_OVERFLOW;          // more distinct words in one window than the table holds
@@ -143,8 +173,11 @@ inline int Compressor::dicpick(const uint8_t* h_in, const uint8_t* d_in, uint64_
     if (getenv("CRGPU_TIMING")) fprintf(stderr, "crgpu timing: %zu words with count > 5\n", words.size());
     text = hd_dictionary_text(words);
     lap("dp text");
+    bool bad = false;
+    CR_TRY(collided(&bad));
+    lap("dp verify wait");
     chain->timer.mark("dp_host");
-    return CRGPU_OK;
+    return bad ? CRGPU_ERR_HASH_COLLISION : CRGPU_OK;
 }
 
 // Exact vocabulary-overflow path.  Leaves the final table in t_key/t_count/t_first and the selected
@@ -358,7 +391,7 @@ inline int Compressor::compress(const CrConfig& cfg, const uint8_t* in, uint64_t
 #ifndef CRGPU_SIM
         const uint64_t CH = 16ull << 20;
         if (n > 2 * CH) {
-            if (!copy_stream) CR_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+            if (!copy_stream) CR_TRY(make_copy_stream());
             const uint64_t nchunks = (n + CH - 1) / CH;
             while (copy_ev.size() < nchunks + 1) { cudaEvent_t e; CR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); copy_ev.push_back(e); }
             CR_CUDA(cudaEventRecord(copy_ev[nchunks], stream));                 // the buffer exists (stream-ordered allocation) and nothing reads it any more

@@ -25,7 +25,7 @@ struct DpTable {
     unsigned long long* key;   // [DP_SLOTS] 0 = empty
     uint32_t* count;           // [DP_SLOTS]
     uint32_t* first;           // [DP_SLOTS] smallest position at which the word starts
-    uint32_t* stats;           // [0] distinct words, [1] error flags, [2] number of selected entries
+    uint32_t* stats;           // [0] distinct words, [1] error flags, [2] number of selected entries, [8] set by k_dp_verify: two spellings share a hash
 };
 
 CR_HD uint32_t dp_byte(const uint8_t* in, uint64_t chunk0, uint32_t c, uint32_t flen) {
@@ -147,7 +147,7 @@ __global__ void k_dp_verify(const uint8_t* __restrict__ in, uint64_t n, uint64_t
     bool same = true;
     for (uint32_t i = 0; i < len; i++) same &= (a[i] | 32) == (b[i] | 32);
     same &= !cr_is_lower(b[len]);
-    if (!same) atomicOr(&T.stats[1], 2u);
+    if (!same) atomicOr(&T.stats[8], 1u);
 }
 // ---- exact handling of vocabulary overflow (cr-dicpick.c:115-144).  When the 325001st distinct word
 // arrives the reference drops every word whose count is <= (smallest count) + 5 and carries on, so the result

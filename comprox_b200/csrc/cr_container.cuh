@@ -55,6 +55,8 @@ struct Compressor {
     cudaStream_t dict_stream = 0;
     DevBuf d_dictout;
     int dict_mode = 1;
+    bool crowded = false;                   // set by crgpu_compress_batch when three or more handles share the device: no extra streams
+                                            // (every stream beyond the 32 hardware queues aliases behind some other handle's serial walk)
     int dp_tiles = 0;                       // 1: k_dp_count_tiles (shared-memory table per tile) instead of k_dp_count; measured slower, see cr_dict.cuh
 
     void release() {
@@ -125,11 +127,13 @@ inline int Compressor::dicpick(const uint8_t* h_in, const uint8_t* d_in, uint64_
     // ordering of the words; its flag is read at the end of this function.
     cudaStream_t vstream = stream;
 #ifndef CRGPU_SIM
+    if (!crowded) {
     if (!copy_stream) CR_TRY(make_copy_stream());
     if (!ev_counted) CR_CUDA(cudaEventCreateWithFlags(&ev_counted, cudaEventDisableTiming));
     CR_CUDA(cudaEventRecord(ev_counted, stream));
     CR_CUDA(cudaStreamWaitEvent(copy_stream, ev_counted, 0));
     vstream = copy_stream;
+    }
 #endif
     for (uint64_t x0 = 0; x0 < n; x0 += step) {
         uint64_t x1 = x0 + step < n ? x0 + step : n;
@@ -390,7 +394,7 @@ inline int Compressor::compress(const CrConfig& cfg, const uint8_t* in, uint64_t
         CR_CUDA(cudaMemsetAsync(d_raw.as<uint8_t>() + n, 0, 128, stream));
 #ifndef CRGPU_SIM
         const uint64_t CH = 16ull << 20;
-        if (n > 2 * CH) {
+        if (n > 2 * CH && !crowded) {
             if (!copy_stream) CR_TRY(make_copy_stream());
             const uint64_t nchunks = (n + CH - 1) / CH;
             while (copy_ev.size() < nchunks + 1) { cudaEvent_t e; CR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); copy_ev.push_back(e); }
@@ -430,7 +434,7 @@ inline int Compressor::compress(const CrConfig& cfg, const uint8_t* in, uint64_t
 #ifndef CRGPU_SIM
     std::thread dict_thread;
     int dict_rc = CRGPU_OK;
-    if (dict_mode == 1) {
+    if (dict_mode == 1 && !crowded) {
         int dev = 0;
         CR_CUDA(cudaGetDevice(&dev));
         if (!dict_chain) {

@@ -484,6 +484,7 @@ extern "C" int crgpu_compress_batch(crgpu_handle* const* hs, uint32_t nhandles, 
         uint32_t same = 0;
         for (uint32_t k = 0; k < nhandles; k++) same += hs[k]->device == hs[i]->device;
         hs[i]->chain.rcpar.crowded = same >= 3 && count >= 3;
+        hs[i]->comp.crowded = hs[i]->chain.rcpar.crowded;
     }
 #endif
     std::atomic<uint32_t> next(0);
@@ -502,7 +503,7 @@ extern "C" int crgpu_compress_batch(crgpu_handle* const* hs, uint32_t nhandles, 
     if (nthreads) worker(0);
     for (auto& t : pool) t.join();
 #ifndef CRGPU_SIM
-    for (uint32_t i = 0; i < nhandles; i++) hs[i]->chain.rcpar.crowded = false;
+    for (uint32_t i = 0; i < nhandles; i++) { hs[i]->chain.rcpar.crowded = false; hs[i]->comp.crowded = false; }
 #endif
     return first_error.load();
 }

@@ -476,7 +476,7 @@ inline int LzChain::encode_window(const uint8_t* dD, std::vector<BlockIO>& blk, 
         if (!scalar_models && hot_contexts) {
             const uint32_t hot_cap = nev / O3_HANDOVER + 16;
             CR_TRY(b_o3hot.reserve((size_t)hot_cap * sizeof(O3Hot) + 16));
-            CR_CUDA(cudaMemsetAsync(b_esccount.as<uint32_t>() + 1, 0, 4, stream));
+            CR_CUDA(cudaMemsetAsync(b_esccount.as<uint32_t>() + 1, 0, 8, stream));      // hot-segment count and the queue head of k_o3_hot_spec
             // list the slot segments, longest first
             CR_TRY(b_flag.reserve((size_t)(nev + 1) * 4 + 16)); CR_TRY(b_escord.reserve((size_t)(nev + 1) * 4 + 16));
             CR_LAUNCH(k_o3_headflags, dim3(cr_div_up(nev + 1, 256)), dim3(256), stream, b_k1.as<uint32_t>(), nev, b_flag.as<uint32_t>());

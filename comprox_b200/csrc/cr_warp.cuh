@@ -145,10 +145,18 @@ CR_D void o3_step(uint32_t& byte, uint32_t& conf, uint32_t sym) {          // pp
 }
 __global__ void __launch_bounds__(O3S_THREADS) k_o3_hot_spec(const uint32_t* __restrict__ K, const uint32_t* __restrict__ V, uint32_t n, const uint32_t* __restrict__ seg_start,
                                                              PpmState st, uint8_t* __restrict__ pred, const O3Hot* __restrict__ hot, const uint32_t* __restrict__ hot_count, uint32_t hot_cap) {
-    __shared__ uint32_t s_guess[O3S_THREADS], s_end[O3S_THREADS];          // byte | conf << 8
-    __shared__ uint32_t s_true;
+    __shared__ uint32_t s_guess[O3S_THREADS], s_end[O3S_THREADS], s_entry[O3S_THREADS];          // byte | conf << 8
+    __shared__ uint32_t s_true, s_chain, s_fail;
     uint32_t total = *hot_count; if (total > hot_cap) total = hot_cap;
-    for (uint32_t e = blockIdx.x; e < total; e += gridDim.x) {
+    // the list comes longest segment first (k_o3_pass_sorted hands segments over in that order): CTAs take the next entry when they
+    // are done with theirs (hot_count[1] is the queue), which is longest-processing-time-first scheduling; a fixed round robin gave
+    // the first CTAs the longest segment of every round (ncu: sm__cycles_active avg 1.26 M, max 4.93 M)
+    __shared__ uint32_t s_e;
+    for (;;) {
+        if (threadIdx.x == 0) s_e = atomicAdd(const_cast<uint32_t*>(hot_count) + 1, 1u);
+        __syncthreads();
+        const uint32_t e = s_e;
+        if (e >= total) break;
         const O3Hot H = hot[e];
         const uint32_t r0 = H.rank;
         uint32_t r1 = r0;                                                  // end of the slot's segment
@@ -174,18 +182,40 @@ __global__ void __launch_bounds__(O3S_THREADS) k_o3_hot_spec(const uint32_t* __r
                 s_end[threadIdx.x] = byte | conf << 8;
             }
             __syncthreads();
-            if (threadIdx.x == 0) {
-                uint32_t cur = s_true;
-                const uint32_t nch = (r1 - pass0 + O3S_CHUNK - 1) / O3S_CHUNK < O3S_THREADS ? (r1 - pass0 + O3S_CHUNK - 1) / O3S_CHUNK : O3S_THREADS;
-                for (uint32_t c = 0; c < nch; c++) {
-                    if (s_guess[c] == cur) { cur = s_end[c]; continue; }
-                    uint32_t b = cur & 255, cf = cur >> 8;                 // wrong guess: replay this chunk from the true state
+            // Verification.  A wrong guess used to be replayed by thread 0 on the spot -- 256 events one after the other while 255 threads
+            // waited (ncu: 38 barrier-stall cycles per issue, the hottest slot's CTA 4.9 M cycles of a 2.5 ms kernel).  The automaton
+            // forgets, so a chunk entered in the wrong state still ENDS in the state its speculative run ended in, nearly always: thread 0
+            // walks the chain assuming just that, notes the true entry of every chunk whose guess was wrong, all those chunks are replayed
+            // side by side, and each replay checks the assumption (its end against the end the chain used).  The first chunk whose end
+            // differs restarts the walk behind it.  Every accepted chunk's last run started from its true entry state.
+            const uint32_t nch = (r1 - pass0 + O3S_CHUNK - 1) / O3S_CHUNK < O3S_THREADS ? (r1 - pass0 + O3S_CHUNK - 1) / O3S_CHUNK : O3S_THREADS;
+            uint32_t from = 0;
+            for (;;) {
+                if (threadIdx.x == 0) {
+                    uint32_t cur = s_true;
+                    for (uint32_t c = from; c < nch; c++) { s_entry[c] = s_guess[c] == cur ? 0xFFFFFFFFu : cur; cur = s_end[c]; }
+                    s_chain = cur; s_fail = 0xFFFFFFFFu;
+                }
+                __syncthreads();
+                const uint32_t c = threadIdx.x;
+                if (c >= from && c < nch && s_entry[c] != 0xFFFFFFFFu) {
+                    uint32_t b = s_entry[c] & 255, cf = s_entry[c] >> 8;
                     const uint32_t a0 = pass0 + c * O3S_CHUNK, a1 = a0 + O3S_CHUNK < r1 ? a0 + O3S_CHUNK : r1;
                     for (uint32_t i = a0; i < a1; i++) { pred[V[i]] = (uint8_t)b; o3_step(b, cf, K[i] >> 24); }
-                    cur = b | cf << 8;
+                    const uint32_t e = b | cf << 8;
+                    if (e != s_end[c]) atomicMin(&s_fail, c);
+                    s_guess[c] = s_entry[c]; s_end[c] = e;                 // the chunk's latest run: entry -> end
                 }
-                s_true = cur;
+                __syncthreads();
+                const uint32_t f = s_fail;
+                if (f == 0xFFFFFFFFu) break;
+                // chunks up to f are settled (every replayed end before f matched); the chain behind f starts from f's true end
+                if (threadIdx.x == 0) s_true = s_end[f];
+                from = f + 1;
+                __syncthreads();
+                if (from >= nch) { if (threadIdx.x == 0) s_chain = s_true; __syncthreads(); break; }
             }
+            if (threadIdx.x == 0) s_true = s_chain;
             __syncthreads();
         }
         if (threadIdx.x == 0) { st.o3_byte[H.slot] = (uint8_t)(s_true & 255); st.o3_conf[H.slot] = (uint8_t)(s_true >> 8); }

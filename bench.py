@@ -344,8 +344,12 @@ def corpus_leg(args, L, api, torch, dist, rank, local_rank, world, peak):
             if world > 1:
                 dist.barrier()
             dst = np.memmap(spath, dtype=np.uint8, mode="r+", shape=(max(total, 1),))
-            for k, s in enumerate(shard_slots):
-                dst[offs[mine[s]]:offs[mine[s]] + sizes[k]] = conts[k]
+            # one memmove per container, on a few host threads (ctypes releases the GIL): 1.3 GB through one core was 0.4 s of a 2.9 s leg
+            from concurrent.futures import ThreadPoolExecutor
+            def put(k):
+                ctypes.memmove(dst.ctypes.data + int(offs[mine[shard_slots[k]]]), conts[k].ctypes.data, sizes[k])
+            with ThreadPoolExecutor(max_workers=max(1, min(8, host_cores() // world))) as ex:
+                list(ex.map(put, range(m)))
             dst.flush()
             if world > 1:
                 dist.barrier()

@@ -28,6 +28,8 @@ struct Compressor {
     DevBuf d_raw, d_D, d_out, d_dic;
     DevBuf t_key, t_count, t_first, t_stats, t_entries;          // dicpick table
     DevBuf d_trie_edge, d_trie_id;
+    DevBuf b_dcoff, b_dclist;
+    int dc_listed = 1;                      // 1: word starts are listed and the trie is walked one listed word per lane (k_dc_walk); 0: k_dc_spans
     DevBuf b_subs, b_hist, b_esc10, b_escmask, b_span, b_hit, b_segs, b_xt, b_entry, b_cnt, b_scan, b_chunk0, b_hdr, b_copy, b_segoff, b_seglen;
     HdTrie trie;
     FilterHost filt;
@@ -64,7 +66,7 @@ struct Compressor {
                           &b_esc10, &b_escmask, &b_span, &b_hit, &b_segs, &b_xt, &b_entry, &b_cnt, &b_scan, &b_chunk0, &b_hdr, &b_copy, &b_segoff, &b_seglen };
         for (DevBuf* b : all) b->release();
         filt.release();
-        d_dictout.release();
+        d_dictout.release(); b_dcoff.release(); b_dclist.release();
         if (dict_chain) { dict_chain->release(); delete dict_chain; dict_chain = nullptr; }
 #ifndef CRGPU_SIM
         if (dict_stream) { cudaStreamDestroy(dict_stream); dict_stream = 0; }
@@ -306,6 +308,19 @@ inline int Compressor::dict_encode_window(const uint8_t* d_rawwin, const std::ve
         CR_TRY(b_span.reserve(rawtotal + 16)); CR_TRY(b_hit.reserve(rawtotal * 4 + 16));
         CR_TRY(b_xt.reserve((size_t)nchunk * 256 + 16)); CR_TRY(b_entry.reserve(nchunk + 16));
         CR_TRY(b_cnt.reserve((size_t)(nchunk + 1) * 4)); CR_TRY(b_scan.reserve((size_t)(nchunk + 1) * 4));
+#ifndef CRGPU_SIM
+        if (dc_listed) {
+            const uint32_t gx = cr_div_up(DC_SUB, DCS_TH);
+            const size_t nct = (size_t)gx * nsub;
+            CR_TRY(b_dcoff.reserve((nct + 1) * 4 + 16)); CR_TRY(b_dclist.reserve(rawtotal / 2 * sizeof(uint2) + 64));       // a word start needs a non-letter in front of it
+            CR_CUDA(cudaMemsetAsync(b_dcoff.as<uint32_t>() + nct, 0, 4, stream));
+            CR_LAUNCH(k_dc_count_starts, dim3(gx, nsub), dim3(DCS_TH), stream, d_rawwin, b_subs.as<DcSub>(), b_dcoff.as<uint32_t>());
+            CR_TRY(cr_exclusive_sum(prims, b_dcoff.as<uint32_t>(), b_dcoff.as<uint32_t>(), nct + 1));                     // [nct] = number of word starts
+            CR_LAUNCH(k_dc_list_starts, dim3(gx, nsub), dim3(DCS_TH), stream, d_rawwin, b_subs.as<DcSub>(), b_dcoff.as<uint32_t>(), b_span.as<uint8_t>(), b_dclist.as<uint2>());
+            CR_LAUNCH(k_dc_walk, dim3(cr_div_up(rawtotal / 2 + 1, DCS_TH)), dim3(DCS_TH), stream, d_rawwin, b_subs.as<DcSub>(), T, b_dclist.as<uint2>(), b_dcoff.as<uint32_t>() + nct,
+                      b_span.as<uint8_t>(), b_hit.as<uint32_t>());
+        } else
+#endif
         CR_LAUNCH(k_dc_spans, dim3(cr_div_up(DC_SUB, 256), nsub), dim3(256), stream, d_rawwin, b_subs.as<DcSub>(), T, b_span.as<uint8_t>(), b_hit.as<uint32_t>());
         CR_CUDA(cudaMemsetAsync(b_cnt.p, 0, (size_t)(nchunk + 1) * 4, stream));
         if (nchunk) {

@@ -254,6 +254,53 @@ __global__ void k_dc_spans(const uint8_t* __restrict__ raw, const DcSub* __restr
     span[S.off + i] = (uint8_t)sp;
 }
 
+#ifndef CRGPU_SIM
+// The same in three steps (default on the GPU).  k_dc_spans gives every byte a thread, and a warp then walks the trie for as long as its
+// longest word while five of its 32 lanes have a word at all (ncu, round 1: 68-78 % of the issue slots, 3 % of the HBM peak).  Here the
+// word starts are listed first -- counted per CTA (__syncthreads_count), offsets from the device scan, positions written in order with
+// a ballot / popcount prefix inside the CTA -- and the trie is walked with one LISTED word per lane.
+#define DCS_TH 256
+CR_D bool dc_is_start(const uint8_t* d, uint32_t i, uint32_t size) { return i > 0 && i + 40 < size && cr_is_alpha(d[i]) && !cr_is_alpha(d[i - 1]); }
+__global__ void __launch_bounds__(DCS_TH) k_dc_count_starts(const uint8_t* __restrict__ raw, const DcSub* __restrict__ subs, uint32_t* __restrict__ cta_count) {
+    const DcSub S = subs[blockIdx.y];
+    const uint32_t i = blockIdx.x * DCS_TH + threadIdx.x;
+    const int c = __syncthreads_count(i < S.size && dc_is_start(raw + S.off, i, S.size));
+    if (threadIdx.x == 0) cta_count[blockIdx.y * gridDim.x + blockIdx.x] = (uint32_t)c;
+}
+__global__ void __launch_bounds__(DCS_TH) k_dc_list_starts(const uint8_t* __restrict__ raw, const DcSub* __restrict__ subs, const uint32_t* __restrict__ cta_off,
+                                                           uint8_t* __restrict__ span, uint2* __restrict__ list) {
+    __shared__ uint32_t wsum[DCS_TH / 32];
+    const DcSub S = subs[blockIdx.y];
+    const uint32_t i = blockIdx.x * DCS_TH + threadIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const bool in = i < S.size;
+    const bool ws = in && dc_is_start(raw + S.off, i, S.size);
+    if (in) span[S.off + i] = 1;                                       // k_dc_walk raises the spans of the words it finds
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, ws);
+    if (lane == 0) wsum[w] = __popc(m);
+    __syncthreads();
+    uint32_t off = cta_off[blockIdx.y * gridDim.x + blockIdx.x];
+    for (uint32_t q = 0; q < w; q++) off += wsum[q];
+    if (ws) list[off + __popc(m & ((1u << lane) - 1u))] = make_uint2((uint32_t)(S.off + i), blockIdx.y);
+}
+__global__ void __launch_bounds__(DCS_TH) k_dc_walk(const uint8_t* __restrict__ raw, const DcSub* __restrict__ subs, DcTrie T, const uint2* __restrict__ list,
+                                                    const uint32_t* __restrict__ total, uint8_t* __restrict__ span, uint32_t* __restrict__ hit) {
+    const uint32_t t = blockIdx.x * DCS_TH + threadIdx.x;
+    if (t >= *total) return;
+    const uint2 e = list[t];
+    const DcSub S = subs[e.y];
+    const uint8_t* d = raw + S.off;
+    const uint32_t i = e.x - (uint32_t)S.off;
+    uint32_t j = i, node = 0;
+    while (d[j] < 128 && (node = dc_child(T, node, d[j])) != 0 && T.id[node] == -1) j++;
+    if (d[j] < 128 && node != 0) {
+        const uint32_t rev = (uint32_t)cr_is_upper(d[i]) ^ (uint32_t)dc_sentence_start(d, i);
+        const uint32_t tail = d[j] == ':' ? 4 : d[j] == ';' ? 3 : d[j] == ',' ? 2 : d[j] == '.' ? 1 : 0;
+        span[e.x] = (uint8_t)(j - i + 1);
+        hit[e.x] = DC_HIT | (uint32_t)T.id[node] | (rev * 5 + tail) << 24;
+    }
+}
+#endif
+
 struct DcCount {
     typedef uint32_t State;
     const uint8_t* raw; const DcSub* subs; const uint8_t* span; const uint32_t* hit; const uint32_t* escmask;   // escmask[block*8 + w]

@@ -212,6 +212,7 @@ extern "C" int crgpu_set_option(crgpu_handle* h, const char* name, int64_t value
     if (!h || !name) return CRGPU_ERR_ARG;
     std::string n(name);
     if (n == "scalar_models") { h->chain.scalar_models = value != 0; return CRGPU_OK; }
+    if (n == "dc_listed") { h->comp.dc_listed = value != 0; return CRGPU_OK; }
     if (n == "dp_tiles") { h->comp.dp_tiles = value != 0; return CRGPU_OK; }
     if (n == "dict_mode") { if (value < 0 || value > 1) return CRGPU_ERR_ARG; h->comp.dict_mode = (int)value; return CRGPU_OK; }
     if (n == "rolz_match_variant") { if (value < 1 || value > 2) return CRGPU_ERR_ARG; h->chain.rolz_match_variant = (int)value; return CRGPU_OK; }

@@ -116,7 +116,7 @@ def test_gpu_model_pass_variants_agree(gpulib, variant):
         want = O.compress(data, variant, 4 * MiB)
         for opts in ({}, {"o2_hot_variant": 2}, {"o2_hot_variant": 1, "o1_hot_variant": 1}, {"o2_rec_cap_test": 37}, {"o2_rec_cap_test": 1},
                      {"o2_width": 256}, {"o2_width": 512}, {"o2_width": 1024}, {"rc_serial": 1}, {"rc_serial": 0}, {"dict_mode": 0},
-                     {"rolz_match_variant": 1}, {"dp_tiles": 1}):
+                     {"rolz_match_variant": 1}, {"dp_tiles": 1}, {"dc_listed": 0}):
             with api.Handle(variant, lib=gpulib) as h:
                 for k, v in opts.items():
                     h.set_option(k, v)

@@ -110,3 +110,27 @@ def test_lzdecode_rejects_truncated_payload(request, which):
     with api.Handle(api.ROLZ, lib=_lib(request, which)) as h:
         with pytest.raises(api.CrgpuError):
             h.lzdecode(b"\x00\x01\x02")
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_dictionary_with_more_candidates_than_places(request, which):
+    """More than 25 000 words with a count above 5 (ties at every count): the dictionary keeps the first 24 998 of the order by
+    (count, word) and re-sorts all but the first ~155 by word -- done here by selection instead of two full sorts
+    (hd_dictionary_text), so the text, the trie built from it and a coded block must still equal the oracle's."""
+    lib = _lib(request, which)
+    rng = np.random.default_rng(17)
+    vocab = 32000
+    lens = rng.integers(3, 9, vocab)
+    letters = rng.integers(97, 123, (vocab, 8)).astype(np.uint8)
+    words = [letters[w, :lens[w]].tobytes() for w in range(vocab)]
+    occ = np.concatenate([np.repeat(np.arange(vocab), rng.integers(6, 10, vocab)), rng.integers(0, 400, 60000)])
+    rng.shuffle(occ)
+    data = b" ".join(words[w] for w in occ) + b" "
+    text = O.dicpick(data)
+    assert text.count(b"\n") > 24000
+    orc = O.Oracle(api.ROLZ)
+    with api.Handle(api.ROLZ, lib=lib) as h:
+        assert h.dicpick(data) == text
+        assert h.dictionary_load(text, 1) == orc.dictionary_load(text, 1)
+        blk = data[:300000]
+        assert h.dictionary_encode(blk) == orc.dictionary_encode(blk)

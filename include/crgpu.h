@@ -200,8 +200,10 @@ int crgpu_debug_rc_parallel(crgpu_handle* h, const uint32_t* frq, const uint32_t
  * Formulation switches (every setting gives the same bytes; the defaults are the measured best, profiles/round2_summary.md):
  * "rc_variant" 1..8 (8 = range chain cut into jobs), "rc_serial" -1 / 0 / 1 (automatic / always cut / one serial job per stream),
  * "rc_job_symbols", "rc_late_cfg"; "o2_hot_variant" 1..3 and "o1_hot_variant" 1..2 (hot-context passes: 3 / 2 = chain of steps +
- * parallel evaluation); "rolz_match_variant" 1..2; "dict_mode" 0 / 1 (1 = the dictionary payload is coded by a second model chain
- * beside the data blocks). */
+ * parallel evaluation), "o2_width" 0 / 256 / 512 / 1024 (events per o2 step, 0 = by the window's hit rate); "rolz_match_variant"
+ * 1..2; "dict_mode" 0 / 1 (1 = the dictionary payload is coded by a second model chain beside the data blocks); "dc_listed" 0 / 1
+ * (1 = dictionary substitution walks the trie one listed word start per lane); "dp_tiles" 0 / 1 (1 = word count through a
+ * shared-memory table per tile: measured slower, off). */
 int crgpu_set_option(crgpu_handle* h, const char* name, int64_t value);
 
 /* Stage timing (CUDA events on the handle's stream, accumulated over calls until reset).

@@ -148,6 +148,14 @@ struct HdTrie {
         while (edge[h & mask].key != 0 && edge[h & mask].key != key) h++;
         edge[h & mask].key = key; edge[h & mask].val = to;
     }
+    void link_if_absent(uint32_t node, uint32_t ch, uint32_t to) {       // one probe sequence for "look up, add if missing"
+        const uint32_t key = ((node << 7) | ch) + 1;
+        for (uint32_t h = hash(key) >> 8;; h++) {
+            HdEdge& e = edge[h & mask];
+            if (e.key == key) return;
+            if (e.key == 0) { e.key = key; e.val = to; return; }
+        }
+    }
     // child(node, ch), made if it does not exist yet (one probe sequence instead of two); *made tells
     uint32_t child_or_new(uint32_t node, uint32_t ch, bool* made) {
         const uint32_t key = ((node << 7) | ch) + 1;
@@ -196,7 +204,7 @@ struct HdTrie {
         // all nodes; only the owners of a blank edge do anything, and they were noted when the edge was made
         for (uint32_t i : space_parents) {
             const uint32_t sp = child(i, ' ');
-            for (char a : { '.', ',', ':', ';' }) if (!child(i, (uint32_t)a)) link(i, (uint32_t)a, sp);
+            for (char a : { '.', ',', ':', ';' }) link_if_absent(i, (uint32_t)a, sp);
         }
     }
 };
